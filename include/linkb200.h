@@ -1,0 +1,202 @@
+/*
+ * linkb200.h -- C ABI of liblinkb200.so: B200 (sm_100a) kernels for the LinK hot path.
+ *
+ * This is the drop-in boundary for the reference's native module `torchsparse.backend`
+ * (reference: segmentation/torchsparse-u/torchsparse/backend/pybind_cuda.cpp:18-39, the
+ * pybind11 table of 10 ops x {cpu,cuda}).  Each entry point below names the reference
+ * function it replaces.  Differences from the reference interface, by design:
+ *
+ *   - plain C: raw device pointers + sizes, no torch types.  The CALLER owns every
+ *     buffer (outputs and workspaces); the library never calls cudaMalloc/cudaFree and
+ *     never synchronises the device, so every call is CUDA-graph capturable.
+ *   - every call takes the CUDA stream to launch on (the reference launches on the
+ *     legacy default stream, e.g. hash_cuda.cu:59,64).
+ *   - return value: 0 on success, negative LK_E* on error; lk_last_error() gives a
+ *     thread-local message.  (Reference: C++ exceptions / no CUDA error checks.)
+ *   - fused entry points (lk_link_*, lk_kmap_*, lk_conv_*) have no single reference
+ *     counterpart; each cites the reference python/CUDA lines it subsumes.
+ *
+ * Pointer naming: d_* = device memory, everything else is passed by value.
+ * All feature matrices are row-major [rows, channels], fp32 unless stated.
+ * Coordinates are int32 [rows, 4] = (x, y, z, batch)  (reference tensor.py:10-20).
+ */
+#ifndef LINKB200_H_
+#define LINKB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LK_OK 0
+#define LK_EINVAL (-1)   /* bad argument (shape, alignment, unsupported width) */
+#define LK_ECUDA (-2)    /* a CUDA runtime call / launch failed */
+#define LK_ENOSPC (-3)   /* caller workspace too small */
+
+typedef void* lk_stream_t; /* cudaStream_t */
+
+const char* lk_last_error(void);
+int lk_version(void);
+/* Number of kernel launches (and memsets) issued through this library by this process. */
+int64_t lk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Hashing -- replaces hash_cuda / kernel_hash_cuda (backend/hash/hash_cuda.cu:10-84).
+ * Bit-exact 64-bit FNV-1a over the 4 int32 fields folded to 60 bits.
+ * ---------------------------------------------------------------------------------- */
+int lk_hash(const int32_t* d_coords, int64_t n, int64_t* d_out, lk_stream_t s);
+/* d_out layout [K, N] (hash_cuda.cu:53); offsets int32 [K,3] are added to x,y,z. */
+int lk_kernel_hash(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
+                   int64_t* d_out, lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Hash table -- replaces hash_query_cuda + CuckooHashTableCuda_Multi
+ * (backend/others/query_cuda.cu:9-58, backend/hashmap/hashmap_cuda.cu:9-204).
+ * Open addressing over 16-byte slots {int64 key, int32 value}; capacity is a power of
+ * two >= 2n.  Duplicate keys keep the LOWEST value (the reference CPU map keeps the first
+ * insert, query_cpu.cpp:22-26).  Keys must not equal -1 (the empty marker); sphash
+ * outputs are 60-bit non-negative.
+ * ---------------------------------------------------------------------------------- */
+int64_t lk_table_capacity(int64_t n);                 /* slots; bytes = 16 * slots */
+int lk_table_build(const int64_t* d_keys, int64_t n, void* d_table, int64_t capacity,
+                   lk_stream_t s);                    /* value of key i is i */
+/* d_out[i] = value of d_queries[i] or -1 (the reference returns value+1 / 0 and python
+ * subtracts 1: nn/functional/query.py:32). */
+int lk_table_query(const int64_t* d_queries, int64_t nq, const void* d_table,
+                   int64_t capacity, int64_t* d_out, lk_stream_t s);
+
+/* count_cuda (backend/others/count_cuda.cu:10-31): histogram of idx>=0 into d_out[num]. */
+int lk_count(const int32_t* d_idx, int64_t n, int32_t* d_out, int64_t num, lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * voxelize / devoxelize -- replace voxelize_{forward,backward}_cuda
+ * (backend/voxelize/voxelize_cuda.cu:12-80) and devoxelize_{forward,backward}_cuda
+ * (backend/devoxelize/devoxelize_cuda.cu:11-101).  `r3` is R = r^3 neighbours per row.
+ * ---------------------------------------------------------------------------------- */
+int lk_voxelize_fwd(const float* d_feats, const int32_t* d_idx, const int32_t* d_counts,
+                    int64_t n, int64_t m, int c, float* d_out /*[m,c]*/, lk_stream_t s);
+int lk_voxelize_bwd(const float* d_top /*[m,c]*/, const int32_t* d_idx, const int32_t* d_counts,
+                    int64_t n, int64_t m, int c, float* d_bottom /*[n,c]*/, lk_stream_t s);
+int lk_devoxelize_fwd(const float* d_feat /*[n,c]*/, const int32_t* d_idx /*[N,r3]*/,
+                      const float* d_w /*[N,r3]*/, int64_t N, int r3, int c,
+                      float* d_out /*[N,c]*/, lk_stream_t s);
+int lk_devoxelize_bwd(const float* d_top /*[N,c]*/, const int32_t* d_idx, const float* d_w,
+                      int64_t N, int r3, int c, int64_t n, float* d_bottom /*[n,c]*/,
+                      lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Key packing + radix sort/unique: the device-side replacement for torch.unique(dim=0)
+ * used by voxel_to_aux (segmentation/core/models/utils.py:47), spdownsample
+ * (nn/functional/downsample.py:48-50) and initial_voxelize (utils.py:239).
+ *
+ * A packed key is sum_f ((q[order[f]] - lo[order[f]]) << shift_f), most significant field
+ * first, where q[a] = floor(coord[a] / div[a]) for a < 3 and q[3] = batch.  Ascending key
+ * order == ascending signed lexicographic order on (q[order[0]], ..., q[order[3]]).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t div[3];   /* floor-divisor per spatial axis (>= 1) */
+  int32_t mul[3];   /* multiplier applied on unpack (spdownsample: stride; blocks: 1) */
+  int32_t order[4]; /* field order, most significant first; e.g. {0,1,2,3} or {3,0,1,2} */
+  int32_t lo[4];    /* minimum of q per field (host-known bound) */
+  int32_t bits[4];  /* field widths; sum <= 64 */
+} lk_keyspec_t;
+
+int lk_pack_keys(const int32_t* d_coords, int64_t n, const lk_keyspec_t* spec,
+                 uint64_t* d_keys, lk_stream_t s);
+int lk_unpack_keys(const uint64_t* d_keys, const int32_t* d_count /*device scalar, or NULL*/,
+                   int64_t n, const lk_keyspec_t* spec, int32_t* d_coords /*[n,4]*/,
+                   lk_stream_t s);
+
+int64_t lk_sort_unique_ws_bytes(int64_t n);
+/* Stable LSD radix sort of (key, row id) on the low `key_bits` bits, then unique.
+ * Outputs (any may be NULL): d_unique[n] ascending distinct keys, d_inverse[n] rank of each
+ * input row's key, d_order[n] row ids in sorted order (stable), d_seg[n+1] start of each
+ * distinct key's run in d_order (d_seg[M] = n), d_counts[n] run lengths, d_num device
+ * scalar M.  Entries past M are unspecified. */
+int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
+                   int32_t* d_inverse, int32_t* d_order, int32_t* d_seg, int32_t* d_counts,
+                   int32_t* d_num, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * LinK block -- fused replacement for the kernel generator + voxel_to_aux + aux_to_voxel
+ * (segmentation/core/models/semantic_kitti/linkencoder.py:124-185,
+ *  segmentation/core/models/utils.py:44-84, detection/det3d/models/utils/ts_elk.py:68-230).
+ * ---------------------------------------------------------------------------------- */
+/* Neighbour-block table (utils.py:65-73): for each of the M sorted unique block keys and
+ * each of the R offsets (int32 [R,3], get_kernel_offsets order) the row of the neighbour
+ * block or -1.  d_nbr is [capacity rows, R]; rows >= M are not written. */
+int lk_block_neighbors(const uint64_t* d_unique, const int32_t* d_num, int64_t capacity,
+                       const lk_keyspec_t* spec, const int32_t* d_offsets, int r3,
+                       int32_t* d_nbr, lk_stream_t s);
+
+#define LK_OP_COS 0   /* planes [cos, sin]           linkencoder.py:150-162 */
+#define LK_OP_SIN 1   /* planes [sin, cos]           linkencoder.py:135-148 */
+#define LK_OP_COSX 2  /* planes [cos, sin, linear]   linkencoder.py:164-176 */
+
+typedef struct {
+  int32_t op;          /* LK_OP_* */
+  int32_t c;           /* channels C (multiple of 4, <= 256) */
+  int32_t wrows;       /* rows of pos_weight: channel ch uses row ch % wrows (C/groups) */
+  float coord_scale;   /* coords are divided by this before the Linear (cos_x encoder:
+                          tensor stride, linkencoder.py:165; otherwise 1) */
+  const float* d_pos_weight; /* [wrows, 3]   pos_weight.0.weight */
+  const float* d_alpha;      /* [wrows] or NULL  (cos_x) */
+} lk_kernelgen_t;
+
+/* Zero the first *d_num rows of a [capacity, row_floats] fp32 buffer (row_floats % 4 == 0).
+ * Lets block-level buffers be allocated for the worst case M = N without touching dead rows. */
+int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity, int row_floats,
+                 lk_stream_t s);
+
+/* Pass 1: per-block sums of the weighted planes.  d_sums [M, k*C] fp32 must be zeroed by
+ * the caller, e.g. with lk_zero_rows (k = 2, or 3 for COSX).  Reads voxels in storage order; runs of equal block
+ * index are reduced in registers and flushed with vector red.global.add. */
+int lk_link_preagg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords,
+                       const int32_t* d_blk /*[n] voxel -> block row*/, int64_t n,
+                       const lk_kernelgen_t* gen, float* d_sums, lk_stream_t s);
+/* Pass 2a: window mean per block: (sum over the R neighbour blocks of sums) / (sum of
+ * counts).  d_mean [M, k*C].  M read from d_num (device scalar). */
+int lk_link_window_mean(const float* d_sums, const int32_t* d_counts, const int32_t* d_nbr,
+                        const int32_t* d_num, int64_t capacity, int r3, int kc, float* d_mean,
+                        lk_stream_t s);
+/* Pass 2b: per voxel combine with its own phase.  Writes d_out [n,C]:
+ *   fuse_norm == 0 : pre-LayerNorm value (linkencoder.py:162 / 148 / 176)
+ *   fuse_norm == 1 : relu(LN(value; g1,b1) + LN(local; g2,b2)), eps 1e-6
+ *                    (linkencoder.py:178-181); d_local [n,C] is local_mix.F. */
+int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else NULL*/,
+                      const int32_t* d_coords, const int32_t* d_blk, int64_t n,
+                      const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
+                      const float* d_g1, const float* d_b1, const float* d_g2,
+                      const float* d_b2, float* d_out, lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Kernel maps + sparse convolution -- replace the python kmap build
+ * (nn/functional/conv.py:103-122) and convolution_{forward,backward}_cuda
+ * (backend/convolution/convolution_cuda.cu:53-278).
+ *
+ * Our kernel map is OUTPUT-STATIONARY: d_nbr int32 [K, n_out], d_nbr[k, o] = input row
+ * feeding output row o through kernel offset k, or -1 (this is the reference's `results`
+ * tensor, conv.py:114).  The reference's (nbmaps, nbsizes) pair is the compaction of the
+ * non-negative entries in (k, o) order.
+ * ---------------------------------------------------------------------------------- */
+/* d_table: hash table built over lk_hash(input coords).  offsets int32 [K,3]. */
+int lk_kmap_query(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_offsets, int k,
+                  const void* d_table, int64_t capacity, int32_t* d_nbr, lk_stream_t s);
+/* Transposed relation: d_inv [K, n_in] (prefilled with -1 by this call):
+ * d_inv[k, i] = o  whenever d_nbr[k, o] = i. */
+int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_t n_in, int32_t* d_inv,
+                   lk_stream_t s);
+/* out[o, :] = sum_k in[nbr[k, o], :] @ W[k]   (+ bias).  W is [K, c_in, c_out] row-major
+ * (module parameter layout, nn/modules/conv.py:33-38).  No atomics, out fully written. */
+int lk_conv_fwd(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out,
+                int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
+                lk_stream_t s);
+/* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
+int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
+                       int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINKB200_H_ */

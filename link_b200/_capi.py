@@ -1,0 +1,106 @@
+"""ctypes binding of liblinkb200.so (C ABI declared in include/linkb200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  Tensors are passed as raw device pointers together with torch's
+current CUDA stream; all memory (outputs, workspaces) is allocated by the caller as torch
+tensors, so the library itself never allocates or synchronises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblinkb200.so')
+
+_lib = None
+
+c_i32p = C.c_void_p
+vp = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int
+
+
+class KeySpec(C.Structure):
+    _fields_ = [('div', C.c_int32 * 3), ('mul', C.c_int32 * 3), ('order', C.c_int32 * 4),
+                ('lo', C.c_int32 * 4), ('bits', C.c_int32 * 4)]
+
+
+class KernelGen(C.Structure):
+    _fields_ = [('op', C.c_int32), ('c', C.c_int32), ('wrows', C.c_int32),
+                ('coord_scale', C.c_float), ('d_pos_weight', C.c_void_p),
+                ('d_alpha', C.c_void_p)]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/linkb200.h
+PROTOTYPES = {
+    'lk_last_error': (C.c_char_p, []),
+    'lk_version': (i32, []),
+    'lk_launch_count': (i64, []),
+    'lk_hash': (i32, [vp, i64, vp, vp]),
+    'lk_kernel_hash': (i32, [vp, i64, vp, i32, vp, vp]),
+    'lk_table_capacity': (i64, [i64]),
+    'lk_table_build': (i32, [vp, i64, vp, i64, vp]),
+    'lk_table_query': (i32, [vp, i64, vp, i64, vp, vp]),
+    'lk_count': (i32, [vp, i64, vp, i64, vp]),
+    'lk_voxelize_fwd': (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    'lk_voxelize_bwd': (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    'lk_devoxelize_fwd': (i32, [vp, vp, vp, i64, i32, i32, vp, vp]),
+    'lk_devoxelize_bwd': (i32, [vp, vp, vp, i64, i32, i32, i64, vp, vp]),
+    'lk_pack_keys': (i32, [vp, i64, C.POINTER(KeySpec), vp, vp]),
+    'lk_unpack_keys': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, vp]),
+    'lk_sort_unique_ws_bytes': (i64, [i64]),
+    'lk_sort_unique': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    'lk_block_neighbors': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, i32, vp, vp]),
+    'lk_zero_rows': (i32, [vp, vp, i64, i32, vp]),
+    'lk_link_preagg_fwd': (i32, [vp, vp, vp, i64, C.POINTER(KernelGen), vp, vp]),
+    'lk_link_window_mean': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
+    'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
+                                vp, vp, vp]),
+    'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
+    'lk_kmap_invert': (i32, [vp, i64, i32, i64, vp, vp]),
+    'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
+    'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m link_b200._build` '
+                '(link_b200 has no CPU or PyTorch fallback)')
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().lk_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('link_b200 kernels need CUDA tensors (there is no CPU fallback); got '
+                           f'a {t.device} tensor')
+    if not t.is_contiguous():
+        raise RuntimeError('link_b200 kernels need contiguous tensors')
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f'expected dtype {dtype}, got {t.dtype}')
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().lk_launch_count())

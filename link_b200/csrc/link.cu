@@ -1,0 +1,393 @@
+// The LinK block's linear-kernel path as three kernels (reference: ELKBlock.forward,
+// segmentation/core/models/semantic_kitti/linkencoder.py:124-185; voxel_to_aux / aux_to_voxel,
+// segmentation/core/models/utils.py:44-84):
+//
+//   preagg      : S[b]  += F_in[i] * {cos,sin,(lin)}(p_i)      for every voxel i of block b
+//   window_mean : A[b]   = (sum_{b' in N(b)} S[b']) / (sum_{b' in N(b)} n[b'])
+//   apply       : out[i] = A_c[b(i)] cos p_i + A_s[b(i)] sin p_i (+ A_l - F_in p)  (+ fused norms)
+//
+// The reference materialises [N,kC] weighted planes (cat), scatter-means them with one CTA per
+// voxel and float atomics per element, multiplies back by the counts, gathers r^3 neighbours with
+// a global read-modify-write per neighbour, divides, gathers [N,kC] back to voxels and combines in
+// five more elementwise kernels.  Here the phase p = W.x is recomputed from the integer coordinate
+// in both passes (12 FMAs + one sincos per 4 channels), so the only HBM streams are: read F_in
+// once, read coords + block index twice, write out once; block sums / means are L2 resident.
+//
+// Thread mapping: a row of C floats is owned by a group of LPR = pow2 >= C/4 lanes, 4 channels
+// (one 128-bit transaction) per lane, so a warp handles G = 32/LPR rows per step.
+#include "common.cuh"
+
+struct GenDev {
+  int op, c, wrows;
+  float coord_scale;
+  const float* pw;
+  const float* alpha;
+};
+
+struct LaneGen {       // per-lane kernel-generator state for its 4 channels
+  float w0[4], w1[4], w2[4], al[4];
+};
+
+__device__ __forceinline__ void load_lane_gen(const GenDev& g, int ch, bool active, LaneGen& lg) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int row = active ? (ch + e) % g.wrows : 0;
+    lg.w0[e] = active ? g.pw[row * 3 + 0] : 0.f;
+    lg.w1[e] = active ? g.pw[row * 3 + 1] : 0.f;
+    lg.w2[e] = active ? g.pw[row * 3 + 2] : 0.f;
+    lg.al[e] = (active && g.alpha) ? g.alpha[row] : 1.f;
+  }
+}
+
+// phase of the 4 channels of this lane for voxel (x,y,z); same operation order as
+// nn.Linear(3, .) followed by "* alpha" (linkencoder.py:151,165)
+template <bool COSX>
+__device__ __forceinline__ void lane_phase(const GenDev& g, const LaneGen& lg, int4 c, float p[4]) {
+  float x = (float)c.x, y = (float)c.y, z = (float)c.z;
+  if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v = fmaf(z, lg.w2[e], fmaf(y, lg.w1[e], x * lg.w0[e]));
+    p[e] = COSX ? v * lg.al[e] : v;
+  }
+}
+
+#define PREAGG_ROWS_PER_GROUP 16
+#define PREAGG_UNROLL 4
+
+// ------------------------------------------------------------------ pass 1: block sums
+template <int LPR, int OP>
+__global__ void __launch_bounds__(256) link_preagg_kernel(const float* __restrict__ fin,
+                                                          const int4* __restrict__ coords,
+                                                          const int* __restrict__ blk, int64_t n,
+                                                          GenDev g, float* sums) {
+  constexpr int G = 32 / LPR;
+  constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
+  constexpr bool COSX = (OP == LK_OP_COSX);
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int ch = (lane % LPR) * 4;
+  const bool active = ch < g.c;
+  const int kc = K * g.c;
+  LaneGen lg;
+  load_lane_gen(g, ch, active, lg);
+
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t rows_per_warp = (int64_t)PREAGG_ROWS_PER_GROUP * G;
+  for (int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * rows_per_warp;
+       wbase < n; wbase += warps_total * rows_per_warp) {
+    int64_t r0 = wbase + (int64_t)grp * PREAGG_ROWS_PER_GROUP;
+    int64_t r1 = r0 + PREAGG_ROWS_PER_GROUP;
+    if (r1 > n) r1 = n;
+    float acc[K][4];
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+    int cur = -1;
+    for (int64_t r = r0; r < r1; r += PREAGG_UNROLL) {
+      int b[PREAGG_UNROLL];
+      int4 cc[PREAGG_UNROLL];
+      float4 f[PREAGG_UNROLL];
+#pragma unroll
+      for (int u = 0; u < PREAGG_UNROLL; ++u) {   // all loads of the batch first (MLP)
+        bool ok = r + u < r1;
+        b[u] = ok ? __ldg(blk + r + u) : -1;
+        cc[u] = ok ? __ldg(coords + r + u) : make_int4(0, 0, 0, 0);
+        f[u] = (ok && active) ? lk_ldg_stream((const float4*)(fin + (r + u) * g.c + ch))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < PREAGG_UNROLL; ++u) {
+        if (b[u] < 0) continue;                    // tail of the batch (or unmapped voxel)
+        if (b[u] != cur) {                         // run boundary: flush the finished block
+          if (cur >= 0 && active) {
+#pragma unroll
+            for (int q = 0; q < K; ++q)
+              lk_red_add_v4(sums + (int64_t)cur * kc + q * g.c + ch,
+                            make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+          }
+#pragma unroll
+          for (int q = 0; q < K; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+          cur = b[u];
+        }
+        float p[4], sn[4], cs[4];
+        lane_phase<COSX>(g, lg, cc[u], p);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
+        const float fv[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // plane order: cos -> [cos, sin]; sin -> [sin, cos]; cos_x -> [cos, sin, lin]
+          acc[0][e] += fv[e] * (OP == LK_OP_SIN ? sn[e] : cs[e]);
+          acc[1][e] += fv[e] * (OP == LK_OP_SIN ? cs[e] : sn[e]);
+          if (COSX) acc[K - 1][e] += fv[e] * p[e];
+        }
+      }
+    }
+    if (cur >= 0 && active) {
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+        lk_red_add_v4(sums + (int64_t)cur * kc + q * g.c + ch,
+                      make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+    }
+  }
+}
+
+// zero the first *d_num rows of a [capacity, row_floats] buffer (block sums are allocated for the
+// worst case M = N but only the M live rows are ever touched)
+__global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p,
+                                                        const int* __restrict__ d_num,
+                                                        int64_t capacity, int row_vec) {
+  int64_t m = *d_num;
+  if (m > capacity) m = capacity;
+  int64_t total = m * row_vec;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x)
+    p[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+extern "C" int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity, int row_floats,
+                            lk_stream_t s) {
+  LK_REQUIRE(capacity >= 0 && row_floats > 0 && row_floats % 4 == 0, "lk_zero_rows: bad sizes");
+  if (capacity == 0) return LK_OK;
+  LK_REQUIRE(d_buf && d_num && (uintptr_t)d_buf % 16 == 0, "lk_zero_rows: bad pointer");
+  zero_rows_kernel<<<lk_grid(capacity * (row_floats / 4), 256, 8), 256, 0, (cudaStream_t)s>>>(
+      (float4*)d_buf, d_num, capacity, row_floats / 4);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+// ------------------------------------------------------------------ pass 2a: window means
+__global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __restrict__ sums,
+                                                               const int* __restrict__ counts,
+                                                               const int* __restrict__ nbr,
+                                                               const int* __restrict__ d_num,
+                                                               int64_t capacity, int R, int kc,
+                                                               float* __restrict__ mean) {
+  int64_t m = *d_num;
+  if (m > capacity) m = capacity;
+  int vpr = kc >> 2;
+  int64_t total = m * vpr;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / vpr;
+    int j = (int)(t - b * vpr) * 4;
+    const int* nb = nbr + b * R;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float tot = 0.f;
+    for (int k = 0; k < R; ++k) {
+      int src = __ldg(nb + k);
+      if (src < 0) continue;
+      float4 v = __ldg((const float4*)(sums + (int64_t)src * kc + j));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      tot += (float)__ldg(counts + src);
+    }
+    acc.x /= tot; acc.y /= tot; acc.z /= tot; acc.w /= tot;
+    *(float4*)(mean + b * kc + j) = acc;
+  }
+}
+
+// ------------------------------------------------------------------ pass 2b: combine (+ norms)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR>
+__device__ __forceinline__ void group_layernorm(float v[4], bool active, int c, const float* gam,
+                                                const float* bet, int ch) {
+  float s = active ? (v[0] + v[1] + v[2] + v[3]) : 0.f;
+  float mean = group_sum<LPR>(s) / (float)c;
+  float d[4], q = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { d[e] = v[e] - mean; q += d[e] * d[e]; }
+  float var = group_sum<LPR>(active ? q : 0.f) / (float)c;
+  float rstd = 1.0f / sqrtf(var + 1e-6f);
+  if (active) {
+    float4 gg = __ldg((const float4*)(gam + ch));
+    float4 bb = __ldg((const float4*)(bet + ch));
+    v[0] = d[0] * rstd * gg.x + bb.x; v[1] = d[1] * rstd * gg.y + bb.y;
+    v[2] = d[2] * rstd * gg.z + bb.z; v[3] = d[3] * rstd * gg.w + bb.w;
+  }
+}
+
+template <int LPR, int OP, bool NORM>
+__global__ void __launch_bounds__(256) link_apply_kernel(
+    const float* __restrict__ mean, const float* __restrict__ fin, const int4* __restrict__ coords,
+    const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
+    const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+    const float* __restrict__ b2, float* __restrict__ out) {
+  constexpr int G = 32 / LPR;
+  constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
+  constexpr bool COSX = (OP == LK_OP_COSX);
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int ch = (lane % LPR) * 4;
+  const bool active = ch < g.c;
+  const int kc = K * g.c;
+  LaneGen lg;
+  load_lane_gen(g, ch, active, lg);
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t steps = (n + G - 1) / G;
+  for (int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; step < steps;
+       step += warps_total) {
+    int64_t r = step * G + grp;
+    bool ok = r < n;                     // NB: whole groups go inactive together; shuffles stay
+    int b = ok ? __ldg(blk + r) : -1;    // inside a group, so no divergence hazard
+    int4 cc = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok && active && b >= 0) {
+      float p[4], sn[4], cs[4];
+      lane_phase<COSX>(g, lg, cc, p);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
+      const float* mrow = mean + (int64_t)b * kc + ch;
+      float4 m0 = __ldg((const float4*)mrow);
+      float4 m1 = __ldg((const float4*)(mrow + g.c));
+      const float a0[4] = {m0.x, m0.y, m0.z, m0.w};
+      const float a1[4] = {m1.x, m1.y, m1.z, m1.w};
+      if (OP == LK_OP_SIN) {             // planes [sin, cos]: F[:, :C]*cos - F[:, C:]*sin
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = a0[e] * cs[e] - a1[e] * sn[e];
+      } else {                           // planes [cos, sin]: F[:, :C]*cos + F[:, C:]*sin
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = a0[e] * cs[e] + a1[e] * sn[e];
+      }
+      if (COSX) {                        // + (mean(F*pos) - F*pos), linkencoder.py:176
+        float4 m2 = __ldg((const float4*)(mrow + 2 * g.c));
+        float4 f = lk_ldg_stream((const float4*)(fin + r * g.c + ch));
+        v[0] += m2.x - f.x * p[0]; v[1] += m2.y - f.y * p[1];
+        v[2] += m2.z - f.z * p[2]; v[3] += m2.w - f.w * p[3];
+      }
+    }
+    if (NORM) {
+      float l[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ok && active) {
+        float4 lv = lk_ldg_stream((const float4*)(local + r * g.c + ch));
+        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+      }
+      group_layernorm<LPR>(v, active, g.c, g1, b1, ch);
+      group_layernorm<LPR>(l, active, g.c, g2, b2, ch);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e] + l[e], 0.f);
+    }
+    if (ok && active)
+      lk_stg_stream((float4*)(out + r * g.c + ch), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
+  if (!gen || !gen->d_pos_weight || gen->c <= 0 || gen->c % 4 != 0 || gen->c > 128 ||
+      gen->wrows <= 0 || gen->op < 0 || gen->op > 2 || !(gen->coord_scale > 0.f)) {
+    lk_set_error("%s: invalid kernel generator (C must be a multiple of 4, <= 128)", who);
+    return LK_EINVAL;
+  }
+  g->op = gen->op; g->c = gen->c; g->wrows = gen->wrows; g->coord_scale = gen->coord_scale;
+  g->pw = gen->d_pos_weight; g->alpha = gen->d_alpha;
+  return LK_OK;
+}
+
+static int lpr_of(int c) {
+  int v = c / 4, l = 1;
+  while (l < v) l <<= 1;
+  return l;
+}
+
+#define DISPATCH_LPR(LPRV, MACRO) \
+  switch (LPRV) {                 \
+    case 1: MACRO(1); break;      \
+    case 2: MACRO(2); break;      \
+    case 4: MACRO(4); break;      \
+    case 8: MACRO(8); break;      \
+    case 16: MACRO(16); break;    \
+    default: MACRO(32); break;    \
+  }
+
+extern "C" int lk_link_preagg_fwd(const float* d_fin, const int32_t* d_coords, const int32_t* d_blk,
+                                  int64_t n, const lk_kernelgen_t* gen, float* d_sums,
+                                  lk_stream_t s) {
+  GenDev g;
+  int rc = check_gen(gen, &g, "lk_link_preagg_fwd");
+  if (rc) return rc;
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_fin && d_coords && d_blk && d_sums && n > 0, "lk_link_preagg_fwd: null pointer");
+  LK_REQUIRE((uintptr_t)d_fin % 16 == 0 && (uintptr_t)d_sums % 16 == 0,
+             "lk_link_preagg_fwd: feature buffers must be 16-byte aligned");
+  int lpr = lpr_of(g.c);
+  int64_t rows_per_warp = (int64_t)PREAGG_ROWS_PER_GROUP * (32 / lpr);
+  int64_t warps = (n + rows_per_warp - 1) / rows_per_warp;
+  int grid = lk_grid(warps * 32, 256, 8);
+  cudaStream_t st = (cudaStream_t)s;
+#define LAUNCH_PRE(L)                                                                              \
+  do {                                                                                             \
+    if (g.op == LK_OP_COS)                                                                         \
+      link_preagg_kernel<L, LK_OP_COS><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
+    else if (g.op == LK_OP_SIN)                                                                    \
+      link_preagg_kernel<L, LK_OP_SIN><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
+    else                                                                                           \
+      link_preagg_kernel<L, LK_OP_COSX><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
+  } while (0)
+  DISPATCH_LPR(lpr, LAUNCH_PRE);
+#undef LAUNCH_PRE
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
+                                   const int32_t* d_nbr, const int32_t* d_num, int64_t capacity,
+                                   int r3, int kc, float* d_mean, lk_stream_t s) {
+  LK_REQUIRE(capacity >= 0 && r3 > 0 && kc > 0 && kc % 4 == 0, "lk_link_window_mean: bad sizes");
+  if (capacity == 0) return LK_OK;
+  LK_REQUIRE(d_sums && d_counts && d_nbr && d_num && d_mean, "lk_link_window_mean: null pointer");
+  link_window_mean_kernel<<<lk_grid(capacity * (kc / 4), 256, 8), 256, 0, (cudaStream_t)s>>>(
+      d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const int32_t* d_coords,
+                                 const int32_t* d_blk, int64_t n, const lk_kernelgen_t* gen,
+                                 int fuse_norm, const float* d_local, const float* d_g1,
+                                 const float* d_b1, const float* d_g2, const float* d_b2,
+                                 float* d_out, lk_stream_t s) {
+  GenDev g;
+  int rc = check_gen(gen, &g, "lk_link_apply_fwd");
+  if (rc) return rc;
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_mean && d_coords && d_blk && d_out && n > 0, "lk_link_apply_fwd: null pointer");
+  LK_REQUIRE(g.op != LK_OP_COSX || d_fin, "lk_link_apply_fwd: cos_x needs the input features");
+  LK_REQUIRE(!fuse_norm || (d_local && d_g1 && d_b1 && d_g2 && d_b2),
+             "lk_link_apply_fwd: fused norms need local features and both LayerNorm parameters");
+  int lpr = lpr_of(g.c);
+  int64_t steps = (n + (32 / lpr) - 1) / (32 / lpr);
+  int grid = lk_grid(steps * 32, 256, 8);
+  cudaStream_t st = (cudaStream_t)s;
+#define LAUNCH_APPLY2(L, O)                                                                        \
+  do {                                                                                             \
+    if (fuse_norm)                                                                                 \
+      link_apply_kernel<L, O, true><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,    \
+                                                          d_blk, n, g, d_local, d_g1, d_b1, d_g2,  \
+                                                          d_b2, d_out);                            \
+    else                                                                                           \
+      link_apply_kernel<L, O, false><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,   \
+                                                           d_blk, n, g, d_local, d_g1, d_b1, d_g2, \
+                                                           d_b2, d_out);                           \
+  } while (0)
+#define LAUNCH_APPLY(L)                                         \
+  do {                                                          \
+    if (g.op == LK_OP_COS) LAUNCH_APPLY2(L, LK_OP_COS);         \
+    else if (g.op == LK_OP_SIN) LAUNCH_APPLY2(L, LK_OP_SIN);    \
+    else LAUNCH_APPLY2(L, LK_OP_COSX);                          \
+  } while (0)
+  DISPATCH_LPR(lpr, LAUNCH_APPLY);
+#undef LAUNCH_APPLY
+#undef LAUNCH_APPLY2
+  LK_LAUNCHED();
+  return LK_OK;
+}

@@ -1,0 +1,20 @@
+// Error string, version and launch counter of liblinkb200.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void lk_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void lk_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" const char* lk_last_error(void) { return g_err; }
+extern "C" int lk_version(void) { return 100; }
+extern "C" int64_t lk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,297 @@
+"""The LinK block on B200: block index build, the reference's voxel_to_aux / aux_to_voxel API and
+the fused ELKBlock.
+
+Reference: ELKBlock (segmentation/core/models/semantic_kitti/linkencoder.py:94-185; UNet variant
+linkunet.py:94-185), voxel_to_aux / aux_to_voxel / upsample_voxel / initial_voxelize
+(segmentation/core/models/utils.py:44-84, 234-254, 327-340).
+
+Two execution paths, both on liblinkb200 kernels (there is no PyTorch/CPU fallback):
+  * fused (no autograd needed): block index -> lk_link_preagg_fwd -> lk_link_window_mean ->
+    lk_link_apply_fwd with both LayerNorms, the add and the ReLU folded in.  No host sync.
+  * composed (autograd): the reference's own op sequence on our differentiable
+    spvoxelize / spdevoxelize kernels, used when gradients are required.
+"""
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from link_b200 import _capi
+import link_b200.nn as spnn
+import link_b200.nn.functional as F
+from link_b200.nn.functional import _index
+from link_b200.nn.utils import get_kernel_offsets
+from link_b200.tensor import PointTensor, SparseTensor
+
+__all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsample_voxel',
+           'initial_voxelize', 'link_aggregate', 'ELKBlock', 'LinKBlock']
+
+_OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
+
+
+class BlockIndex:
+    """Device-resident index maps of one (coords, s) block partition (+ r^3 neighbour table).
+
+    Everything is allocated for the worst case M = N and the true M stays on the device
+    (`num`), so building and using the index needs no host synchronisation.  `.m` reads M back
+    on demand (used only by the shape-returning reference API and by tests)."""
+
+    def __init__(self, coords: torch.Tensor, s: int, cache: Optional[Dict]):
+        self.n = coords.shape[0]
+        self.s = int(s)
+        bounds = _index.coord_bounds(coords, cache)
+        self.spec, self.bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
+        keys = _index.pack_keys(coords, self.spec)
+        su = _index.sort_unique(keys, self.bits)
+        self.unique_keys = su.unique       # [n] int64, first M valid, ascending == torch.unique order
+        self.idx_query = su.inverse        # [n] int32  voxel -> block row
+        self.counts = su.counts            # [n] int32, first M valid
+        self.num = su.num                  # [1] int32 device scalar M
+        self._m = None
+        self._nbr = {}
+        self._small_C = None
+
+    @property
+    def m(self) -> int:
+        if self._m is None:
+            self._m = int(self.num.item())
+        return self._m
+
+    @property
+    def small_C(self) -> torch.Tensor:
+        """[M,4] int32 block coordinates == torch.unique(x_C, dim=0) of the reference."""
+        if self._small_C is None:
+            self._small_C = _index.unpack_keys(self.unique_keys, self.m, self.spec)
+        return self._small_C
+
+    def neighbors(self, r: int) -> torch.Tensor:
+        """[n, r^3] int32 (first M rows valid): row of each neighbour block in
+        get_kernel_offsets(r,1,1) order, -1 if that block is empty (utils.py:65-73)."""
+        nbr = self._nbr.get(r)
+        if nbr is None:
+            offsets = get_kernel_offsets(r, 1, 1, device=self.unique_keys.device)
+            R = offsets.shape[0]
+            nbr = torch.empty(self.n, R, dtype=torch.int32, device=self.unique_keys.device)
+            _capi.check(_capi.lib().lk_block_neighbors(
+                _capi.ptr(self.unique_keys), _capi.ptr(self.num), self.n, C.byref(self.spec),
+                _capi.ptr(offsets), R, _capi.ptr(nbr), _capi.stream()), 'lk_block_neighbors')
+            self._nbr[r] = nbr
+        return nbr
+
+
+def block_index(st: SparseTensor, s: int) -> BlockIndex:
+    """Block partition of `st` with block edge `s` (absolute voxel units), cached in the tensor
+    family's shared `kmaps` (the reference recomputes it on every call)."""
+    key = ('lk', 'blocks', st.stride, int(s), st.coords.data_ptr(), st.coords.shape[0])
+    bi = st.kmaps.get(key)
+    if bi is None:
+        bi = BlockIndex(st.coords.contiguous(), s, st.kmaps)
+        st.kmaps[key] = bi
+    return bi
+
+
+# ----------------------------------------------------------------------------- reference API
+def voxel_to_aux(large_x: SparseTensor, s: int):
+    """Block-local pre-aggregation with the reference signature and return values
+    (utils.py:44-58): (aux SparseTensor with per-block MEAN features and stride s,
+    idx_query [N] int64, counts [M] int32)."""
+    bi = block_index(large_x, s)
+    m = bi.m
+    counts = bi.counts[:m]
+    inserted = F.spvoxelize(large_x.F, bi.idx_query, counts)
+    small_x = SparseTensor(inserted, bi.small_C, s)
+    small_x.cmaps = large_x.cmaps
+    small_x.kmaps = large_x.kmaps
+    small_x._lk_block_index = bi
+    return small_x, bi.idx_query.long(), counts
+
+
+def aux_to_voxel(small_x: SparseTensor, large_x: SparseTensor, idx: torch.Tensor,
+                 counts: torch.Tensor, r: int = 2) -> SparseTensor:
+    """Outer-block reuse with the reference signature (utils.py:61-84): window mean over the r^3
+    neighbour blocks, gathered back to the voxels.  Mutates and returns `large_x`."""
+    bi = getattr(small_x, '_lk_block_index', None)
+    m = small_x.F.shape[0]
+    if bi is not None:
+        nbr = bi.neighbors(r)[:m]
+    else:   # foreign aux tensor: rebuild the neighbour table from its coordinates
+        offsets = get_kernel_offsets(r, 1, 1, device=large_x.F.device)
+        nbr = F.sphashquery(F.sphash(small_x.C.contiguous(), offsets),
+                            F.sphash(small_x.C.contiguous())).t().contiguous().int()
+    f = torch.cat([small_x.F, torch.ones_like(small_x.F[:, :1])], dim=1)
+    f = f * counts.unsqueeze(dim=-1)
+    weights = (nbr != -1).float()
+    new_feat = F.spdevoxelize(f, nbr, weights, r)
+    new_feat = new_feat[:, :-1] / new_feat[:, -1:]
+    large_x.F = new_feat[idx.long()]
+    return large_x
+
+
+def upsample_voxel(x: SparseTensor, ref_x: SparseTensor) -> SparseTensor:
+    """Nearest-parent gather from a coarse level to the fine level (utils.py:327-340)."""
+    stride = x.s[0]
+    key = ('lk', 'upsample', x.s, ref_x.s, x.C.data_ptr(), ref_x.C.data_ptr())
+    idx_query = x.kmaps.get(key)
+    if idx_query is None:
+        x_C = torch.cat([torch.div(x.C[:, :3], stride, rounding_mode='floor').int(), x.C[:, 3:]], dim=1)
+        ref_C = torch.cat([torch.div(ref_x.C[:, :3], stride, rounding_mode='floor').int(),
+                           ref_x.C[:, 3:]], dim=1)
+        idx_query = F.sphashquery(F.sphash(ref_C), F.sphash(x_C))
+        x.kmaps[key] = idx_query
+    new_tensor = SparseTensor(x.F[idx_query], ref_x.C, ref_x.s)
+    new_tensor.cmaps.setdefault(new_tensor.stride, new_tensor.coords)
+    return new_tensor
+
+
+def initial_voxelize(z: PointTensor, init_res, after_res) -> SparseTensor:
+    """Points -> voxels (utils.py:234-254).  Voxel order = ascending FNV hash, exactly like the
+    reference's `torch.unique(pc_hash)`; the unique runs on our radix sort (60-bit keys)."""
+    new_float_coord = torch.cat([(z.C[:, :3] * init_res) / after_res, z.C[:, -1].view(-1, 1)], 1)
+    fl = torch.floor(new_float_coord)
+    pc_hash = F.sphash(fl.int())
+    su = _index.sort_unique(pc_hash, 60)
+    m = int(su.num.item())
+    idx_query = su.inverse.long()
+    counts = su.counts[:m].contiguous()
+    inserted_coords = torch.round(F.spvoxelize(fl, su.inverse, counts)).int()
+    inserted_feat = F.spvoxelize(z.F, su.inverse, counts)
+    new_tensor = SparseTensor(inserted_feat, inserted_coords, 1)
+    new_tensor.cmaps.setdefault(new_tensor.stride, new_tensor.coords)
+    z.additional_features['idx_query'][1] = idx_query
+    z.additional_features['counts'][1] = counts
+    z.C = new_float_coord
+    return new_tensor
+
+
+# ----------------------------------------------------------------------------- fused path
+def _kernel_gen(op: str, c: int, pos_weight: torch.Tensor, alpha: Optional[torch.Tensor],
+                coord_scale: float) -> _capi.KernelGen:
+    g = _capi.KernelGen()
+    g.op = _OPS[op]
+    g.c = c
+    g.wrows = pos_weight.shape[0]
+    g.coord_scale = float(coord_scale)
+    g.d_pos_weight = _capi.ptr(pos_weight, torch.float32)
+    g.d_alpha = _capi.ptr(alpha, torch.float32) if alpha is not None else None
+    return g
+
+
+def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, r: int, op: str,
+                   pos_weight: torch.Tensor, alpha: Optional[torch.Tensor] = None,
+                   coord_scale: float = 1.0, local: Optional[torch.Tensor] = None,
+                   norm: Optional[Tuple[torch.Tensor, ...]] = None) -> torch.Tensor:
+    """Fused kernel generator + block pre-aggregation + outer-block reuse + combine.
+
+    f_input [N,C] fp32 (output of pre_mix), coords int32 [N,4].  Returns the pre-LayerNorm value
+    of linkencoder.py:162/148/176, or, when `local` [N,C] and `norm` = (g1, b1, g2, b2) are
+    given, relu(LN(value) + LN(local)) of linkencoder.py:178-181.  Forward only."""
+    n, c = f_input.shape
+    f_input = f_input.contiguous()
+    coords = coords.contiguous()
+    pos_weight = pos_weight.detach().contiguous().float()
+    alpha_v = alpha.detach().reshape(-1).contiguous().float() if alpha is not None else None
+    gen = _kernel_gen(op, c, pos_weight, alpha_v, coord_scale)
+    k = 3 if op == 'cos_x' else 2
+    L, st = _capi.lib(), _capi.stream()
+    dev = f_input.device
+    sums = torch.empty(n, k * c, dtype=torch.float32, device=dev)
+    mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
+    out = torch.empty(n, c, dtype=torch.float32, device=dev)
+    nbr = bi.neighbors(r)
+    _capi.check(L.lk_zero_rows(_capi.ptr(sums), _capi.ptr(bi.num), n, k * c, st), 'lk_zero_rows')
+    _capi.check(L.lk_link_preagg_fwd(_capi.ptr(f_input, torch.float32), _capi.ptr(coords, torch.int32),
+                                     _capi.ptr(bi.idx_query), n, C.byref(gen), _capi.ptr(sums), st),
+                'lk_link_preagg_fwd')
+    _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
+                                      _capi.ptr(bi.num), n, nbr.shape[1], k * c, _capi.ptr(mean),
+                                      st), 'lk_link_window_mean')
+    fuse = 1 if (local is not None and norm is not None) else 0
+    g1 = b1 = g2 = b2 = None
+    if fuse:
+        local = local.contiguous()
+        g1, b1, g2, b2 = (t.detach().contiguous().float() for t in norm)
+    _capi.check(L.lk_link_apply_fwd(_capi.ptr(mean), _capi.ptr(f_input), _capi.ptr(coords),
+                                    _capi.ptr(bi.idx_query), n, C.byref(gen), fuse,
+                                    _capi.ptr(local) if fuse else None, _capi.ptr(g1), _capi.ptr(b1),
+                                    _capi.ptr(g2), _capi.ptr(b2), _capi.ptr(out), st),
+                'lk_link_apply_fwd')
+    return out
+
+
+class ELKBlock(nn.Module):
+    """LinK block.  Constructor, parameters (names and shapes) and call signature are the
+    reference's (linkencoder.py:94-185): `ELKBlock(inc, outc, groups, baseop)(st, s, r)`.
+
+    `variant='unet'` reproduces linkunet.py:165 (cos_x phase not divided by the tensor stride)."""
+
+    def __init__(self, inc, outc, groups=1, baseop='cos_x', variant='encoder'):
+        super().__init__()
+        self.inc, self.outc, self.groups, self.baseop = inc, outc, groups, baseop
+        self.variant = variant
+        assert inc % groups == 0
+        assert baseop in ['cos', 'sin', 'cos_x']
+        if baseop == 'cos_x':
+            self.alpha = nn.Parameter(torch.ones(1, inc // groups).float(), requires_grad=True)
+        self.pos_weight = nn.Sequential(nn.Linear(3, inc // groups, bias=False))
+        self.pre_mix = nn.Sequential(nn.Linear(inc, inc, bias=False), nn.LayerNorm(inc, eps=1e-6))
+        self.local_mix = nn.Sequential(spnn.Conv3d(inc, inc, kernel_size=3, dilation=1, stride=1))
+        self.norm_local = nn.LayerNorm(inc, eps=1e-6)
+        self.norm = nn.LayerNorm(inc, eps=1e-6)
+        self.activate = nn.ReLU(True)
+
+    def _needs_grad(self, st: SparseTensor) -> bool:
+        return torch.is_grad_enabled() and (st.F.requires_grad or
+                                            any(p.requires_grad for p in self.parameters()))
+
+    def forward(self, st: SparseTensor, s, r):
+        F_input = self.pre_mix(st.F)
+        local_mix = self.local_mix(st)
+        if self._needs_grad(st) or st.F.dtype != torch.float32:
+            return self._forward_composed(st, F_input, local_mix, s, r)
+        if self.baseop == 'cos_x' and self.groups != 1:
+            raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor is "
+                               "not repeated over groups, linkencoder.py:165)")
+        bi = block_index(st, s)
+        scale = float(st.s[0]) if (self.baseop == 'cos_x' and self.variant == 'encoder') else 1.0
+        out = link_aggregate(F_input, st.C, bi, r, self.baseop, self.pos_weight[0].weight,
+                             getattr(self, 'alpha', None), scale, local_mix.F,
+                             (self.norm.weight, self.norm.bias, self.norm_local.weight,
+                              self.norm_local.bias))
+        st.F = out          # like aux_to_voxel, the input tensor object carries the result
+        return st
+
+    def _forward_composed(self, st, F_input, local_mix, s, r):
+        """The reference's op sequence (linkencoder.py:135-183) on differentiable kernels."""
+        C_ = self.inc
+        xyz = st.C[:, :3].float()
+        if self.baseop == 'cos_x':
+            if self.variant == 'encoder':
+                xyz = xyz / st.s[0]
+            pos = self.pos_weight(xyz) * self.alpha
+        else:
+            pos = self.pos_weight(xyz).repeat([1, self.groups])
+        sin, cos = torch.sin(pos), torch.cos(pos)
+        if self.baseop == 'sin':
+            planes = [F_input * sin, F_input * cos]
+        elif self.baseop == 'cos':
+            planes = [F_input * cos, F_input * sin]
+        else:
+            lin = F_input * pos
+            planes = [F_input * cos, F_input * sin, lin]
+        st.F = torch.cat(planes, dim=1).contiguous()
+        aux_st, idx, counts = voxel_to_aux(st, s)
+        voxel_st = aux_to_voxel(aux_st, st, idx, counts, r)
+        vf = voxel_st.F
+        if self.baseop == 'sin':
+            new = vf[:, :C_] * cos - vf[:, C_:] * sin
+        elif self.baseop == 'cos':
+            new = vf[:, :C_] * cos + vf[:, C_:] * sin
+        else:
+            new = vf[:, :C_] * cos + vf[:, C_:2 * C_] * sin + (vf[:, 2 * C_:] - lin)
+        new = self.activate(self.norm(new) + self.norm_local(local_mix.F))
+        voxel_st.F = new
+        return voxel_st
+
+
+LinKBlock = ELKBlock

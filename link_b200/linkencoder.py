@@ -1,0 +1,151 @@
+"""ELKEncoder (a.k.a. LinKEncoder): the LinK encoder-only segmentation backbone.
+
+Same constructor kwargs (`num_classes, cr, baseop, r, s, groups, run_up`), sub-module names and
+parameter shapes as the reference (segmentation/core/models/semantic_kitti/linkencoder.py:188-381)
+so that `seg/core/builder.make_model` can instantiate it and published state dicts load; every
+sparse op underneath runs on liblinkb200."""
+import torch
+import torch.nn as nn
+
+import link_b200.nn as spnn
+from link_b200.elk import ELKBlock, upsample_voxel
+from link_b200.tensor import SparseTensor
+
+__all__ = ['ELKEncoder', 'LinKEncoder', 'BasicConvolutionBlock', 'BasicDeconvolutionBlock',
+           'ResidualBlock']
+
+
+class BasicConvolutionBlock(nn.Module):
+    """Conv3d -> BatchNorm -> ReLU (linkencoder.py:23-39)."""
+
+    def __init__(self, inc, outc, ks=3, stride=1, dilation=1):
+        super().__init__()
+        self.net = nn.Sequential(
+            spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
+            spnn.BatchNorm(outc),
+            spnn.ReLU(True),
+        )
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class BasicDeconvolutionBlock(nn.Module):
+    """Transposed Conv3d -> BatchNorm -> ReLU (linkencoder.py:42-58)."""
+
+    def __init__(self, inc, outc, ks=3, stride=1):
+        super().__init__()
+        self.net = nn.Sequential(
+            spnn.Conv3d(inc, outc, kernel_size=ks, stride=stride, transposed=True),
+            spnn.BatchNorm(outc),
+            spnn.ReLU(True),
+        )
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class ResidualBlock(nn.Module):
+    """Two 3^3 convs with an identity / 1x1 shortcut (linkencoder.py:61-91)."""
+
+    def __init__(self, inc, outc, ks=3, stride=1, dilation=1):
+        super().__init__()
+        self.net = nn.Sequential(
+            spnn.Conv3d(inc, outc, kernel_size=ks, dilation=dilation, stride=stride),
+            spnn.BatchNorm(outc),
+            spnn.ReLU(True),
+            spnn.Conv3d(outc, outc, kernel_size=ks, dilation=dilation, stride=1),
+            spnn.BatchNorm(outc),
+        )
+        if inc == outc and stride == 1:
+            self.downsample = nn.Sequential()
+        else:
+            self.downsample = nn.Sequential(
+                spnn.Conv3d(inc, outc, kernel_size=1, dilation=1, stride=stride),
+                spnn.BatchNorm(outc),
+            )
+        self.relu = spnn.ReLU(True)
+
+    def forward(self, x):
+        return self.relu(self.net(x) + self.downsample(x))
+
+
+def _tail(inc, outc):
+    return nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=3, stride=1), spnn.BatchNorm(outc))
+
+
+class ELKEncoder(nn.Module):
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.kwargs = kwargs
+        cr = kwargs.get('cr', 1.0)
+        baseop = kwargs.get('baseop')
+        groups = kwargs.get('groups')
+        cs = [int(cr * 64)] * 9
+        self.run_up = kwargs.get('run_up', True)
+
+        self.stem = nn.Sequential(
+            spnn.Conv3d(4, cs[0], kernel_size=3, stride=1), spnn.BatchNorm(cs[0]), spnn.ReLU(True),
+            spnn.Conv3d(cs[0], cs[0], kernel_size=3, stride=1), spnn.BatchNorm(cs[0]), spnn.ReLU(True))
+
+        for lv in (1, 2, 3, 4):
+            cin, cout = cs[lv - 1], cs[lv]
+            setattr(self, f'down{lv}', nn.Sequential(
+                BasicConvolutionBlock(cin, cin, ks=2, stride=2, dilation=1)))
+            setattr(self, f'stage{lv}', nn.Sequential(
+                ResidualBlock(cin, cout, ks=3, stride=1, dilation=1),
+                ResidualBlock(cout, cout, ks=3, stride=1, dilation=1)))
+            setattr(self, f'stage{lv}_tail', _tail(cout, cout))
+            setattr(self, f'elk{lv}', ELKBlock(cin, cin, groups, baseop=baseop))
+            setattr(self, f'elk{lv}_tail', _tail(cin, cout))
+            setattr(self, f'activate{lv}', nn.ReLU(True))
+
+        # Decoder branches exist in the reference's state dict but are never run by forward
+        # (linkencoder.py:289-320 vs 339-381); they are kept so checkpoints load with strict=True.
+        for u, (cin, cskip, cout) in enumerate([(cs[4], cs[3], cs[5]), (cs[5], cs[2], cs[6]),
+                                                (cs[6], cs[1], cs[7]), (cs[7], cs[0], cs[8])], 1):
+            setattr(self, f'up{u}', nn.ModuleList([
+                BasicDeconvolutionBlock(cin, cout, ks=2, stride=2),
+                nn.Sequential(ResidualBlock(cout + cskip, cout, ks=3, stride=1, dilation=1),
+                              ResidualBlock(cout, cout, ks=3, stride=1, dilation=1))]))
+
+        self.classifier = nn.Sequential(
+            nn.Conv1d(in_channels=cs[8] * 5, out_channels=120, kernel_size=1, groups=5),
+            nn.ReLU(True),
+            nn.Conv1d(in_channels=120, out_channels=kwargs['num_classes'], kernel_size=1, groups=1))
+        self.weight_initialization()
+
+    def weight_initialization(self):
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm1d, nn.LayerNorm)):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def forward_levels(self, x: SparseTensor):
+        """Stem + the four (conv stage || LinK block) levels; returns [x0, x1, x2, x3, x4]."""
+        s, r = self.kwargs.get('s'), self.kwargs.get('r')
+        x.cmaps.setdefault(x.stride, x.coords)
+        x0 = self.stem(x)
+        feats = [x0]
+        cur = x0
+        for lv in (1, 2, 3, 4):
+            x_in = getattr(self, f'down{lv}')(cur)
+            x_conv = getattr(self, f'stage{lv}_tail')(getattr(self, f'stage{lv}')(x_in))
+            # NB: the block mutates x_in (it then carries the LinK output); the conv stage above
+            # has already consumed it -- same ordering as linkencoder.py:348-349.
+            x_lk = getattr(self, f'elk{lv}_tail')(getattr(self, f'elk{lv}')(x_in, x_in.s[0] * s, r))
+            x_conv.F = getattr(self, f'activate{lv}')(x_conv.F + x_lk.F)
+            feats.append(x_conv)
+            cur = x_conv
+        return feats
+
+    def forward(self, x: SparseTensor) -> torch.Tensor:
+        x0, x1, x2, x3, x4 = self.forward_levels(x)
+        ys = [upsample_voxel(lv, x0).F for lv in (x4, x3, x2, x1)]
+        F_cat = torch.cat(ys + [x0.F], dim=1).unsqueeze(dim=0).permute(0, 2, 1)
+        out = self.classifier(F_cat)
+        return out.squeeze(dim=0).T
+
+
+LinKEncoder = ELKEncoder

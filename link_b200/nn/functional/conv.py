@@ -1,0 +1,182 @@
+"""Sparse 3D convolution: kernel-map build + output-stationary fused gather-GEMM.
+
+Public surface = the reference's `F.conv3d(input, weight, kernel_size, bias, stride, dilation,
+transposed)` (torchsparse/nn/functional/conv.py:83-147) with the same caching contract: kernel
+maps live in `input.kmaps[(input.stride, kernel_size, stride, dilation)]` and every derived
+tensor shares the `cmaps` / `kmaps` dict objects."""
+from typing import Optional, Tuple, Union
+
+import torch
+from torch.autograd import Function
+
+from link_b200 import _capi
+from link_b200.nn.functional.downsample import spdownsample
+from link_b200.nn.functional.hash import sphash
+from link_b200.nn.functional.query import HashTable
+from link_b200.nn.utils import get_kernel_offsets
+from link_b200.tensor import SparseTensor
+from link_b200.utils import make_ntuple
+
+__all__ = ['conv3d', 'KernelMap', 'build_kernel_map']
+
+
+class KernelMap:
+    """Output-stationary kernel map: `nbr` int32 [K, n_out], nbr[k, o] = input row that feeds
+    output row o through offset k, or -1 (the reference's `results`, conv.py:114).
+
+    Indexing (`kmap[0]`, `kmap[1]`, `kmap[2]`) yields the reference's list layout
+    [nbmaps [P,2] (input row, output row) ordered by (k, output row), nbsizes [K], (n_in, n_out)]
+    -- materialised lazily, only parity tests and foreign code need it."""
+
+    def __init__(self, nbr: torch.Tensor, n_in: int, n_out: int, out_coords: torch.Tensor):
+        self.nbr = nbr
+        self.n_in = n_in
+        self.n_out = n_out
+        self.out_coords = out_coords
+        self._inv = None
+        self._ref = None
+
+    @property
+    def inv(self) -> torch.Tensor:
+        """Transposed relation int32 [K, n_in]: inv[k, i] = o whenever nbr[k, o] = i."""
+        if self._inv is None:
+            k = self.nbr.shape[0]
+            inv = torch.empty(k, self.n_in, dtype=torch.int32, device=self.nbr.device)
+            _capi.check(_capi.lib().lk_kmap_invert(_capi.ptr(self.nbr), self.n_out, k, self.n_in,
+                                                   _capi.ptr(inv), _capi.stream()),
+                        'lk_kmap_invert')
+            self._inv = inv
+        return self._inv
+
+    def _reference_layout(self):
+        if self._ref is None:
+            hit = self.nbr != -1
+            nbsizes = torch.sum(hit, dim=1)
+            nbmaps = torch.nonzero(hit)
+            nbmaps[:, 0] = self.nbr[hit].long()
+            self._ref = [nbmaps, nbsizes, (self.n_in, self.n_out)]
+        return self._ref
+
+    def __getitem__(self, i):
+        return self._reference_layout()[i]
+
+    def __len__(self):
+        return 3
+
+    def __iter__(self):
+        return iter(self._reference_layout())
+
+
+def _table_for(input: SparseTensor) -> HashTable:
+    key = ('lk', 'table', input.stride)
+    tab = input.kmaps.get(key)
+    if tab is None or tab.n != input.coords.shape[0]:
+        tab = HashTable(sphash(input.coords.contiguous()))
+        input.kmaps[key] = tab
+    return tab
+
+
+def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> KernelMap:
+    coords = input.coords.contiguous()
+    # NB: like the reference (conv.py:105-107) the offsets ignore `dilation`.
+    offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=coords.device)
+    table = _table_for(input)
+    out_coords = coords
+    if any(s > 1 for s in stride):
+        out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
+    k, n_out = offsets.shape[0], out_coords.shape[0]
+    nbr = torch.empty(k, n_out, dtype=torch.int32, device=coords.device)
+    _capi.check(_capi.lib().lk_kmap_query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
+                                          _capi.ptr(table.table), table.capacity, _capi.ptr(nbr),
+                                          _capi.stream()), 'lk_kmap_query')
+    return KernelMap(nbr, coords.shape[0], n_out, out_coords)
+
+
+def _conv_fwd(feats, weight, nbr, n_out, bias=None):
+    k, c_in, c_out = weight.shape
+    if feats.shape[1] != c_in:
+        raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
+    out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
+    _capi.check(_capi.lib().lk_conv_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
+                                        _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
+                                        _capi.ptr(bias), _capi.ptr(out), _capi.stream()),
+                'lk_conv_fwd')
+    return out
+
+
+class ConvolutionFunction(Function):
+    """Autograd wrapper (reference: ConvolutionFunction, conv.py:16-80).  forward and both
+    backward products run on liblinkb200 kernels; fp32 compute."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool = False):
+        in_dtype = feats.dtype
+        feats = feats.contiguous().float()
+        weight = weight.contiguous().float()
+        if not transposed:
+            out = _conv_fwd(feats, weight, kmap.nbr, kmap.n_out)
+        else:
+            out = _conv_fwd(feats, weight, kmap.inv, kmap.n_in)
+        ctx.save_for_backward(feats, weight)
+        ctx.kmap, ctx.transposed, ctx.in_dtype = kmap, transposed, in_dtype
+        return out.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        feats, weight = ctx.saved_tensors
+        kmap, transposed = ctx.kmap, ctx.transposed
+        g = grad_output.contiguous().float()
+        k, c_in, c_out = weight.shape
+        grad_feats = grad_weight = None
+        # the relation seen from the forward INPUT rows / from the forward OUTPUT rows
+        to_in = kmap.inv if not transposed else kmap.nbr
+        to_out = kmap.nbr if not transposed else kmap.inv
+        n_in_rows = feats.shape[0]
+        if ctx.needs_input_grad[0]:
+            wt = weight.transpose(1, 2).contiguous()
+            grad_feats = _conv_fwd(g, wt, to_in, n_in_rows).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            grad_weight = torch.empty_like(weight)
+            _capi.check(_capi.lib().lk_conv_bwd_weight(
+                _capi.ptr(feats), _capi.ptr(g), _capi.ptr(to_out), g.shape[0], k, c_in, c_out,
+                _capi.ptr(grad_weight), _capi.stream()), 'lk_conv_bwd_weight')
+        return grad_feats, grad_weight, None, None
+
+
+def conv3d(input: SparseTensor, weight: torch.Tensor,
+           kernel_size: Union[int, Tuple[int, ...]], bias: Optional[torch.Tensor] = None,
+           stride: Union[int, Tuple[int, ...]] = 1, dilation: Union[int, Tuple[int, ...]] = 1,
+           transposed: bool = False) -> SparseTensor:
+    feats, coords = input.feats, input.coords
+    kernel_size = make_ntuple(kernel_size, ndim=3)
+    stride = make_ntuple(stride, ndim=3)
+    dilation = make_ntuple(dilation, ndim=3)
+
+    if kernel_size == (1, 1, 1) and stride == (1, 1, 1) and dilation == (1, 1, 1):
+        feats = feats.matmul(weight)
+        if bias is not None:
+            feats += bias
+        output = SparseTensor(coords=coords, feats=feats, stride=input.stride)
+    elif not transposed:
+        key = (input.stride, kernel_size, stride, dilation)
+        kmap = input.kmaps.get(key)
+        if kmap is None:
+            kmap = build_kernel_map(input, kernel_size, stride, dilation)
+            input.kmaps[key] = kmap
+        feats = ConvolutionFunction.apply(feats, weight, kmap, False)
+        if bias is not None:
+            feats += bias
+        output = SparseTensor(coords=kmap.out_coords, feats=feats,
+                              stride=tuple(input.stride[k] * stride[k] for k in range(3)))
+    else:
+        tensor_stride = tuple(input.stride[k] // stride[k] for k in range(3))
+        kmap = input.kmaps[(tensor_stride, kernel_size, stride, dilation)]
+        feats = ConvolutionFunction.apply(feats, weight, kmap, True)
+        if bias is not None:
+            feats += bias
+        output = SparseTensor(coords=input.cmaps[tensor_stride], feats=feats, stride=tensor_stride)
+
+    output.cmaps = input.cmaps
+    output.cmaps.setdefault(output.stride, output.coords)
+    output.kmaps = input.kmaps
+    return output

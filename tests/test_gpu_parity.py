@@ -1,0 +1,390 @@
+"""GPU parity tests: every call goes through the C-ABI library (liblinkb200.so) and is compared
+with (a) the reference-generated golden fixtures and (b) the CPU oracle on the same seeded
+inputs.  Integer / index results must be bit-exact; fp32 features within the stated tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_sd, load_golden
+from oracle import link_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BLOCKS = ['block_g1_cosx_2x3', 'block_cos_g2_2x3', 'block_sin_g1_2x5', 'block_cosx_stride2']
+# fp32 tolerance for block / conv outputs (rtol 1e-4, atol 1e-5); LayerNorm'd block
+# outputs carry the reference's own accumulation-order noise, measured ~2e-5 abs on the fixtures.
+RTOL, ATOL = 1e-4, 2e-5
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'gpu-marked tests need a CUDA device'
+    from link_b200 import _capi
+    _capi.lib()
+    return torch.device('cuda:0')
+
+
+def cu(x, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------ integer ops
+def test_hash_kat(dev):
+    import link_b200.nn.functional as F
+    g = load_golden('kat')
+    assert np.array_equal(F.sphash(cu(g['coords'], dev)).cpu().numpy(), g['hash'])
+    for off, key in [(g['off2'], 'khash2'), (g['off3'], 'khash3')]:
+        got = F.sphash(cu(g['coords_b0'], dev), cu(off, dev))
+        assert np.array_equal(got.cpu().numpy(), g[key])
+    q = F.sphash(cu(np.asarray([[1, 2, 3, 0], [9, 9, 9, 0], [0, 0, 0, 0]], dtype=np.int32), dev))
+    assert F.sphashquery(q, cu(g['hash'], dev)).tolist() == [1, -1, 0]
+    assert F.spcount(cu(np.asarray([0, 0, 2, -1, 2, 2], dtype=np.int32), dev), 4).tolist() == [2, 0, 3, 0]
+    # empty inputs
+    assert F.sphash(torch.zeros(0, 4, dtype=torch.int, device=dev)).shape == (0,)
+    assert F.sphashquery(torch.zeros(0, dtype=torch.long, device=dev), cu(g['hash'], dev)).shape == (0,)
+    assert F.sphashquery(q, torch.zeros(0, dtype=torch.long, device=dev)).tolist() == [-1, -1, -1]
+    assert F.spcount(torch.zeros(0, dtype=torch.int, device=dev), 3).tolist() == [0, 0, 0]
+
+
+def test_hash_and_query_random_vs_oracle(dev):
+    import link_b200.nn.functional as F
+    rng = np.random.default_rng(1)
+    c = rng.integers(-5000, 5000, size=(200_000, 4)).astype(np.int32)
+    c[:, 3] = rng.integers(0, 4, size=len(c))
+    h = F.sphash(cu(c, dev)).cpu().numpy()
+    assert np.array_equal(h, O.sphash(c))
+    off = O.get_kernel_offsets(3, 2)
+    kh = F.sphash(cu(c[:5000], dev), cu(off, dev)).cpu().numpy()
+    assert np.array_equal(kh, O.sphash(c[:5000], off))
+    # duplicates in the references: lowest index wins; misses -> -1
+    ref = np.concatenate([h[:50_000], h[:10_000]])
+    qry = np.concatenate([h[40_000:60_000], rng.integers(0, 2 ** 59, size=1000)])
+    got = F.sphashquery(cu(qry, dev), cu(ref, dev)).cpu().numpy()
+    assert np.array_equal(got, O.sphashquery(qry, ref))
+    # 2-D query shape is preserved
+    got2 = F.sphashquery(cu(kh, dev), cu(h[:5000], dev))
+    assert got2.shape == kh.shape and np.array_equal(got2.cpu().numpy(), O.sphashquery(kh, h[:5000]))
+
+
+@pytest.mark.parametrize('n,bits', [(1, 1), (2, 3), (2047, 8), (2048, 9), (2049, 16), (10_000, 5),
+                                    (100_003, 24), (300_000, 40), (65_536, 64)])
+def test_sort_unique_vs_numpy(dev, n, bits):
+    from link_b200.nn.functional import _index
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, hi, size=n, dtype=np.uint64, endpoint=True) if bits < 64 else \
+        rng.integers(0, 2 ** 63 - 1, size=n, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    if n > 10:
+        keys[rng.integers(0, n, size=n // 3)] = keys[rng.integers(0, n, size=n // 3)]  # duplicates
+    su = _index.sort_unique(cu(keys.view(np.int64), dev), bits, want_order=True)
+    m = int(su.num.item())
+    uq, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
+    assert m == len(uq)
+    assert np.array_equal(su.unique[:m].cpu().numpy().view(np.uint64), uq)
+    assert np.array_equal(su.inverse.cpu().numpy(), inv.reshape(-1))
+    assert np.array_equal(su.counts[:m].cpu().numpy(), cnt)
+    assert np.array_equal(su.order.cpu().numpy(), np.argsort(keys, kind='stable'))
+    seg = su.seg[:m + 1].cpu().numpy()
+    assert seg[0] == 0 and seg[-1] == n and np.array_equal(np.diff(seg), cnt)
+
+
+def test_sort_unique_empty(dev):
+    from link_b200.nn.functional import _index
+    su = _index.sort_unique(torch.zeros(0, dtype=torch.int64, device=dev), 8, want_order=True)
+    assert int(su.num.item()) == 0
+
+
+@pytest.mark.parametrize('name', BLOCKS)
+def test_block_index_maps_bit_exact(dev, name):
+    import link_b200.nn.functional as F
+    from link_b200 import SparseTensor
+    from link_b200.elk import block_index
+    g = load_golden(name)
+    s, r = int(g['s']), int(g['r'])
+    coords = cu(g['coords'], dev)
+    assert np.array_equal(F.sphash(coords).cpu().numpy(), g['hash'])
+    st = SparseTensor(cu(g['feats'], dev), coords, int(g['tstride']))
+    bi = block_index(st, s)
+    assert bi.m == len(g['small_C'])
+    assert np.array_equal(bi.small_C.cpu().numpy(), g['small_C'])
+    assert np.array_equal(bi.idx_query.cpu().numpy(), g['idx_query'])
+    assert np.array_equal(bi.counts[:bi.m].cpu().numpy(), g['counts'])
+    assert np.array_equal(bi.neighbors(r)[:bi.m].cpu().numpy(), g['nbr_idx'])
+
+
+def test_block_index_negative_coords_batches_and_r3(dev):
+    from link_b200 import SparseTensor
+    from link_b200.elk import block_index
+    rng = np.random.default_rng(3)
+    c = np.unique(rng.integers(-300, 500, size=(60_000, 3)), axis=0).astype(np.int32)
+    c = c[rng.permutation(len(c))]
+    c = np.concatenate([c, rng.integers(0, 3, size=(len(c), 1)).astype(np.int32)], 1)
+    for s, r in [(7, 3), (14, 3), (3, 2), (1, 2)]:
+        st = SparseTensor(torch.zeros(len(c), 4, device=dev), cu(c, dev), 1)
+        bi = block_index(st, s)
+        small_C, idx, counts = O.block_index(c, s)
+        assert bi.m == len(small_C)
+        assert np.array_equal(bi.small_C.cpu().numpy(), small_C)
+        assert np.array_equal(bi.idx_query.cpu().numpy(), idx)
+        assert np.array_equal(bi.counts[:bi.m].cpu().numpy(), counts)
+        assert np.array_equal(bi.neighbors(r)[:bi.m].cpu().numpy(), O.block_neighbors(small_C, r))
+
+
+# ------------------------------------------------------------------ float ops
+def test_voxelize_devoxelize_vs_golden_and_grads(dev):
+    import link_b200.nn.functional as F
+    g = load_golden('ops')
+    feats = cu(g['feats'], dev).requires_grad_(True)
+    idx, counts = cu(g['idx'], dev), cu(g['counts'], dev)
+    vox = F.spvoxelize(feats, idx, counts)
+    np.testing.assert_allclose(vox.detach().cpu().numpy(), g['vox'], rtol=1e-5, atol=1e-6)
+    nb, w = cu(g['nb'], dev), cu(g['w'], dev)
+    dev_out = F.spdevoxelize(vox, nb, w, 2)
+    np.testing.assert_allclose(dev_out.detach().cpu().numpy(), g['dev'], rtol=1e-5, atol=2e-6)
+    # gradients against the oracle's autograd
+    go = torch.randn(dev_out.shape, generator=torch.Generator().manual_seed(0))
+    dev_out.backward(go.to(dev))
+    f_cpu = torch.from_numpy(g['feats']).requires_grad_(True)
+    o = O.spdevoxelize(O.spvoxelize(f_cpu, g['idx'], g['counts']), g['nb'], torch.from_numpy(g['w']))
+    o.backward(go)
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), f_cpu.grad.numpy(), rtol=1e-4, atol=1e-6)
+    # odd channel count -> scalar path; r^3 = 27
+    rng = np.random.default_rng(0)
+    f2 = rng.standard_normal((3000, 7)).astype(np.float32)
+    i2 = rng.integers(-1, 400, size=3000).astype(np.int32)
+    c2 = O.spcount(i2, 400)
+    got = F.spvoxelize(cu(f2, dev), cu(i2, dev), cu(c2, dev)).cpu().numpy()
+    np.testing.assert_allclose(got, O.spvoxelize(torch.from_numpy(f2), i2, c2).numpy(), rtol=1e-5, atol=1e-6)
+    nb3 = rng.integers(-1, 400, size=(500, 27)).astype(np.int32)
+    w3 = rng.random((500, 27)).astype(np.float32)
+    got = F.spdevoxelize(cu(got, dev), cu(nb3, dev), cu(w3, dev), 3).cpu().numpy()
+    want = O.spdevoxelize(O.spvoxelize(torch.from_numpy(f2), i2, c2), nb3, torch.from_numpy(w3)).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
+
+
+def test_aux_batch2_reference_api(dev):
+    from link_b200 import SparseTensor
+    from link_b200.elk import voxel_to_aux
+    g = load_golden('aux_batch2')
+    st = SparseTensor(cu(g['feats'], dev), cu(g['coords'], dev), 1)
+    aux, idx, counts = voxel_to_aux(st, int(g['s']))
+    assert np.array_equal(aux.C.cpu().numpy(), g['aux_C'])
+    assert np.array_equal(idx.cpu().numpy(), g['idx']) and idx.dtype == torch.int64
+    assert np.array_equal(counts.cpu().numpy(), g['counts'])
+    np.testing.assert_allclose(aux.F.cpu().numpy(), g['aux_F'], rtol=1e-5, atol=1e-6)
+    assert aux.s == (int(g['s']),) * 3 and aux.kmaps is st.kmaps
+
+
+def test_window_mean_semantics_r3(dev):
+    from link_b200 import SparseTensor
+    from link_b200.elk import aux_to_voxel, voxel_to_aux
+    rng = np.random.default_rng(0)
+    c = np.unique(rng.integers(-9, 14, size=(400, 3)), axis=0).astype(np.int32)
+    c = np.concatenate([c, rng.integers(0, 2, size=(len(c), 1)).astype(np.int32)], 1)
+    f = torch.randn(len(c), 8, generator=torch.Generator().manual_seed(0))
+    for s, r in [(3, 2), (2, 3), (5, 3)]:
+        st = SparseTensor(f.to(dev), cu(c, dev), 1)
+        aux, idx, counts = voxel_to_aux(st, s)
+        out = aux_to_voxel(aux, st, idx, counts, r)
+        assert out is st
+        np.testing.assert_allclose(out.F.cpu().numpy(), O.window_mean_bruteforce(f, c, s, r).numpy(),
+                                   rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ conv + kernel maps
+def test_conv_chain_kmaps_and_outputs(dev):
+    import link_b200.nn as spnn
+    import link_b200.nn.functional as F
+    from link_b200 import SparseTensor
+    g = load_golden('conv')
+    coords = cu(g['coords'], dev)
+    assert np.array_equal(F.spdownsample(coords, 2, 3, 1).cpu().numpy(), g['ds_k3s2'])
+    assert np.array_equal(F.spdownsample(cu(g['y2_C'], dev), 2, 2, 2).cpu().numpy(), g['ds_k2s2_t2'])
+    x = SparseTensor(cu(g['feats'], dev), coords, 1)
+    x.cmaps[x.stride] = x.coords
+    mods = [spnn.Conv3d(12, 20, 3), spnn.Conv3d(20, 24, 2, stride=2), spnn.Conv3d(24, 8, 3),
+            spnn.Conv3d(8, 6, 2, stride=2, transposed=True), spnn.Conv3d(6, 5, 1)]
+    ys = []
+    with torch.no_grad():
+        for m, wk in zip(mods, ['w1', 'w2', 'w3', 'w4', 'w5']):
+            m.kernel.copy_(torch.from_numpy(g[wk]))
+            m.to(dev)
+            x = m(x)
+            ys.append(x)
+    assert np.array_equal(ys[1].C.cpu().numpy(), g['y2_C']) and ys[1].s == (2, 2, 2)
+    assert np.array_equal(ys[3].C.cpu().numpy(), g['y4_C']) and ys[3].s == (1, 1, 1)
+    for key, km in x.kmaps.items():
+        if not (isinstance(key, tuple) and len(key) == 4 and isinstance(key[0], tuple)):
+            continue
+        tag = 'kmap_s%d_k%d_st%d' % (key[0][0], key[1][0], key[2][0])
+        assert np.array_equal(km[0].cpu().numpy(), g[tag + '_nbmaps']), tag
+        assert np.array_equal(km[1].cpu().numpy(), g[tag + '_nbsizes']), tag
+    for y, k in zip(ys, ['y1', 'y2', 'y3', 'y4', 'y5']):
+        np.testing.assert_allclose(y.F.cpu().numpy(), g[k], rtol=RTOL, atol=1e-5, err_msg=k)
+
+
+def test_conv_backward_vs_oracle_autograd(dev):
+    import link_b200.nn.functional as F
+    from link_b200 import SparseTensor
+    rng = np.random.default_rng(5)
+    c = np.unique(rng.integers(0, 24, size=(3000, 3)), axis=0).astype(np.int32)
+    c = np.concatenate([c, np.zeros((len(c), 1), np.int32)], 1)
+    f = rng.standard_normal((len(c), 8)).astype(np.float32)
+    w1 = (rng.standard_normal((27, 8, 12)) * 0.2).astype(np.float32)
+    w2 = (rng.standard_normal((8, 12, 16)) * 0.2).astype(np.float32)
+    w3 = (rng.standard_normal((8, 16, 4)) * 0.2).astype(np.float32)
+
+    xg = SparseTensor(cu(f, dev).requires_grad_(True), cu(c, dev), 1)
+    xg.cmaps[xg.stride] = xg.coords
+    wg = [cu(w, dev).requires_grad_(True) for w in (w1, w2, w3)]
+    yg = F.conv3d(F.conv3d(F.conv3d(xg, wg[0], 3), wg[1], 2, stride=2), wg[2], 2, stride=2,
+                  transposed=True)
+    xo = O.OTensor(torch.from_numpy(f.copy()).requires_grad_(True), c, 1)
+    xo.cmaps[xo.s] = xo.C
+    wo = [torch.from_numpy(w.copy()).requires_grad_(True) for w in (w1, w2, w3)]
+    yo = O.conv3d(O.conv3d(O.conv3d(xo, wo[0], 3), wo[1], 2, stride=2), wo[2], 2, stride=2,
+                  transposed=True)
+    np.testing.assert_allclose(yg.F.detach().cpu().numpy(), yo.F.detach().numpy(), rtol=RTOL, atol=1e-5)
+    go = torch.randn(yo.F.shape, generator=torch.Generator().manual_seed(1))
+    yg.F.backward(go.to(dev))
+    yo.F.backward(go)
+    np.testing.assert_allclose(xg.F.grad.cpu().numpy(), xo.F.grad.numpy(), rtol=1e-3, atol=1e-5)
+    for a, b in zip(wg, wo):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------ the LinK block
+def _make_block(g, dev, variant='encoder'):
+    from link_b200.elk import ELKBlock
+    C = int(g['C'])
+    blk = ELKBlock(C, C, groups=int(g['groups']), baseop=str(g['baseop']), variant=variant)
+    missing = blk.load_state_dict(golden_sd(g), strict=True)
+    return blk.to(dev)
+
+
+@pytest.mark.parametrize('name', BLOCKS)
+def test_block_forward_fused_vs_golden(dev, name):
+    from link_b200 import SparseTensor
+    g = load_golden(name)
+    blk = _make_block(g, dev).eval()
+    st = SparseTensor(cu(g['feats'], dev), cu(g['coords'], dev), int(g['tstride']))
+    with torch.no_grad():
+        out = blk(st, int(g['s']), int(g['r']))
+    assert out is st
+    key = ((int(g['tstride']),) * 3, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    assert np.array_equal(st.kmaps[key][0].cpu().numpy(), g['nbmaps'])
+    assert np.array_equal(st.kmaps[key][1].cpu().numpy(), g['nbsizes'])
+    np.testing.assert_allclose(out.F.cpu().numpy(), g['out'], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize('name', BLOCKS)
+def test_block_forward_composed_and_grads(dev, name):
+    from link_b200 import SparseTensor
+    g = load_golden(name)
+    blk = _make_block(g, dev).train()
+    feats = cu(g['feats'], dev).requires_grad_(True)
+    st = SparseTensor(feats, cu(g['coords'], dev), int(g['tstride']))
+    out = blk(st, int(g['s']), int(g['r']))
+    np.testing.assert_allclose(out.F.detach().cpu().numpy(), g['out'], rtol=RTOL, atol=ATOL)
+    go = torch.randn(out.F.shape, generator=torch.Generator().manual_seed(2))
+    out.F.backward(go.to(dev))
+    # oracle gradients
+    p = {k: v.clone().requires_grad_(True) for k, v in golden_sd(g).items()}
+    f_cpu = torch.from_numpy(g['feats']).requires_grad_(True)
+    o = O.elk_block_forward(f_cpu, g['coords'], int(g['tstride']), p, int(g['s']), int(g['r']),
+                            str(g['baseop']), int(g['groups']))
+    o.backward(go)
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), f_cpu.grad.numpy(), rtol=2e-3, atol=2e-5)
+    ours = dict(blk.named_parameters())
+    for k in ['pre_mix.0.weight', 'pos_weight.0.weight', 'local_mix.0.kernel', 'norm.weight']:
+        ref = p[k].grad.numpy()
+        np.testing.assert_allclose(ours[k].grad.cpu().numpy(), ref, rtol=5e-3,
+                                   atol=5e-5 * max(1.0, float(np.abs(ref).max())), err_msg=k)
+
+
+@pytest.mark.parametrize('baseop,groups,C,s,r', [('cos', 2, 64, 7, 3), ('cos', 2, 32, 5, 3),
+                                                 ('cos_x', 1, 16, 3, 2), ('sin', 4, 128, 7, 3),
+                                                 ('cos', 1, 48, 7, 3), ('cos', 2, 8, 3, 3)])
+def test_block_fused_vs_oracle_r3_multibatch(dev, baseop, groups, C, s, r):
+    """Configurations the reference CPU path cannot run (r=3, batch>1): compare with the oracle."""
+    from link_b200 import SparseTensor
+    from link_b200.elk import ELKBlock
+    from link_b200.utils.synthetic import random_voxels
+    coords = random_voxels(4000, 48, seed=C + s, batch=2)
+    torch.manual_seed(C)
+    blk = ELKBlock(C, C, groups=groups, baseop=baseop).eval()
+    with torch.no_grad():
+        for m in (blk.pre_mix[1], blk.norm, blk.norm_local):
+            m.weight.uniform_(0.5, 1.5)
+            m.bias.uniform_(-0.5, 0.5)
+    feats = torch.randn(len(coords), C)
+    want = O.elk_block_forward(feats, coords, 1, {k: v.detach() for k, v in blk.state_dict().items()},
+                               s, r, baseop, groups)
+    blk = blk.to(dev)
+    with torch.no_grad():
+        got = blk(SparseTensor(feats.to(dev), cu(coords, dev), 1), s, r).F
+    np.testing.assert_allclose(got.cpu().numpy(), want.detach().numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_encoder_forward_vs_golden(dev):
+    from link_b200 import SparseTensor
+    from link_b200.linkencoder import ELKEncoder
+    g = load_golden('encoder_cosx_2x3')
+    enc = ELKEncoder(num_classes=19, cr=0.25, baseop='cos_x', r=2, s=3, groups=1)
+    res = enc.load_state_dict(golden_sd(g), strict=False)
+    assert all(k.startswith('up') for k in res.missing_keys) and not res.unexpected_keys
+    enc = enc.to(dev).eval()
+    st = SparseTensor(cu(g['feats'], dev), cu(g['coords'], dev), 1)
+    with torch.no_grad():
+        logits = enc(st)
+    sizes = [v.shape[0] for k, v in st.cmaps.items()]
+    assert sizes == g['level_sizes'].tolist()
+    np.testing.assert_allclose(logits.cpu().numpy(), g['logits'], rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_scan_properties(dev):
+    """~120k-voxel SemanticKITTI-shaped scan, LinK cos (3x7)^3, C=64: index maps bit-exact vs the
+    oracle; fused == composed; row-permutation equivariance; linearity in the features."""
+    from link_b200 import SparseTensor
+    from link_b200.elk import ELKBlock, block_index
+    from link_b200.utils.synthetic import kitti_like_voxels
+    c3, _ = kitti_like_voxels(120_000, seed=0)
+    coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    N = len(coords)
+    assert abs(N - 120_000) < 2400
+    s, r, C = 7, 3, 64
+    st = SparseTensor(torch.zeros(N, C, device=dev), cu(coords, dev), 1)
+    bi = block_index(st, s)
+    small_C, idx, counts = O.block_index(coords, s)
+    assert bi.m == len(small_C) and np.array_equal(bi.small_C.cpu().numpy(), small_C)
+    assert np.array_equal(bi.idx_query.cpu().numpy(), idx)
+    assert np.array_equal(bi.counts[:bi.m].cpu().numpy(), counts)
+    assert np.array_equal(bi.neighbors(r)[:bi.m].cpu().numpy(), O.block_neighbors(small_C, r))
+    assert int(bi.counts[:bi.m].sum()) == N
+
+    torch.manual_seed(0)
+    blk = ELKBlock(C, C, groups=2, baseop='cos').to(dev).eval()
+    feats = torch.randn(N, C, device=dev)
+    with torch.no_grad():
+        fused = blk(SparseTensor(feats.clone(), cu(coords, dev), 1), s, r).F
+    blk.train()
+    composed = blk(SparseTensor(feats.clone().requires_grad_(True), cu(coords, dev), 1), s, r).F.detach()
+    blk.eval()
+    # phases reach |p| ~ 3e3 rad here: fp32 phase round-off (1 ulp of p ~ 2e-4) bounds agreement
+    np.testing.assert_allclose(fused.cpu().numpy(), composed.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # permutation equivariance (index build must not depend on row order)
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(0)).to(dev)
+    with torch.no_grad():
+        fp = blk(SparseTensor(feats[perm].clone(), cu(coords, dev)[perm].contiguous(), 1), s, r).F
+    np.testing.assert_allclose(fp.cpu().numpy(), fused[perm].cpu().numpy(), rtol=1e-3, atol=2e-4)
+    # linearity of the aggregation in its input features
+    from link_b200.elk import link_aggregate
+    w = blk.pos_weight[0].weight
+    f1, f2 = torch.randn(N, C, device=dev), torch.randn(N, C, device=dev)
+    cc = cu(coords, dev)
+    a = link_aggregate(f1, cc, bi, r, 'cos', w)
+    b = link_aggregate(f2, cc, bi, r, 'cos', w)
+    ab = link_aggregate(f1 + 2 * f2, cc, bi, r, 'cos', w)
+    np.testing.assert_allclose(ab.cpu().numpy(), (a + 2 * b).cpu().numpy(), rtol=1e-4, atol=1e-5)
