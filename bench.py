@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- LinK hot-path throughput on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload block|encoder] [--voxels 120000]
+
+A "step" is one pass of the hot path over one fresh synthetic SemanticKITTI-shaped scan:
+  block   : ELKBlock(64,64, groups=2, 'cos'), (3x7)^3  (pre_mix, local_mix 3^3 sparse conv, block
+            index build, pre-aggregation, outer-block reuse, LayerNorms) on ~120k active voxels
+  encoder : full ELKEncoder cos:(3x7)^3 forward on the same scan (BASELINE config 2)
+Every step starts from raw (coords, feats): kernel maps and block index maps are REBUILT each
+step (nothing cached across steps).  Multi-GPU: one process per GPU, each rank runs its own scans
+(frames are independent: no data-path collective, weak scaling); value = voxels of all ranks /
+max-over-ranks time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'LinK-block voxels/sec @120k active voxels'
+UNIT = 'voxels/s'
+C_BLOCK, GROUPS, BASEOP, S_BLK, R_BLK = 64, 2, 'cos', 7, 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='block', choices=['block', 'encoder'])
+    ap.add_argument('--voxels', type=int, default=120_000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def make_scan(n_voxels, seed):
+    from link_b200.utils.synthetic import kitti_like_voxels
+    c3, f4 = kitti_like_voxels(n_voxels, seed=seed)
+    coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    return coords, f4.astype(np.float32)
+
+
+def block_params(seed=0):
+    """Random-init ELKBlock weights as a plain state dict (same init as the module)."""
+    from link_b200.elk import ELKBlock
+    torch.manual_seed(seed)
+    blk = ELKBlock(C_BLOCK, C_BLOCK, groups=GROUPS, baseop=BASEOP)
+    return blk
+
+
+def workload_name(args, n):
+    if args.workload == 'block':
+        return (f'ELKBlock cos:(3x7)^3 C={C_BLOCK} groups={GROUPS} fwd, synthetic '
+                f'SemanticKITTI-shaped scan, N={n} active voxels, index+kernel maps rebuilt per step')
+    return (f'ELKEncoder cos:(3x7)^3 cr=1.0 fwd, synthetic SemanticKITTI-shaped scan, N={n} active '
+            'voxels, all maps rebuilt per step')
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    def __init__(self, index=0):
+        self.rows, self.index, self.stop = [], index, threading.Event()
+        self.proc = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [p.strip() for p in line.split(',')]))
+
+    def finish(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_block_step(O, blk_sd, feats_t, coords):
+    return O.elk_block_forward(feats_t, coords, 1, blk_sd, S_BLK, R_BLK, BASEOP, GROUPS)
+
+
+def run_cpu(args, n_sample, steps, warmup):
+    """Reference arm / cpu_baseline: the CPU restatement of the same path (oracle port; the
+    reference's own CPU devoxelize is wrong for r=3 -- devoxelize_cpu.cpp:19-24 -- so
+    oracle/_ref cannot run this configuration), all host threads torch gives us."""
+    from oracle import link_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    coords, f4 = make_scan(n_sample, seed=0)
+    n = len(coords)
+    if args.workload == 'block':
+        blk = block_params()
+        sd = {k: v.detach() for k, v in blk.state_dict().items()}
+        feats = torch.randn(n, C_BLOCK, generator=torch.Generator().manual_seed(1))
+        fn = lambda: cpu_block_step(O, sd, feats, coords)
+    else:
+        from link_b200.linkencoder import ELKEncoder
+        torch.manual_seed(0)
+        enc = ELKEncoder(num_classes=19, cr=1.0, baseop=BASEOP, r=R_BLK, s=S_BLK, groups=GROUPS).eval()
+        sd = {k: v.detach() for k, v in enc.state_dict().items()}
+        feats = torch.from_numpy(f4)
+        fn = lambda: O.elk_encoder_forward(sd, feats, coords, s=S_BLK, r=R_BLK, baseop=BASEOP,
+                                           groups=GROUPS)
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt, n, cores
+
+
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_sample = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    v, dt, n, cores = run_cpu(args, n_sample, steps, warmup)
+    sample = f'{steps} steps after {warmup} warm-up of the same workload at N={n} voxels'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args, n)},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main_ours(args):
+    import torch.distributed as dist
+    from link_b200 import SparseTensor, _capi
+    from link_b200.nn.functional import _index
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _capi.lib()
+
+    # per-rank scans (weak scaling): 2 distinct scans alternate so that no step can reuse state
+    scans = [make_scan(args.voxels, seed=rank * 1000 + i) for i in range(2)]
+    if args.workload == 'block':
+        model = block_params().to(dev).eval()
+        in_ch = C_BLOCK
+        feats_host = [torch.randn(len(c), in_ch, generator=torch.Generator().manual_seed(i)).pin_memory()
+                      for i, (c, _) in enumerate(scans)]
+    else:
+        from link_b200.linkencoder import ELKEncoder
+        torch.manual_seed(0)
+        model = ELKEncoder(num_classes=19, cr=1.0, baseop=BASEOP, r=R_BLK, s=S_BLK, groups=GROUPS)
+        model = model.to(dev).eval()
+        feats_host = [torch.from_numpy(f).pin_memory() for _, f in scans]
+    coords_host = [torch.from_numpy(c).pin_memory() for c, _ in scans]
+    bounds = [(c.min(0), c.max(0)) for c, _ in scans]     # dataset property, known on the host
+    coords_dev = [c.to(dev) for c in coords_host]
+    feats_dev = [f.to(dev) for f in feats_host]
+    n_vox = [len(c) for c, _ in scans]
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(i, coords, feats):
+        st = SparseTensor(feats, coords, 1)
+        _index.set_coord_bounds(st.kmaps, bounds[i][0], bounds[i][1])
+        with torch.no_grad():
+            if args.workload == 'block':
+                return model(st, S_BLK, R_BLK).F
+            return model(st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop (value) ------------------------------------------------------
+    for w in range(args.warmup):
+        step(w % 2, coords_dev[w % 2], feats_dev[w % 2].clone())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _capi.TIMERS = {}
+    launches0 = _capi.launch_count()
+    evs = []
+    t_wall0 = time.time()
+    barrier()
+    for k in range(args.steps):
+        i = k % 2
+        f = feats_dev[i].clone()          # the block overwrites st.F; clone outside the timed region
+        flush.zero_()                     # L2 flush between timed iterations (outside the events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(i, coords_dev[i], f)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall1 = time.time()
+    launches = _capi.launch_count() - launches0
+    timers, _capi.TIMERS = _capi.TIMERS, None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    vox_done = sum(n_vox[k % 2] for k in range(args.steps))
+
+    # ---- end-to-end loop: pinned host buffers -> H2D -> step -> D2H of a per-channel checksum --
+    h2d = d2h = 0
+    e2e_evs = []
+    out_host = torch.empty(64 if args.workload == 'block' else 19, dtype=torch.float32).pin_memory()
+    for k in range(min(3, args.warmup) + args.steps):
+        i = k % 2
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c = coords_host[i].to(dev, non_blocking=True)
+        f = feats_host[i].to(dev, non_blocking=True)
+        out = step(i, c, f)
+        out_host.copy_(out.sum(dim=0), non_blocking=True)
+        e1.record()
+        if k >= min(3, args.warmup):
+            e2e_evs.append((e0, e1))
+            h2d = coords_host[i].numel() * 4 + feats_host[i].numel() * 4
+            d2h = out_host.numel() * 4
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+
+    # ---- max over ranks ---------------------------------------------------------------------
+    stats = torch.tensor([dev_ms, e2e_ms, float(vox_done)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, vox_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        vox_total = float(vox_done)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clocks = sampler.finish(t_wall0, t_wall1)
+    value = vox_total / (dev_ms * 1e-3)
+    e2e_value = vox_total / (e2e_ms * 1e-3)
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel ------------------------------
+    peaks = {}
+    pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak, peak_src = (peaks.get('hbm_gbs'), 'measured') if peaks.get('hbm_gbs') else (6650.0, 'fallback')
+    kern = {}
+    for name, lst in timers.items():
+        ms = [a.elapsed_time(b) for a, b, _ in lst]
+        kern[name] = {'launches': len(ms), 'avg_us': 1e3 * float(np.mean(ms)),
+                      'bytes': float(np.mean([x[2] for x in lst]))}
+    step_us = 1e3 * dev_ms / args.steps
+    for v in kern.values():
+        v['share_of_step'] = v['avg_us'] * v['launches'] / args.steps / step_us
+        v['gbs'] = v['bytes'] / (v['avg_us'] * 1e-6) / 1e9 if v['bytes'] else None
+    roof = None
+    # the HBM-bound kernel BASELINE.json names: the pre-aggregation pass
+    if 'lk_link_preagg_fwd' in kern:
+        kp = kern['lk_link_preagg_fwd']
+        roof = {'kernel': 'link_preagg_kernel', 'bound': 'hbm', 'achieved': kp['gbs'], 'peak': hbm_peak,
+                'peak_source': peak_src, 'unit': 'GB/s', 'frac': kp['gbs'] / hbm_peak, 'traffic': None,
+                'algorithmic_bytes_per_launch': kp['bytes'], 'avg_us': kp['avg_us']}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args, n_vox[0]),
+                   'l2': 'flushed between timed iterations (256 MiB memset, outside the events)',
+                   'parallelism': f'{world} independent frame streams (no data-path collective)'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': int(launches),
+        'roofline': roof,
+        'kernels': kern,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_s = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
+        v, dt, n, cores = run_cpu(args, n_s, 2, 1)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': f'2 steps after 1 warm-up of the same workload at N={n} voxels, '
+                                          f'{dt:.2f} s/step'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -104,3 +104,29 @@ def ptr(t, dtype=None):
 
 def launch_count() -> int:
     return int(lib().lk_launch_count())
+
+
+# Optional per-kernel timing (bench.py): when TIMERS is a dict, `timed(name, bytes)` brackets a
+# library call with CUDA events on the launching stream and appends (start, end, algorithmic
+# bytes) to TIMERS[name].  Disabled (None) it costs one attribute test.
+TIMERS = None
+
+
+class timed:
+    __slots__ = ('name', 'nbytes', 'e0')
+
+    def __init__(self, name: str, nbytes: float = 0.0):
+        self.name, self.nbytes, self.e0 = name, nbytes, None
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and TIMERS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMERS.setdefault(self.name, []).append((self.e0, e1, float(self.nbytes)))
+        return False

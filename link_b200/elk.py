@@ -199,23 +199,30 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
     mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
     out = torch.empty(n, c, dtype=torch.float32, device=dev)
     nbr = bi.neighbors(r)
+    m_hint = bi._m if bi._m is not None else 0      # only for the byte accounting of bench.py
     _capi.check(L.lk_zero_rows(_capi.ptr(sums), _capi.ptr(bi.num), n, k * c, st), 'lk_zero_rows')
-    _capi.check(L.lk_link_preagg_fwd(_capi.ptr(f_input, torch.float32), _capi.ptr(coords, torch.int32),
-                                     _capi.ptr(bi.idx_query), n, C.byref(gen), _capi.ptr(sums), st),
-                'lk_link_preagg_fwd')
-    _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
-                                      _capi.ptr(bi.num), n, nbr.shape[1], k * c, _capi.ptr(mean),
-                                      st), 'lk_link_window_mean')
+    # algorithmic bytes: read F_in + coords + block index once, write the M block-sum rows
+    with _capi.timed('lk_link_preagg_fwd', n * (4 * c + 16 + 4) + m_hint * 4 * k * c):
+        _capi.check(L.lk_link_preagg_fwd(_capi.ptr(f_input, torch.float32),
+                                         _capi.ptr(coords, torch.int32), _capi.ptr(bi.idx_query), n,
+                                         C.byref(gen), _capi.ptr(sums), st), 'lk_link_preagg_fwd')
+    with _capi.timed('lk_link_window_mean', m_hint * (2 * 4 * k * c + 4 * nbr.shape[1] + 4)):
+        _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
+                                          _capi.ptr(bi.num), n, nbr.shape[1], k * c,
+                                          _capi.ptr(mean), st), 'lk_link_window_mean')
     fuse = 1 if (local is not None and norm is not None) else 0
     g1 = b1 = g2 = b2 = None
     if fuse:
         local = local.contiguous()
         g1, b1, g2, b2 = (t.detach().contiguous().float() for t in norm)
-    _capi.check(L.lk_link_apply_fwd(_capi.ptr(mean), _capi.ptr(f_input), _capi.ptr(coords),
-                                    _capi.ptr(bi.idx_query), n, C.byref(gen), fuse,
-                                    _capi.ptr(local) if fuse else None, _capi.ptr(g1), _capi.ptr(b1),
-                                    _capi.ptr(g2), _capi.ptr(b2), _capi.ptr(out), st),
-                'lk_link_apply_fwd')
+    # read coords + block index (+ local, + F_in for cos_x) once, the M mean rows, write out
+    nb = n * (16 + 4 + 4 * c * (1 + fuse + (1 if op == 'cos_x' else 0))) + m_hint * 4 * k * c
+    with _capi.timed('lk_link_apply_fwd', nb):
+        _capi.check(L.lk_link_apply_fwd(_capi.ptr(mean), _capi.ptr(f_input), _capi.ptr(coords),
+                                        _capi.ptr(bi.idx_query), n, C.byref(gen), fuse,
+                                        _capi.ptr(local) if fuse else None, _capi.ptr(g1),
+                                        _capi.ptr(b1), _capi.ptr(g2), _capi.ptr(b2), _capi.ptr(out),
+                                        st), 'lk_link_apply_fwd')
     return out
 
 

@@ -93,10 +93,11 @@ def sort_unique(keys: torch.Tensor, key_bits: int, want_order: bool = False) -> 
     L = _capi.lib()
     ws_bytes = L.lk_sort_unique_ws_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _capi.check(L.lk_sort_unique(_capi.ptr(keys), n, int(key_bits), _capi.ptr(r.unique),
-                                 _capi.ptr(r.inverse), _capi.ptr(r.order), _capi.ptr(r.seg),
-                                 _capi.ptr(r.counts), _capi.ptr(r.num), _capi.ptr(ws), ws_bytes,
-                                 _capi.stream()), 'lk_sort_unique')
+    with _capi.timed('lk_sort_unique', n * 12 * 2 * ((int(key_bits) + 7) // 8)):
+        _capi.check(L.lk_sort_unique(_capi.ptr(keys), n, int(key_bits), _capi.ptr(r.unique),
+                                     _capi.ptr(r.inverse), _capi.ptr(r.order), _capi.ptr(r.seg),
+                                     _capi.ptr(r.counts), _capi.ptr(r.num), _capi.ptr(ws), ws_bytes,
+                                     _capi.stream()), 'lk_sort_unique')
     return r
 
 

@@ -86,9 +86,10 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
         out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
     k, n_out = offsets.shape[0], out_coords.shape[0]
     nbr = torch.empty(k, n_out, dtype=torch.int32, device=coords.device)
-    _capi.check(_capi.lib().lk_kmap_query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
-                                          _capi.ptr(table.table), table.capacity, _capi.ptr(nbr),
-                                          _capi.stream()), 'lk_kmap_query')
+    with _capi.timed('lk_kmap_query', n_out * (16 + 4 * k)):
+        _capi.check(_capi.lib().lk_kmap_query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
+                                              _capi.ptr(table.table), table.capacity,
+                                              _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
     return KernelMap(nbr, coords.shape[0], n_out, out_coords)
 
 
@@ -97,10 +98,14 @@ def _conv_fwd(feats, weight, nbr, n_out, bias=None):
     if feats.shape[1] != c_in:
         raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
     out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
-    _capi.check(_capi.lib().lk_conv_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
-                                        _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
-                                        _capi.ptr(bias), _capi.ptr(out), _capi.stream()),
-                'lk_conv_fwd')
+    # algorithmic bytes: kernel map + each input row once + output once + the weights
+    nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
+    with _capi.timed('lk_conv_fwd', nb):
+        _capi.check(_capi.lib().lk_conv_fwd(_capi.ptr(feats, torch.float32),
+                                            _capi.ptr(weight, torch.float32),
+                                            _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
+                                            _capi.ptr(bias), _capi.ptr(out), _capi.stream()),
+                    'lk_conv_fwd')
     return out
 
 
