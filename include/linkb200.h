@@ -170,6 +170,17 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
                       const float* d_g1, const float* d_b1, const float* d_g2,
                       const float* d_b2, float* d_out, lk_stream_t s);
 
+/* Fused bias-free Linear + LayerNorm: out = LN(x @ W^T; gamma, beta, eps); x, out [n, c],
+ * W [c, c] (nn.Linear layout).  ELKBlock.pre_mix (linkencoder.py:112-115).  c in {16,32,64,128}. */
+int lk_linear_ln_fwd(const float* d_x, const float* d_w, const float* d_gamma, const float* d_beta,
+                     float eps, int64_t n, int c, float* d_out, lk_stream_t s);
+
+/* Same contract on the tcgen05 tensor cores (kind::tf32 with the 3xTF32 split => fp32-level
+ * accuracy, accumulators in TMEM, LayerNorm in the TMEM epilogue).  c in {32,64}. */
+int lk_linear_ln_tc_fwd(const float* d_x, const float* d_w, const float* d_gamma,
+                        const float* d_beta, float eps, int64_t n, int c, float* d_out,
+                        lk_stream_t s);
+
 /* ------------------------------------------------------------------------------------
  * Kernel maps + sparse convolution -- replace the python kmap build
  * (nn/functional/conv.py:103-122) and convolution_{forward,backward}_cuda
@@ -183,6 +194,11 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
 /* d_table: hash table built over lk_hash(input coords).  offsets int32 [K,3]. */
 int lk_kmap_query(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_offsets, int k,
                   const void* d_table, int64_t capacity, int32_t* d_nbr, lk_stream_t s);
+/* Submanifold special case (output coords == input coords, odd kernel => offsets[K-1-k] ==
+ * -offsets[k]): only the first K/2 offsets are probed and each hit (i, j) fills both nbr[k, i] = j
+ * and nbr[K-1-k, j] = i; the centre offset is the identity.  Same result as lk_kmap_query. */
+int lk_kmap_query_subm(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
+                       const void* d_table, int64_t capacity, int32_t* d_nbr, lk_stream_t s);
 /* Transposed relation: d_inv [K, n_in] (prefilled with -1 by this call):
  * d_inv[k, i] = o  whenever d_nbr[k, o] = i. */
 int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_t n_in, int32_t* d_inv,

@@ -56,7 +56,10 @@ PROTOTYPES = {
     'lk_link_window_mean': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
+    'lk_linear_ln_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
+    'lk_linear_ln_tc_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
+    'lk_kmap_query_subm': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
     'lk_kmap_invert': (i32, [vp, i64, i32, i64, vp, vp]),
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),

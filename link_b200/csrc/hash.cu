@@ -168,6 +168,49 @@ extern "C" int lk_kmap_query(const int32_t* d_out_coords, int64_t n_out, const i
   return LK_OK;
 }
 
+// Submanifold maps are symmetric: (i --k--> j)  <=>  (j --(K-1-k)--> i).  One thread per
+// (voxel, k < K/2) pair: half the probes of the generic kernel and K/2-fold more parallelism.
+__global__ void __launch_bounds__(256) kmap_query_subm_kernel(const int4* __restrict__ coords,
+                                                              int64_t n, const int* __restrict__ offsets,
+                                                              int K, const Slot* __restrict__ table,
+                                                              uint64_t mask, unsigned* nbr) {
+  const int half = K / 2;
+  int64_t total = n * (half + 1);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(t / n);
+    int64_t i = t - (int64_t)k * n;
+    if (k == half) {                                  // centre offset: identity
+      nbr[(int64_t)half * n + i] = (unsigned)i;
+      continue;
+    }
+    int4 c = coords[i];
+    int64_t h = lk_fnv4(c.x + __ldg(offsets + 3 * k), c.y + __ldg(offsets + 3 * k + 1),
+                        c.z + __ldg(offsets + 3 * k + 2), c.w);
+    int j = table_find(table, mask, (unsigned long long)h);
+    if (j >= 0) {
+      nbr[(int64_t)k * n + i] = (unsigned)j;
+      atomicMin(&nbr[(int64_t)(K - 1 - k) * n + j], (unsigned)i);   // 0xFFFFFFFF == -1 prefill
+    }
+  }
+}
+
+extern "C" int lk_kmap_query_subm(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
+                                  const void* d_table, int64_t capacity, int32_t* d_nbr,
+                                  lk_stream_t s) {
+  if (n == 0 || k == 0) return LK_OK;
+  LK_REQUIRE(d_coords && d_offsets && d_table && d_nbr && k > 0 && (k & 1) == 1,
+             "lk_kmap_query_subm: needs an odd kernel volume");
+  cudaStream_t st = (cudaStream_t)s;
+  LK_CUDA(cudaMemsetAsync(d_nbr, 0xFF, (size_t)k * n * sizeof(int), st));
+  lk_count_launch();
+  kmap_query_subm_kernel<<<lk_grid(n * (k / 2 + 1), 256, 8), 256, 0, st>>>(
+      (const int4*)d_coords, n, d_offsets, k, (const Slot*)d_table, (uint64_t)capacity - 1,
+      (unsigned*)d_nbr);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 __global__ void __launch_bounds__(256) kmap_invert_kernel(const int* __restrict__ nbr,
                                                           int64_t n_out, int K, int64_t n_in,
                                                           int* __restrict__ inv) {

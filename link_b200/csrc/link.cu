@@ -52,12 +52,42 @@ __device__ __forceinline__ void lane_phase(const GenDev& g, const LaneGen& lg, i
   }
 }
 
-#define PREAGG_ROWS_PER_GROUP 16
+// sin/cos of the lane's 4 phases.  With channel groups (pos.repeat([1, groups]), linkencoder.py:152)
+// the SH = C/wrows lanes {l0 + j*S} of a row own IDENTICAL phases, so each of them evaluates only
+// 4/SH of the sincosf and the rest arrive by shuffle: the transcendental work per row drops SH-fold.
+// Must be called by all 32 lanes (full-mask shuffles).
+template <int LPR, int SH>
+__device__ __forceinline__ void lane_sincos(const float p[4], int lane, float sn[4], float cs[4]) {
+  if (SH == 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
+  } else {
+    constexpr int N = 4 / SH;            // elements evaluated by this lane
+    constexpr int S = LPR / SH;          // lane distance between copies
+    const int li = lane % LPR, j = li / S, base = lane - li + (li % S);
+    float ms[N], mc[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      float pe = p[0];
+#pragma unroll
+      for (int e = 1; e < 4; ++e) pe = (e == j * N + q) ? p[e] : pe;
+      sincosf(pe, &ms[q], &mc[q]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int src = base + (e / N) * S;
+      sn[e] = __shfl_sync(0xffffffffu, ms[e % N], src);
+      cs[e] = __shfl_sync(0xffffffffu, mc[e % N], src);
+    }
+  }
+}
+
+#define PREAGG_ROWS_PER_GROUP 8
 #define PREAGG_UNROLL 4
 
 // ------------------------------------------------------------------ pass 1: block sums
-template <int LPR, int OP>
-__global__ void __launch_bounds__(256) link_preagg_kernel(const float* __restrict__ fin,
+template <int LPR, int OP, int SH>
+__global__ void __launch_bounds__(256, 3) link_preagg_kernel(const float* __restrict__ fin,
                                                           const int4* __restrict__ coords,
                                                           const int* __restrict__ blk, int64_t n,
                                                           GenDev g, float* sums) {
@@ -85,7 +115,8 @@ __global__ void __launch_bounds__(256) link_preagg_kernel(const float* __restric
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
     int cur = -1;
-    for (int64_t r = r0; r < r1; r += PREAGG_UNROLL) {
+    // NB: trip count is warp-uniform (r1 - r0 may be shorter for the last group; `ok` masks it)
+    for (int64_t r = r0; r < r0 + PREAGG_ROWS_PER_GROUP; r += PREAGG_UNROLL) {
       int b[PREAGG_UNROLL];
       int4 cc[PREAGG_UNROLL];
       float4 f[PREAGG_UNROLL];
@@ -99,6 +130,9 @@ __global__ void __launch_bounds__(256) link_preagg_kernel(const float* __restric
       }
 #pragma unroll
       for (int u = 0; u < PREAGG_UNROLL; ++u) {
+        float p[4], sn[4], cs[4];
+        lane_phase<COSX>(g, lg, cc[u], p);
+        lane_sincos<LPR, SH>(p, lane, sn, cs);     // all lanes: contains full-mask shuffles
         if (b[u] < 0) continue;                    // tail of the batch (or unmapped voxel)
         if (b[u] != cur) {                         // run boundary: flush the finished block
           if (cur >= 0 && active) {
@@ -113,10 +147,6 @@ __global__ void __launch_bounds__(256) link_preagg_kernel(const float* __restric
             for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
           cur = b[u];
         }
-        float p[4], sn[4], cs[4];
-        lane_phase<COSX>(g, lg, cc[u], p);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
         const float fv[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -178,12 +208,14 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
     const int* nb = nbr + b * R;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float tot = 0.f;
-    for (int k = 0; k < R; ++k) {
+#pragma unroll 9
+    for (int k = 0; k < R; ++k) {            // branch-free so the R row loads can be in flight
       int src = __ldg(nb + k);
-      if (src < 0) continue;
+      float wgt = src >= 0 ? 1.f : 0.f;
+      src = max(src, 0);
       float4 v = __ldg((const float4*)(sums + (int64_t)src * kc + j));
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      tot += (float)__ldg(counts + src);
+      acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+      tot += wgt * (float)__ldg(counts + src);
     }
     acc.x /= tot; acc.y /= tot; acc.z /= tot; acc.w /= tot;
     *(float4*)(mean + b * kc + j) = acc;
@@ -216,8 +248,8 @@ __device__ __forceinline__ void group_layernorm(float v[4], bool active, int c, 
   }
 }
 
-template <int LPR, int OP, bool NORM>
-__global__ void __launch_bounds__(256) link_apply_kernel(
+template <int LPR, int OP, bool NORM, int SH>
+__global__ void __launch_bounds__(256, 4) link_apply_kernel(
     const float* __restrict__ mean, const float* __restrict__ fin, const int4* __restrict__ coords,
     const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
@@ -241,11 +273,10 @@ __global__ void __launch_bounds__(256) link_apply_kernel(
     int b = ok ? __ldg(blk + r) : -1;    // inside a group, so no divergence hazard
     int4 cc = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
     float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float p[4], sn[4], cs[4];
+    lane_phase<COSX>(g, lg, cc, p);
+    lane_sincos<LPR, SH>(p, lane, sn, cs);       // all lanes: contains full-mask shuffles
     if (ok && active && b >= 0) {
-      float p[4], sn[4], cs[4];
-      lane_phase<COSX>(g, lg, cc, p);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
       const float* mrow = mean + (int64_t)b * kc + ch;
       float4 m0 = __ldg((const float4*)mrow);
       float4 m1 = __ldg((const float4*)(mrow + g.c));
@@ -293,6 +324,14 @@ static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
   return LK_OK;
 }
 
+// number of lanes of a row that own identical phases (channel groups), if the layout allows the
+// shuffle exchange: C/4 a power of two, wrows a multiple of 4, C/wrows in {2,4}
+static int share_of(const GenDev& g, int lpr) {
+  if (lpr * 4 != g.c || g.wrows % 4 != 0 || g.c % g.wrows != 0) return 1;
+  int sh = g.c / g.wrows;
+  return (sh == 2 || sh == 4) ? sh : 1;
+}
+
 static int lpr_of(int c) {
   int v = c / 4, l = 1;
   while (l < v) l <<= 1;
@@ -324,17 +363,25 @@ extern "C" int lk_link_preagg_fwd(const float* d_fin, const int32_t* d_coords, c
   int64_t warps = (n + rows_per_warp - 1) / rows_per_warp;
   int grid = lk_grid(warps * 32, 256, 8);
   cudaStream_t st = (cudaStream_t)s;
-#define LAUNCH_PRE(L)                                                                              \
-  do {                                                                                             \
-    if (g.op == LK_OP_COS)                                                                         \
-      link_preagg_kernel<L, LK_OP_COS><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
-    else if (g.op == LK_OP_SIN)                                                                    \
-      link_preagg_kernel<L, LK_OP_SIN><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
-    else                                                                                           \
-      link_preagg_kernel<L, LK_OP_COSX><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums); \
+  const int sh = share_of(g, lpr);
+#define LAUNCH_PRE2(L, O, S) \
+  link_preagg_kernel<L, O, S><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums)
+#define LAUNCH_PRE1(L, O)                                           \
+  do {                                                              \
+    if (sh == 2 && L >= 2) LAUNCH_PRE2(L, O, (L >= 2 ? 2 : 1));     \
+    else if (sh == 4 && L >= 4) LAUNCH_PRE2(L, O, (L >= 4 ? 4 : 1)); \
+    else LAUNCH_PRE2(L, O, 1);                                      \
+  } while (0)
+#define LAUNCH_PRE(L)                                   \
+  do {                                                  \
+    if (g.op == LK_OP_COS) LAUNCH_PRE1(L, LK_OP_COS);   \
+    else if (g.op == LK_OP_SIN) LAUNCH_PRE1(L, LK_OP_SIN); \
+    else LAUNCH_PRE1(L, LK_OP_COSX);                    \
   } while (0)
   DISPATCH_LPR(lpr, LAUNCH_PRE);
 #undef LAUNCH_PRE
+#undef LAUNCH_PRE1
+#undef LAUNCH_PRE2
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -368,16 +415,21 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
   int64_t steps = (n + (32 / lpr) - 1) / (32 / lpr);
   int grid = lk_grid(steps * 32, 256, 8);
   cudaStream_t st = (cudaStream_t)s;
-#define LAUNCH_APPLY2(L, O)                                                                        \
-  do {                                                                                             \
-    if (fuse_norm)                                                                                 \
-      link_apply_kernel<L, O, true><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,    \
-                                                          d_blk, n, g, d_local, d_g1, d_b1, d_g2,  \
-                                                          d_b2, d_out);                            \
-    else                                                                                           \
-      link_apply_kernel<L, O, false><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,   \
-                                                           d_blk, n, g, d_local, d_g1, d_b1, d_g2, \
-                                                           d_b2, d_out);                           \
+  const int sh = share_of(g, lpr);
+#define LAUNCH_APPLY3(L, O, NRM, S)                                                              \
+  link_apply_kernel<L, O, NRM, S><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,    \
+                                                        d_blk, n, g, d_local, d_g1, d_b1, d_g2,  \
+                                                        d_b2, d_out)
+#define LAUNCH_APPLY2N(L, O, NRM)                                       \
+  do {                                                                  \
+    if (sh == 2 && L >= 2) LAUNCH_APPLY3(L, O, NRM, (L >= 2 ? 2 : 1));  \
+    else if (sh == 4 && L >= 4) LAUNCH_APPLY3(L, O, NRM, (L >= 4 ? 4 : 1)); \
+    else LAUNCH_APPLY3(L, O, NRM, 1);                                   \
+  } while (0)
+#define LAUNCH_APPLY2(L, O)                      \
+  do {                                           \
+    if (fuse_norm) LAUNCH_APPLY2N(L, O, true);   \
+    else LAUNCH_APPLY2N(L, O, false);            \
   } while (0)
 #define LAUNCH_APPLY(L)                                         \
   do {                                                          \
@@ -388,6 +440,8 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
   DISPATCH_LPR(lpr, LAUNCH_APPLY);
 #undef LAUNCH_APPLY
 #undef LAUNCH_APPLY2
+#undef LAUNCH_APPLY2N
+#undef LAUNCH_APPLY3
   LK_LAUNCHED();
   return LK_OK;
 }

@@ -1,0 +1,126 @@
+// Blackwell (sm_100a) tensor-core plumbing used by the dense and sparse GEMM kernels:
+// tcgen05.mma (kind::tf32) with accumulators in TMEM, operands in shared memory in the canonical
+// K-major SWIZZLE_128B layout, mbarrier completion via tcgen05.commit, tcgen05.ld epilogues.
+//
+// fp32 accuracy on tf32 tensor cores ("3xTF32"): x = hi + lo with hi = x truncated to tf32 and
+// lo = x - hi (exact in fp32);  A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo  (error ~2^-21 relative),
+// i.e. three tcgen05.mma per k-slice accumulating into the same TMEM tile.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// ---- proxy / tcgen05 fences -------------------------------------------------------------------
+// generic-proxy st.shared -> visible to the async proxy (tensor core reads of smem operands)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- TMEM allocation (one full warp calls alloc/dealloc) --------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+               ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows at a 128-byte pitch, 8-row groups
+// 1024 bytes apart (SBO), leading-byte-offset field unused for swizzled K-major (encoded 1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  Tile base 1024-byte aligned;
+// a k-slice inside the 128-byte atom is selected by adding its byte offset to `addr`.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 B
+  d |= (uint64_t)1 << 46;                 // version = 1
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major.
+__device__ __forceinline__ uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+  uint32_t d = 0;
+  d |= 1u << 4;            // D format: F32
+  d |= 2u << 7;            // A format: TF32
+  d |= 2u << 10;           // B format: TF32
+  d |= (N >> 3) << 17;     // N / 8
+  d |= (M >> 4) << 24;     // M / 16
+  return d;
+}
+
+// ---- MMA issue / completion (single thread) ---------------------------------------------------
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns --------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand staging --------------------------------------------------------------------------
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside one [rows x 32 fp32] K-block
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+// split a float4 into its tf32-truncated part and the fp32 remainder
+__device__ __forceinline__ void split_tf32(const float4& v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+
+}  // namespace tc

@@ -12,6 +12,7 @@ Two execution paths, both on liblinkb200 kernels (there is no PyTorch/CPU fallba
     spvoxelize / spdevoxelize kernels, used when gradients are required.
 """
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -28,6 +29,8 @@ __all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsampl
            'initial_voxelize', 'link_aggregate', 'ELKBlock', 'LinKBlock']
 
 _OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
+# dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); False selects the FFMA kernels
+USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 
 
 class BlockIndex:
@@ -251,10 +254,29 @@ class ELKBlock(nn.Module):
         return torch.is_grad_enabled() and (st.F.requires_grad or
                                             any(p.requires_grad for p in self.parameters()))
 
+    def _pre_mix_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """pre_mix = Linear(no bias) + LayerNorm in one liblinkb200 kernel (forward only)."""
+        lin, ln = self.pre_mix[0], self.pre_mix[1]
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        n, c = x.shape
+        L = _capi.lib()
+        fn = L.lk_linear_ln_tc_fwd if (c in (32, 64) and USE_TENSOR_CORES) else L.lk_linear_ln_fwd
+        with _capi.timed('lk_linear_ln_fwd', n * 8 * c + 4 * c * c):
+            _capi.check(fn(
+                _capi.ptr(x, torch.float32), _capi.ptr(lin.weight.detach().contiguous()),
+                _capi.ptr(ln.weight.detach().contiguous()), _capi.ptr(ln.bias.detach().contiguous()),
+                float(ln.eps), n, c, _capi.ptr(out), _capi.stream()), 'lk_linear_ln_fwd')
+        return out
+
     def forward(self, st: SparseTensor, s, r):
-        F_input = self.pre_mix(st.F)
+        composed = self._needs_grad(st) or st.F.dtype != torch.float32
+        if composed or self.inc not in (16, 32, 64, 128):
+            F_input = self.pre_mix(st.F)
+        else:
+            F_input = self._pre_mix_fused(st.F)
         local_mix = self.local_mix(st)
-        if self._needs_grad(st) or st.F.dtype != torch.float32:
+        if composed:
             return self._forward_composed(st, F_input, local_mix, s, r)
         if self.baseop == 'cos_x' and self.groups != 1:
             raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor is "

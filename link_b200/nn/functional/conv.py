@@ -86,10 +86,12 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
         out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
     k, n_out = offsets.shape[0], out_coords.shape[0]
     nbr = torch.empty(k, n_out, dtype=torch.int32, device=coords.device)
+    subm = all(s == 1 for s in stride) and k % 2 == 1
+    query = _capi.lib().lk_kmap_query_subm if subm else _capi.lib().lk_kmap_query
     with _capi.timed('lk_kmap_query', n_out * (16 + 4 * k)):
-        _capi.check(_capi.lib().lk_kmap_query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
-                                              _capi.ptr(table.table), table.capacity,
-                                              _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
+        _capi.check(query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
+                          _capi.ptr(table.table), table.capacity, _capi.ptr(nbr), _capi.stream()),
+                    'lk_kmap_query')
     return KernelMap(nbr, coords.shape[0], n_out, out_coords)
 
 

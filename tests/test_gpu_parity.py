@@ -388,3 +388,25 @@ def test_full_size_scan_properties(dev):
     b = link_aggregate(f2, cc, bi, r, 'cos', w)
     ab = link_aggregate(f1 + 2 * f2, cc, bi, r, 'cos', w)
     np.testing.assert_allclose(ab.cpu().numpy(), (a + 2 * b).cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ dense pre_mix kernels
+@pytest.mark.parametrize('c,tcore', [(16, False), (32, False), (64, False), (128, False),
+                                     (32, True), (64, True)])
+@pytest.mark.parametrize('n', [1, 127, 128, 129, 20_011])
+def test_linear_layernorm_kernels(dev, c, tcore, n):
+    """Fused Linear+LayerNorm (FFMA and tcgen05/3xTF32 variants) vs torch fp32."""
+    from link_b200 import _capi
+    g = torch.Generator().manual_seed(c + n)
+    x = (torch.randn(n, c, generator=g) * 3).to(dev)
+    w = (torch.randn(c, c, generator=g) / c ** 0.5).to(dev)
+    gam = (torch.rand(c, generator=g) + 0.5).to(dev)
+    bet = torch.randn(c, generator=g).to(dev)
+    out = torch.empty_like(x)
+    L = _capi.lib()
+    fn = L.lk_linear_ln_tc_fwd if tcore else L.lk_linear_ln_fwd
+    _capi.check(fn(_capi.ptr(x), _capi.ptr(w), _capi.ptr(gam), _capi.ptr(bet), 1e-6, n, c,
+                   _capi.ptr(out), _capi.stream()), 'linear_ln')
+    want = torch.nn.functional.layer_norm(x.double() @ w.double().t(), (c,), gam.double(),
+                                          bet.double(), 1e-6).float()
+    np.testing.assert_allclose(out.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5)
