@@ -208,6 +208,14 @@ int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_t n_in, int
 int lk_conv_fwd(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out,
                 int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
                 lk_stream_t s);
+/* Same contraction on the tcgen05 tensor cores (kind::tf32, 3xTF32 split => fp32-level accuracy):
+ * weight-stationary persistent CTAs, the accumulators of up to 512/c_out output tiles resident in
+ * TMEM, operands gathered into SWIZZLE_128B shared-memory tiles.  Takes the weights TRANSPOSED,
+ * d_wt [K, c_out, c_in] (K-major B operand).  lk_conv_tc_supported: c_in, c_out in {32, 64}. */
+int lk_conv_tc_supported(int c_in, int c_out);
+int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_t* d_nbr, int64_t n_out,
+                   int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
+                   lk_stream_t s);
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);

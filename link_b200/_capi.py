@@ -62,6 +62,8 @@ PROTOTYPES = {
     'lk_kmap_query_subm': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
     'lk_kmap_invert': (i32, [vp, i64, i32, i64, vp, vp]),
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
+    'lk_conv_tc_supported': (i32, [i32, i32]),
+    'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
 }
 

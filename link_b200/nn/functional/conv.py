@@ -4,6 +4,7 @@ Public surface = the reference's `F.conv3d(input, weight, kernel_size, bias, str
 transposed)` (torchsparse/nn/functional/conv.py:83-147) with the same caching contract: kernel
 maps live in `input.kmaps[(input.stride, kernel_size, stride, dilation)]` and every derived
 tensor shares the `cmaps` / `kmaps` dict objects."""
+import os
 from typing import Optional, Tuple, Union
 
 import torch
@@ -95,19 +96,50 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
     return KernelMap(nbr, coords.shape[0], n_out, out_coords)
 
 
-def _conv_fwd(feats, weight, nbr, n_out, bias=None):
-    k, c_in, c_out = weight.shape
+# dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); '0' selects the FFMA kernel
+USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
+_wt_cache = {}
+
+
+def _transposed(weight: torch.Tensor) -> torch.Tensor:
+    """[K, Cin, Cout] -> contiguous [K, Cout, Cin] (K-major B operand of the tensor-core kernel),
+    cached per (storage, version) so a module's weights are transposed once per update."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    wt = _wt_cache.get(key)
+    if wt is None:
+        if len(_wt_cache) > 512:
+            _wt_cache.clear()
+        wt = weight.detach().transpose(1, 2).contiguous()
+        _wt_cache[key] = wt
+    return wt
+
+
+def _conv_fwd(feats, weight, nbr, n_out, weight_t=None):
+    """out[o] = sum_k feats[nbr[k, o]] @ weight[k].  `weight` is [K, Cin, Cout] (may be None when
+    its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies)."""
+    if weight is not None:
+        k, c_in, c_out = weight.shape
+    else:
+        k, c_out, c_in = weight_t.shape
     if feats.shape[1] != c_in:
         raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
     out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
+    L = _capi.lib()
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
+    if USE_TENSOR_CORES and L.lk_conv_tc_supported(c_in, c_out):
+        wt = weight_t if weight_t is not None else _transposed(weight)
+        with _capi.timed('lk_conv_fwd', nb):
+            _capi.check(L.lk_conv_tc_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
+                                         _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, None,
+                                         _capi.ptr(out), _capi.stream()), 'lk_conv_tc_fwd')
+        return out
+    if weight is None:
+        weight = weight_t.transpose(1, 2).contiguous()
     with _capi.timed('lk_conv_fwd', nb):
-        _capi.check(_capi.lib().lk_conv_fwd(_capi.ptr(feats, torch.float32),
-                                            _capi.ptr(weight, torch.float32),
-                                            _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
-                                            _capi.ptr(bias), _capi.ptr(out), _capi.stream()),
-                    'lk_conv_fwd')
+        _capi.check(L.lk_conv_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
+                                  _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, None,
+                                  _capi.ptr(out), _capi.stream()), 'lk_conv_fwd')
     return out
 
 
@@ -140,8 +172,8 @@ class ConvolutionFunction(Function):
         to_out = kmap.nbr if not transposed else kmap.inv
         n_in_rows = feats.shape[0]
         if ctx.needs_input_grad[0]:
-            wt = weight.transpose(1, 2).contiguous()
-            grad_feats = _conv_fwd(g, wt, to_in, n_in_rows).to(ctx.in_dtype)
+            # dX = sum_k dY[to_in[k]] @ W[k]^T: the forward weight IS the transposed operand
+            grad_feats = _conv_fwd(g, None, to_in, n_in_rows, weight_t=weight).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             _capi.check(_capi.lib().lk_conv_bwd_weight(
