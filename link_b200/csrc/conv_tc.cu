@@ -12,8 +12,11 @@
 //     128-bit loads (missing neighbours -> zero rows), split into tf32 hi/lo planes and written in
 //     the canonical K-major SWIZZLE_128B layout; one thread issues 3*C_in/8 tcgen05.mma
 //     (M=128, N=C_out, K=8) accumulating into that tile's TMEM columns; tcgen05.commit -> mbarrier
-//     releases the operand stage.  Two operand stages: the gather of step j+1 overlaps the MMAs
-//     of step j.  (tile, offset) steps with no neighbour at all are skipped.
+//     releases the operand stage;
+//   * warp-specialised: 8 producer warps (gather/split/store, then the epilogue) and 1 MMA-issuer
+//     warp talk only through full/empty mbarriers (no __syncthreads in the main loop); two operand
+//     stages in shared memory plus a register stage (rows of step j+1 and indices of step j+2
+//     are in flight while step j is being written);
 //   * epilogue: tcgen05.ld 32x32b (thread = output row) -> + bias -> one streaming store per row.
 //
 // No atomics, no temporaries, deterministic, output written exactly once.
@@ -21,7 +24,7 @@
 #include "tc.cuh"
 
 #define CT_ROWS 128
-#define CT_THREADS 256
+#define CT_THREADS 512      // producer threads (16 warps); one more warp issues the MMAs
 
 template <int CIN, int COUT>
 struct ConvTcCfg {
@@ -38,150 +41,178 @@ struct ConvTcCfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(
+__global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wt /*[K][COUT][CIN]*/,
     const int* __restrict__ nbr, int64_t n_out, int K, int tiles_per_cta,
     const float* __restrict__ bias, float* __restrict__ out) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   constexpr int KB = Cfg::KB;
+  constexpr int NI = Cfg::ITEMS_A;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_stage[2] = {smem, smem + Cfg::A_STAGE};
-  uint8_t* b_stage[2] = {smem + 2 * Cfg::A_STAGE, smem + 2 * Cfg::A_STAGE + Cfg::B_STAGE};
-  __shared__ uint64_t mma_bar[2];
+  uint8_t* const a_base = smem;                          // 2 A stages, then 2 B stages
+  uint8_t* const b_base = smem + 2 * Cfg::A_STAGE;
+  __shared__ uint64_t full_bar[2];    // operand stage written   (256 producer arrivals)
+  __shared__ uint64_t empty_bar[2];   // operand stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t total_tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
   const int ntiles = (int)min((int64_t)tiles_per_cta, total_tiles - tile0);
+  const int total_steps = K * ntiles;            // step j = (offset k = j / ntiles, tile t = j % ntiles)
   uint32_t ncols = 32;
   while (ncols < (uint32_t)(tiles_per_cta * COUT)) ncols <<= 1;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
   if (tid == 0) {
-    tc::mbar_init(&mma_bar[0], 1);
-    tc::mbar_init(&mma_bar[1], 1);
+    tc::mbar_init(&full_bar[0], CT_THREADS);
+    tc::mbar_init(&full_bar[1], CT_THREADS);
+    tc::mbar_init(&empty_bar[0], 1);
+    tc::mbar_init(&empty_bar[1], 1);
     tc::fence_mbar_init();
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t idesc = tc::idesc_tf32(128, COUT);
 
-  uint32_t commits[2] = {0, 0};      // CTA-uniform: commits issued so far on each operand stage
-  uint32_t touched = 0;              // CTA-uniform bitmask: tiles that received at least one MMA
-  uint32_t step = 0;                 // CTA-uniform: operand stage = step & 1
-
-  // row / chunk owned by this thread for item i of a step (8 lanes = one 128-byte K-block of a row)
-  // item t = tid + i*256: chunk = t & 7, kb = (t >> 3) % KB, row = t / (8*KB)
-  for (int k = 0; k < K; ++k) {
-    // ---- stage W[k]: wait until every MMA that may still read this B buffer has completed ----
-    if (commits[0]) tc::mbar_wait(&mma_bar[0], (commits[0] - 1) & 1);
-    if (commits[1]) tc::mbar_wait(&mma_bar[1], (commits[1] - 1) & 1);
-    {
-      uint8_t* bh = b_stage[k & 1];
-      uint8_t* bl = bh + Cfg::B_PLANE;
-      const float* wk = wt + (int64_t)k * COUT * CIN;
-      for (int t = tid; t < COUT * KB * 8; t += CT_THREADS) {
-        int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
-        float4 v = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), hi, lo;
-        tc::split_tf32(v, hi, lo);
-        uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
-        *(float4*)(bh + off) = hi;
-        *(float4*)(bl + off) = lo;
-      }
-    }
-    for (int t = 0; t < ntiles; ++t) {
-      const int64_t row0 = (tile0 + t) * CT_ROWS;
-      // ---- neighbour rows of this (tile, offset) ----
-      int src[Cfg::ITEMS_A];
-      int any = 0;
-#pragma unroll
-      for (int i = 0; i < Cfg::ITEMS_A; ++i) {
-        int row = (tid + i * CT_THREADS) / (8 * KB);
-        int64_t o = row0 + row;
-        src[i] = (o < n_out) ? __ldg(nbr + (int64_t)k * n_out + o) : -1;
-        any |= (src[i] >= 0);
-      }
-      if (!__syncthreads_or(any)) continue;          // nothing feeds this tile through offset k
-      const int stage = step & 1;
-      if (commits[stage]) tc::mbar_wait(&mma_bar[stage], (commits[stage] - 1) & 1);
-      // ---- gather + tf32 split into the swizzled operand planes ----
-      uint8_t* ah = a_stage[stage];
-      uint8_t* al = ah + Cfg::A_PLANE;
-      float4 v[Cfg::ITEMS_A];
-#pragma unroll
-      for (int i = 0; i < Cfg::ITEMS_A; ++i) {       // all loads first (memory-level parallelism)
-        int tt = tid + i * CT_THREADS;
-        int chunk = tt & 7, kb = (tt >> 3) % KB;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src[i] >= 0) v[i] = __ldg((const float4*)(in + (int64_t)src[i] * CIN + kb * 32 + chunk * 4));
-      }
-#pragma unroll
-      for (int i = 0; i < Cfg::ITEMS_A; ++i) {
-        int tt = tid + i * CT_THREADS;
-        int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
-        float4 hi, lo;
-        tc::split_tf32(v[i], hi, lo);
-        uint32_t off = kb * Cfg::A_BLK + tc::sw128_offset(row, chunk);
-        *(float4*)(ah + off) = hi;
-        *(float4*)(al + off) = lo;
-      }
-      tc::fence_proxy_async();
-      __syncthreads();
-      // ---- MMA issue: one thread ----
-      if (tid == 0) {
-        tc::fence_after_sync();
+  if (warp == CT_THREADS / 32) {
+    // ================= MMA issuer warp =================
+    const uint32_t idesc = tc::idesc_tf32(128, COUT);
+    // descriptors of stage 0; the start-address field counts 16-byte units, so other stages,
+    // planes and k-slices are plain additions
+    const uint64_t da0 = tc::smem_desc_sw128(tc::smem_u32(a_base));
+    const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(b_base));
+    for (int j = 0; j < total_steps; ++j) {
+      const int k = j / ntiles, t = j - k * ntiles, stage = j & 1;
+      tc::mbar_wait(&full_bar[stage], (uint32_t)(j >> 1) & 1u);
+      tc::fence_after_sync();
+      if (lane == 0) {
         const uint32_t d = tmem_base + (uint32_t)(t * COUT);
-        const uint32_t ah_u = tc::smem_u32(ah), al_u = tc::smem_u32(al);
-        const uint32_t bh_u = tc::smem_u32(b_stage[k & 1]), bl_u = bh_u + Cfg::B_PLANE;
-        uint32_t acc = (touched >> t) & 1u;
+        const uint64_t da_hi = da0 + (uint64_t)((stage * Cfg::A_STAGE) >> 4);
+        const uint64_t da_lo = da_hi + (uint64_t)(Cfg::A_PLANE >> 4);
+        const uint64_t db_hi = db0 + (uint64_t)(((k & 1) * Cfg::B_STAGE) >> 4);
+        const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
+        uint32_t acc = k > 0 ? 1u : 0u;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            uint32_t ao = kb * Cfg::A_BLK + ks * 32, bo = kb * Cfg::B_BLK + ks * 32;
-            uint64_t dah = tc::smem_desc_sw128(ah_u + ao), dal = tc::smem_desc_sw128(al_u + ao);
-            uint64_t dbh = tc::smem_desc_sw128(bh_u + bo), dbl = tc::smem_desc_sw128(bl_u + bo);
-            tc::mma_tf32(d, dal, dbh, idesc, acc);
-            tc::mma_tf32(d, dah, dbl, idesc, 1);
-            tc::mma_tf32(d, dah, dbh, idesc, 1);
+            // descriptor start-address field is in 16-byte units: advance inside the swizzle atom
+            const uint64_t ao = (uint64_t)((kb * Cfg::A_BLK + ks * 32) >> 4);
+            const uint64_t bo = (uint64_t)((kb * Cfg::B_BLK + ks * 32) >> 4);
+            tc::mma_tf32(d, da_lo + ao, db_hi + bo, idesc, acc);
+            tc::mma_tf32(d, da_hi + ao, db_lo + bo, idesc, 1);
+            tc::mma_tf32(d, da_hi + ao, db_hi + bo, idesc, 1);
             acc = 1;
           }
         }
-        tc::mma_commit(&mma_bar[stage]);
+        tc::mma_commit(&empty_bar[stage]);
       }
-      touched |= 1u << t;
-      commits[stage]++;
-      step++;
+      __syncwarp();
     }
-  }
-  // ---- drain, then epilogue ----
-  if (commits[0]) tc::mbar_wait(&mma_bar[0], (commits[0] - 1) & 1);
-  if (commits[1]) tc::mbar_wait(&mma_bar[1], (commits[1] - 1) & 1);
-  tc::fence_after_sync();
-  {
-    constexpr int HALF = COUT / 2;                   // warps 0-3: columns [0,HALF), warps 4-7: rest
-    const int q = warp & 3, c_base = (warp >> 2) * HALF;
-    for (int t = 0; t < ntiles; ++t) {
-      const int64_t o = (tile0 + t) * CT_ROWS + q * 32 + lane;
-      const bool live = (touched >> t) & 1u;
+  } else {
+    // ================= producer warps (gather + tf32 split), later the epilogue =================
+    // item i of a step: tt = tid + i*CT_THREADS -> chunk = tt & 7, kb = (tt >> 3) % KB,
+    // row = tt / (8*KB).  The (row, chunk) position of an item is the same in every step, so its
+    // swizzled shared-memory offset is computed once.
+    uint32_t soff[NI];
+    int irow[NI], icol[NI];
 #pragma unroll
-      for (int c0 = 0; c0 < HALF; c0 += 16) {
-        float acc[16];
-        if (live) {
-          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c_base + c0), acc);
-        } else {
+    for (int i = 0; i < NI; ++i) {
+      int tt = tid + i * CT_THREADS;
+      int chunk = tt & 7, kb = (tt >> 3) % KB;
+      irow[i] = tt / (8 * KB);
+      icol[i] = kb * 32 + chunk * 4;
+      soff[i] = kb * Cfg::A_BLK + tc::sw128_offset(irow[i], chunk);
+    }
+    auto load_idx = [&](int j, int* src) {
+      const int k = j / ntiles, t = j - k * ntiles;
+      const int64_t row0 = (tile0 + t) * CT_ROWS;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      for (int i = 0; i < NI; ++i) {
+        int64_t o = row0 + irow[i];
+        src[i] = (j < total_steps && o < n_out) ? __ldg(nbr + (int64_t)k * n_out + o) : -1;
+      }
+    };
+    auto load_rows = [&](const int* src, float4* v) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src[i] >= 0) v[i] = __ldg((const float4*)(in + (int64_t)src[i] * CIN + icol[i]));
+      }
+    };
+    int src_a[NI], src_b[NI], src_c[NI];
+    float4 v[NI], v_next[NI];
+    // bit (stage*NI + i): my slot of item i in that stage currently holds non-zero data.  About
+    // 70 % of the gathered rows are missing neighbours (zero rows): a slot that is already zero
+    // is not rewritten, which halves the split + store work.
+    uint32_t dirty = 0xFFFFFFFFu;             // shared memory starts uninitialised
+    load_idx(0, src_a);
+    load_rows(src_a, v);
+    load_idx(1, src_b);
+    for (int j = 0; j < total_steps; ++j) {
+      const int k = j / ntiles, t = j - k * ntiles, stage = j & 1;
+      load_idx(j + 2, src_c);                 // index prefetch distance 2
+      load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
+      if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
+      if (t == 0) {
+        // stage W[k]: every MMA of offset k-2 (last reader of this buffer) precedes step j-2's
+        // commit, which the wait above has just observed
+        uint8_t* bh = b_base + (k & 1) * Cfg::B_STAGE;
+        uint8_t* bl = bh + Cfg::B_PLANE;
+        const float* wk = wt + (int64_t)k * COUT * CIN;
+        for (int tt = tid; tt < COUT * KB * 8; tt += CT_THREADS) {
+          int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
+          float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), hi, lo;
+          tc::split_tf32(w4, hi, lo);
+          uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
+          *(float4*)(bh + off) = hi;
+          *(float4*)(bl + off) = lo;
         }
+      }
+      uint8_t* ah = a_base + stage * Cfg::A_STAGE;
+      uint8_t* al = ah + Cfg::A_PLANE;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const uint32_t bit = 1u << (stage * NI + i);
+        if (src_a[i] >= 0) {
+          float4 hi, lo;
+          tc::split_tf32(v[i], hi, lo);
+          *(float4*)(ah + soff[i]) = hi;
+          *(float4*)(al + soff[i]) = lo;
+          dirty |= bit;
+        } else if (dirty & bit) {
+          *(float4*)(ah + soff[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *(float4*)(al + soff[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          dirty &= ~bit;
+        }
+      }
+      tc::fence_proxy_async();                // my generic-proxy stores -> visible to the tensor core
+      tc::mbar_arrive(&full_bar[stage]);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) { v[i] = v_next[i]; src_a[i] = src_b[i]; src_b[i] = src_c[i]; }
+    }
+    // ---- drain: the last commit on each stage ----
+    const int c0 = (total_steps + 1) >> 1, c1 = total_steps >> 1;
+    if (c0) tc::mbar_wait(&empty_bar[0], (uint32_t)(c0 - 1) & 1u);
+    if (c1) tc::mbar_wait(&empty_bar[1], (uint32_t)(c1 - 1) & 1u);
+    tc::fence_after_sync();
+    // ---- epilogue: thread = output row (TMEM lane quarter q = warp & 3), 16 columns per warp ----
+    constexpr int NSLICE = COUT / 16;
+    const int q = warp & 3, slice = warp >> 2;
+    if (slice < NSLICE) {
+      const int c_base = slice * 16;
+      for (int t = 0; t < ntiles; ++t) {
+        const int64_t o = (tile0 + t) * CT_ROWS + q * 32 + lane;
+        float acc[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c_base), acc);
         if (o < n_out) {
-          float* dst = out + o * COUT + c_base + c0;
+          float* dst = out + o * COUT + c_base;
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
-            float4 b = bias ? __ldg((const float4*)(bias + c_base + c0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 b = bias ? __ldg((const float4*)(bias + c_base + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
             lk_stg_stream((float4*)(dst + e),
                           make_float4(acc[e] + b.x, acc[e + 1] + b.y, acc[e + 2] + b.z, acc[e + 3] + b.w));
           }
@@ -209,7 +240,7 @@ static int launch_conv_tc(const float* in, const float* wt, const int* nbr, int6
   if (tpc > Cfg::MAX_TILES) tpc = Cfg::MAX_TILES;            // ... within the 512 TMEM columns
   if (tpc < 1) tpc = 1;
   int grid = (int)((tiles + tpc - 1) / tpc);
-  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS, Cfg::SMEM, st>>>(in, wt, nbr, n_out, k, (int)tpc, bias, out);
+  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, n_out, k, (int)tpc, bias, out);
   LK_LAUNCHED();
   return LK_OK;
 }

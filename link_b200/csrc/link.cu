@@ -28,57 +28,67 @@ struct LaneGen {       // per-lane kernel-generator state for its 4 channels
   float w0[4], w1[4], w2[4], al[4];
 };
 
-__device__ __forceinline__ void load_lane_gen(const GenDev& g, int ch, bool active, LaneGen& lg) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    int row = active ? (ch + e) % g.wrows : 0;
-    lg.w0[e] = active ? g.pw[row * 3 + 0] : 0.f;
-    lg.w1[e] = active ? g.pw[row * 3 + 1] : 0.f;
-    lg.w2[e] = active ? g.pw[row * 3 + 2] : 0.f;
-    lg.al[e] = (active && g.alpha) ? g.alpha[row] : 1.f;
-  }
+// sin and cos of one fp32 phase: two-term Cody-Waite reduction to [-pi, pi] (exact for the
+// |p| < ~1e5 rad that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7) followed by the SFU
+// approximations (sin.approx / cos.approx, max abs error 2^-20.9 on [-pi, pi]).  ~9 instructions
+// instead of ~20 for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
+__device__ __forceinline__ void fast_sincos(float p, float& s, float& c) {
+  float k = rintf(p * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831855f, p);
+  r = fmaf(k, 1.7484555e-7f, r);
+  s = __sinf(r);
+  c = __cosf(r);
 }
 
-// phase of the 4 channels of this lane for voxel (x,y,z); same operation order as
-// nn.Linear(3, .) followed by "* alpha" (linkencoder.py:151,165)
-template <bool COSX>
-__device__ __forceinline__ void lane_phase(const GenDev& g, const LaneGen& lg, int4 c, float p[4]) {
+// Phase, sin and cos of the lane's 4 channels for voxel (x,y,z); the phase follows the operation
+// order of nn.Linear(3, .) [ (x*w0 + y*w1) + z*w2 ] followed by "* alpha" (linkencoder.py:151,165).
+// With channel groups (pos.repeat([1, groups]), linkencoder.py:152) the SH = C/wrows lanes
+// {l0 + j*S} of a row own IDENTICAL phases: each evaluates only N = 4/SH of them (its weights for
+// exactly those were loaded by load_lane_gen_owned) and the rest arrive by shuffle, so the
+// transcendental work per row drops SH-fold.  Must be called by all 32 lanes.
+template <int LPR, int SH, bool COSX>
+__device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen& lg, int4 c, int lane,
+                                          float p[4], float sn[4], float cs[4]) {
+  constexpr int N = 4 / SH;            // phases evaluated by this lane
   float x = (float)c.x, y = (float)c.y, z = (float)c.z;
   if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
+  float mp[N], ms[N], mc[N];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float v = fmaf(z, lg.w2[e], fmaf(y, lg.w1[e], x * lg.w0[e]));
-    p[e] = COSX ? v * lg.al[e] : v;
+  for (int q = 0; q < N; ++q) {
+    float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
+    mp[q] = COSX ? v * lg.al[q] : v;
+    fast_sincos(mp[q], ms[q], mc[q]);
+  }
+  if (SH == 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { p[e] = mp[e % N]; sn[e] = ms[e % N]; cs[e] = mc[e % N]; }
+  } else {
+    constexpr int S = LPR / SH;        // lane distance between the copies
+    const int li = lane % LPR, base = lane - li + (li % S);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int src = base + (e / N) * S;
+      sn[e] = __shfl_sync(0xffffffffu, ms[e % N], src);
+      cs[e] = __shfl_sync(0xffffffffu, mc[e % N], src);
+      if (COSX) p[e] = __shfl_sync(0xffffffffu, mp[e % N], src);
+    }
   }
 }
 
-// sin/cos of the lane's 4 phases.  With channel groups (pos.repeat([1, groups]), linkencoder.py:152)
-// the SH = C/wrows lanes {l0 + j*S} of a row own IDENTICAL phases, so each of them evaluates only
-// 4/SH of the sincosf and the rest arrive by shuffle: the transcendental work per row drops SH-fold.
-// Must be called by all 32 lanes (full-mask shuffles).
+// weights of the phases this lane evaluates: element q <-> channel ch + j*N + q, j = copy index
 template <int LPR, int SH>
-__device__ __forceinline__ void lane_sincos(const float p[4], int lane, float sn[4], float cs[4]) {
-  if (SH == 1) {
+__device__ __forceinline__ void load_lane_gen_owned(const GenDev& g, int lane, int ch, bool active,
+                                                    LaneGen& lg) {
+  constexpr int N = 4 / SH;
+  const int j = (SH == 1) ? 0 : (lane % LPR) / (LPR / SH);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) sincosf(p[e], &sn[e], &cs[e]);
-  } else {
-    constexpr int N = 4 / SH;            // elements evaluated by this lane
-    constexpr int S = LPR / SH;          // lane distance between copies
-    const int li = lane % LPR, j = li / S, base = lane - li + (li % S);
-    float ms[N], mc[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-      float pe = p[0];
-#pragma unroll
-      for (int e = 1; e < 4; ++e) pe = (e == j * N + q) ? p[e] : pe;
-      sincosf(pe, &ms[q], &mc[q]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int src = base + (e / N) * S;
-      sn[e] = __shfl_sync(0xffffffffu, ms[e % N], src);
-      cs[e] = __shfl_sync(0xffffffffu, mc[e % N], src);
-    }
+  for (int q = 0; q < 4; ++q) {
+    int row = (active && q < N) ? (ch + j * N + q) % g.wrows : 0;
+    bool on = active && q < N;
+    lg.w0[q] = on ? g.pw[row * 3 + 0] : 0.f;
+    lg.w1[q] = on ? g.pw[row * 3 + 1] : 0.f;
+    lg.w2[q] = on ? g.pw[row * 3 + 2] : 0.f;
+    lg.al[q] = (on && g.alpha) ? g.alpha[row] : 1.f;
   }
 }
 
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(256, 3) link_preagg_kernel(const float* __rest
   const bool active = ch < g.c;
   const int kc = K * g.c;
   LaneGen lg;
-  load_lane_gen(g, ch, active, lg);
+  load_lane_gen_owned<LPR, SH>(g, lane, ch, active, lg);
 
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t rows_per_warp = (int64_t)PREAGG_ROWS_PER_GROUP * G;
@@ -131,8 +141,7 @@ __global__ void __launch_bounds__(256, 3) link_preagg_kernel(const float* __rest
 #pragma unroll
       for (int u = 0; u < PREAGG_UNROLL; ++u) {
         float p[4], sn[4], cs[4];
-        lane_phase<COSX>(g, lg, cc[u], p);
-        lane_sincos<LPR, SH>(p, lane, sn, cs);     // all lanes: contains full-mask shuffles
+        lane_trig<LPR, SH, COSX>(g, lg, cc[u], lane, p, sn, cs);   // all lanes: full-mask shuffles
         if (b[u] < 0) continue;                    // tail of the batch (or unmapped voxel)
         if (b[u] != cur) {                         // run boundary: flush the finished block
           if (cur >= 0 && active) {
@@ -231,15 +240,15 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 template <int LPR>
-__device__ __forceinline__ void group_layernorm(float v[4], bool active, int c, const float* gam,
+__device__ __forceinline__ void group_layernorm(float v[4], bool active, float inv_c, const float* gam,
                                                 const float* bet, int ch) {
   float s = active ? (v[0] + v[1] + v[2] + v[3]) : 0.f;
-  float mean = group_sum<LPR>(s) / (float)c;
+  float mean = group_sum<LPR>(s) * inv_c;
   float d[4], q = 0.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) { d[e] = v[e] - mean; q += d[e] * d[e]; }
-  float var = group_sum<LPR>(active ? q : 0.f) / (float)c;
-  float rstd = 1.0f / sqrtf(var + 1e-6f);
+  float var = group_sum<LPR>(active ? q : 0.f) * inv_c;
+  float rstd = rsqrtf(var + 1e-6f);
   if (active) {
     float4 gg = __ldg((const float4*)(gam + ch));
     float4 bb = __ldg((const float4*)(bet + ch));
@@ -263,7 +272,8 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
   const bool active = ch < g.c;
   const int kc = K * g.c;
   LaneGen lg;
-  load_lane_gen(g, ch, active, lg);
+  load_lane_gen_owned<LPR, SH>(g, lane, ch, active, lg);
+  const float inv_c = 1.0f / (float)g.c;
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t steps = (n + G - 1) / G;
   for (int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; step < steps;
@@ -274,8 +284,7 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
     int4 cc = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float p[4], sn[4], cs[4];
-    lane_phase<COSX>(g, lg, cc, p);
-    lane_sincos<LPR, SH>(p, lane, sn, cs);       // all lanes: contains full-mask shuffles
+    lane_trig<LPR, SH, COSX>(g, lg, cc, lane, p, sn, cs);   // all lanes: full-mask shuffles
     if (ok && active && b >= 0) {
       const float* mrow = mean + (int64_t)b * kc + ch;
       float4 m0 = __ldg((const float4*)mrow);
@@ -302,8 +311,8 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
         float4 lv = lk_ldg_stream((const float4*)(local + r * g.c + ch));
         l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
       }
-      group_layernorm<LPR>(v, active, g.c, g1, b1, ch);
-      group_layernorm<LPR>(l, active, g.c, g2, b2, ch);
+      group_layernorm<LPR>(v, active, inv_c, g1, b1, ch);
+      group_layernorm<LPR>(l, active, inv_c, g2, b2, ch);
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e] + l[e], 0.f);
     }
