@@ -227,6 +227,7 @@ def main_ours(args):
     evs = []
     t_wall0 = time.time()
     barrier()
+    t_cpu0 = time.perf_counter()
     for k in range(args.steps):
         i = k % 2
         f = feats_dev[i].clone()          # the block overwrites st.F; clone outside the timed region
@@ -236,6 +237,7 @@ def main_ours(args):
         step(i, coords_dev[i], f)
         e1.record()
         evs.append((e0, e1))
+    host_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / args.steps   # python + launch cost
     barrier()
     t_wall1 = time.time()
     launches = _capi.launch_count() - launches0
@@ -317,6 +319,7 @@ def main_ours(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches),
+        'host_enqueue_ms_per_step': host_enqueue_ms,
         'roofline': roof,
         'kernels': kern,
     }

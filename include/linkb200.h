@@ -142,6 +142,9 @@ typedef struct {
                           tensor stride, linkencoder.py:165; otherwise 1) */
   const float* d_pos_weight; /* [wrows, 3]   pos_weight.0.weight */
   const float* d_alpha;      /* [wrows] or NULL  (cos_x) */
+  int32_t accurate_trig;     /* 0: Cody-Waite reduction + SFU sin/cos (abs err 2^-20.9, default);
+                                1: libdevice sincosf (~1 ulp) */
+  int32_t reserved;
 } lk_kernelgen_t;
 
 /* Zero the first *d_num rows of a [capacity, row_floats] fp32 buffer (row_floats % 4 == 0).

@@ -28,7 +28,7 @@ class KeySpec(C.Structure):
 class KernelGen(C.Structure):
     _fields_ = [('op', C.c_int32), ('c', C.c_int32), ('wrows', C.c_int32),
                 ('coord_scale', C.c_float), ('d_pos_weight', C.c_void_p),
-                ('d_alpha', C.c_void_p)]
+                ('d_alpha', C.c_void_p), ('accurate_trig', C.c_int32), ('reserved', C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/linkb200.h

@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     // planes and k-slices are plain additions
     const uint64_t da0 = tc::smem_desc_sw128(tc::smem_u32(a_base));
     const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(b_base));
+    int k = 0, t = 0;
     for (int j = 0; j < total_steps; ++j) {
-      const int k = j / ntiles, t = j - k * ntiles, stage = j & 1;
+      const int stage = j & 1;
       tc::mbar_wait(&full_bar[stage], (uint32_t)(j >> 1) & 1u);
       tc::fence_after_sync();
       if (lane == 0) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         tc::mma_commit(&empty_bar[stage]);
       }
       __syncwarp();
+      if (++t == ntiles) { t = 0; ++k; }
     }
   } else {
     // ================= producer warps (gather + tf32 split), later the epilogue =================
@@ -127,14 +129,14 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       icol[i] = kb * 32 + chunk * 4;
       soff[i] = kb * Cfg::A_BLK + tc::sw128_offset(irow[i], chunk);
     }
-    auto load_idx = [&](int j, int* src) {
-      const int k = j / ntiles, t = j - k * ntiles;
-      const int64_t row0 = (tile0 + t) * CT_ROWS;
+    // neighbour indices of step (k2, t2); no integer division in the steady state
+    const int64_t row_base = tile0 * CT_ROWS;
+    auto load_idx = [&](int k2, int t2, int* src) {
+      const int* col = nbr + (int64_t)k2 * n_out + row_base + (int64_t)t2 * CT_ROWS;
+      const int64_t left = n_out - row_base - (int64_t)t2 * CT_ROWS;     // rows of this tile in range
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        int64_t o = row0 + irow[i];
-        src[i] = (j < total_steps && o < n_out) ? __ldg(nbr + (int64_t)k * n_out + o) : -1;
-      }
+      for (int i = 0; i < NI; ++i)
+        src[i] = (k2 < K && irow[i] < left) ? __ldg(col + irow[i]) : -1;
     };
     auto load_rows = [&](const int* src, float4* v) {
 #pragma unroll
@@ -149,12 +151,18 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     // 70 % of the gathered rows are missing neighbours (zero rows): a slot that is already zero
     // is not rewritten, which halves the split + store work.
     uint32_t dirty = 0xFFFFFFFFu;             // shared memory starts uninitialised
-    load_idx(0, src_a);
+    int k = 0, t = 0;                         // step j
+    int kb1 = 0, tb1 = 0, kc = 0, tc2 = 0;    // steps j+1 and j+2
+    auto advance = [&](int& kk, int& tt) { if (++tt == ntiles) { tt = 0; ++kk; } };
+    load_idx(0, 0, src_a);
     load_rows(src_a, v);
-    load_idx(1, src_b);
+    advance(kb1, tb1);
+    load_idx(kb1, tb1, src_b);
+    kc = kb1; tc2 = tb1;
+    advance(kc, tc2);
     for (int j = 0; j < total_steps; ++j) {
-      const int k = j / ntiles, t = j - k * ntiles, stage = j & 1;
-      load_idx(j + 2, src_c);                 // index prefetch distance 2
+      const int stage = j & 1;
+      load_idx(kc, tc2, src_c);               // index prefetch distance 2
       load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
       if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
       if (t == 0) {
@@ -193,6 +201,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       tc::mbar_arrive(&full_bar[stage]);
 #pragma unroll
       for (int i = 0; i < NI; ++i) { v[i] = v_next[i]; src_a[i] = src_b[i]; src_b[i] = src_c[i]; }
+      advance(k, t);
+      advance(kc, tc2);
     }
     // ---- drain: the last commit on each stage ----
     const int c0 = (total_steps + 1) >> 1, c1 = total_steps >> 1;

@@ -18,7 +18,7 @@
 #include "common.cuh"
 
 struct GenDev {
-  int op, c, wrows;
+  int op, c, wrows, accurate;
   float coord_scale;
   const float* pw;
   const float* alpha;
@@ -32,7 +32,8 @@ struct LaneGen {       // per-lane kernel-generator state for its 4 channels
 // |p| < ~1e5 rad that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7) followed by the SFU
 // approximations (sin.approx / cos.approx, max abs error 2^-20.9 on [-pi, pi]).  ~9 instructions
 // instead of ~20 for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
-__device__ __forceinline__ void fast_sincos(float p, float& s, float& c) {
+__device__ __forceinline__ void fast_sincos(float p, bool accurate, float& s, float& c) {
+  if (accurate) { sincosf(p, &s, &c); return; }      // warp-uniform switch
   float k = rintf(p * 0.15915494309189535f);
   float r = fmaf(k, -6.2831855f, p);
   r = fmaf(k, 1.7484555e-7f, r);
@@ -57,7 +58,7 @@ __device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen& lg, in
   for (int q = 0; q < N; ++q) {
     float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
     mp[q] = COSX ? v * lg.al[q] : v;
-    fast_sincos(mp[q], ms[q], mc[q]);
+    fast_sincos(mp[q], g.accurate != 0, ms[q], mc[q]);
   }
   if (SH == 1) {
 #pragma unroll
@@ -329,6 +330,7 @@ static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
     return LK_EINVAL;
   }
   g->op = gen->op; g->c = gen->c; g->wrows = gen->wrows; g->coord_scale = gen->coord_scale;
+  g->accurate = gen->accurate_trig;
   g->pw = gen->d_pos_weight; g->alpha = gen->d_alpha;
   return LK_OK;
 }

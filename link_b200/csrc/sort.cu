@@ -381,12 +381,203 @@ __global__ void __launch_bounds__(256) seg_counts_kernel(const int* __restrict__
     counts[i] = seg[i + 1] - seg[i];
 }
 
+// ---------------------------------------------------------------- fused variants (T <= RS_MAX_FUSED_TILES)
+// The single-CTA scan launches are folded into their consumers: every scatter CTA derives its own
+// digit bases from the (L2-resident) [T][256] tile-histogram matrix, and accumulates the NEXT pass's
+// tile histograms with atomics on the destination tile of each element, so a P-pass sort is
+// 1 histogram + P scatter launches instead of 3P.
+#define RS_MAX_FUSED_TILES 1024
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_tm_kernel(
+    const unsigned long long* __restrict__ keys, int64_t n, int shift, unsigned* __restrict__ hist) {
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = base + j * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];   // tile-major
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
+    const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
+    unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out, int64_t n,
+    int shift, const unsigned* __restrict__ hist /*[T][256]*/, unsigned* hist_next /*or NULL*/,
+    int T) {
+  __shared__ unsigned cnt[RS_WARPS][257];
+  __shared__ unsigned wsum[RS_WARPS];
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < RS_WARPS * 257; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+
+  // ---- digit `tid`: elements of this digit in earlier tiles, and in all tiles ----
+  unsigned below = 0, total = 0;
+  {
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {
+      unsigned a0 = __ldg(hist + (int64_t)(t + 0) * 256 + tid), a1 = __ldg(hist + (int64_t)(t + 1) * 256 + tid);
+      unsigned a2 = __ldg(hist + (int64_t)(t + 2) * 256 + tid), a3 = __ldg(hist + (int64_t)(t + 3) * 256 + tid);
+      total += a0 + a1 + a2 + a3;
+      below += (t + 0 < (int)blockIdx.x ? a0 : 0u) + (t + 1 < (int)blockIdx.x ? a1 : 0u) +
+               (t + 2 < (int)blockIdx.x ? a2 : 0u) + (t + 3 < (int)blockIdx.x ? a3 : 0u);
+    }
+    for (; t < T; ++t) {
+      unsigned a = __ldg(hist + (int64_t)t * 256 + tid);
+      total += a;
+      below += t < (int)blockIdx.x ? a : 0u;
+    }
+  }
+  // exclusive scan of `total` over the 256 digits
+  unsigned incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  unsigned wbase = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) wbase += (w < warp) ? wsum[w] : 0u;
+  const unsigned my_base = wbase + (incl - total) + below;      // global base of (digit tid, this tile)
+
+  int64_t wbase_i = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+  unsigned long long key[RS_ITEMS];
+  unsigned val[RS_ITEMS];
+  unsigned short dig[RS_ITEMS];
+  unsigned rank[RS_ITEMS];
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = wbase_i + j * 32 + lane;
+    bool valid = i < n;
+    key[j] = valid ? keys_in[i] : 0ULL;
+    val[j] = valid ? (vals_in ? vals_in[i] : (unsigned)i) : 0u;
+    dig[j] = valid ? (unsigned short)((unsigned)(key[j] >> shift) & 255u) : (unsigned short)256;
+  }
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    unsigned d = dig[j];
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    unsigned before = __popc(peers & ((1u << lane) - 1u));
+    unsigned base = 0;
+    if (lane == leader) {
+      base = cnt[warp][d];
+      cnt[warp][d] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[j] = base + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    unsigned run = my_base;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      unsigned c = cnt[w][tid];
+      cnt[w][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    if (dig[j] < 256) {
+      unsigned pos = cnt[warp][dig[j]] + rank[j];
+      keys_out[pos] = key[j];
+      vals_out[pos] = val[j];
+      if (hist_next)
+        atomicAdd(hist_next + (int64_t)(pos / RS_TILE) * 256 + ((unsigned)(key[j] >> (shift + 8)) & 255u), 1u);
+    }
+  }
+}
+
+// unique: write pass with the tile prefix computed in-kernel; CTA 0 publishes M and the sentinel
+__global__ void __launch_bounds__(RS_THREADS) uniq_write_fused_kernel(
+    const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, int64_t n,
+    const unsigned* __restrict__ tile_heads, int T, unsigned long long* __restrict__ uniq,
+    int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg, int* __restrict__ d_num) {
+  __shared__ unsigned wsum[RS_WARPS];
+  __shared__ unsigned red[2][RS_WARPS];
+  __shared__ unsigned tile_base_s;
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned below = 0, total = 0;
+  for (int t = tid; t < T; t += RS_THREADS) {
+    unsigned a = __ldg(tile_heads + t);
+    total += a;
+    below += t < (int)blockIdx.x ? a : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    below += __shfl_xor_sync(0xffffffffu, below, o);
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+  }
+  if (lane == 0) { red[0][warp] = below; red[1][warp] = total; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned b = 0, tt = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) { b += red[0][w]; tt += red[1][w]; }
+    tile_base_s = b;
+    if (blockIdx.x == 0) {
+      if (d_num) *d_num = (int)tt;
+      if (seg) seg[tt] = (int)n;
+    }
+  }
+  __syncthreads();
+  const unsigned tile_base = tile_base_s;
+
+  int64_t i0 = (int64_t)blockIdx.x * RS_TILE + (int64_t)tid * RS_ITEMS;
+  unsigned long long k[RS_ITEMS];
+  unsigned head[RS_ITEMS];
+  unsigned c = 0;
+  unsigned long long prev = (i0 > 0 && i0 - 1 < n) ? keys[i0 - 1] : 0ULL;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = i0 + j;
+    k[j] = (i < n) ? keys[i] : 0ULL;
+    head[j] = (i < n && (i == 0 || k[j] != prev)) ? 1u : 0u;
+    prev = k[j];
+    c += head[j];
+  }
+  unsigned incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  unsigned wbase = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) wbase += (w < warp) ? wsum[w] : 0u;
+  unsigned running = tile_base + wbase + (incl - c);
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = i0 + j;
+    if (i < n) {
+      running += head[j];
+      unsigned r = running - 1u;
+      unsigned v = vals[i];
+      if (head[j]) {
+        if (uniq) uniq[r] = k[j];
+        if (seg) seg[r] = (int)i;
+      }
+      if (inverse) inverse[v] = (int)r;
+      if (order) order[i] = (int)v;
+    }
+  }
+}
+
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 extern "C" int64_t lk_sort_unique_ws_bytes(int64_t n) {
   int64_t T = (n + RS_TILE - 1) / RS_TILE;
   if (T < 1) T = 1;
-  return 2 * align256(n * 8) + 2 * align256(n * 4) + align256(256 * T * 4) +
+  return 2 * align256(n * 8) + 2 * align256(n * 4) + align256(8 * 256 * T * 4) +
          align256((T + 1) * 4) + align256((n + 1) * 4) + align256(4);
 }
 
@@ -414,7 +605,7 @@ extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, u
   unsigned long long* kb = (unsigned long long*)p; p += align256(n * 8);
   unsigned* va = (unsigned*)p; p += align256(n * 4);
   unsigned* vb = (unsigned*)p; p += align256(n * 4);
-  unsigned* hist = (unsigned*)p; p += align256(256 * (int64_t)T * 4);
+  unsigned* hist = (unsigned*)p; p += align256(8 * 256 * (int64_t)T * 4);
   unsigned* tile_heads = (unsigned*)p; p += align256(((int64_t)T + 1) * 4);
   int* seg_tmp = (int*)p; p += align256((n + 1) * 4);
   int* num_tmp = (int*)p;
@@ -425,7 +616,26 @@ extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, u
   const unsigned* vin = nullptr;
   unsigned long long* kout = ka;
   unsigned* vout = va;
-  for (int pss = 0; pss < passes; ++pss) {
+  const bool fused = T <= RS_MAX_FUSED_TILES;
+  if (fused) {
+    const int64_t hsz = 256 * (int64_t)T;          // one [T][256] matrix per pass
+    if (passes > 1) {
+      LK_CUDA(cudaMemsetAsync(hist + hsz, 0, (size_t)(passes - 1) * hsz * sizeof(unsigned), st));
+      lk_count_launch();
+    }
+    radix_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, 0, hist);
+    LK_LAUNCHED();
+    for (int pss = 0; pss < passes; ++pss) {
+      radix_scatter_fused_kernel<<<T, RS_THREADS, 0, st>>>(
+          kin, vin, kout, vout, n, 8 * pss, hist + pss * hsz,
+          pss + 1 < passes ? hist + (pss + 1) * hsz : nullptr, T);
+      LK_LAUNCHED();
+      kin = kout; vin = vout;
+      kout = (kout == ka) ? kb : ka;
+      vout = (vout == va) ? vb : va;
+    }
+  }
+  for (int pss = 0; pss < (fused ? 0 : passes); ++pss) {
     int shift = 8 * pss;
     radix_hist_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, shift, hist, T);
     LK_LAUNCHED();
@@ -441,11 +651,18 @@ extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, u
   int* num = d_num ? d_num : num_tmp;
   uniq_count_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, tile_heads);
   LK_LAUNCHED();
-  scan_single_cta_kernel<<<1, 1024, 0, st>>>(tile_heads, T, num, seg, (int)n);
-  LK_LAUNCHED();
-  uniq_write_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads,
-                                              (unsigned long long*)d_unique, d_inverse, d_order, seg);
-  LK_LAUNCHED();
+  if (fused) {
+    uniq_write_fused_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads, T,
+                                                      (unsigned long long*)d_unique, d_inverse,
+                                                      d_order, seg, num);
+    LK_LAUNCHED();
+  } else {
+    scan_single_cta_kernel<<<1, 1024, 0, st>>>(tile_heads, T, num, seg, (int)n);
+    LK_LAUNCHED();
+    uniq_write_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads,
+                                                (unsigned long long*)d_unique, d_inverse, d_order, seg);
+    LK_LAUNCHED();
+  }
   if (d_counts) {
     seg_counts_kernel<<<lk_grid(n, 256, 8), 256, 0, st>>>(seg, num, n, d_counts);
     LK_LAUNCHED();

@@ -30,6 +30,9 @@ __all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsampl
 
 _OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
 # dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); False selects the FFMA kernels
+# 1: libdevice sincosf (~1 ulp) in the kernel generator; 0 (default): two-term Cody-Waite reduction
+# + SFU sin/cos (absolute error 2^-20.9), ~2x fewer instructions in the pre-aggregation kernel
+ACCURATE_TRIG = os.environ.get('LINKB200_ACCURATE_TRIG', '0') == '1'
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 
 
@@ -177,6 +180,7 @@ def _kernel_gen(op: str, c: int, pos_weight: torch.Tensor, alpha: Optional[torch
     g.coord_scale = float(coord_scale)
     g.d_pos_weight = _capi.ptr(pos_weight, torch.float32)
     g.d_alpha = _capi.ptr(alpha, torch.float32) if alpha is not None else None
+    g.accurate_trig = 1 if ACCURATE_TRIG else 0
     return g
 
 

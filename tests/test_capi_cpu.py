@@ -43,7 +43,7 @@ def test_missing_gpu_fails_loudly():
 def test_struct_layout_matches_header():
     from link_b200 import _capi
     assert ctypes.sizeof(_capi.KeySpec) == 4 * (3 + 3 + 4 + 4 + 4)
-    assert ctypes.sizeof(_capi.KernelGen) == 32
+    assert ctypes.sizeof(_capi.KernelGen) == 40
     assert _capi.KernelGen.d_pos_weight.offset == 16 and _capi.KernelGen.d_alpha.offset == 24
 
 

@@ -68,7 +68,8 @@ def test_hash_and_query_random_vs_oracle(dev):
 
 
 @pytest.mark.parametrize('n,bits', [(1, 1), (2, 3), (2047, 8), (2048, 9), (2049, 16), (10_000, 5),
-                                    (100_003, 24), (300_000, 40), (65_536, 64)])
+                                    (100_003, 24), (300_000, 40), (65_536, 64),
+                                    (2_200_000, 21)])   # > 1024 tiles: unfused scan path
 def test_sort_unique_vs_numpy(dev, n, bits):
     from link_b200.nn.functional import _index
     rng = np.random.default_rng(n + bits)
@@ -263,9 +264,16 @@ def _make_block(g, dev, variant='encoder'):
     return blk.to(dev)
 
 
+@pytest.mark.parametrize('accurate', [False, True])
 @pytest.mark.parametrize('name', BLOCKS)
-def test_block_forward_fused_vs_golden(dev, name):
+def test_block_forward_fused_vs_golden(dev, name, accurate, monkeypatch):
+    """accurate=True: libdevice sincosf, held to ATOL; accurate=False (default): SFU sin/cos after
+    Cody-Waite reduction (abs error 2^-20.9 ~ 5e-7 per phase), which LayerNorm over as few as 8
+    channels amplifies to at most ~3e-5 on the unit-scale outputs -> atol 4e-5."""
+    import link_b200.elk as elk
     from link_b200 import SparseTensor
+    monkeypatch.setattr(elk, 'ACCURATE_TRIG', accurate)
+    atol = ATOL if accurate else 4e-5
     g = load_golden(name)
     blk = _make_block(g, dev).eval()
     st = SparseTensor(cu(g['feats'], dev), cu(g['coords'], dev), int(g['tstride']))
@@ -275,7 +283,7 @@ def test_block_forward_fused_vs_golden(dev, name):
     key = ((int(g['tstride']),) * 3, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     assert np.array_equal(st.kmaps[key][0].cpu().numpy(), g['nbmaps'])
     assert np.array_equal(st.kmaps[key][1].cpu().numpy(), g['nbsizes'])
-    np.testing.assert_allclose(out.F.cpu().numpy(), g['out'], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.F.cpu().numpy(), g['out'], rtol=RTOL, atol=atol)
 
 
 @pytest.mark.parametrize('name', BLOCKS)
@@ -324,7 +332,7 @@ def test_block_fused_vs_oracle_r3_multibatch(dev, baseop, groups, C, s, r):
     blk = blk.to(dev)
     with torch.no_grad():
         got = blk(SparseTensor(feats.to(dev), cu(coords, dev), 1), s, r).F
-    np.testing.assert_allclose(got.cpu().numpy(), want.detach().numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(got.cpu().numpy(), want.detach().numpy(), rtol=RTOL, atol=4e-5)
 
 
 def test_encoder_forward_vs_golden(dev):
