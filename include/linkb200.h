@@ -173,6 +173,45 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
                       const float* d_g1, const float* d_b1, const float* d_g2,
                       const float* d_b2, float* d_out, lk_stream_t s);
 
+/* ------------------------------------------------------------------------------------
+ * Native executor: one call enqueues the whole fused ELKBlock forward
+ * (linkencoder.py:124-185): [hash -> table -> kernel map] -> pre_mix (Linear+LN) -> local_mix
+ * (3^3 SubM conv) -> block keys -> sort/unique -> neighbour table -> pre-aggregation -> window
+ * mean -> apply (+ both LayerNorms, add, ReLU).  One workspace arena, no sync, no allocation.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n;                     /* active voxels */
+  const int32_t* d_coords;       /* [n,4] */
+  const float* d_feats;          /* [n,C]  block input (st.F) */
+  float* d_out;                  /* [n,C]  block output */
+  const float* d_premix_w;       /* [C,C]  pre_mix.0.weight */
+  const float* d_premix_g;       /* [C]    pre_mix.1.weight */
+  const float* d_premix_b;       /* [C]    pre_mix.1.bias */
+  float premix_eps;
+  int32_t kvol;                  /* kernel volume of local_mix (27) */
+  const float* d_conv_w;         /* [kvol,C,C]  local_mix.0.kernel (FFMA path), may be NULL */
+  const float* d_conv_wt;        /* [kvol,C,C]  its per-offset transpose (tensor-core path) */
+  const int32_t* d_conv_offsets; /* [kvol,3] kernel offsets (already scaled by the tensor stride) */
+  int32_t* d_kmap;               /* caller-owned [kvol,n] kernel map of local_mix */
+  int32_t build_kmap;            /* 1: build it here (hash -> table -> query) into d_kmap; 0: use it */
+  int32_t reserved0;
+  lk_keyspec_t keyspec;          /* block-key layout (div = block edge) */
+  int32_t key_bits;
+  int32_t r3;                    /* r^3 */
+  const int32_t* d_block_offsets;/* [r3,3] neighbour-block offsets */
+  lk_kernelgen_t gen;
+  const float* d_g1; const float* d_b1;   /* norm        weight / bias */
+  const float* d_g2; const float* d_b2;   /* norm_local  weight / bias */
+  int32_t use_tensor_cores;
+  int32_t reserved;
+  void* d_ws; int64_t ws_bytes;
+} lk_elk_block_args_t;
+/* sizeof of the structs above as compiled (0: lk_keyspec_t, 1: lk_kernelgen_t,
+ * 2: lk_elk_block_args_t): lets an FFI binding verify its struct layouts at load time. */
+int lk_abi_sizeof(int which);
+int64_t lk_elk_block_ws_bytes(int64_t n, int c, int op, int r3, int kvol, int need_kmap);
+int lk_elk_block_fwd(const lk_elk_block_args_t* args, lk_stream_t s);
+
 /* Fused bias-free Linear + LayerNorm: out = LN(x @ W^T; gamma, beta, eps); x, out [n, c],
  * W [c, c] (nn.Linear layout).  ELKBlock.pre_mix (linkencoder.py:112-115).  c in {16,32,64,128}. */
 int lk_linear_ln_fwd(const float* d_x, const float* d_w, const float* d_gamma, const float* d_beta,
@@ -211,6 +250,23 @@ int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_t n_in, int
 int lk_conv_fwd(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out,
                 int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
                 lk_stream_t s);
+/* Fused epilogue for both convolution kernels:  y = relu?( acc * scale + shift + residual ).
+ * Folds an eval-mode BatchNorm (scale = gamma / sqrt(var + eps), shift = beta - mean * scale), a
+ * bias, the residual add of ResidualBlock (linkencoder.py:89-91) and the ReLU into the single
+ * output store.  Any pointer may be NULL (scale -> 1, shift -> 0, residual -> none). */
+typedef struct {
+  const float* d_scale;     /* [c_out] or NULL */
+  const float* d_shift;     /* [c_out] or NULL */
+  const float* d_residual;  /* [n_out, c_out] or NULL */
+  int32_t relu;
+  int32_t reserved;
+} lk_conv_epilogue_t;
+int lk_conv_fwd_ex(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out, int k,
+                   int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out, lk_stream_t s);
+int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wt, const int32_t* d_nbr, int64_t n_out,
+                      int k, int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
+                      lk_stream_t s);
+
 /* Same contraction on the tcgen05 tensor cores (kind::tf32, 3xTF32 split => fp32-level accuracy):
  * weight-stationary persistent CTAs, the accumulators of up to 512/c_out output tiles resident in
  * TMEM, operands gathered into SWIZZLE_128B shared-memory tiles.  Takes the weights TRANSPOSED,

@@ -31,6 +31,24 @@ class KernelGen(C.Structure):
                 ('d_alpha', C.c_void_p), ('accurate_trig', C.c_int32), ('reserved', C.c_int32)]
 
 
+class ConvEpilogue(C.Structure):
+    _fields_ = [('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('d_residual', C.c_void_p),
+                ('relu', C.c_int32), ('reserved', C.c_int32)]
+
+
+class ElkBlockArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_coords', C.c_void_p), ('d_feats', C.c_void_p),
+                ('d_out', C.c_void_p), ('d_premix_w', C.c_void_p), ('d_premix_g', C.c_void_p),
+                ('d_premix_b', C.c_void_p), ('premix_eps', C.c_float), ('kvol', C.c_int32),
+                ('d_conv_w', C.c_void_p), ('d_conv_wt', C.c_void_p), ('d_conv_offsets', C.c_void_p),
+                ('d_kmap', C.c_void_p), ('build_kmap', C.c_int32), ('reserved0', C.c_int32),
+                ('keyspec', KeySpec), ('key_bits', C.c_int32), ('r3', C.c_int32),
+                ('d_block_offsets', C.c_void_p), ('gen', KernelGen),
+                ('d_g1', C.c_void_p), ('d_b1', C.c_void_p), ('d_g2', C.c_void_p), ('d_b2', C.c_void_p),
+                ('use_tensor_cores', C.c_int32), ('reserved', C.c_int32),
+                ('d_ws', C.c_void_p), ('ws_bytes', C.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/linkb200.h
 PROTOTYPES = {
     'lk_last_error': (C.c_char_p, []),
@@ -56,12 +74,17 @@ PROTOTYPES = {
     'lk_link_window_mean': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
+    'lk_abi_sizeof': (i32, [i32]),
+    'lk_elk_block_ws_bytes': (i64, [i64, i32, i32, i32, i32, i32]),
+    'lk_elk_block_fwd': (i32, [C.POINTER(ElkBlockArgs), vp]),
     'lk_linear_ln_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_linear_ln_tc_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
     'lk_kmap_query_subm': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
     'lk_kmap_invert': (i32, [vp, i64, i32, i64, vp, vp]),
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
+    'lk_conv_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
+    'lk_conv_tc_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
@@ -80,6 +103,10 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
+        for which, struct in enumerate((KeySpec, KernelGen, ElkBlockArgs)):
+            if _lib.lk_abi_sizeof(which) != C.sizeof(struct):
+                raise RuntimeError(f'ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, '
+                                   f'{_lib.lk_abi_sizeof(which)} in liblinkb200.so -- rebuild the library')
     return _lib
 
 

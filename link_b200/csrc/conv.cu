@@ -21,7 +21,7 @@
 
 __global__ void __launch_bounds__(CV_THREADS) conv_fwd_kernel(
     const float* __restrict__ in, const float* __restrict__ w, const int* __restrict__ nbr,
-    int64_t n_out, int K, int c_in, int c_out, const float* __restrict__ bias,
+    int64_t n_out, int K, int c_in, int c_out, lk_conv_epilogue_t ep,
     float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float (*s_acc)[CV_BN + 4] = (float (*)[CV_BN + 4])smem_raw;                 // output tile
@@ -118,14 +118,29 @@ __global__ void __launch_bounds__(CV_THREADS) conv_fwd_kernel(
   for (int t = tid; t < CV_BM * CV_BN; t += CV_THREADS) {
     int r = t / CV_BN, nn = t % CV_BN;
     int64_t o = row0 + r;
-    if (o < n_out && n0 + nn < c_out)
-      out[o * c_out + n0 + nn] = s_acc[r][nn] + (bias ? __ldg(bias + n0 + nn) : 0.f);
+    if (o < n_out && n0 + nn < c_out) {
+      float v = s_acc[r][nn];
+      if (ep.d_scale) v *= __ldg(ep.d_scale + n0 + nn);
+      if (ep.d_shift) v += __ldg(ep.d_shift + n0 + nn);
+      if (ep.d_residual) v += __ldg(ep.d_residual + o * c_out + n0 + nn);
+      if (ep.relu) v = fmaxf(v, 0.f);
+      out[o * c_out + n0 + nn] = v;
+    }
   }
 }
 
 extern "C" int lk_conv_fwd(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out,
                            int k, int c_in, int c_out, const float* d_bias, float* d_out,
                            lk_stream_t s) {
+  lk_conv_epilogue_t ep = {nullptr, d_bias, nullptr, 0, 0};
+  return lk_conv_fwd_ex(d_in, d_w, d_nbr, n_out, k, c_in, c_out, &ep, d_out, s);
+}
+
+extern "C" int lk_conv_fwd_ex(const float* d_in, const float* d_w, const int32_t* d_nbr,
+                              int64_t n_out, int k, int c_in, int c_out,
+                              const lk_conv_epilogue_t* epp, float* d_out, lk_stream_t s) {
+  lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, 0};
+  if (epp) ep = *epp;
   LK_REQUIRE(n_out >= 0 && k > 0 && c_in > 0 && c_out > 0, "lk_conv_fwd: bad sizes");
   if (n_out == 0) return LK_OK;
   LK_REQUIRE(d_in && d_w && d_nbr && d_out, "lk_conv_fwd: null pointer");
@@ -138,7 +153,7 @@ extern "C" int lk_conv_fwd(const float* d_in, const float* d_w, const int32_t* d
     attr_set = true;
   }
   conv_fwd_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)s>>>(d_in, d_w, d_nbr, n_out, k, c_in,
-                                                           c_out, d_bias, d_out);
+                                                           c_out, ep, d_out);
   LK_LAUNCHED();
   return LK_OK;
 }

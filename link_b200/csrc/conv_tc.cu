@@ -44,7 +44,7 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wt /*[K][COUT][CIN]*/,
     const int* __restrict__ nbr, int64_t n_out, int K, int tiles_per_cta,
-    const float* __restrict__ bias, float* __restrict__ out) {
+    lk_conv_epilogue_t ep, float* __restrict__ out) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   constexpr int KB = Cfg::KB;
   constexpr int NI = Cfg::ITEMS_A;
@@ -222,9 +222,23 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           float* dst = out + o * COUT + c_base;
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
-            float4 b = bias ? __ldg((const float4*)(bias + c_base + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            lk_stg_stream((float4*)(dst + e),
-                          make_float4(acc[e] + b.x, acc[e + 1] + b.y, acc[e + 2] + b.z, acc[e + 3] + b.w));
+            float4 y = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+            if (ep.d_scale) {
+              float4 sc = __ldg((const float4*)(ep.d_scale + c_base + e));
+              y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+            }
+            if (ep.d_shift) {
+              float4 sh = __ldg((const float4*)(ep.d_shift + c_base + e));
+              y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
+            }
+            if (ep.d_residual) {
+              float4 rr = lk_ldg_stream((const float4*)(ep.d_residual + o * COUT + c_base + e));
+              y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+            }
+            if (ep.relu) {
+              y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+            }
+            lk_stg_stream((float4*)(dst + e), y);
           }
         }
       }
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 
 template <int CIN, int COUT>
 static int launch_conv_tc(const float* in, const float* wt, const int* nbr, int64_t n_out, int k,
-                          const float* bias, float* out, cudaStream_t st) {
+                          const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -250,7 +264,7 @@ static int launch_conv_tc(const float* in, const float* wt, const int* nbr, int6
   if (tpc > Cfg::MAX_TILES) tpc = Cfg::MAX_TILES;            // ... within the 512 TMEM columns
   if (tpc < 1) tpc = 1;
   int grid = (int)((tiles + tpc - 1) / tpc);
-  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, n_out, k, (int)tpc, bias, out);
+  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, n_out, k, (int)tpc, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -262,6 +276,15 @@ extern "C" int lk_conv_tc_supported(int c_in, int c_out) {
 extern "C" int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_t* d_nbr,
                               int64_t n_out, int k, int c_in, int c_out, const float* d_bias,
                               float* d_out, lk_stream_t s) {
+  lk_conv_epilogue_t ep = {nullptr, d_bias, nullptr, 0, 0};
+  return lk_conv_tc_fwd_ex(d_in, d_wt, d_nbr, n_out, k, c_in, c_out, &ep, d_out, s);
+}
+
+extern "C" int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wt, const int32_t* d_nbr,
+                                 int64_t n_out, int k, int c_in, int c_out,
+                                 const lk_conv_epilogue_t* epp, float* d_out, lk_stream_t s) {
+  lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, 0};
+  if (epp) ep = *epp;
   LK_REQUIRE(n_out >= 0 && k > 0, "lk_conv_tc_fwd: bad sizes");
   LK_REQUIRE(lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_fwd: channels must be 32 or 64");
   if (n_out == 0) return LK_OK;
@@ -269,8 +292,8 @@ extern "C" int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_
   LK_REQUIRE((uintptr_t)d_in % 16 == 0 && (uintptr_t)d_wt % 16 == 0 && (uintptr_t)d_out % 16 == 0,
              "lk_conv_tc_fwd: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)s;
-  if (c_in == 32 && c_out == 32) return launch_conv_tc<32, 32>(d_in, d_wt, d_nbr, n_out, k, d_bias, d_out, st);
-  if (c_in == 32 && c_out == 64) return launch_conv_tc<32, 64>(d_in, d_wt, d_nbr, n_out, k, d_bias, d_out, st);
-  if (c_in == 64 && c_out == 32) return launch_conv_tc<64, 32>(d_in, d_wt, d_nbr, n_out, k, d_bias, d_out, st);
-  return launch_conv_tc<64, 64>(d_in, d_wt, d_nbr, n_out, k, d_bias, d_out, st);
+  if (c_in == 32 && c_out == 32) return launch_conv_tc<32, 32>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
+  if (c_in == 32 && c_out == 64) return launch_conv_tc<32, 64>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
+  if (c_in == 64 && c_out == 32) return launch_conv_tc<64, 32>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
+  return launch_conv_tc<64, 64>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
 }

@@ -33,6 +33,8 @@ _OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
 # 1: libdevice sincosf (~1 ulp) in the kernel generator; 0 (default): two-term Cody-Waite reduction
 # + SFU sin/cos (absolute error 2^-20.9), ~2x fewer instructions in the pre-aggregation kernel
 ACCURATE_TRIG = os.environ.get('LINKB200_ACCURATE_TRIG', '0') == '1'
+# 1 (default): one lk_elk_block_fwd call per block; 0: one python-level call per kernel
+NATIVE_EXECUTOR = os.environ.get('LINKB200_NATIVE_EXECUTOR', '1') != '0'
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 
 
@@ -273,8 +275,66 @@ class ELKBlock(nn.Module):
                 float(ln.eps), n, c, _capi.ptr(out), _capi.stream()), 'lk_linear_ln_fwd')
         return out
 
+    def _forward_native(self, st: SparseTensor, s, r, scale) -> torch.Tensor:
+        """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
+        from link_b200.nn.functional.conv import KernelMap, _transposed
+        L = _capi.lib()
+        x = st.F.contiguous()
+        coords = st.C.contiguous()
+        n, c = x.shape
+        dev = x.device
+        conv = self.local_mix[0]
+        key = (st.stride, conv.kernel_size, conv.stride, (1, 1, 1))
+        kmap = st.kmaps.get(key)
+        build = kmap is None
+        if build:
+            kmap = KernelMap(torch.empty(conv.kernel_volume, n, dtype=torch.int32, device=dev), n, n, coords)
+            st.kmaps[key] = kmap
+        conv_off = get_kernel_offsets(conv.kernel_size, stride=st.stride, device=dev)
+        blk_off = get_kernel_offsets(r, 1, 1, device=dev)
+        r3 = blk_off.shape[0]
+        a = _capi.ElkBlockArgs()
+        a.n = n
+        a.d_coords, a.d_feats = _capi.ptr(coords, torch.int32), _capi.ptr(x, torch.float32)
+        out = torch.empty_like(x)
+        a.d_out = _capi.ptr(out)
+        lin, ln = self.pre_mix[0], self.pre_mix[1]
+        a.d_premix_w = _capi.ptr(lin.weight.detach().contiguous())
+        a.d_premix_g, a.d_premix_b = _capi.ptr(ln.weight.detach()), _capi.ptr(ln.bias.detach())
+        a.premix_eps = float(ln.eps)
+        a.kvol = conv.kernel_volume
+        w = conv.kernel.detach()
+        a.d_conv_w = _capi.ptr(w.contiguous())
+        a.d_conv_wt = _capi.ptr(_transposed(w)) if USE_TENSOR_CORES else None
+        a.d_conv_offsets = _capi.ptr(conv_off)
+        a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
+        bounds = _index.coord_bounds(coords, st.kmaps)
+        spec, bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
+        a.keyspec, a.key_bits, a.r3 = spec, bits, r3
+        a.d_block_offsets = _capi.ptr(blk_off)
+        pw = self.pos_weight[0].weight.detach().contiguous()
+        alpha = self.alpha.detach().reshape(-1).contiguous() if self.baseop == 'cos_x' else None
+        a.gen = _kernel_gen(self.baseop, c, pw, alpha, scale)
+        a.d_g1, a.d_b1 = _capi.ptr(self.norm.weight.detach()), _capi.ptr(self.norm.bias.detach())
+        a.d_g2, a.d_b2 = (_capi.ptr(self.norm_local.weight.detach()),
+                          _capi.ptr(self.norm_local.bias.detach()))
+        a.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
+        ws_bytes = L.lk_elk_block_ws_bytes(n, c, a.gen.op, r3, a.kvol, a.build_kmap)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
+        _capi.check(L.lk_elk_block_fwd(C.byref(a), _capi.stream()), 'lk_elk_block_fwd')
+        return out
+
     def forward(self, st: SparseTensor, s, r):
         composed = self._needs_grad(st) or st.F.dtype != torch.float32
+        if self.baseop == 'cos_x' and self.groups != 1 and not composed:
+            raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor is "
+                               "not repeated over groups, linkencoder.py:165)")
+        if (not composed and NATIVE_EXECUTOR and _capi.TIMERS is None
+                and self.inc in (16, 32, 64, 128)):
+            scale = float(st.s[0]) if (self.baseop == 'cos_x' and self.variant == 'encoder') else 1.0
+            st.F = self._forward_native(st, s, r, scale)
+            return st
         if composed or self.inc not in (16, 32, 64, 128):
             F_input = self.pre_mix(st.F)
         else:
@@ -282,11 +342,8 @@ class ELKBlock(nn.Module):
         local_mix = self.local_mix(st)
         if composed:
             return self._forward_composed(st, F_input, local_mix, s, r)
-        if self.baseop == 'cos_x' and self.groups != 1:
-            raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor is "
-                               "not repeated over groups, linkencoder.py:165)")
-        bi = block_index(st, s)
         scale = float(st.s[0]) if (self.baseop == 'cos_x' and self.variant == 'encoder') else 1.0
+        bi = block_index(st, s)
         out = link_aggregate(F_input, st.C, bi, r, self.baseop, self.pos_weight[0].weight,
                              getattr(self, 'alpha', None), scale, local_mix.F,
                              (self.norm.weight, self.norm.bias, self.norm_local.weight,

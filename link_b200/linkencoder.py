@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 import link_b200.nn as spnn
+import link_b200.nn.functional as F
 from link_b200.elk import ELKBlock, upsample_voxel
 from link_b200.tensor import SparseTensor
 
@@ -27,6 +28,8 @@ class BasicConvolutionBlock(nn.Module):
         )
 
     def forward(self, x):
+        if F.fusable(self.net[0], self.net[1], x):
+            return F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
         return self.net(x)
 
 
@@ -42,6 +45,8 @@ class BasicDeconvolutionBlock(nn.Module):
         )
 
     def forward(self, x):
+        if F.fusable(self.net[0], self.net[1], x):
+            return F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
         return self.net(x)
 
 
@@ -67,14 +72,39 @@ class ResidualBlock(nn.Module):
         self.relu = spnn.ReLU(True)
 
     def forward(self, x):
+        if F.fusable(self.net[0], self.net[1], x) and F.fusable(self.net[3], self.net[4], x):
+            # conv+BN+ReLU, then conv+BN+shortcut+ReLU: two launches instead of seven
+            shortcut = self.downsample(x).F if len(self.downsample) else x.F
+            y = F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
+            return F.conv_bn_act(y, self.net[3], self.net[4], relu=True, residual=shortcut.contiguous())
         return self.relu(self.net(x) + self.downsample(x))
 
 
+class ConvBN(nn.Sequential):
+    """Conv3d -> BatchNorm (`stageN_tail` / `elkN_tail`, linkencoder.py:216-224); same state-dict
+    keys as the reference's nn.Sequential, one fused launch in eval mode.  `residual` / `relu`
+    additionally fold the level's merge  relu(x_conv + x_lk)  (linkencoder.py:350) into it."""
+
+    def forward(self, x, residual=None, relu=False):
+        if F.fusable(self[0], self[1], x):
+            return F.conv_bn_act(x, self[0], self[1], relu=relu, residual=residual)
+        y = self[1](self[0](x))
+        if residual is not None:
+            y.F = y.F + residual
+        if relu:
+            y.F = torch.relu(y.F)
+        return y
+
+
 def _tail(inc, outc):
-    return nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=3, stride=1), spnn.BatchNorm(outc))
+    return ConvBN(spnn.Conv3d(inc, outc, kernel_size=3, stride=1), spnn.BatchNorm(outc))
 
 
-class ELKEncoder(nn.Module):
+class _ELKBackbone(nn.Module):
+    """Stem + four (conv stage || LinK block) levels + the decoder branches, with the reference's
+    sub-module names (linkencoder.py:188-320 == linkunet.py:188-320)."""
+
+    block_variant = 'encoder'
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -83,6 +113,7 @@ class ELKEncoder(nn.Module):
         baseop = kwargs.get('baseop')
         groups = kwargs.get('groups')
         cs = [int(cr * 64)] * 9
+        self.cs = cs
         self.run_up = kwargs.get('run_up', True)
 
         self.stem = nn.Sequential(
@@ -97,24 +128,19 @@ class ELKEncoder(nn.Module):
                 ResidualBlock(cin, cout, ks=3, stride=1, dilation=1),
                 ResidualBlock(cout, cout, ks=3, stride=1, dilation=1)))
             setattr(self, f'stage{lv}_tail', _tail(cout, cout))
-            setattr(self, f'elk{lv}', ELKBlock(cin, cin, groups, baseop=baseop))
+            setattr(self, f'elk{lv}', ELKBlock(cin, cin, groups, baseop=baseop,
+                                               variant=self.block_variant))
             setattr(self, f'elk{lv}_tail', _tail(cin, cout))
             setattr(self, f'activate{lv}', nn.ReLU(True))
 
-        # Decoder branches exist in the reference's state dict but are never run by forward
-        # (linkencoder.py:289-320 vs 339-381); they are kept so checkpoints load with strict=True.
+        # Decoder branches: used by ELKUNet; in ELKEncoder they exist in the reference's state dict
+        # but are never run (linkencoder.py:289-320 vs 339-381) -- kept so checkpoints load strictly.
         for u, (cin, cskip, cout) in enumerate([(cs[4], cs[3], cs[5]), (cs[5], cs[2], cs[6]),
                                                 (cs[6], cs[1], cs[7]), (cs[7], cs[0], cs[8])], 1):
             setattr(self, f'up{u}', nn.ModuleList([
                 BasicDeconvolutionBlock(cin, cout, ks=2, stride=2),
                 nn.Sequential(ResidualBlock(cout + cskip, cout, ks=3, stride=1, dilation=1),
                               ResidualBlock(cout, cout, ks=3, stride=1, dilation=1))]))
-
-        self.classifier = nn.Sequential(
-            nn.Conv1d(in_channels=cs[8] * 5, out_channels=120, kernel_size=1, groups=5),
-            nn.ReLU(True),
-            nn.Conv1d(in_channels=120, out_channels=kwargs['num_classes'], kernel_size=1, groups=1))
-        self.weight_initialization()
 
     def weight_initialization(self):
         for m in self.modules():
@@ -126,7 +152,11 @@ class ELKEncoder(nn.Module):
         """Stem + the four (conv stage || LinK block) levels; returns [x0, x1, x2, x3, x4]."""
         s, r = self.kwargs.get('s'), self.kwargs.get('r')
         x.cmaps.setdefault(x.stride, x.coords)
-        x0 = self.stem(x)
+        if F.fusable(self.stem[0], self.stem[1], x):
+            x0 = F.conv_bn_act(F.conv_bn_act(x, self.stem[0], self.stem[1], relu=True),
+                               self.stem[3], self.stem[4], relu=True)
+        else:
+            x0 = self.stem(x)
         feats = [x0]
         cur = x0
         for lv in (1, 2, 3, 4):
@@ -134,11 +164,24 @@ class ELKEncoder(nn.Module):
             x_conv = getattr(self, f'stage{lv}_tail')(getattr(self, f'stage{lv}')(x_in))
             # NB: the block mutates x_in (it then carries the LinK output); the conv stage above
             # has already consumed it -- same ordering as linkencoder.py:348-349.
-            x_lk = getattr(self, f'elk{lv}_tail')(getattr(self, f'elk{lv}')(x_in, x_in.s[0] * s, r))
-            x_conv.F = getattr(self, f'activate{lv}')(x_conv.F + x_lk.F)
+            # relu(x_conv + BN(conv(x_lk))) -- the merge is folded into the tail conv's epilogue
+            x_lk = getattr(self, f'elk{lv}')(x_in, x_in.s[0] * s, r)
+            x_conv = getattr(self, f'elk{lv}_tail')(x_lk, residual=x_conv.F.contiguous(), relu=True)
             feats.append(x_conv)
             cur = x_conv
         return feats
+
+
+class ELKEncoder(_ELKBackbone):
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        cs = self.cs
+        self.classifier = nn.Sequential(
+            nn.Conv1d(in_channels=cs[8] * 5, out_channels=120, kernel_size=1, groups=5),
+            nn.ReLU(True),
+            nn.Conv1d(in_channels=120, out_channels=kwargs['num_classes'], kernel_size=1, groups=1))
+        self.weight_initialization()
 
     def forward(self, x: SparseTensor) -> torch.Tensor:
         x0, x1, x2, x3, x4 = self.forward_levels(x)

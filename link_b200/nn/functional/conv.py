@@ -4,6 +4,7 @@ Public surface = the reference's `F.conv3d(input, weight, kernel_size, bias, str
 transposed)` (torchsparse/nn/functional/conv.py:83-147) with the same caching contract: kernel
 maps live in `input.kmaps[(input.stride, kernel_size, stride, dilation)]` and every derived
 tensor shares the `cmaps` / `kmaps` dict objects."""
+import ctypes as C
 import os
 from typing import Optional, Tuple, Union
 
@@ -18,7 +19,7 @@ from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import SparseTensor
 from link_b200.utils import make_ntuple
 
-__all__ = ['conv3d', 'KernelMap', 'build_kernel_map']
+__all__ = ['conv3d', 'conv_bn_act', 'fusable', 'KernelMap', 'build_kernel_map']
 
 
 class KernelMap:
@@ -114,9 +115,11 @@ def _transposed(weight: torch.Tensor) -> torch.Tensor:
     return wt
 
 
-def _conv_fwd(feats, weight, nbr, n_out, weight_t=None):
-    """out[o] = sum_k feats[nbr[k, o]] @ weight[k].  `weight` is [K, Cin, Cout] (may be None when
-    its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies)."""
+def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
+              relu=False):
+    """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
+    None when its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies).
+    epilogue: y = relu?(acc * scale + shift + residual), each part optional."""
     if weight is not None:
         k, c_in, c_out = weight.shape
     else:
@@ -127,19 +130,26 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None):
     L = _capi.lib()
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
+    ep = _capi.ConvEpilogue()
+    ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
+    ep.d_residual = _capi.ptr(residual)
+    ep.relu = 1 if relu else 0
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == torch.float32
     if USE_TENSOR_CORES and L.lk_conv_tc_supported(c_in, c_out):
         wt = weight_t if weight_t is not None else _transposed(weight)
         with _capi.timed('lk_conv_fwd', nb):
-            _capi.check(L.lk_conv_tc_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
-                                         _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, None,
-                                         _capi.ptr(out), _capi.stream()), 'lk_conv_tc_fwd')
+            _capi.check(L.lk_conv_tc_fwd_ex(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
+                                            _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
+                                            C.byref(ep), _capi.ptr(out), _capi.stream()),
+                        'lk_conv_tc_fwd')
         return out
     if weight is None:
         weight = weight_t.transpose(1, 2).contiguous()
     with _capi.timed('lk_conv_fwd', nb):
-        _capi.check(L.lk_conv_fwd(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
-                                  _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, None,
-                                  _capi.ptr(out), _capi.stream()), 'lk_conv_fwd')
+        _capi.check(L.lk_conv_fwd_ex(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
+                                     _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, C.byref(ep),
+                                     _capi.ptr(out), _capi.stream()), 'lk_conv_fwd')
     return out
 
 
@@ -180,6 +190,65 @@ class ConvolutionFunction(Function):
                 _capi.ptr(feats), _capi.ptr(g), _capi.ptr(to_out), g.shape[0], k, c_in, c_out,
                 _capi.ptr(grad_weight), _capi.stream()), 'lk_conv_bwd_weight')
         return grad_feats, grad_weight, None, None
+
+
+_bn_fold_cache = {}
+
+
+def _folded_bn(bn):
+    """Eval-mode BatchNorm as a per-channel affine (scale, shift), cached until a parameter or
+    running statistic of the module changes."""
+    ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+    hit = _bn_fold_cache.get(id(bn))
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+        shift = (bn.bias - bn.running_mean * scale).float().contiguous()
+    _bn_fold_cache[id(bn)] = (ver, scale, shift)
+    return scale, shift
+
+
+def fusable(conv, bn, x: SparseTensor) -> bool:
+    """True when conv (+ eval-mode BatchNorm) can run as ONE kernel with a fused epilogue:
+    inference only (no autograd, BN in eval mode), fp32, a real sparse kernel (volume > 1)."""
+    return (not torch.is_grad_enabled() and conv.kernel_volume > 1 and conv.bias is None
+            and x.feats.dtype == torch.float32 and x.feats.is_cuda
+            and (bn is None or (not bn.training and bn.track_running_stats and bn.affine)))
+
+
+def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
+                residual: Optional[torch.Tensor] = None) -> SparseTensor:
+    """Inference fast path for  relu?(BN_eval(conv(x)) + residual):  the reference's three or four
+    separate ops (spnn.Conv3d -> spnn.BatchNorm -> [+ shortcut] -> spnn.ReLU, linkencoder.py:26-37,
+    64-91) in one sparse-conv launch whose epilogue applies the folded BatchNorm affine, the
+    residual and the ReLU before the single output store.  Same kernel-map caching as conv3d."""
+    feats = input.feats.contiguous()
+    kernel_size, stride = conv.kernel_size, conv.stride
+    dilation = make_ntuple(conv.dilation, ndim=3)
+    scale = shift = None
+    if bn is not None:
+        scale, shift = _folded_bn(bn)
+    w = conv.kernel.detach()
+    if not conv.transposed:
+        key = (input.stride, kernel_size, stride, dilation)
+        kmap = input.kmaps.get(key)
+        if kmap is None:
+            kmap = build_kernel_map(input, kernel_size, stride, dilation)
+            input.kmaps[key] = kmap
+        out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu)
+        output = SparseTensor(coords=kmap.out_coords, feats=out,
+                              stride=tuple(input.stride[k] * stride[k] for k in range(3)))
+    else:
+        tensor_stride = tuple(input.stride[k] // stride[k] for k in range(3))
+        kmap = input.kmaps[(tensor_stride, kernel_size, stride, dilation)]
+        out = _conv_fwd(feats, w, kmap.inv, kmap.n_in, None, scale, shift, residual, relu)
+        output = SparseTensor(coords=input.cmaps[tensor_stride], feats=out, stride=tensor_stride)
+    output.cmaps = input.cmaps
+    output.cmaps.setdefault(output.stride, output.coords)
+    output.kmaps = input.kmaps
+    return output
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor,

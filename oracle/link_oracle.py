@@ -414,11 +414,14 @@ def _conv_bn(x: OTensor, sd, prefix, ks, stride=1, relu=False, training=False) -
 
 
 def _residual(x: OTensor, sd, prefix, training) -> OTensor:
-    # linkencoder.py:61-91 (inc == outc, stride 1 -> identity shortcut)
+    # linkencoder.py:61-91: identity shortcut when inc == outc, else 1x1 conv + BN
     y = _conv_bn(x, sd, prefix + 'net.', 3, relu=True, training=training)
     y2 = conv3d(y, sd[prefix + 'net.3.kernel'], 3)
     y2.F = _bn(y2.F, _sub(sd, prefix + 'net.4.'), training)
-    y2.F = torch.relu(y2.F + x.F)
+    short = x.F
+    if prefix + 'downsample.0.kernel' in sd:
+        short = _bn(x.F @ sd[prefix + 'downsample.0.kernel'], _sub(sd, prefix + 'downsample.1.'), training)
+    y2.F = torch.relu(y2.F + short)
     return y2
 
 
@@ -432,9 +435,25 @@ def upsample_voxel(xF: torch.Tensor, xC, x_stride, refC) -> torch.Tensor:
     return xF[_t(idx, torch.long)]
 
 
+def elk_unet_forward(sd: Dict[str, torch.Tensor], feats: torch.Tensor, coords, *, s: int, r: int,
+                     baseop: str, groups: int, training: bool = False) -> torch.Tensor:
+    """ELKUNet.forward, segmentation/core/models/semantic_kitti/linkunet.py:331-385."""
+    _, (x0, x1, x2, x3, x4) = elk_encoder_forward(sd, feats, coords, s=s, r=r, baseop=baseop,
+                                                  groups=groups, training=training,
+                                                  return_levels=True, variant='unet', head=False)
+    y = x4
+    for u, skip in ((1, x3), (2, x2), (3, x1), (4, x0)):
+        d = conv3d(y, sd[f'up{u}.0.net.0.kernel'], 2, stride=2, transposed=True)
+        d.F = torch.relu(_bn(d.F, _sub(sd, f'up{u}.0.net.1.'), training))
+        cat = OTensor(torch.cat([d.F, skip.F], dim=1), d.C, d.s)
+        cat.cmaps, cat.kmaps = d.cmaps, d.kmaps
+        y = _residual(_residual(cat, sd, f'up{u}.1.0.', training), sd, f'up{u}.1.1.', training)
+    return TF.linear(y.F, sd['classifier.0.weight'], sd['classifier.0.bias'])
+
+
 def elk_encoder_forward(sd: Dict[str, torch.Tensor], feats: torch.Tensor, coords, *, s: int,
                         r: int, baseop: str, groups: int, training: bool = False,
-                        return_levels: bool = False):
+                        return_levels: bool = False, variant: str = 'encoder', head: bool = True):
     """ELKEncoder.forward, linkencoder.py:339-381."""
     x = OTensor(feats, coords, 1)
     x.cmaps[x.s] = x.C
@@ -449,13 +468,15 @@ def elk_encoder_forward(sd: Dict[str, torch.Tensor], feats: torch.Tensor, coords
         z = _residual(z, sd, f'stage{l}.1.', training)
         xl = _conv_bn(z, sd, f'stage{l}_tail.', 3, training=training)
         lk_F = elk_block_forward(xl0.F, xl0.C, xl0.s, _sub(sd, f'elk{l}.'), xl0.s[0] * s, r,
-                                 baseop, groups, 'encoder', kmaps=xl0.kmaps)
+                                 baseop, groups, variant, kmaps=xl0.kmaps)
         lk = OTensor(lk_F, xl0.C, xl0.s)
         lk.cmaps, lk.kmaps = xl0.cmaps, xl0.kmaps
         lk = _conv_bn(lk, sd, f'elk{l}_tail.', 3, training=training)
         xl.F = torch.relu(xl.F + lk.F)
         levels.append(xl)
         cur = xl
+    if not head:
+        return None, [x0] + levels
     ups = [upsample_voxel(lv.F, lv.C, lv.s, x0.C) for lv in reversed(levels)]
     F_cat = torch.cat(ups + [x0.F], dim=1).unsqueeze(0).permute(0, 2, 1)
     h = torch.relu(TF.conv1d(F_cat, sd['classifier.0.weight'], sd['classifier.0.bias'], groups=5))

@@ -185,6 +185,29 @@ def main():
                         **{'sd.' + k: v for k, v in sd.items()})
     print('encoder', logits.shape, float(logits.abs().mean()), [v.shape[0] for v in st.cmaps.values()])
 
+    # ---- 6b. ELKUNet (cr=0.25), cos_x (2x3)^3, eval mode: decoder with transposed convs ------
+    import core.models.semantic_kitti.linkunet as linkunet
+    coords = cloud(31, 7000, 5000, 44)
+    torch.manual_seed(31)
+    feats = torch.randn(len(coords), 4)
+    unet = linkunet.ELKUNet(num_classes=19, cr=0.25, baseop='cos_x', r=2, s=3, groups=1).eval()
+    with torch.no_grad():
+        for m in unet.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    st = ts.SparseTensor(feats.clone(), coords.clone(), 1)
+    st.cmaps[st.stride] = st.coords
+    with torch.no_grad():
+        logits = unet(st)
+    sd = {k: v for k, v in sd_np(unet).items() if not k.endswith('num_batches_tracked')}
+    np.savez_compressed(os.path.join(OUT, 'unet_cosx_2x3.npz'), coords=coords.numpy(),
+                        feats=feats.numpy(), logits=logits.numpy(),
+                        **{'sd.' + k: v for k, v in sd.items()})
+    print('unet', logits.shape, float(logits.abs().mean()))
+
     # ---- 7. voxelisation front-ends ---------------------------------------------------
     g = torch.Generator().manual_seed(3)
     pts = (torch.rand(4000, 3, generator=g) * 20 - 5).numpy()

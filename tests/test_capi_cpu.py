@@ -97,6 +97,16 @@ def test_module_surface_and_state_dict_compat():
                                              groups=2).parameters()) > 5_000_000
 
 
+def test_unet_state_dict_compat():
+    from link_b200.linkunet import ELKUNet
+    g = load_golden('unet_cosx_2x3')
+    net = ELKUNet(num_classes=19, cr=0.25, baseop='cos_x', r=2, s=3, groups=1)
+    ours = {k: tuple(v.shape) for k, v in net.state_dict().items()
+            if not k.endswith('num_batches_tracked')}
+    ref = {k[3:]: tuple(v.shape) for k, v in g.items() if k.startswith('sd.')}
+    assert ours == ref
+
+
 def test_compat_shim_lets_reference_style_imports_resolve():
     import link_b200.compat as compat
     compat.install()

@@ -418,3 +418,16 @@ def test_linear_layernorm_kernels(dev, c, tcore, n):
     want = torch.nn.functional.layer_norm(x.double() @ w.double().t(), (c,), gam.double(),
                                           bet.double(), 1e-6).float()
     np.testing.assert_allclose(out.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_unet_forward_vs_golden(dev):
+    from link_b200 import SparseTensor
+    from link_b200.linkunet import ELKUNet
+    g = load_golden('unet_cosx_2x3')
+    net = ELKUNet(num_classes=19, cr=0.25, baseop='cos_x', r=2, s=3, groups=1)
+    net.load_state_dict(golden_sd(g), strict=True)
+    net = net.to(dev).eval()
+    st = SparseTensor(cu(g['feats'], dev), cu(g['coords'], dev), 1)
+    with torch.no_grad():
+        logits = net(st)
+    np.testing.assert_allclose(logits.cpu().numpy(), g['logits'], rtol=1e-3, atol=2e-4)
