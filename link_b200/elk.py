@@ -26,7 +26,7 @@ from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import PointTensor, SparseTensor
 
 __all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsample_voxel',
-           'initial_voxelize', 'link_aggregate', 'ELKBlock', 'LinKBlock']
+           'initial_voxelize', 'link_aggregate', 'elk_forward_fused', 'ELKBlock', 'LinKBlock']
 
 _OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
 # dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); False selects the FFMA kernels
@@ -235,6 +235,92 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
     return out
 
 
+def _pre_mix_fused(pre_mix, x: torch.Tensor) -> torch.Tensor:
+    """pre_mix = Linear(no bias) + LayerNorm in one liblinkb200 kernel (forward only)."""
+    lin, ln = pre_mix[0], pre_mix[1]
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    n, c = x.shape
+    L = _capi.lib()
+    fn = L.lk_linear_ln_tc_fwd if (c in (32, 64) and USE_TENSOR_CORES) else L.lk_linear_ln_fwd
+    with _capi.timed('lk_linear_ln_fwd', n * 8 * c + 4 * c * c):
+        _capi.check(fn(
+            _capi.ptr(x, torch.float32), _capi.ptr(lin.weight.detach().contiguous()),
+            _capi.ptr(ln.weight.detach().contiguous()), _capi.ptr(ln.bias.detach().contiguous()),
+            float(ln.eps), n, c, _capi.ptr(out), _capi.stream()), 'lk_linear_ln_fwd')
+    return out
+
+
+def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, alpha, coord_scale, norm,
+                    norm_local) -> torch.Tensor:
+    """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
+    from link_b200.nn.functional.conv import KernelMap, _transposed
+    L = _capi.lib()
+    x = st.F.contiguous()
+    coords = st.C.contiguous()
+    n, c = x.shape
+    dev = x.device
+    key = (st.stride, conv.kernel_size, conv.stride, (1, 1, 1))
+    kmap = st.kmaps.get(key)
+    build = kmap is None
+    if build:
+        kmap = KernelMap(torch.empty(conv.kernel_volume, n, dtype=torch.int32, device=dev), n, n, coords)
+        st.kmaps[key] = kmap
+    conv_off = get_kernel_offsets(conv.kernel_size, stride=st.stride, device=dev)
+    blk_off = get_kernel_offsets(r, 1, 1, device=dev)
+    r3 = blk_off.shape[0]
+    a = _capi.ElkBlockArgs()
+    a.n = n
+    a.d_coords, a.d_feats = _capi.ptr(coords, torch.int32), _capi.ptr(x, torch.float32)
+    out = torch.empty_like(x)
+    a.d_out = _capi.ptr(out)
+    lin, ln = pre_mix[0], pre_mix[1]
+    a.d_premix_w = _capi.ptr(lin.weight.detach().contiguous())
+    a.d_premix_g, a.d_premix_b = _capi.ptr(ln.weight.detach()), _capi.ptr(ln.bias.detach())
+    a.premix_eps = float(ln.eps)
+    a.kvol = conv.kernel_volume
+    w = conv.kernel.detach()
+    a.d_conv_w = _capi.ptr(w.contiguous())
+    a.d_conv_wt = _capi.ptr(_transposed(w)) if USE_TENSOR_CORES else None
+    a.d_conv_offsets = _capi.ptr(conv_off)
+    a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
+    bounds = _index.coord_bounds(coords, st.kmaps)
+    spec, bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
+    a.keyspec, a.key_bits, a.r3 = spec, bits, r3
+    a.d_block_offsets = _capi.ptr(blk_off)
+    pw = pos_weight.detach().contiguous().float()
+    alpha_v = alpha.detach().reshape(-1).contiguous().float() if alpha is not None else None
+    a.gen = _kernel_gen(op, c, pw, alpha_v, coord_scale)
+    a.d_g1, a.d_b1 = _capi.ptr(norm.weight.detach()), _capi.ptr(norm.bias.detach())
+    a.d_g2, a.d_b2 = (_capi.ptr(norm_local.weight.detach()),
+                      _capi.ptr(norm_local.bias.detach()))
+    a.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
+    ws_bytes = L.lk_elk_block_ws_bytes(n, c, a.gen.op, r3, a.kvol, a.build_kmap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
+    _capi.check(L.lk_elk_block_fwd(C.byref(a), _capi.stream()), 'lk_elk_block_fwd')
+    return out
+
+
+def elk_forward_fused(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, alpha, coord_scale,
+                      norm, norm_local) -> torch.Tensor:
+    """Fused forward of a LinK block given its sub-modules (shared by ELKBlock and TSELKBlock):
+    the native executor when available, else one python-level call per kernel."""
+    c = st.F.shape[1]
+    if NATIVE_EXECUTOR and _capi.TIMERS is None and c in (16, 32, 64, 128):
+        return _forward_native(st, s, r, op=op, pre_mix=pre_mix, conv=conv, pos_weight=pos_weight,
+                               alpha=alpha, coord_scale=coord_scale, norm=norm, norm_local=norm_local)
+    if c in (16, 32, 64, 128):
+        f_input = _pre_mix_fused(pre_mix, st.F)
+    else:
+        f_input = pre_mix(st.F)
+    local = F.conv3d(st, conv.kernel, kernel_size=conv.kernel_size, bias=conv.bias,
+                     stride=conv.stride, dilation=conv.dilation)
+    bi = block_index(st, s)
+    return link_aggregate(f_input, st.C, bi, r, op, pos_weight, alpha, coord_scale, local.F,
+                          (norm.weight, norm.bias, norm_local.weight, norm_local.bias))
+
+
 class ELKBlock(nn.Module):
     """LinK block.  Constructor, parameters (names and shapes) and call signature are the
     reference's (linkencoder.py:94-185): `ELKBlock(inc, outc, groups, baseop)(st, s, r)`.
@@ -260,96 +346,19 @@ class ELKBlock(nn.Module):
         return torch.is_grad_enabled() and (st.F.requires_grad or
                                             any(p.requires_grad for p in self.parameters()))
 
-    def _pre_mix_fused(self, x: torch.Tensor) -> torch.Tensor:
-        """pre_mix = Linear(no bias) + LayerNorm in one liblinkb200 kernel (forward only)."""
-        lin, ln = self.pre_mix[0], self.pre_mix[1]
-        x = x.contiguous()
-        out = torch.empty_like(x)
-        n, c = x.shape
-        L = _capi.lib()
-        fn = L.lk_linear_ln_tc_fwd if (c in (32, 64) and USE_TENSOR_CORES) else L.lk_linear_ln_fwd
-        with _capi.timed('lk_linear_ln_fwd', n * 8 * c + 4 * c * c):
-            _capi.check(fn(
-                _capi.ptr(x, torch.float32), _capi.ptr(lin.weight.detach().contiguous()),
-                _capi.ptr(ln.weight.detach().contiguous()), _capi.ptr(ln.bias.detach().contiguous()),
-                float(ln.eps), n, c, _capi.ptr(out), _capi.stream()), 'lk_linear_ln_fwd')
-        return out
-
-    def _forward_native(self, st: SparseTensor, s, r, scale) -> torch.Tensor:
-        """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
-        from link_b200.nn.functional.conv import KernelMap, _transposed
-        L = _capi.lib()
-        x = st.F.contiguous()
-        coords = st.C.contiguous()
-        n, c = x.shape
-        dev = x.device
-        conv = self.local_mix[0]
-        key = (st.stride, conv.kernel_size, conv.stride, (1, 1, 1))
-        kmap = st.kmaps.get(key)
-        build = kmap is None
-        if build:
-            kmap = KernelMap(torch.empty(conv.kernel_volume, n, dtype=torch.int32, device=dev), n, n, coords)
-            st.kmaps[key] = kmap
-        conv_off = get_kernel_offsets(conv.kernel_size, stride=st.stride, device=dev)
-        blk_off = get_kernel_offsets(r, 1, 1, device=dev)
-        r3 = blk_off.shape[0]
-        a = _capi.ElkBlockArgs()
-        a.n = n
-        a.d_coords, a.d_feats = _capi.ptr(coords, torch.int32), _capi.ptr(x, torch.float32)
-        out = torch.empty_like(x)
-        a.d_out = _capi.ptr(out)
-        lin, ln = self.pre_mix[0], self.pre_mix[1]
-        a.d_premix_w = _capi.ptr(lin.weight.detach().contiguous())
-        a.d_premix_g, a.d_premix_b = _capi.ptr(ln.weight.detach()), _capi.ptr(ln.bias.detach())
-        a.premix_eps = float(ln.eps)
-        a.kvol = conv.kernel_volume
-        w = conv.kernel.detach()
-        a.d_conv_w = _capi.ptr(w.contiguous())
-        a.d_conv_wt = _capi.ptr(_transposed(w)) if USE_TENSOR_CORES else None
-        a.d_conv_offsets = _capi.ptr(conv_off)
-        a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
-        bounds = _index.coord_bounds(coords, st.kmaps)
-        spec, bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
-        a.keyspec, a.key_bits, a.r3 = spec, bits, r3
-        a.d_block_offsets = _capi.ptr(blk_off)
-        pw = self.pos_weight[0].weight.detach().contiguous()
-        alpha = self.alpha.detach().reshape(-1).contiguous() if self.baseop == 'cos_x' else None
-        a.gen = _kernel_gen(self.baseop, c, pw, alpha, scale)
-        a.d_g1, a.d_b1 = _capi.ptr(self.norm.weight.detach()), _capi.ptr(self.norm.bias.detach())
-        a.d_g2, a.d_b2 = (_capi.ptr(self.norm_local.weight.detach()),
-                          _capi.ptr(self.norm_local.bias.detach()))
-        a.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
-        ws_bytes = L.lk_elk_block_ws_bytes(n, c, a.gen.op, r3, a.kvol, a.build_kmap)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
-        _capi.check(L.lk_elk_block_fwd(C.byref(a), _capi.stream()), 'lk_elk_block_fwd')
-        return out
-
     def forward(self, st: SparseTensor, s, r):
         composed = self._needs_grad(st) or st.F.dtype != torch.float32
-        if self.baseop == 'cos_x' and self.groups != 1 and not composed:
-            raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor is "
-                               "not repeated over groups, linkencoder.py:165)")
-        if (not composed and NATIVE_EXECUTOR and _capi.TIMERS is None
-                and self.inc in (16, 32, 64, 128)):
+        if not composed:
+            if self.baseop == 'cos_x' and self.groups != 1:
+                raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor "
+                                   "is not repeated over groups, linkencoder.py:165)")
             scale = float(st.s[0]) if (self.baseop == 'cos_x' and self.variant == 'encoder') else 1.0
-            st.F = self._forward_native(st, s, r, scale)
-            return st
-        if composed or self.inc not in (16, 32, 64, 128):
-            F_input = self.pre_mix(st.F)
-        else:
-            F_input = self._pre_mix_fused(st.F)
-        local_mix = self.local_mix(st)
-        if composed:
-            return self._forward_composed(st, F_input, local_mix, s, r)
-        scale = float(st.s[0]) if (self.baseop == 'cos_x' and self.variant == 'encoder') else 1.0
-        bi = block_index(st, s)
-        out = link_aggregate(F_input, st.C, bi, r, self.baseop, self.pos_weight[0].weight,
-                             getattr(self, 'alpha', None), scale, local_mix.F,
-                             (self.norm.weight, self.norm.bias, self.norm_local.weight,
-                              self.norm_local.bias))
-        st.F = out          # like aux_to_voxel, the input tensor object carries the result
-        return st
+            st.F = elk_forward_fused(st, s, r, op=self.baseop, pre_mix=self.pre_mix,
+                                     conv=self.local_mix[0], pos_weight=self.pos_weight[0].weight,
+                                     alpha=getattr(self, 'alpha', None), coord_scale=scale,
+                                     norm=self.norm, norm_local=self.norm_local)
+            return st          # like aux_to_voxel, the input tensor object carries the result
+        return self._forward_composed(st, self.pre_mix(st.F), self.local_mix(st), s, r)
 
     def _forward_composed(self, st, F_input, local_mix, s, r):
         """The reference's op sequence (linkencoder.py:135-183) on differentiable kernels."""

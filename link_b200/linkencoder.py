@@ -11,6 +11,7 @@ import link_b200.nn as spnn
 import link_b200.nn.functional as F
 from link_b200.elk import ELKBlock, upsample_voxel
 from link_b200.tensor import SparseTensor
+from link_b200.utils import make_ntuple
 
 __all__ = ['ELKEncoder', 'LinKEncoder', 'BasicConvolutionBlock', 'BasicDeconvolutionBlock',
            'ResidualBlock']
@@ -148,10 +149,32 @@ class _ELKBackbone(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    def plan_levels(self, x: SparseTensor) -> None:
+        """Index-only prologue: builds the coordinate pyramid (the four stride-2 kernel maps and
+        their output coordinates) before any feature kernel is enqueued.  The output size of each
+        strided conv is data dependent (one 4-byte read-back per level); doing those read-backs
+        here, while only tiny index kernels are in flight, lets the whole feature pipeline that
+        follows be enqueued without a single host<->device synchronisation."""
+        t = x
+        for lv in (1, 2, 3, 4):
+            conv = getattr(self, f'down{lv}')[0].net[0]
+            dil = make_ntuple(conv.dilation, ndim=3)
+            key = (t.stride, conv.kernel_size, conv.stride, dil)
+            kmap = t.kmaps.get(key)
+            if kmap is None:
+                kmap = F.build_kernel_map(t, conv.kernel_size, conv.stride, dil)
+                t.kmaps[key] = kmap
+            nxt = SparseTensor(t.feats, kmap.out_coords,
+                               tuple(t.stride[k] * conv.stride[k] for k in range(3)))
+            nxt.cmaps, nxt.kmaps = t.cmaps, t.kmaps
+            nxt.cmaps.setdefault(nxt.stride, nxt.coords)
+            t = nxt
+
     def forward_levels(self, x: SparseTensor):
         """Stem + the four (conv stage || LinK block) levels; returns [x0, x1, x2, x3, x4]."""
         s, r = self.kwargs.get('s'), self.kwargs.get('r')
         x.cmaps.setdefault(x.stride, x.coords)
+        self.plan_levels(x)
         if F.fusable(self.stem[0], self.stem[1], x):
             x0 = F.conv_bn_act(F.conv_bn_act(x, self.stem[0], self.stem[1], relu=True),
                                self.stem[3], self.stem[4], relu=True)

@@ -100,6 +100,7 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
 # dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); '0' selects the FFMA kernel
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 _wt_cache = {}
+_tc_supported = {}
 
 
 def _transposed(weight: torch.Tensor) -> torch.Tensor:
@@ -130,13 +131,16 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
     L = _capi.lib()
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
+    tc_ok = _tc_supported.get((c_in, c_out))
+    if tc_ok is None:
+        tc_ok = _tc_supported[(c_in, c_out)] = bool(L.lk_conv_tc_supported(c_in, c_out))
     ep = _capi.ConvEpilogue()
     ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
     ep.d_residual = _capi.ptr(residual)
     ep.relu = 1 if relu else 0
     if residual is not None:
         assert residual.shape == out.shape and residual.dtype == torch.float32
-    if USE_TENSOR_CORES and L.lk_conv_tc_supported(c_in, c_out):
+    if USE_TENSOR_CORES and tc_ok:
         wt = weight_t if weight_t is not None else _transposed(weight)
         with _capi.timed('lk_conv_fwd', nb):
             _capi.check(L.lk_conv_tc_fwd_ex(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),

@@ -431,3 +431,53 @@ def test_unet_forward_vs_golden(dev):
     with torch.no_grad():
         logits = net(st)
     np.testing.assert_allclose(logits.cpu().numpy(), g['logits'], rtol=1e-3, atol=2e-4)
+
+
+# ------------------------------------------------------------------ detection block (TSELKBlock)
+@pytest.mark.parametrize('baseop,C', [('cos', 16), ('cos', 64), ('sin', 32), ('cos_sin', 16), ('x', 16)])
+def test_tselk_block_vs_oracle(dev, baseop, C):
+    """TSELKBlock through the spconv-style adapter ((b,z,y,x) indices) vs the oracle's 'det'
+    variant (ts_elk.py:144-230): fused path for cos/sin, composed path for cos_sin/x."""
+    from link_b200.ts_elk import SparseConvTensor, TSELKBlock
+    from link_b200.utils.synthetic import random_voxels
+    coords = random_voxels(3000, 40, seed=C, batch=2)              # (x, y, z, b)
+    torch.manual_seed(C)
+    blk = TSELKBlock(C, C, baseop=baseop).eval()
+    with torch.no_grad():
+        for m in (blk.pre_mix[1], blk.norm, blk.norm_local):
+            m.weight.uniform_(0.5, 1.5)
+            m.bias.uniform_(-0.5, 0.5)
+    feats = torch.randn(len(coords), C)
+    sd = {k: v.detach() for k, v in blk.state_dict().items()}
+    if baseop in ('cos', 'sin'):
+        want = O.elk_block_forward(feats, coords, 1, sd, 7, 3, baseop, 1, variant='det')
+    else:   # restated inline from ts_elk.py:196-222
+        want = _tselk_reference(feats, coords, sd, baseop, C)
+    blk = blk.to(dev)
+    idx_bzyx = cu(coords[:, [3, 2, 1, 0]].copy(), dev)
+    sct = SparseConvTensor(feats.to(dev), idx_bzyx, [41, 41, 41], 2)
+    with torch.no_grad():
+        out = blk(sct, 7)
+    assert isinstance(out, SparseConvTensor) and torch.equal(out.indices, idx_bzyx)
+    np.testing.assert_allclose(out.features.cpu().numpy(), want.detach().numpy(), rtol=RTOL, atol=4e-5)
+
+
+def _tselk_reference(feats, coords, p, baseop, C):
+    import torch.nn.functional as TF
+    F_input = TF.layer_norm(TF.linear(feats, p['pre_mix.0.weight']), (C,), p['pre_mix.1.weight'],
+                            p['pre_mix.1.bias'], 1e-6)
+    local = O.conv3d(O.OTensor(feats, coords, 1), p['local_mix.0.kernel'], 3).F
+    pos = TF.linear(torch.from_numpy(coords[:, :3].astype(np.float32)), p['pos_weight.0.weight'])
+    if baseop == 'x':
+        pos = pos[:, :C // 2].repeat(1, 2)
+        lin = F_input * pos
+        aux, sc, idx, cnt = O.voxel_to_aux(lin.contiguous(), coords, 7)
+        new = O.aux_to_voxel(aux, sc, idx, cnt, 3) - lin
+    else:
+        sin, cos = torch.sin(pos), torch.cos(pos)
+        aux, sc, idx, cnt = O.voxel_to_aux(torch.cat([F_input * cos, F_input * sin], 1), coords, 7)
+        vf = O.aux_to_voxel(aux, sc, idx, cnt, 3)
+        new = (vf[:, :C] * cos + vf[:, C:] * sin) + (vf[:, C:] * cos - vf[:, :C] * sin)
+    new = TF.layer_norm(new, (C,), p['norm.weight'], p['norm.bias'], 1e-6)
+    loc = TF.layer_norm(local, (C,), p['norm_local.weight'], p['norm_local.bias'], 1e-6)
+    return torch.relu(new + loc)
