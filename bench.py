@@ -226,6 +226,11 @@ def main_ours(args):
     evs = []
     t_wall0 = time.time()
     barrier()
+    prof = None
+    if os.environ.get('LINKB200_PROFILE_HOST') == '1' and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t_cpu0 = time.perf_counter()
     for k in range(args.steps):
         i = k % 2
@@ -237,6 +242,10 @@ def main_ours(args):
         e1.record()
         evs.append((e0, e1))
     host_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / args.steps   # python + launch cost
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
     barrier()
     t_wall1 = time.time()
     launches = _capi.launch_count() - launches0

@@ -66,6 +66,12 @@ int lk_table_build(const int64_t* d_keys, int64_t n, void* d_table, int64_t capa
 int lk_table_query(const int64_t* d_queries, int64_t nq, const void* d_table,
                    int64_t capacity, int64_t* d_out, lk_stream_t s);
 
+/* Fused pieces of upsample_voxel (segmentation/core/models/utils.py:327-340): hash of
+ * (floor(x/div), floor(y/div), floor(z/div), b), and a table probe with that hash. */
+int lk_hash_div(const int32_t* d_coords, int64_t n, int div, int64_t* d_out, lk_stream_t s);
+int lk_table_query_div(const int32_t* d_coords, int64_t n, int div, const void* d_table,
+                       int64_t capacity, int64_t* d_out, lk_stream_t s);
+
 /* count_cuda (backend/others/count_cuda.cu:10-31): histogram of idx>=0 into d_out[num]. */
 int lk_count(const int32_t* d_idx, int64_t n, int32_t* d_out, int64_t num, lk_stream_t s);
 

@@ -59,6 +59,8 @@ PROTOTYPES = {
     'lk_table_capacity': (i64, [i64]),
     'lk_table_build': (i32, [vp, i64, vp, i64, vp]),
     'lk_table_query': (i32, [vp, i64, vp, i64, vp, vp]),
+    'lk_hash_div': (i32, [vp, i64, i32, vp, vp]),
+    'lk_table_query_div': (i32, [vp, i64, i32, vp, i64, vp, vp]),
     'lk_count': (i32, [vp, i64, vp, i64, vp]),
     'lk_voxelize_fwd': (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     'lk_voxelize_bwd': (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),

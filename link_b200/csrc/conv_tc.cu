@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       const int stage = j & 1;
       tc::mbar_wait(&full_bar[stage], (uint32_t)(j >> 1) & 1u);
       tc::fence_after_sync();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(t * COUT);
         const uint64_t da_hi = da0 + (uint64_t)((stage * Cfg::A_STAGE) >> 4);
         const uint64_t da_lo = da_hi + (uint64_t)(Cfg::A_PLANE >> 4);

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
     tc::fence_proxy_async();
     __syncthreads();
     // ---- MMA: one thread, 3 * C/8 instructions ----
-    if (tid == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       uint32_t acc = 0;
 #pragma unroll

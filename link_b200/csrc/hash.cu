@@ -239,6 +239,50 @@ extern "C" int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_
   return LK_OK;
 }
 
+// ---------------------------------------------------------------- coarse-parent lookup
+// upsample_voxel (segmentation/core/models/utils.py:327-340) hashes floor(coord / stride) of the
+// coarse and of the fine level and queries one against the other; the floor-division is folded
+// into the hash / probe kernels so no intermediate coordinate or hash tensor is materialised.
+__global__ void __launch_bounds__(256) hash_div_kernel(const int4* __restrict__ coords, int64_t n,
+                                                       int div, int64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    out[i] = lk_fnv4(lk_floordiv(c.x, div), lk_floordiv(c.y, div), lk_floordiv(c.z, div), c.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) table_query_div_kernel(const int4* __restrict__ coords,
+                                                              int64_t n, int div,
+                                                              const Slot* __restrict__ table,
+                                                              uint64_t mask, int64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    int64_t h = lk_fnv4(lk_floordiv(c.x, div), lk_floordiv(c.y, div), lk_floordiv(c.z, div), c.w);
+    out[i] = table_find(table, mask, (unsigned long long)h);
+  }
+}
+
+extern "C" int lk_hash_div(const int32_t* d_coords, int64_t n, int div, int64_t* d_out,
+                           lk_stream_t s) {
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_coords && d_out && n > 0 && div >= 1, "lk_hash_div: bad arguments");
+  hash_div_kernel<<<lk_grid(n, 256, 8), 256, 0, (cudaStream_t)s>>>((const int4*)d_coords, n, div, d_out);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_table_query_div(const int32_t* d_coords, int64_t n, int div, const void* d_table,
+                                  int64_t capacity, int64_t* d_out, lk_stream_t s) {
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_coords && d_table && d_out && n > 0 && div >= 1, "lk_table_query_div: bad arguments");
+  table_query_div_kernel<<<lk_grid(n, 256, 8), 256, 0, (cudaStream_t)s>>>(
+      (const int4*)d_coords, n, div, (const Slot*)d_table, (uint64_t)capacity - 1, d_out);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 // ---------------------------------------------------------------- count
 __global__ void __launch_bounds__(256) count_kernel(const int* __restrict__ idx, int64_t n,
                                                     int* out, int64_t num) {

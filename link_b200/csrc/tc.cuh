@@ -83,6 +83,19 @@ __device__ __forceinline__ uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return d;
 }
 
+// One lane of a fully converged warp.  tcgen05.mma / tcgen05.commit are issued from inside
+// `if (elect_one())`: with a data-dependent predicate such as `lane == 0` the compiler cannot
+// prove that a single thread is active and wraps EVERY UTCHMMA in an elect-and-retry loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue / completion (single thread) ---------------------------------------------------
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                          uint32_t idesc, uint32_t accumulate) {

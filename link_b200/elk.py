@@ -142,10 +142,18 @@ def upsample_voxel(x: SparseTensor, ref_x: SparseTensor) -> SparseTensor:
     key = ('lk', 'upsample', x.s, ref_x.s, x.C.data_ptr(), ref_x.C.data_ptr())
     idx_query = x.kmaps.get(key)
     if idx_query is None:
-        x_C = torch.cat([torch.div(x.C[:, :3], stride, rounding_mode='floor').int(), x.C[:, 3:]], dim=1)
-        ref_C = torch.cat([torch.div(ref_x.C[:, :3], stride, rounding_mode='floor').int(),
-                           ref_x.C[:, 3:]], dim=1)
-        idx_query = F.sphashquery(F.sphash(ref_C), F.sphash(x_C))
+        # hash(floor(C / stride)) of the coarse level -> table; probe with the fine level's
+        # floor-divided coordinates (floor-division folded into the kernels)
+        L, st = _capi.lib(), _capi.stream()
+        xc, rc = x.C.contiguous(), ref_x.C.contiguous()
+        h = torch.empty(xc.shape[0], dtype=torch.int64, device=xc.device)
+        _capi.check(L.lk_hash_div(_capi.ptr(xc, torch.int32), xc.shape[0], int(stride), _capi.ptr(h), st),
+                    'lk_hash_div')
+        table = F.HashTable(h)
+        idx_query = torch.empty(rc.shape[0], dtype=torch.int64, device=rc.device)
+        _capi.check(L.lk_table_query_div(_capi.ptr(rc, torch.int32), rc.shape[0], int(stride),
+                                         _capi.ptr(table.table), table.capacity,
+                                         _capi.ptr(idx_query), st), 'lk_table_query_div')
         x.kmaps[key] = idx_query
     new_tensor = SparseTensor(x.F[idx_query], ref_x.C, ref_x.s)
     new_tensor.cmaps.setdefault(new_tensor.stride, new_tensor.coords)
@@ -279,9 +287,10 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     a.d_premix_g, a.d_premix_b = _capi.ptr(ln.weight.detach()), _capi.ptr(ln.bias.detach())
     a.premix_eps = float(ln.eps)
     a.kvol = conv.kernel_volume
-    w = conv.kernel.detach()
-    a.d_conv_w = _capi.ptr(w.contiguous())
-    a.d_conv_wt = _capi.ptr(_transposed(w)) if USE_TENSOR_CORES else None
+    w = conv.kernel.detach().contiguous()
+    a.d_conv_w = _capi.ptr(w)
+    wt = _transposed(conv.kernel) if USE_TENSOR_CORES else None   # cached on the Parameter
+    a.d_conv_wt = _capi.ptr(wt)
     a.d_conv_offsets = _capi.ptr(conv_off)
     a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
     bounds = _index.coord_bounds(coords, st.kmaps)

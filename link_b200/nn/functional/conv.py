@@ -99,20 +99,22 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
 
 # dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); '0' selects the FFMA kernel
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
-_wt_cache = {}
 _tc_supported = {}
 
 
 def _transposed(weight: torch.Tensor) -> torch.Tensor:
-    """[K, Cin, Cout] -> contiguous [K, Cout, Cin] (K-major B operand of the tensor-core kernel),
-    cached per (storage, version) so a module's weights are transposed once per update."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    wt = _wt_cache.get(key)
-    if wt is None:
-        if len(_wt_cache) > 512:
-            _wt_cache.clear()
-        wt = weight.detach().transpose(1, 2).contiguous()
-        _wt_cache[key] = wt
+    """[K, Cin, Cout] -> contiguous [K, Cout, Cin] (K-major B operand of the tensor-core kernel).
+    For an nn.Parameter the result is cached ON the parameter object (keyed by its version and
+    storage address), so a module's weights are transposed once per update; the cache lives and
+    dies with the parameter, so a recycled address can never alias another tensor's entry."""
+    if not isinstance(weight, torch.nn.Parameter):
+        return weight.detach().transpose(1, 2).contiguous()
+    ver = (weight._version, weight.data_ptr())
+    hit = weight.__dict__.get('_lk_wt')
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    wt = weight.detach().transpose(1, 2).contiguous()
+    weight.__dict__['_lk_wt'] = (ver, wt)
     return wt
 
 
@@ -196,21 +198,18 @@ class ConvolutionFunction(Function):
         return grad_feats, grad_weight, None, None
 
 
-_bn_fold_cache = {}
-
-
 def _folded_bn(bn):
     """Eval-mode BatchNorm as a per-channel affine (scale, shift), cached until a parameter or
     running statistic of the module changes."""
     ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
            bn.weight.data_ptr(), bn.running_mean.data_ptr())
-    hit = _bn_fold_cache.get(id(bn))
+    hit = bn.__dict__.get('_lk_fold')           # cached on the module object itself
     if hit is not None and hit[0] == ver:
         return hit[1], hit[2]
     with torch.no_grad():
         scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
         shift = (bn.bias - bn.running_mean * scale).float().contiguous()
-    _bn_fold_cache[id(bn)] = (ver, scale, shift)
+    bn.__dict__['_lk_fold'] = (ver, scale, shift)
     return scale, shift
 
 
@@ -234,7 +233,7 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
     scale = shift = None
     if bn is not None:
         scale, shift = _folded_bn(bn)
-    w = conv.kernel.detach()
+    w = conv.kernel            # the Parameter itself: its transposed copy is cached on it
     if not conv.transposed:
         key = (input.stride, kernel_size, stride, dilation)
         kmap = input.kmaps.get(key)
