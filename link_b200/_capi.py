@@ -118,7 +118,13 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f'{what} failed (code {rc}): {msg}')
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream() -> int:
+    """Handle of torch's current CUDA stream on the current device (raw cudaStream_t as int)."""
+    if _raw_stream is not None:      # ~0.3 us; torch.cuda.current_stream() costs ~8 us per call
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

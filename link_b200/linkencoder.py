@@ -170,11 +170,53 @@ class _ELKBackbone(nn.Module):
             nxt.cmaps.setdefault(nxt.stride, nxt.coords)
             t = nxt
 
+    def _fused_refs(self):
+        """Module references of the inference fast path, resolved once (no getattr / Sequential
+        indexing / nn.Module.__call__ on the per-scan hot path)."""
+        refs = self.__dict__.get('_lk_refs')
+        if refs is None:
+            lv_refs = []
+            for lv in (1, 2, 3, 4):
+                d = getattr(self, f'down{lv}')[0].net
+                stage = [(rb.net[0], rb.net[1], rb.net[3], rb.net[4]) for rb in getattr(self, f'stage{lv}')]
+                tl, et = getattr(self, f'stage{lv}_tail'), getattr(self, f'elk{lv}_tail')
+                lv_refs.append(((d[0], d[1]), stage, (tl[0], tl[1]), getattr(self, f'elk{lv}'),
+                                (et[0], et[1])))
+            st = self.stem
+            refs = ((st[0], st[1], st[3], st[4]), lv_refs)
+            self.__dict__['_lk_refs'] = refs
+        return refs
+
+    def _forward_levels_fused(self, x: SparseTensor):
+        """forward_levels for inference: every Conv3d -> BatchNorm(eval) [-> + shortcut] [-> ReLU]
+        group is one fused sparse-conv launch, every LinK block one native-executor call."""
+        s, r = self.kwargs.get('s'), self.kwargs.get('r')
+        cba = F.conv_bn_act
+        (c0, b0, c1, b1), lv_refs = self._fused_refs()
+        x0 = cba(cba(x, c0, b0, True), c1, b1, True)
+        feats = [x0]
+        cur = x0
+        for (dc, db), stage, (tc_, tb), elk_mod, (ec, eb) in lv_refs:
+            x_in = cba(cur, dc, db, True)
+            y = x_in
+            for ca, ba, cb, bb in stage:
+                y = cba(cba(y, ca, ba, True), cb, bb, True, y.feats)
+            x_conv = cba(y, tc_, tb, False)
+            x_lk = elk_mod.forward(x_in, x_in.stride[0] * s, r)
+            cur = cba(x_lk, ec, eb, True, x_conv.feats)
+            feats.append(cur)
+        return feats
+
     def forward_levels(self, x: SparseTensor):
         """Stem + the four (conv stage || LinK block) levels; returns [x0, x1, x2, x3, x4]."""
         s, r = self.kwargs.get('s'), self.kwargs.get('r')
         x.cmaps.setdefault(x.stride, x.coords)
         self.plan_levels(x)
+        if (F.fusable(self.stem[0], self.stem[1], x) and not self.training
+                and self.stem[0].in_channels == x.feats.shape[1]
+                and all(len(rb.downsample) == 0 for lv in (1, 2, 3, 4)
+                        for rb in getattr(self, f'stage{lv}'))):
+            return self._forward_levels_fused(x)
         if F.fusable(self.stem[0], self.stem[1], x):
             x0 = F.conv_bn_act(F.conv_bn_act(x, self.stem[0], self.stem[1], relu=True),
                                self.stem[3], self.stem[4], relu=True)

@@ -227,9 +227,13 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
     separate ops (spnn.Conv3d -> spnn.BatchNorm -> [+ shortcut] -> spnn.ReLU, linkencoder.py:26-37,
     64-91) in one sparse-conv launch whose epilogue applies the folded BatchNorm affine, the
     residual and the ReLU before the single output store.  Same kernel-map caching as conv3d."""
-    feats = input.feats.contiguous()
+    feats = input.feats
+    if not feats.is_contiguous():
+        feats = feats.contiguous()
     kernel_size, stride = conv.kernel_size, conv.stride
-    dilation = make_ntuple(conv.dilation, ndim=3)
+    dilation = conv.__dict__.get('_lk_dil')
+    if dilation is None:
+        dilation = conv.__dict__['_lk_dil'] = make_ntuple(conv.dilation, ndim=3)
     scale = shift = None
     if bn is not None:
         scale, shift = _folded_bn(bn)
