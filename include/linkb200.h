@@ -91,6 +91,13 @@ int lk_devoxelize_bwd(const float* d_top /*[N,c]*/, const int32_t* d_idx, const 
                       int64_t N, int r3, int c, int64_t n, float* d_bottom /*[n,c]*/,
                       lk_stream_t s);
 
+/* out[i, g*c:(g+1)*c] = relu?(src_g[idx_g[i], :] + bias[g*c:(g+1)*c]) for g < groups (<= 8).
+ * d_src / d_idx are HOST arrays of device pointers; idx_g == NULL is the identity map, a negative
+ * index yields a zero row.  Head of ELKEncoder (linkencoder.py:371-379): nearest-parent upsample
+ * (utils.py:327-340) + concat + bias + ReLU in one pass.  c % 4 == 0. */
+int lk_gather_concat(const float* const* d_src, const int64_t* const* d_idx, int groups, int c,
+                     int64_t n, const float* d_bias, int relu, float* d_out, lk_stream_t s);
+
 /* ------------------------------------------------------------------------------------
  * Key packing + radix sort/unique: the device-side replacement for torch.unique(dim=0)
  * used by voxel_to_aux (segmentation/core/models/utils.py:47), spdownsample

@@ -66,6 +66,7 @@ PROTOTYPES = {
     'lk_voxelize_bwd': (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     'lk_devoxelize_fwd': (i32, [vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_devoxelize_bwd': (i32, [vp, vp, vp, i64, i32, i32, i64, vp, vp]),
+    'lk_gather_concat': (i32, [vp, vp, i32, i32, i64, vp, i32, vp, vp]),
     'lk_pack_keys': (i32, [vp, i64, C.POINTER(KeySpec), vp, vp]),
     'lk_unpack_keys': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, vp]),
     'lk_sort_unique_ws_bytes': (i64, [i64]),

@@ -192,3 +192,54 @@ extern "C" int lk_devoxelize_bwd(const float* d_top, const int32_t* d_idx, const
   LK_LAUNCHED();
   return LK_OK;
 }
+
+// ---------------------------------------------------------------- classifier head gather
+// out[i, g*c : (g+1)*c] = relu( src_g[idx_g[i], :] + bias[g*c : (g+1)*c] ) for g < G; idx_g == NULL
+// means the identity map.  Used by the ELKEncoder head (linkencoder.py:371-379): the grouped 1x1
+// conv is applied at each level's own (coarse) resolution and only its c-channel result is
+// upsampled, instead of upsampling 64-channel features and concatenating them.
+struct GatherArgs {
+  const float* src[8];
+  const int64_t* idx[8];
+};
+
+__global__ void __launch_bounds__(256) gather_concat_bias_relu_kernel(GatherArgs a, int G, int c,
+                                                                      int64_t n,
+                                                                      const float* __restrict__ bias,
+                                                                      int relu, float* __restrict__ out) {
+  const int vpr = c >> 2;                 // float4 per source row
+  const int64_t total = n * G * vpr;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t / (G * vpr);
+    int rem = (int)(t - i * (G * vpr));
+    int g = rem / vpr, j = (rem - g * vpr) * 4;
+    int64_t row = a.idx[g] ? __ldg(a.idx[g] + i) : i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0) v = __ldg((const float4*)(a.src[g] + row * c + j));
+    if (bias) {
+      float4 b = __ldg((const float4*)(bias + g * c + j));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    *(float4*)(out + i * (int64_t)(G * c) + g * c + j) = v;
+  }
+}
+
+extern "C" int lk_gather_concat(const float* const* d_src, const int64_t* const* d_idx, int groups,
+                                int c, int64_t n, const float* d_bias, int relu, float* d_out,
+                                lk_stream_t s) {
+  LK_REQUIRE(groups >= 1 && groups <= 8 && c > 0 && c % 4 == 0 && n >= 0, "lk_gather_concat: bad sizes");
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_src && d_idx && d_out, "lk_gather_concat: null pointer");
+  GatherArgs a;
+  for (int g = 0; g < 8; ++g) {
+    a.src[g] = g < groups ? d_src[g] : nullptr;
+    a.idx[g] = g < groups ? d_idx[g] : nullptr;
+    LK_REQUIRE(g >= groups || a.src[g], "lk_gather_concat: null source");
+  }
+  gather_concat_bias_relu_kernel<<<lk_grid(n * groups * (c / 4), 256, 8), 256, 0, (cudaStream_t)s>>>(
+      a, groups, c, n, d_bias, relu, d_out);
+  LK_LAUNCHED();
+  return LK_OK;
+}

@@ -25,7 +25,7 @@ from link_b200.nn.functional import _index
 from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import PointTensor, SparseTensor
 
-__all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsample_voxel',
+__all__ = ['BlockIndex', 'block_index', 'voxel_to_aux', 'aux_to_voxel', 'upsample_voxel', 'upsample_index',
            'initial_voxelize', 'link_aggregate', 'elk_forward_fused', 'ELKBlock', 'LinKBlock']
 
 _OPS = {'cos': 0, 'sin': 1, 'cos_x': 2}
@@ -136,8 +136,9 @@ def aux_to_voxel(small_x: SparseTensor, large_x: SparseTensor, idx: torch.Tensor
     return large_x
 
 
-def upsample_voxel(x: SparseTensor, ref_x: SparseTensor) -> SparseTensor:
-    """Nearest-parent gather from a coarse level to the fine level (utils.py:327-340)."""
+def upsample_index(x: SparseTensor, ref_x: SparseTensor) -> torch.Tensor:
+    """int64 [N_ref]: row of `x` (coarse level) that is the parent of each voxel of `ref_x`
+    (the index map of upsample_voxel, utils.py:329-335), cached in the family's kmaps."""
     stride = x.s[0]
     key = ('lk', 'upsample', x.s, ref_x.s, x.C.data_ptr(), ref_x.C.data_ptr())
     idx_query = x.kmaps.get(key)
@@ -155,6 +156,12 @@ def upsample_voxel(x: SparseTensor, ref_x: SparseTensor) -> SparseTensor:
                                          _capi.ptr(table.table), table.capacity,
                                          _capi.ptr(idx_query), st), 'lk_table_query_div')
         x.kmaps[key] = idx_query
+    return idx_query
+
+
+def upsample_voxel(x: SparseTensor, ref_x: SparseTensor) -> SparseTensor:
+    """Nearest-parent gather from a coarse level to the fine level (utils.py:327-340)."""
+    idx_query = upsample_index(x, ref_x)
     new_tensor = SparseTensor(x.F[idx_query], ref_x.C, ref_x.s)
     new_tensor.cmaps.setdefault(new_tensor.stride, new_tensor.coords)
     return new_tensor

@@ -9,7 +9,10 @@ import torch.nn as nn
 
 import link_b200.nn as spnn
 import link_b200.nn.functional as F
-from link_b200.elk import ELKBlock, upsample_voxel
+import ctypes as C
+
+from link_b200 import _capi
+from link_b200.elk import ELKBlock, upsample_index, upsample_voxel
 from link_b200.tensor import SparseTensor
 from link_b200.utils import make_ntuple
 
@@ -250,8 +253,32 @@ class ELKEncoder(_ELKBackbone):
 
     def forward(self, x: SparseTensor) -> torch.Tensor:
         x0, x1, x2, x3, x4 = self.forward_levels(x)
+        if not torch.is_grad_enabled() and x0.F.dtype == torch.float32 and x0.F.is_cuda:
+            return self._classify_pushdown([x4, x3, x2, x1, x0])
         ys = [upsample_voxel(lv, x0).F for lv in (x4, x3, x2, x1)]
         return self._classify(torch.cat(ys + [x0.F], dim=1))
+
+    def _classify_pushdown(self, levels) -> torch.Tensor:
+        """Inference head.  The reference upsamples every level to N0 rows x 64 channels,
+        concatenates them ([N0, 320]) and applies the grouped 1x1 conv (one group per level).  A
+        1x1 conv commutes with a row gather, so the group of level l is applied at that level's own
+        (coarse) size, and one kernel gathers the five 24-channel results, adds the bias and
+        applies the ReLU: same values, ~5x less gather traffic, no [N0, 320] temporary."""
+        c0, c2 = self.classifier[0], self.classifier[2]
+        g = c0.groups
+        oc = c0.out_channels // g
+        w0 = c0.weight.view(g, oc, -1)
+        x0 = levels[-1]
+        n0 = x0.F.shape[0]
+        z = [torch.mm(lv.F, w0[i].t()) for i, lv in enumerate(levels)]        # [N_l, 24] each
+        idx = [upsample_index(lv, x0) for lv in levels[:-1]] + [None]
+        h = torch.empty(n0, g * oc, dtype=torch.float32, device=x0.F.device)
+        src_arr = (C.c_void_p * g)(*[t.data_ptr() for t in z])
+        idx_arr = (C.c_void_p * g)(*[(t.data_ptr() if t is not None else None) for t in idx])
+        _capi.check(_capi.lib().lk_gather_concat(src_arr, idx_arr, g, oc, n0,
+                                                 _capi.ptr(c0.bias.detach()), 1, _capi.ptr(h),
+                                                 _capi.stream()), 'lk_gather_concat')
+        return torch.addmm(c2.bias, h, c2.weight.view(c2.out_channels, -1).t())
 
     def _classify(self, f_cat: torch.Tensor) -> torch.Tensor:
         """The reference's grouped 1x1 Conv1d head (linkencoder.py:323-327, 376-379) evaluated as

@@ -118,6 +118,24 @@ def _transposed(weight: torch.Tensor) -> torch.Tensor:
     return wt
 
 
+def _tc_ok(L, c_in, c_out) -> bool:
+    ok = _tc_supported.get((c_in, c_out))
+    if ok is None:
+        ok = _tc_supported[(c_in, c_out)] = bool(L.lk_conv_tc_supported(c_in, c_out))
+    return ok
+
+
+def _transposed_padded(weight: torch.nn.Parameter, c_pad: int) -> torch.Tensor:
+    """[K, Cin, Cout] -> [K, Cout, c_pad] with zero-padded input channels, cached on the parameter."""
+    ver = (weight._version, weight.data_ptr(), c_pad)
+    hit = weight.__dict__.get('_lk_wtp')
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    wt = torch.nn.functional.pad(weight.detach().transpose(1, 2), (0, c_pad - weight.shape[1])).contiguous()
+    weight.__dict__['_lk_wtp'] = (ver, wt)
+    return wt
+
+
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
               relu=False):
     """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
@@ -133,15 +151,20 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
     L = _capi.lib()
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
-    tc_ok = _tc_supported.get((c_in, c_out))
-    if tc_ok is None:
-        tc_ok = _tc_supported[(c_in, c_out)] = bool(L.lk_conv_tc_supported(c_in, c_out))
+    tc_ok = _tc_ok(L, c_in, c_out)
     ep = _capi.ConvEpilogue()
     ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
     ep.d_residual = _capi.ptr(residual)
     ep.relu = 1 if relu else 0
     if residual is not None:
         assert residual.shape == out.shape and residual.dtype == torch.float32
+    if (USE_TENSOR_CORES and not tc_ok and weight is not None and c_in < 32 and c_in % 4 == 0
+            and _tc_ok(L, 32, c_out) and isinstance(weight, torch.nn.Parameter)):
+        # narrow input layer (the 4-channel stem): zero-pad C_in to one 32-float K-block and run on
+        # the tensor cores; the zero K-columns cost tensor time only (and that pipe has slack)
+        feats = torch.nn.functional.pad(feats, (0, 32 - c_in))
+        weight_t = _transposed_padded(weight, 32)
+        weight, c_in, tc_ok = None, 32, True
     if USE_TENSOR_CORES and tc_ok:
         wt = weight_t if weight_t is not None else _transposed(weight)
         with _capi.timed('lk_conv_fwd', nb):
