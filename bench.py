@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--workload', default='block', choices=['block', 'encoder'])
     ap.add_argument('--voxels', type=int, default=120_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-encoder', action='store_true', help='skip the extra encoder measurement')
     return ap.parse_args()
 
 
@@ -59,8 +60,17 @@ def block_params(seed=0):
     return blk
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# captures (profiles/), keyed by kernel; None = not captured for this build.
+NCU_TRAFFIC = {'link_preagg_kernel': None}
+
+
 def workload_name(args, n):
-    if args.workload == 'block':
+    return workload_name_for(args.workload, n)
+
+
+def workload_name_for(workload, n):
+    if workload == 'block':
         return (f'ELKBlock cos:(3x7)^3 C={C_BLOCK} groups={GROUPS} fwd, synthetic '
                 f'SemanticKITTI-shaped scan, N={n} active voxels, index+kernel maps rebuilt per step')
     return (f'ELKEncoder cos:(3x7)^3 cr=1.0 fwd, synthetic SemanticKITTI-shaped scan, N={n} active '
@@ -166,27 +176,19 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def main_ours(args):
+def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_clocks):
+    """Times `steps` steps of one workload on this rank.  Returns a dict of local measurements
+    (device ms, e2e ms, voxels, launches, per-kernel timers, clocks)."""
     import torch.distributed as dist
     from link_b200 import SparseTensor, _capi
     from link_b200.nn.functional import _index
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    _capi.lib()
+    from link_b200.sharding import frame_seed
 
     # per-rank scans (weak scaling): 2 distinct scans alternate so that no step can reuse state
-    scans = [make_scan(args.voxels, seed=rank * 1000 + i) for i in range(2)]
-    if args.workload == 'block':
+    scans = [make_scan(args.voxels, seed=frame_seed(rank, i)) for i in range(2)]
+    if workload == 'block':
         model = block_params().to(dev).eval()
-        in_ch = C_BLOCK
-        feats_host = [torch.randn(len(c), in_ch, generator=torch.Generator().manual_seed(i)).pin_memory()
+        feats_host = [torch.randn(len(c), C_BLOCK, generator=torch.Generator().manual_seed(i)).pin_memory()
                       for i, (c, _) in enumerate(scans)]
     else:
         from link_b200.linkencoder import ELKEncoder
@@ -199,14 +201,13 @@ def main_ours(args):
     coords_dev = [c.to(dev) for c in coords_host]
     feats_dev = [f.to(dev) for f in feats_host]
     n_vox = [len(c) for c, _ in scans]
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(i, coords, feats):
         st = SparseTensor(feats, coords, 1)
         _index.set_coord_bounds(st.kmaps, bounds[i][0], bounds[i][1])
         with torch.no_grad():
-            if args.workload == 'block':
+            if workload == 'block':
                 return model(st, S_BLK, R_BLK).F
             return model(st)
 
@@ -216,11 +217,11 @@ def main_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident loop (value) ------------------------------------------------------
-    for w in range(args.warmup):
+    for w in range(warmup):
         step(w % 2, coords_dev[w % 2], feats_dev[w % 2].clone())
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if with_clocks:
         sampler.start()
     launches0 = _capi.launch_count()
     evs = []
@@ -232,7 +233,7 @@ def main_ours(args):
         prof = cProfile.Profile()
         prof.enable()
     t_cpu0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         i = k % 2
         f = feats_dev[i].clone()          # the block overwrites st.F; clone outside the timed region
         flush.zero_()                     # L2 flush between timed iterations (outside the events)
@@ -241,7 +242,7 @@ def main_ours(args):
         step(i, coords_dev[i], f)
         e1.record()
         evs.append((e0, e1))
-    host_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / args.steps   # python + launch cost
+    host_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / steps   # python + launch cost
     if prof is not None:
         import pstats
         prof.disable()
@@ -250,23 +251,28 @@ def main_ours(args):
     t_wall1 = time.time()
     launches = _capi.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.finish(t_wall0, t_wall1) if with_clocks else None
     # ---- instrumented pass: same steps with one python-level call per kernel, CUDA events around
     #      each library call on the launching stream (per-kernel times for `kernels`/`roofline`) ----
     _capi.TIMERS = {}
-    for k in range(args.steps):
+    for k in range(steps):
         i = k % 2
         f = feats_dev[i].clone()
         flush.zero_()
         step(i, coords_dev[i], f)
     barrier()
     timers, _capi.TIMERS = _capi.TIMERS, None
-    vox_done = sum(n_vox[k % 2] for k in range(args.steps))
-
+    kern = {}
+    for name, lst in timers.items():
+        ms = [a.elapsed_time(b) for a, b, _ in lst]
+        kern[name] = {'launches_per_step': len(ms) / steps, 'avg_us': 1e3 * float(np.mean(ms)),
+                      'bytes': float(np.mean([x[2] for x in lst]))}
     # ---- end-to-end loop: pinned host buffers -> H2D -> step -> D2H of a per-channel checksum --
     h2d = d2h = 0
     e2e_evs = []
-    out_host = torch.empty(64 if args.workload == 'block' else 19, dtype=torch.float32).pin_memory()
-    for k in range(min(3, args.warmup) + args.steps):
+    out_host = torch.empty(C_BLOCK if workload == 'block' else 19, dtype=torch.float32).pin_memory()
+    w_e2e = min(3, warmup)
+    for k in range(w_e2e + steps):
         i = k % 2
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -276,70 +282,99 @@ def main_ours(args):
         out = step(i, c, f)
         out_host.copy_(out.sum(dim=0), non_blocking=True)
         e1.record()
-        if k >= min(3, args.warmup):
+        if k >= w_e2e:
             e2e_evs.append((e0, e1))
             h2d = coords_host[i].numel() * 4 + feats_host[i].numel() * 4
             d2h = out_host.numel() * 4
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
+            'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,
+            'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
 
-    # ---- max over ranks ---------------------------------------------------------------------
-    stats = torch.tensor([dev_ms, e2e_ms, float(vox_done)], dtype=torch.float64, device=dev)
+
+def summarize(m, world, dev):
+    """Local measurements -> whole-job numbers (max time over ranks, summed voxels)."""
+    from link_b200.sharding import reduce_throughput
+    dev_ms, vox = reduce_throughput(m['dev_ms'], m['voxels'], dev)
+    e2e_ms, _ = reduce_throughput(m['e2e_ms'], m['voxels'], dev)
+    return dev_ms, e2e_ms, vox
+
+
+def main_ours(args):
+    import torch.distributed as dist
+    from link_b200 import _capi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
     if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, vox_total = float(mx[0]), float(mx[1]), float(sm[2])
-    else:
-        vox_total = float(vox_done)
+        dist.init_process_group('nccl', device_id=dev)
+    _capi.lib()
+
+    m = run_workload(args, args.workload, args.steps, args.warmup, dev, rank, world, local, rank == 0)
+    dev_ms, e2e_ms, vox_total = summarize(m, world, dev)
+    extra = None
+    if args.workload == 'block' and not args.no_encoder:
+        # BASELINE config 2 on the same scans, as additional evidence (not the headline metric)
+        me = run_workload(args, 'encoder', max(3, args.steps // 2), min(3, args.warmup), dev, rank,
+                          world, local, False)
+        ed, ee, ev = summarize(me, world, dev)
+        extra = {'workload': workload_name_for('encoder', me['n0']), 'value': ev / (ed * 1e-3),
+                 'unit': UNIT, 'ms_per_step': ed / me['steps'], 'steps': me['steps'],
+                 'e2e': {'value': ev / (ee * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': me['h2d'],
+                         'd2h_bytes_per_step': me['d2h']},
+                 'gpu_launches': me['launches'], 'host_enqueue_ms_per_step': me['host_enqueue_ms']}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    clocks = sampler.finish(t_wall0, t_wall1)
     value = vox_total / (dev_ms * 1e-3)
     e2e_value = vox_total / (e2e_ms * 1e-3)
+    steps = m['steps']
 
-    # ---- per-kernel breakdown + roofline of the dominant kernel ------------------------------
+    # ---- per-kernel breakdown + roofline of the HBM-bound kernel BASELINE.json names ----------
     peaks = {}
     pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     hbm_peak, peak_src = (peaks.get('hbm_gbs'), 'measured') if peaks.get('hbm_gbs') else (6650.0, 'fallback')
-    kern = {}
-    for name, lst in timers.items():
-        ms = [a.elapsed_time(b) for a, b, _ in lst]
-        kern[name] = {'launches': len(ms), 'avg_us': 1e3 * float(np.mean(ms)),
-                      'bytes': float(np.mean([x[2] for x in lst]))}
-    step_us = 1e3 * dev_ms / args.steps
+    kern = m['kernels']
+    step_us = 1e3 * m['dev_ms'] / steps
     for v in kern.values():
-        v['share_of_step'] = v['avg_us'] * v['launches'] / args.steps / step_us
+        v['share_of_step'] = v['avg_us'] * v['launches_per_step'] / step_us
         v['gbs'] = v['bytes'] / (v['avg_us'] * 1e-6) / 1e9 if v['bytes'] else None
     roof = None
-    # the HBM-bound kernel BASELINE.json names: the pre-aggregation pass
     if 'lk_link_preagg_fwd' in kern:
         kp = kern['lk_link_preagg_fwd']
         roof = {'kernel': 'link_preagg_kernel', 'bound': 'hbm', 'achieved': kp['gbs'], 'peak': hbm_peak,
-                'peak_source': peak_src, 'unit': 'GB/s', 'frac': kp['gbs'] / hbm_peak, 'traffic': None,
-                'algorithmic_bytes_per_launch': kp['bytes'], 'avg_us': kp['avg_us']}
+                'peak_source': peak_src, 'unit': 'GB/s', 'frac': kp['gbs'] / hbm_peak,
+                'traffic': NCU_TRAFFIC.get('link_preagg_kernel'),
+                'algorithmic_bytes_per_launch': kp['bytes'], 'avg_us': kp['avg_us'],
+                'note': 'timed with CUDA events around the kernel in the instrumented pass '
+                        '(one python-level call per kernel); see profiles/ for the ncu captures'}
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+        'warmup': m['warmup'], 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args, n_vox[0]),
+        'config': {'workload': workload_name_for(args.workload, m['n0']),
                    'l2': 'flushed between timed iterations (256 MiB memset, outside the events)',
                    'parallelism': f'{world} independent frame streams (no data-path collective)'},
-        'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
-        'gpu_launches': int(launches),
-        'host_enqueue_ms_per_step': host_enqueue_ms,
+        'clocks': m['clocks'],
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'],
+                'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps},
+        'gpu_launches': m['launches'],
+        'host_enqueue_ms_per_step': m['host_enqueue_ms'],
         'roofline': roof,
         'kernels': kern,
     }
+    if extra is not None:
+        line['encoder'] = extra
     if world == 1 and not args.no_cpu_baseline:
         n_s = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
         v, dt, n, cores = run_cpu(args, n_s, 2, 1)

@@ -91,7 +91,7 @@ class _SparseConvBase(nn.Module):
         w.__dict__['_lk_kio'] = (ver, kio)
         return kio
 
-    def _apply(self, x: SparseConvTensor, kmap: KernelMap, out_indices, out_shape,
+    def _run(self, x: SparseConvTensor, kmap: KernelMap, out_indices, out_shape,
                scale=None, shift=None, relu=False, residual=None) -> SparseConvTensor:
         w = self._weight_kio()
         fused = not torch.is_grad_enabled()
@@ -138,7 +138,7 @@ class SubMConv3d(_SparseConvBase):
         return kmap
 
     def forward(self, x: SparseConvTensor, **epilogue) -> SparseConvTensor:
-        return self._apply(x, self.kernel_map(x), x.indices, x.spatial_shape, **epilogue)
+        return self._run(x, self.kernel_map(x), x.indices, x.spatial_shape, **epilogue)
 
 
 class SparseConv3d(_SparseConvBase):
@@ -177,7 +177,7 @@ class SparseConv3d(_SparseConvBase):
                                               _capi.ptr(table.table), table.capacity,
                                               _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
         kmap = KernelMap(nbr, coords.shape[0], n_out, q)
-        return self._apply(x, kmap, out_indices, out_shape, **epilogue)
+        return self._run(x, kmap, out_indices, out_shape, **epilogue)
 
 
 class SparseSequential(nn.Sequential):
