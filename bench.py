@@ -212,8 +212,9 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
             return model(st)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(torch.zeros(1))      # CPU tensor -> gloo: a barrier across ranks
         torch.cuda.synchronize()
 
     # ---- device-resident loop (value) ------------------------------------------------------
@@ -296,8 +297,8 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
 def summarize(m, world, dev):
     """Local measurements -> whole-job numbers (max time over ranks, summed voxels)."""
     from link_b200.sharding import reduce_throughput
-    dev_ms, vox = reduce_throughput(m['dev_ms'], m['voxels'], dev)
-    e2e_ms, _ = reduce_throughput(m['e2e_ms'], m['voxels'], dev)
+    dev_ms, vox = reduce_throughput(m['dev_ms'], m['voxels'], None)     # CPU tensors -> gloo
+    e2e_ms, _ = reduce_throughput(m['e2e_ms'], m['voxels'], None)
     return dev_ms, e2e_ms, vox
 
 
@@ -312,7 +313,10 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL is registered for CUDA tensors (a training loop's DDP all-reduce would use it), but the
+        # forward hot path has NO data-path collective: the only communication is the timing
+        # bookkeeping below, done on CPU tensors over gloo, so no NCCL communicator is ever created
+        dist.init_process_group('cpu:gloo,cuda:nccl')
     _capi.lib()
 
     m = run_workload(args, args.workload, args.steps, args.warmup, dev, rank, world, local, rank == 0)

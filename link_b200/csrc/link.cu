@@ -94,11 +94,11 @@ __device__ __forceinline__ void load_lane_gen_owned(const GenDev& g, int lane, i
 }
 
 #define PREAGG_ROWS_PER_GROUP 8
-#define PREAGG_UNROLL 4
+#define PREAGG_UNROLL 2
 
 // ------------------------------------------------------------------ pass 1: block sums
 template <int LPR, int OP, int SH>
-__global__ void __launch_bounds__(256, 3) link_preagg_kernel(const float* __restrict__ fin,
+__global__ void __launch_bounds__(256, 4) link_preagg_kernel(const float* __restrict__ fin,
                                                           const int4* __restrict__ coords,
                                                           const int* __restrict__ blk, int64_t n,
                                                           GenDev g, float* sums) {
