@@ -116,53 +116,51 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     }
   } else {
     // ================= producer warps (gather + tf32 split), later the epilogue =================
-    // item i of a step: tt = tid + i*CT_THREADS -> chunk = tt & 7, kb = (tt >> 3) % KB,
-    // row = tt / (8*KB).  The (row, chunk) position of an item is the same in every step, so its
-    // swizzled shared-memory offset is computed once.
+    // Thread -> (row, quarter): TPR = CT_THREADS/128 threads share one gathered row; thread q of a
+    // row owns the 16-byte chunks {q, q + TPR, q + 2 TPR, ...} of that row, so the TPR lanes of a
+    // row read TPR*16 contiguous bytes per load instruction (full sectors) and ONE neighbour index
+    // / validity test / dirty bit per thread and step covers all of its NI chunks.
+    constexpr int TPR = CT_THREADS / CT_ROWS;              // 4
+    static_assert(NI * TPR == KB * 8, "chunks of a row must tile over its threads");
+    const int prow = tid / TPR, pq = tid % TPR;
     uint32_t soff[NI];
-    int irow[NI], icol[NI];
+    int icol[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      int tt = tid + i * CT_THREADS;
-      int chunk = tt & 7, kb = (tt >> 3) % KB;
-      irow[i] = tt / (8 * KB);
-      icol[i] = kb * 32 + chunk * 4;
-      soff[i] = kb * Cfg::A_BLK + tc::sw128_offset(irow[i], chunk);
+      const int cch = pq + i * TPR;                        // chunk index within the row (0 .. 8*KB)
+      const int kb = cch >> 3, chunk = cch & 7;
+      icol[i] = cch * 4;
+      soff[i] = kb * Cfg::A_BLK + tc::sw128_offset(prow, chunk);
     }
-    // neighbour indices of step (k2, t2); no integer division in the steady state
     const int64_t row_base = tile0 * CT_ROWS;
-    auto load_idx = [&](int k2, int t2, int* src) {
-      const int* col = nbr + (int64_t)k2 * n_out + row_base + (int64_t)t2 * CT_ROWS;
-      const int64_t left = n_out - row_base - (int64_t)t2 * CT_ROWS;     // rows of this tile in range
-#pragma unroll
-      for (int i = 0; i < NI; ++i)
-        src[i] = (k2 < K && irow[i] < left) ? __ldg(col + irow[i]) : -1;
+    // neighbour index of my row for step (k2, t2); no integer division in the steady state
+    auto load_idx = [&](int k2, int t2) -> int {
+      const int64_t o = row_base + (int64_t)t2 * CT_ROWS + prow;
+      return (k2 < K && o < n_out) ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
     };
-    auto load_rows = [&](const int* src, float4* v) {
+    auto load_rows = [&](int src, float4* v) {
+      if (src >= 0) {
+        const float* rp = in + (int64_t)src * CIN;
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src[i] >= 0) v[i] = __ldg((const float4*)(in + (int64_t)src[i] * CIN + icol[i]));
+        for (int i = 0; i < NI; ++i) v[i] = __ldg((const float4*)(rp + icol[i]));
       }
     };
-    int src_a[NI], src_b[NI], src_c[NI];
     float4 v[NI], v_next[NI];
-    // bit (stage*NI + i): my slot of item i in that stage currently holds non-zero data.  About
-    // 70 % of the gathered rows are missing neighbours (zero rows): a slot that is already zero
-    // is not rewritten, which halves the split + store work.
-    uint32_t dirty = 0xFFFFFFFFu;             // shared memory starts uninitialised
+    // bit `stage`: my slots of that operand stage currently hold non-zero data.  ~70 % of the
+    // gathered rows are missing neighbours (zero rows): slots that are already zero are not
+    // rewritten, which halves the split + store work.
+    uint32_t dirty = 3u;                      // shared memory starts uninitialised
     int k = 0, t = 0;                         // step j
-    int kb1 = 0, tb1 = 0, kc = 0, tc2 = 0;    // steps j+1 and j+2
+    int kc = 0, tc2 = 0;                      // step j + 2
     auto advance = [&](int& kk, int& tt) { if (++tt == ntiles) { tt = 0; ++kk; } };
-    load_idx(0, 0, src_a);
+    int src_a = load_idx(0, 0);
     load_rows(src_a, v);
-    advance(kb1, tb1);
-    load_idx(kb1, tb1, src_b);
-    kc = kb1; tc2 = tb1;
+    advance(kc, tc2);
+    int src_b = load_idx(kc, tc2);
     advance(kc, tc2);
     for (int j = 0; j < total_steps; ++j) {
       const int stage = j & 1;
-      load_idx(kc, tc2, src_c);               // index prefetch distance 2
+      const int src_c = load_idx(kc, tc2);    // index prefetch distance 2
       load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
       if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
       if (t == 0) {
@@ -182,25 +180,31 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       }
       uint8_t* ah = a_base + stage * Cfg::A_STAGE;
       uint8_t* al = ah + Cfg::A_PLANE;
+      const uint32_t bit = 1u << stage;
+      if (src_a >= 0) {
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const uint32_t bit = 1u << (stage * NI + i);
-        if (src_a[i] >= 0) {
+        for (int i = 0; i < NI; ++i) {
           float4 hi, lo;
           tc::split_tf32(v[i], hi, lo);
           *(float4*)(ah + soff[i]) = hi;
           *(float4*)(al + soff[i]) = lo;
-          dirty |= bit;
-        } else if (dirty & bit) {
-          *(float4*)(ah + soff[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
-          *(float4*)(al + soff[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
-          dirty &= ~bit;
         }
+        dirty |= bit;
+      } else if (dirty & bit) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          *(float4*)(ah + soff[i]) = z;
+          *(float4*)(al + soff[i]) = z;
+        }
+        dirty &= ~bit;
       }
       tc::fence_proxy_async();                // my generic-proxy stores -> visible to the tensor core
       tc::mbar_arrive(&full_bar[stage]);
 #pragma unroll
-      for (int i = 0; i < NI; ++i) { v[i] = v_next[i]; src_a[i] = src_b[i]; src_b[i] = src_c[i]; }
+      for (int i = 0; i < NI; ++i) v[i] = v_next[i];
+      src_a = src_b;
+      src_b = src_c;
       advance(k, t);
       advance(kc, tc2);
     }
