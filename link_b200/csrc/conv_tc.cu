@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const a_base = smem;                          // 2 A stages, then 2 B stages
   uint8_t* const b_base = smem + 2 * Cfg::A_STAGE;
-  __shared__ uint64_t full_bar[2];    // operand stage written   (256 producer arrivals)
+  __shared__ uint64_t full_bar[2];    // operand stage written   (one arrival per producer warp)
   __shared__ uint64_t empty_bar[2];   // operand stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
 
@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
   if (tid == 0) {
-    tc::mbar_init(&full_bar[0], CT_THREADS);
-    tc::mbar_init(&full_bar[1], CT_THREADS);
+    tc::mbar_init(&full_bar[0], CT_THREADS / 32);      // one arrival per producer warp
+    tc::mbar_init(&full_bar[1], CT_THREADS / 32);
     tc::mbar_init(&empty_bar[0], 1);
     tc::mbar_init(&empty_bar[1], 1);
     tc::fence_mbar_init();
@@ -162,6 +162,13 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       const int stage = j & 1;
       const int src_c = load_idx(kc, tc2);    // index prefetch distance 2
       load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
+      // split BEFORE waiting for the stage: after the wake-up only the stores remain on the
+      // critical path  commit(j-2) -> stores -> full(j) -> MMA(j)
+      float4 hi[NI], lo[NI];
+      if (src_a >= 0) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) tc::split_tf32(v[i], hi[i], lo[i]);
+      }
       if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
       if (t == 0) {
         // stage W[k]: every MMA of offset k-2 (last reader of this buffer) precedes step j-2's
@@ -171,11 +178,11 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         const float* wk = wt + (int64_t)k * COUT * CIN;
         for (int tt = tid; tt < COUT * KB * 8; tt += CT_THREADS) {
           int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
-          float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), hi, lo;
-          tc::split_tf32(w4, hi, lo);
+          float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), whi, wlo;
+          tc::split_tf32(w4, whi, wlo);
           uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
-          *(float4*)(bh + off) = hi;
-          *(float4*)(bl + off) = lo;
+          *(float4*)(bh + off) = whi;
+          *(float4*)(bl + off) = wlo;
         }
       }
       uint8_t* ah = a_base + stage * Cfg::A_STAGE;
@@ -184,10 +191,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       if (src_a >= 0) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-          float4 hi, lo;
-          tc::split_tf32(v[i], hi, lo);
-          *(float4*)(ah + soff[i]) = hi;
-          *(float4*)(al + soff[i]) = lo;
+          *(float4*)(ah + soff[i]) = hi[i];
+          *(float4*)(al + soff[i]) = lo[i];
         }
         dirty |= bit;
       } else if (dirty & bit) {
@@ -200,7 +205,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         dirty &= ~bit;
       }
       tc::fence_proxy_async();                // my generic-proxy stores -> visible to the tensor core
-      tc::mbar_arrive(&full_bar[stage]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);   // 16 arrivals instead of 512 serialised ones
 #pragma unroll
       for (int i = 0; i < NI; ++i) v[i] = v_next[i];
       src_a = src_b;

@@ -57,13 +57,23 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
   const int64_t tiles = (n + DT_ROWS - 1) / DT_ROWS;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * DT_ROWS;
-    // ---- stage A (hi/lo) ----
-#pragma unroll 4
-    for (int t = tid; t < DT_ROWS * KB * 8; t += DT_THREADS) {
+    // ---- stage A (hi/lo): all loads of the tile first (memory-level parallelism), then the
+    //      split + swizzled stores ----
+    constexpr int NLD = DT_ROWS * KB * 8 / DT_THREADS;
+    float4 ld[NLD];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      int t = tid + i * DT_THREADS;
       int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-      if (row0 + row < n) v = lk_ldg_stream((const float4*)(x + (row0 + row) * C + kb * 32 + chunk * 4));
-      tc::split_tf32(v, hi, lo);
+      ld[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + row < n) ld[i] = lk_ldg_stream((const float4*)(x + (row0 + row) * C + kb * 32 + chunk * 4));
+    }
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      int t = tid + i * DT_THREADS;
+      int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
+      float4 hi, lo;
+      tc::split_tf32(ld[i], hi, lo);
       uint32_t off = kb * A_BLK + tc::sw128_offset(row, chunk);
       *(float4*)(a_hi + off) = hi;
       *(float4*)(a_lo + off) = lo;

@@ -277,19 +277,44 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
   const float inv_c = 1.0f / (float)g.c;
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t steps = (n + G - 1) / G;
-  for (int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; step < steps;
-       step += warps_total) {
-    int64_t r = step * G + grp;
-    bool ok = r < n;                     // NB: whole groups go inactive together; shuffles stay
-    int b = ok ? __ldg(blk + r) : -1;    // inside a group, so no divergence hazard
-    int4 cc = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
+  // software pipeline: block index, coordinate and local_mix row of the NEXT step are loaded
+  // while the current step computes (the mean-row loads depend on the block index, so without
+  // the prefetch every step pays two dependent memory latencies back to back)
+  int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int b_n = -1;
+  int4 cc_n = make_int4(0, 0, 0, 0);
+  float4 lv_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int64_t st) {
+    int64_t r = st * G + grp;
+    bool ok = st < steps && r < n;
+    b_n = ok ? __ldg(blk + r) : -1;
+    cc_n = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
+    lv_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NORM && ok && active) lv_n = lk_ldg_stream((const float4*)(local + r * g.c + ch));
+  };
+  prefetch(step);
+  for (; step < steps; step += warps_total) {
+    const int64_t r = step * G + grp;
+    const bool ok = r < n;               // NB: whole groups go inactive together; shuffles stay
+    const int b = b_n;                   // inside a group, so no divergence hazard
+    const int4 cc = cc_n;
+    const float4 lv = lv_n;
+    float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0, m2 = m0, f = m0;
+    const bool live = ok && active && b >= 0;
+    if (live) {                          // issue the dependent loads first ...
+      const float* mrow = mean + (int64_t)b * kc + ch;
+      m0 = __ldg((const float4*)mrow);
+      m1 = __ldg((const float4*)(mrow + g.c));
+      if (COSX) {
+        m2 = __ldg((const float4*)(mrow + 2 * g.c));
+        f = lk_ldg_stream((const float4*)(fin + r * g.c + ch));
+      }
+    }
+    prefetch(step + warps_total);        // ... then the next step's independent ones
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     float p[4], sn[4], cs[4];
     lane_trig<LPR, SH, COSX>(g, lg, cc, lane, p, sn, cs);   // all lanes: full-mask shuffles
-    if (ok && active && b >= 0) {
-      const float* mrow = mean + (int64_t)b * kc + ch;
-      float4 m0 = __ldg((const float4*)mrow);
-      float4 m1 = __ldg((const float4*)(mrow + g.c));
+    if (live) {
       const float a0[4] = {m0.x, m0.y, m0.z, m0.w};
       const float a1[4] = {m1.x, m1.y, m1.z, m1.w};
       if (OP == LK_OP_SIN) {             // planes [sin, cos]: F[:, :C]*cos - F[:, C:]*sin
@@ -300,18 +325,12 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
         for (int e = 0; e < 4; ++e) v[e] = a0[e] * cs[e] + a1[e] * sn[e];
       }
       if (COSX) {                        // + (mean(F*pos) - F*pos), linkencoder.py:176
-        float4 m2 = __ldg((const float4*)(mrow + 2 * g.c));
-        float4 f = lk_ldg_stream((const float4*)(fin + r * g.c + ch));
         v[0] += m2.x - f.x * p[0]; v[1] += m2.y - f.y * p[1];
         v[2] += m2.z - f.z * p[2]; v[3] += m2.w - f.w * p[3];
       }
     }
     if (NORM) {
-      float l[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ok && active) {
-        float4 lv = lk_ldg_stream((const float4*)(local + r * g.c + ch));
-        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
-      }
+      float l[4] = {lv.x, lv.y, lv.z, lv.w};
       group_layernorm<LPR>(v, active, inv_c, g1, b1, ch);
       group_layernorm<LPR>(l, active, inv_c, g2, b2, ch);
 #pragma unroll
