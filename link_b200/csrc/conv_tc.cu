@@ -3,21 +3,25 @@
 // Weight-stationary, TMEM-resident formulation (replaces the reference's host loop of
 // gather -> cuBLAS mm -> scatter per offset, convolution_cuda.cu:101-164):
 //
-//   * a persistent CTA owns up to T = 512/C_out consecutive 128-row output tiles; their fp32
-//     accumulators [128 x C_out] live in TMEM for the whole kernel (all 512 columns = 256 KB/SM),
-//     so partial sums never touch registers, shared memory or HBM;
-//   * outer loop over the K kernel offsets: W[k] (tf32 hi/lo planes, K-major SWIZZLE_128B) is
-//     staged in shared memory ONCE per offset and reused by all T tiles of the CTA;
-//   * inner loop over the tiles: the 128 input rows nbr[k, tile rows] are gathered with coalesced
-//     128-bit loads (missing neighbours -> zero rows), split into tf32 hi/lo planes and written in
-//     the canonical K-major SWIZZLE_128B layout; one thread issues 3*C_in/8 tcgen05.mma
-//     (M=128, N=C_out, K=8) accumulating into that tile's TMEM columns; tcgen05.commit -> mbarrier
-//     releases the operand stage;
-//   * warp-specialised: 8 producer warps (gather/split/store, then the epilogue) and 1 MMA-issuer
-//     warp talk only through full/empty mbarriers (no __syncthreads in the main loop); two operand
-//     stages in shared memory plus a register stage (rows of step j+1 and indices of step j+2
-//     are in flight while step j is being written);
-//   * epilogue: tcgen05.ld 32x32b (thread = output row) -> + bias -> one streaming store per row.
+//   * a persistent CTA owns up to T = 256/C_out consecutive 128-row output tiles; their fp32
+//     accumulators [128 x C_out] live in TMEM columns [0, 256) for the whole kernel, so partial
+//     sums never touch registers, shared memory or HBM;
+//   * the gathered A operand ALSO lives in TMEM (columns [256, 512): two stages of tf32 hi/lo
+//     planes): producers write the rows they gathered straight from registers with tcgen05.st
+//     (lane = row, column = input channel) and the MMA reads A from TMEM ("TS" form).  With A in
+//     shared memory an M=128, N=64, K=8 tf32 MMA has to fetch 4 KB of A + 2 KB of B per 32-cycle
+//     instruction (192 B/clk > the 128 B/clk shared-memory port) and the kernel was operand-fetch
+//     bound at ~45 % tensor-pipe utilisation; from TMEM only B crosses the shared-memory port;
+//   * outer loop over the K kernel offsets: W[k] (tf32 hi/lo planes, K-major SWIZZLE_128B in shared
+//     memory, double buffered) is staged ONCE per offset and reused by all T tiles of the CTA;
+//   * inner loop over the tiles: 16 producer warps gather the 128 input rows nbr[k, tile rows]
+//     (missing neighbours -> zero rows; indices prefetched two steps ahead, rows one step ahead),
+//     split them into tf32 hi/lo and tcgen05.st them; one elected lane of a 17th warp issues
+//     3*C_in/8 tcgen05.mma (M=128, N=C_out, K=8; A_lo.B_hi + A_hi.B_lo + A_hi.B_hi) into the tile's
+//     accumulator columns; tcgen05.commit -> "empty" mbarrier releases the A stage, producers
+//     signal "full" mbarriers (one arrival per warp) -- no __syncthreads in the main loop;
+//   * epilogue: tcgen05.ld 32x32b (thread = output row) -> scale/shift (folded BatchNorm / bias)
+//     -> + residual -> ReLU -> one streaming store per row.
 //
 // No atomics, no temporaries, deterministic, output written exactly once.
 #include "common.cuh"
@@ -25,19 +29,18 @@
 
 #define CT_ROWS 128
 #define CT_THREADS 512      // producer threads (16 warps); one more warp issues the MMAs
+#define CT_ACC_COLS 256     // TMEM columns [0,256): accumulators; [256,512): two A stages
 
 template <int CIN, int COUT>
 struct ConvTcCfg {
-  static constexpr int KB = CIN / 32;                       // 128-byte K-blocks per row
-  static constexpr uint32_t A_BLK = CT_ROWS * 128;          // one [128 x 32] K-block
+  static constexpr int KB = CIN / 32;                       // 128-byte K-blocks per weight row
   static constexpr uint32_t B_BLK = COUT * 128;             // one [COUT x 32] K-block
-  static constexpr uint32_t A_PLANE = KB * A_BLK;           // hi (or lo) plane of one stage
-  static constexpr uint32_t B_PLANE = KB * B_BLK;
-  static constexpr uint32_t A_STAGE = 2 * A_PLANE;          // hi + lo
-  static constexpr uint32_t B_STAGE = 2 * B_PLANE;
-  static constexpr uint32_t SMEM = 2 * A_STAGE + 2 * B_STAGE + 1024;   // + alignment slack
-  static constexpr int MAX_TILES = 512 / COUT;
-  static constexpr int ITEMS_A = CT_ROWS * KB * 8 / CT_THREADS;        // float4 per thread per step
+  static constexpr uint32_t B_PLANE = KB * B_BLK;           // hi (or lo) plane
+  static constexpr uint32_t B_STAGE = 2 * B_PLANE;          // hi + lo
+  static constexpr uint32_t SMEM = 2 * B_STAGE + 1024;      // double-buffered W[k] + alignment slack
+  static constexpr int MAX_TILES = CT_ACC_COLS / COUT;
+  static constexpr int A_STAGE_COLS = 128;                  // hi plane at +0, lo plane at +64
+  static constexpr int CPT = CIN / 4;                       // input channels per producer thread
 };
 
 template <int CIN, int COUT>
@@ -47,13 +50,12 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     lk_conv_epilogue_t ep, float* __restrict__ out) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   constexpr int KB = Cfg::KB;
-  constexpr int NI = Cfg::ITEMS_A;
+  constexpr int CPT = Cfg::CPT;                 // 16 (CIN = 64) or 8 (CIN = 32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* const a_base = smem;                          // 2 A stages, then 2 B stages
-  uint8_t* const b_base = smem + 2 * Cfg::A_STAGE;
-  __shared__ uint64_t full_bar[2];    // operand stage written   (one arrival per producer warp)
-  __shared__ uint64_t empty_bar[2];   // operand stage consumed  (tcgen05.commit)
+  uint8_t* const b_base = smem;
+  __shared__ uint64_t full_bar[2];    // A stage written   (one arrival per producer warp)
+  __shared__ uint64_t empty_bar[2];   // A stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -61,12 +63,10 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
   const int ntiles = (int)min((int64_t)tiles_per_cta, total_tiles - tile0);
   const int total_steps = K * ntiles;            // step j = (offset k = j / ntiles, tile t = j % ntiles)
-  uint32_t ncols = 32;
-  while (ncols < (uint32_t)(tiles_per_cta * COUT)) ncols <<= 1;
 
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    tc::mbar_init(&full_bar[0], CT_THREADS / 32);      // one arrival per producer warp
+    tc::mbar_init(&full_bar[0], CT_THREADS / 32);
     tc::mbar_init(&full_bar[1], CT_THREADS / 32);
     tc::mbar_init(&empty_bar[0], 1);
     tc::mbar_init(&empty_bar[1], 1);
@@ -76,13 +76,11 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_a0 = tmem_base + CT_ACC_COLS;          // A stage s at + s * 128 columns
 
   if (warp == CT_THREADS / 32) {
     // ================= MMA issuer warp =================
     const uint32_t idesc = tc::idesc_tf32(128, COUT);
-    // descriptors of stage 0; the start-address field counts 16-byte units, so other stages,
-    // planes and k-slices are plain additions
-    const uint64_t da0 = tc::smem_desc_sw128(tc::smem_u32(a_base));
     const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(b_base));
     int k = 0, t = 0;
     for (int j = 0; j < total_steps; ++j) {
@@ -91,23 +89,19 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(t * COUT);
-        const uint64_t da_hi = da0 + (uint64_t)((stage * Cfg::A_STAGE) >> 4);
-        const uint64_t da_lo = da_hi + (uint64_t)(Cfg::A_PLANE >> 4);
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS);
+        const uint32_t a_lo = a_hi + 64;
         const uint64_t db_hi = db0 + (uint64_t)(((k & 1) * Cfg::B_STAGE) >> 4);
         const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
         uint32_t acc = k > 0 ? 1u : 0u;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            // descriptor start-address field is in 16-byte units: advance inside the swizzle atom
-            const uint64_t ao = (uint64_t)((kb * Cfg::A_BLK + ks * 32) >> 4);
-            const uint64_t bo = (uint64_t)((kb * Cfg::B_BLK + ks * 32) >> 4);
-            tc::mma_tf32(d, da_lo + ao, db_hi + bo, idesc, acc);
-            tc::mma_tf32(d, da_hi + ao, db_lo + bo, idesc, 1);
-            tc::mma_tf32(d, da_hi + ao, db_hi + bo, idesc, 1);
-            acc = 1;
-          }
+        for (int ks = 0; ks < CIN / 8; ++ks) {
+          // B descriptor start address is in 16-byte units: K-block ks/4, 32-byte slice ks%4
+          const uint64_t bo = (uint64_t)(((ks >> 2) * Cfg::B_BLK + (ks & 3) * 32) >> 4);
+          tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
+          tc::mma_tf32_ts(d, a_hi + 8 * ks, db_lo + bo, idesc, 1);
+          tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
+          acc = 1;
         }
         tc::mma_commit(&empty_bar[stage]);
       }
@@ -115,41 +109,29 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       if (++t == ntiles) { t = 0; ++k; }
     }
   } else {
-    // ================= producer warps (gather + tf32 split), later the epilogue =================
-    // Thread -> (row, quarter): TPR = CT_THREADS/128 threads share one gathered row; thread q of a
-    // row owns the 16-byte chunks {q, q + TPR, q + 2 TPR, ...} of that row, so the TPR lanes of a
-    // row read TPR*16 contiguous bytes per load instruction (full sectors) and ONE neighbour index
-    // / validity test / dirty bit per thread and step covers all of its NI chunks.
-    constexpr int TPR = CT_THREADS / CT_ROWS;              // 4
-    static_assert(NI * TPR == KB * 8, "chunks of a row must tile over its threads");
-    const int prow = tid / TPR, pq = tid % TPR;
-    uint32_t soff[NI];
-    int icol[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int cch = pq + i * TPR;                        // chunk index within the row (0 .. 8*KB)
-      const int kb = cch >> 3, chunk = cch & 7;
-      icol[i] = cch * 4;
-      soff[i] = kb * Cfg::A_BLK + tc::sw128_offset(prow, chunk);
-    }
+    // ================= producer warps (gather + tf32 split + tcgen05.st), later the epilogue ====
+    // TMEM access rule: warp w touches lanes [32 (w%4), +32).  Thread (q = w%4, lane) owns tile row
+    // 32q + lane; the 4 warps of a lane quarter split the C_in input channels into 4 slices.
+    const int q = warp & 3, cs = warp >> 2;
+    const int prow = q * 32 + lane;
+    const int col0 = cs * CPT;                                // my channel slice [col0, col0 + CPT)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int64_t row_base = tile0 * CT_ROWS;
-    // neighbour index of my row for step (k2, t2); no integer division in the steady state
     auto load_idx = [&](int k2, int t2) -> int {
       const int64_t o = row_base + (int64_t)t2 * CT_ROWS + prow;
       return (k2 < K && o < n_out) ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
     };
     auto load_rows = [&](int src, float4* v) {
       if (src >= 0) {
-        const float* rp = in + (int64_t)src * CIN;
+        const float4* rp = (const float4*)(in + (int64_t)src * CIN + col0);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) v[i] = __ldg((const float4*)(rp + icol[i]));
+        for (int i = 0; i < CPT / 4; ++i) v[i] = __ldg(rp + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPT / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 v[NI], v_next[NI];
-    // bit `stage`: my slots of that operand stage currently hold non-zero data.  ~70 % of the
-    // gathered rows are missing neighbours (zero rows): slots that are already zero are not
-    // rewritten, which halves the split + store work.
-    uint32_t dirty = 3u;                      // shared memory starts uninitialised
+    float4 v[CPT / 4], v_next[CPT / 4];
     int k = 0, t = 0;                         // step j
     int kc = 0, tc2 = 0;                      // step j + 2
     auto advance = [&](int& kk, int& tt) { if (++tt == ntiles) { tt = 0; ++kk; } };
@@ -162,14 +144,18 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       const int stage = j & 1;
       const int src_c = load_idx(kc, tc2);    // index prefetch distance 2
       load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
-      // split BEFORE waiting for the stage: after the wake-up only the stores remain on the
-      // critical path  commit(j-2) -> stores -> full(j) -> MMA(j)
-      float4 hi[NI], lo[NI];
-      if (src_a >= 0) {
+      // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on the
+      // critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
+      float hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) tc::split_tf32(v[i], hi[i], lo[i]);
+      for (int i = 0; i < CPT / 4; ++i) {
+        float4 h4, l4;
+        tc::split_tf32(v[i], h4, l4);
+        hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+        lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
       }
       if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
+      tc::fence_after_sync();
       if (t == 0) {
         // stage W[k]: every MMA of offset k-2 (last reader of this buffer) precedes step j-2's
         // commit, which the wait above has just observed
@@ -184,31 +170,22 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           *(float4*)(bh + off) = whi;
           *(float4*)(bl + off) = wlo;
         }
+        tc::fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
       }
-      uint8_t* ah = a_base + stage * Cfg::A_STAGE;
-      uint8_t* al = ah + Cfg::A_PLANE;
-      const uint32_t bit = 1u << stage;
-      if (src_a >= 0) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          *(float4*)(ah + soff[i]) = hi[i];
-          *(float4*)(al + soff[i]) = lo[i];
-        }
-        dirty |= bit;
-      } else if (dirty & bit) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          *(float4*)(ah + soff[i]) = z;
-          *(float4*)(al + soff[i]) = z;
-        }
-        dirty &= ~bit;
+      const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + lane_addr + (uint32_t)col0;
+      if (CPT == 16) {
+        tc::tmem_st16(a_hi, hi);
+        tc::tmem_st16(a_hi + 64, lo);
+      } else {
+        tc::tmem_st8(a_hi, hi);
+        tc::tmem_st8(a_hi + 64, lo);
       }
-      tc::fence_proxy_async();                // my generic-proxy stores -> visible to the tensor core
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);   // 16 arrivals instead of 512 serialised ones
+      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
 #pragma unroll
-      for (int i = 0; i < NI; ++i) v[i] = v_next[i];
+      for (int i = 0; i < CPT / 4; ++i) v[i] = v_next[i];
       src_a = src_b;
       src_b = src_c;
       advance(k, t);
@@ -219,15 +196,14 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     if (c0) tc::mbar_wait(&empty_bar[0], (uint32_t)(c0 - 1) & 1u);
     if (c1) tc::mbar_wait(&empty_bar[1], (uint32_t)(c1 - 1) & 1u);
     tc::fence_after_sync();
-    // ---- epilogue: thread = output row (TMEM lane quarter q = warp & 3), 16 columns per warp ----
+    // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
     constexpr int NSLICE = COUT / 16;
-    const int q = warp & 3, slice = warp >> 2;
-    if (slice < NSLICE) {
-      const int c_base = slice * 16;
-      for (int t = 0; t < ntiles; ++t) {
-        const int64_t o = (tile0 + t) * CT_ROWS + q * 32 + lane;
+    if (cs < NSLICE) {
+      const int c_base = cs * 16;
+      for (int tt = 0; tt < ntiles; ++tt) {
+        const int64_t o = (tile0 + tt) * CT_ROWS + prow;
         float acc[16];
-        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c_base), acc);
+        tc::tmem_ld16(tmem_base + lane_addr + (uint32_t)(tt * COUT + c_base), acc);
         if (o < n_out) {
           float* dst = out + o * COUT + c_base;
 #pragma unroll
@@ -256,7 +232,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, ncols);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
 template <int CIN, int COUT>
