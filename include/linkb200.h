@@ -130,6 +130,13 @@ int64_t lk_sort_unique_ws_bytes(int64_t n);
 int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
                    int32_t* d_inverse, int32_t* d_order, int32_t* d_seg, int32_t* d_counts,
                    int32_t* d_num, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+/* Same, plus d_sorted_rank[n] (may be NULL): rank of the key at each SORTED position, i.e.
+ * d_sorted_rank[i] == d_inverse[d_order[i]] (the block row of the i-th voxel in block order;
+ * feeds the segmented pre-aggregation, lk_link_preagg_seg_fwd). */
+int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
+                      int32_t* d_inverse, int32_t* d_order, int32_t* d_seg, int32_t* d_counts,
+                      int32_t* d_num, int32_t* d_sorted_rank, void* d_ws, int64_t ws_bytes,
+                      lk_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * LinK block -- fused replacement for the kernel generator + voxel_to_aux + aux_to_voxel
@@ -171,6 +178,16 @@ int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity, int row_f
 int lk_link_preagg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords,
                        const int32_t* d_blk /*[n] voxel -> block row*/, int64_t n,
                        const lk_kernelgen_t* gen, float* d_sums, lk_stream_t s);
+/* Pass 1, segmented form (the one the block executor uses): voxels are visited in BLOCK order
+ * through the sort permutation (d_order[i] = voxel row at sorted position i, d_sorted_rank[i] =
+ * its block row; both from lk_sort_unique_ex), so every lane group walks 16 consecutive sorted
+ * positions = 1-2 whole blocks, reduces them in registers (a warp-level segmented reduction over
+ * the variable-length voxel lists of the blocks) and issues one vector reduction per block it
+ * touches: ~8x fewer L2 atomics than the storage-order form, and a block that lies inside one
+ * lane group's span is summed in a fixed order (deterministic).  d_sums must be zeroed. */
+int lk_link_preagg_seg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords,
+                           const int32_t* d_order, const int32_t* d_sorted_rank, int64_t n,
+                           const lk_kernelgen_t* gen, float* d_sums, lk_stream_t s);
 /* Pass 2a: window mean per block: (sum over the R neighbour blocks of sums) / (sum of
  * counts).  d_mean [M, k*C].  M read from d_num (device scalar). */
 int lk_link_window_mean(const float* d_sums, const int32_t* d_counts, const int32_t* d_nbr,
@@ -207,7 +224,10 @@ typedef struct {
   const int32_t* d_conv_offsets; /* [kvol,3] kernel offsets (already scaled by the tensor stride) */
   int32_t* d_kmap;               /* caller-owned [kvol,n] kernel map of local_mix */
   int32_t build_kmap;            /* 1: build it here (hash -> table -> query) into d_kmap; 0: use it */
-  int32_t reserved0;
+  int32_t build_plan;            /* 1: run lk_conv_plan on d_kmap into the three buffers below; 0: use them */
+  int32_t* d_plan_perm;          /* caller-owned tile-skipping plan of the kernel map (lk_conv_plan), */
+  int32_t* d_plan_nbr;           /*   [n], [kvol,n], [ceil(n/128)]; all NULL = run the tensor-core    */
+  uint32_t* d_plan_mask;         /*   conv without a plan                                              */
   lk_keyspec_t keyspec;          /* block-key layout (div = block edge) */
   int32_t key_bits;
   int32_t r3;                    /* r^3 */
@@ -288,6 +308,24 @@ int lk_conv_tc_supported(int c_in, int c_out);
 int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_t* d_nbr, int64_t n_out,
                    int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
                    lk_stream_t s);
+/* Tile-skipping plan for lk_conv_tc_fwd_plan (K <= 32).  Output rows are grouped by the signs of
+ * the offsets they use (a counting sort on a <= 8-bit class derived from d_offsets int32 [K,3];
+ * with K <= 8 or d_offsets == NULL the class is the K-bit presence mask itself), so that 128-row
+ * tiles are homogeneous and (offset, tile) steps without a single pair can be skipped.
+ * Outputs: d_perm [n_out] plan position -> output row; d_nbr_p [K, n_out] the kernel map in plan
+ * order (d_nbr_p[k, i] = d_nbr[k, d_perm[i]]); d_tile_mask [ceil(n_out/128)] bit k set iff some
+ * row of the tile has a neighbour at offset k.  Results of the convolution do not depend on the
+ * plan (same per-row sums in the same order). */
+int64_t lk_conv_plan_ws_bytes(int64_t n_out);
+int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const int32_t* d_offsets /*or NULL*/,
+                 int32_t* d_perm, int32_t* d_nbr_p, uint32_t* d_tile_mask, void* d_ws,
+                 int64_t ws_bytes, lk_stream_t s);
+/* lk_conv_tc_fwd_ex on a planned kernel map: d_nbr is the plan-order map (d_nbr_p), d_perm and
+ * d_tile_mask as produced by lk_conv_plan (both NULL = identity order, no skipping). */
+int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const int32_t* d_nbr,
+                        const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
+                        int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
+                        lk_stream_t s);
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);

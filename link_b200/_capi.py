@@ -41,7 +41,8 @@ class ElkBlockArgs(C.Structure):
                 ('d_out', C.c_void_p), ('d_premix_w', C.c_void_p), ('d_premix_g', C.c_void_p),
                 ('d_premix_b', C.c_void_p), ('premix_eps', C.c_float), ('kvol', C.c_int32),
                 ('d_conv_w', C.c_void_p), ('d_conv_wt', C.c_void_p), ('d_conv_offsets', C.c_void_p),
-                ('d_kmap', C.c_void_p), ('build_kmap', C.c_int32), ('reserved0', C.c_int32),
+                ('d_kmap', C.c_void_p), ('build_kmap', C.c_int32), ('build_plan', C.c_int32),
+                ('d_plan_perm', C.c_void_p), ('d_plan_nbr', C.c_void_p), ('d_plan_mask', C.c_void_p),
                 ('keyspec', KeySpec), ('key_bits', C.c_int32), ('r3', C.c_int32),
                 ('d_block_offsets', C.c_void_p), ('gen', KernelGen),
                 ('d_g1', C.c_void_p), ('d_b1', C.c_void_p), ('d_g2', C.c_void_p), ('d_b2', C.c_void_p),
@@ -71,9 +72,11 @@ PROTOTYPES = {
     'lk_unpack_keys': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, vp]),
     'lk_sort_unique_ws_bytes': (i64, [i64]),
     'lk_sort_unique': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    'lk_sort_unique_ex': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'lk_block_neighbors': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, i32, vp, vp]),
     'lk_zero_rows': (i32, [vp, vp, i64, i32, vp]),
     'lk_link_preagg_fwd': (i32, [vp, vp, vp, i64, C.POINTER(KernelGen), vp, vp]),
+    'lk_link_preagg_seg_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), vp, vp]),
     'lk_link_window_mean': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
@@ -88,6 +91,9 @@ PROTOTYPES = {
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
+    'lk_conv_plan_ws_bytes': (i64, [i64]),
+    'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, i64, vp]),
+    'lk_conv_tc_fwd_plan': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),

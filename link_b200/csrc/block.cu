@@ -5,7 +5,7 @@
 //   pre_mix  = LN(x W^T)                                  (tcgen05 / FFMA)
 //   local    = SubM 3^3 conv(x)                           (tcgen05 / FFMA)
 //   block keys -> radix sort/unique -> neighbour-block table
-//   zero sums -> pre-aggregation -> window mean -> apply (+LN, +LN(local), add, ReLU)
+//   zero sums -> segmented pre-aggregation (block order) -> window mean -> apply (+LN, +LN(local), add, ReLU)
 //
 // so the host pays one FFI crossing and one workspace allocation per block instead of ~27
 // Python-level launches (the reference: ~150-180 launches, >= 4 device syncs, 4 cudaMalloc/Free).
@@ -15,22 +15,26 @@
 static inline int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct BlockWs {
-  int64_t hash, table, kmap, fin, local, keys, uniq, inverse, counts, num, nbr, sums, mean, sort_ws, total;
+  int64_t hash, table, kmap, plan_ws, fin, local, keys, uniq, inverse, order, srank, counts, num, nbr, sums, mean, sort_ws, total;
   int64_t table_cap;
 };
 
-static BlockWs plan(int64_t n, int c, int kc, int r3, int kvol, bool need_kmap) {
+static BlockWs plan(int64_t n, int c, int kc, int r3, int kvol, bool need_kmap, bool need_plan = true) {
   BlockWs w;
   int64_t o = 0;
+  const int64_t cp_bytes = need_plan ? al256(lk_conv_plan_ws_bytes(n)) : 0;
   w.table_cap = lk_table_capacity(n);
   w.hash = o;    o += need_kmap ? al256(n * 8) : 0;
   w.table = o;   o += need_kmap ? al256(w.table_cap * 16) : 0;
   w.kmap = o;
+  w.plan_ws = o; o += cp_bytes;
   w.fin = o;     o += al256(n * c * 4);
   w.local = o;   o += al256(n * c * 4);
   w.keys = o;    o += al256(n * 8);
   w.uniq = o;    o += al256(n * 8);
   w.inverse = o; o += al256(n * 4);
+  w.order = o;   o += al256(n * 4);
+  w.srank = o;   o += al256(n * 4);
   w.counts = o;  o += al256(n * 4);
   w.num = o;     o += 256;
   w.nbr = o;     o += al256(n * (int64_t)r3 * 4);
@@ -83,9 +87,17 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   else
     LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, s));
   // local_mix
-  if (a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt)
-    LK_TRY(lk_conv_tc_fwd(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, nullptr, local, s));
-  else {
+  if (a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt) {
+    if (a->d_plan_perm && a->d_plan_nbr && a->d_plan_mask && a->kvol <= 32) {
+      if (a->build_plan)
+        LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_nbr,
+                            a->d_plan_mask, ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
+      LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, a->d_plan_nbr, a->d_plan_perm,
+                                 a->d_plan_mask, n, a->kvol, c, c, nullptr, local, s));
+    } else {
+      LK_TRY(lk_conv_tc_fwd(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, nullptr, local, s));
+    }
+  } else {
     LK_REQUIRE(a->d_conv_w, "lk_elk_block_fwd: FFMA conv needs the untransposed weights");
     LK_TRY(lk_conv_fwd(a->d_feats, a->d_conv_w, kmap, n, a->kvol, c, c, nullptr, local, s));
   }
@@ -97,14 +109,16 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   int32_t* num = (int32_t*)(ws + w.num);
   int32_t* nbr = (int32_t*)(ws + w.nbr);
   LK_TRY(lk_pack_keys(a->d_coords, n, &a->keyspec, keys, s));
-  LK_TRY(lk_sort_unique(keys, n, a->key_bits, uniq, inverse, nullptr, nullptr, counts, num,
-                        ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
+  int32_t* order = (int32_t*)(ws + w.order);
+  int32_t* srank = (int32_t*)(ws + w.srank);
+  LK_TRY(lk_sort_unique_ex(keys, n, a->key_bits, uniq, inverse, order, nullptr, counts, num, srank,
+                           ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
   LK_TRY(lk_block_neighbors(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, s));
   // linear-kernel aggregation
   float* sums = (float*)(ws + w.sums);
   float* mean = (float*)(ws + w.mean);
   LK_TRY(lk_zero_rows(sums, num, n, kc, s));
-  LK_TRY(lk_link_preagg_fwd(fin, a->d_coords, inverse, n, &a->gen, sums, s));
+  LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, s));
   LK_TRY(lk_link_window_mean(sums, counts, nbr, num, n, a->r3, kc, mean, s));
   LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,
                            a->d_g2, a->d_b2, a->d_out, s));

@@ -1,0 +1,156 @@
+// Tile-skipping plan for the tensor-core sparse convolution (conv_tc.cu).
+//
+// The tcgen05 kernel works on 128-row output tiles and one kernel offset at a time; a (tile, offset)
+// step whose 128 rows have NO neighbour at that offset is pure zero work.  On a LiDAR scan only
+// ~5.5 of the 27 offsets of a 3^3 submanifold kernel are present per voxel, and in storage order
+// half of all (tile, offset) steps are empty.  Grouping output rows by the SIGNS of the offsets
+// they use (is there any neighbour with dx < 0, dx > 0, dy < 0, ... : a 6-bit class; ground voxels
+// have no dz != 0 neighbours, walls no dx or dy ones, ...) makes tiles homogeneous: 27 % of the
+// dense steps remain, and the rows of an active step are 75 % populated (measured on the bench
+// scan).  The plan is a counting sort of the output rows by that class:
+//
+//   class kernel   : per row, the K-bit mask of present offsets and its class; class histogram
+//   scatter kernel : perm[position] = row      (class-major order, order inside a class arbitrary)
+//   tile kernel    : nbr_p[k, i] = nbr[k, perm[i]]  (kernel map in plan order, coalesced for the
+//                    conv) and tile_mask[t] = OR of the masks of the tile's rows
+//
+// Output values do not depend on the plan: every output row is still the same sum over k in the
+// same order, only the tile it is computed in changes.  The reference has no counterpart (its
+// gather -> GEMM -> scatter loop touches only existing pairs but pays 3 launches per offset and a
+// scatter with atomics, convolution_cuda.cu:101-164).
+#include "common.cuh"
+
+#define CP_TILE 128
+
+static inline int64_t cp_al(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+extern "C" int64_t lk_conv_plan_ws_bytes(int64_t n_out) {
+  return cp_al(n_out * 4) + cp_al(n_out) + 2 * cp_al(256 * 4);
+}
+
+__global__ void __launch_bounds__(256) plan_class_kernel(const int* __restrict__ nbr, int64_t n_out,
+                                                         int K, const int* __restrict__ offsets,
+                                                         unsigned* __restrict__ rowmask,
+                                                         unsigned char* __restrict__ cls,
+                                                         unsigned* __restrict__ hist) {
+  __shared__ unsigned h[256];
+  __shared__ unsigned code[32];
+  h[threadIdx.x] = 0;
+  if (threadIdx.x < 32) {
+    unsigned c = 0;
+    if ((int)threadIdx.x < K && offsets) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        int d = offsets[3 * threadIdx.x + a];
+        if (d < 0) c |= 1u << (2 * a);
+        if (d > 0) c |= 1u << (2 * a + 1);
+      }
+    }
+    code[threadIdx.x] = c;
+  }
+  __syncthreads();
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_out;
+       o += (int64_t)gridDim.x * blockDim.x) {
+    unsigned m = 0, c = 0;
+    for (int k = 0; k < K; ++k) {
+      if (__ldg(nbr + (int64_t)k * n_out + o) >= 0) { m |= 1u << k; c |= code[k]; }
+    }
+    if (K <= 8 || !offsets) c = m & 255u;       // small kernels: the mask itself is the class
+    rowmask[o] = m;
+    cls[o] = (unsigned char)c;
+    atomicAdd(&h[c], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) plan_scatter_kernel(const unsigned char* __restrict__ cls,
+                                                           int64_t n_out,
+                                                           const unsigned* __restrict__ hist,
+                                                           unsigned* __restrict__ cursor,
+                                                           int* __restrict__ perm) {
+  __shared__ unsigned base[256];
+  __shared__ unsigned wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // exclusive scan of the 256 class counts
+  unsigned v = hist[tid], incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  unsigned wb = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) wb += (w < warp) ? wsum[w] : 0u;
+  base[tid] = wb + incl - v;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (n_out + stride - 1) / stride;
+  for (int64_t it = 0; it < rounds; ++it) {       // uniform trip count: match_any needs the full warp
+    const int64_t o = it * stride + blockIdx.x * (int64_t)blockDim.x + tid;
+    const bool ok = o < n_out;
+    const unsigned c = ok ? cls[o] : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(peers) - 1;
+    unsigned first = 0;
+    if (lane == leader && ok) first = atomicAdd(&cursor[c], (unsigned)__popc(peers));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (ok) perm[base[c] + first + __popc(peers & ((1u << lane) - 1u))] = (int)o;
+  }
+}
+
+__global__ void __launch_bounds__(CP_TILE) plan_tiles_kernel(const int* __restrict__ nbr, int64_t n_out,
+                                                             int K, const int* __restrict__ perm,
+                                                             const unsigned* __restrict__ rowmask,
+                                                             int* __restrict__ nbr_p,
+                                                             unsigned* __restrict__ tile_mask) {
+  __shared__ unsigned wm[CP_TILE / 32];
+  const int64_t i = (int64_t)blockIdx.x * CP_TILE + threadIdx.x;
+  const int row = i < n_out ? perm[i] : -1;
+  unsigned m = row >= 0 ? rowmask[row] : 0u;
+  unsigned wmask = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = wmask;
+  if (row >= 0) {
+    for (int k = 0; k < K; ++k)
+      nbr_p[(int64_t)k * n_out + i] = (m >> k) & 1u ? __ldg(nbr + (int64_t)k * n_out + row) : -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+#pragma unroll
+    for (int w = 0; w < CP_TILE / 32; ++w) t |= wm[w];
+    tile_mask[blockIdx.x] = t;
+  }
+}
+
+extern "C" int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const int32_t* d_offsets,
+                            int32_t* d_perm, int32_t* d_nbr_p, uint32_t* d_tile_mask, void* d_ws,
+                            int64_t ws_bytes, lk_stream_t s) {
+  LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32, "lk_conv_plan: needs 1 <= K <= 32");
+  if (n_out == 0) return LK_OK;
+  LK_REQUIRE(d_nbr && d_perm && d_nbr_p && d_tile_mask && d_ws, "lk_conv_plan: null pointer");
+  if (ws_bytes < lk_conv_plan_ws_bytes(n_out)) {
+    lk_set_error("lk_conv_plan: workspace %lld < %lld bytes", (long long)ws_bytes,
+                 (long long)lk_conv_plan_ws_bytes(n_out));
+    return LK_ENOSPC;
+  }
+  cudaStream_t st = (cudaStream_t)s;
+  char* p = (char*)d_ws;
+  unsigned* rowmask = (unsigned*)p; p += cp_al(n_out * 4);
+  unsigned char* cls = (unsigned char*)p; p += cp_al(n_out);
+  unsigned* hist = (unsigned*)p; p += cp_al(256 * 4);
+  unsigned* cursor = (unsigned*)p;
+  LK_CUDA(cudaMemsetAsync(hist, 0, 2 * cp_al(256 * 4), st));
+  lk_count_launch();
+  const int grid = lk_grid(n_out, 256, 4);
+  plan_class_kernel<<<grid, 256, 0, st>>>(d_nbr, n_out, k, d_offsets, rowmask, cls, hist);
+  LK_LAUNCHED();
+  plan_scatter_kernel<<<grid, 256, 0, st>>>(cls, n_out, hist, cursor, d_perm);
+  LK_LAUNCHED();
+  const int tiles = (int)((n_out + CP_TILE - 1) / CP_TILE);
+  plan_tiles_kernel<<<tiles, CP_TILE, 0, st>>>(d_nbr, n_out, k, d_perm, rowmask, d_nbr_p, d_tile_mask);
+  LK_LAUNCHED();
+  return LK_OK;
+}

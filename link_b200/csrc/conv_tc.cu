@@ -3,9 +3,13 @@
 // Weight-stationary, TMEM-resident formulation (replaces the reference's host loop of
 // gather -> cuBLAS mm -> scatter per offset, convolution_cuda.cu:101-164):
 //
-//   * a persistent CTA owns up to T = 256/C_out consecutive 128-row output tiles; their fp32
-//     accumulators [128 x C_out] live in TMEM columns [0, 256) for the whole kernel, so partial
-//     sums never touch registers, shared memory or HBM;
+//   * one persistent CTA per SM works in rounds of up to T = 256/C_out 128-row output tiles (tile
+//     slots interleaved over the CTAs); their fp32 accumulators [128 x C_out] live in TMEM columns
+//     [0, 256) for the whole round, so partial sums never touch registers, shared memory or HBM;
+//   * (offset, tile) steps in which no row of the tile has a neighbour are skipped altogether:
+//     lk_conv_plan (conv_plan.cu) orders the output rows so that tiles are homogeneous in the
+//     offsets they use and hands the kernel one offset mask per tile -- on LiDAR scans ~27 % of
+//     the dense steps remain;
 //   * the gathered A operand ALSO lives in TMEM (columns [256, 512): two stages of tf32 hi/lo
 //     planes): producers write the rows they gathered straight from registers with tcgen05.st
 //     (lane = row, column = input channel) and the MMA reads A from TMEM ("TS" form).  With A in
@@ -46,23 +50,28 @@ struct ConvTcCfg {
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wt /*[K][COUT][CIN]*/,
-    const int* __restrict__ nbr, int64_t n_out, int K, int tiles_per_cta,
-    lk_conv_epilogue_t ep, float* __restrict__ out) {
+    const int* __restrict__ nbr /*[K][n_out], in plan order when perm != NULL*/,
+    const int* __restrict__ perm /*[n_out] plan position -> output row, or NULL = identity*/,
+    const unsigned* __restrict__ tile_mask /*[tiles] offsets present in each tile, or NULL = all*/,
+    int64_t n_out, int K, lk_conv_epilogue_t ep, float* __restrict__ out) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   constexpr int KB = Cfg::KB;
   constexpr int CPT = Cfg::CPT;                 // 16 (CIN = 64) or 8 (CIN = 32)
+  constexpr int MAXT = Cfg::MAX_TILES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const b_base = smem;
   __shared__ uint64_t full_bar[2];    // A stage written   (one arrival per producer warp)
   __shared__ uint64_t empty_bar[2];   // A stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint16_t steps_s[32 * MAXT];   // active (offset, tile slot) steps of the round: k << 4 | t
+  __shared__ uint32_t tmask_s[MAXT];
+  __shared__ int warp_cnt_s[8];
+  __shared__ int nsteps_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t total_tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
-  const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
-  const int ntiles = (int)min((int64_t)tiles_per_cta, total_tiles - tile0);
-  const int total_steps = K * ntiles;            // step j = (offset k = j / ntiles, tile t = j % ntiles)
+  const uint32_t kmask = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -78,157 +87,212 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_a0 = tmem_base + CT_ACC_COLS;          // A stage s at + s * 128 columns
 
-  if (warp == CT_THREADS / 32) {
-    // ================= MMA issuer warp =================
-    const uint32_t idesc = tc::idesc_tf32(128, COUT);
-    const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(b_base));
-    int k = 0, t = 0;
-    for (int j = 0; j < total_steps; ++j) {
-      const int stage = j & 1;
-      tc::mbar_wait(&full_bar[stage], (uint32_t)(j >> 1) & 1u);
-      tc::fence_after_sync();
-      if (tc::elect_one()) {
-        const uint32_t d = tmem_base + (uint32_t)(t * COUT);
-        const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS);
-        const uint32_t a_lo = a_hi + 64;
-        const uint64_t db_hi = db0 + (uint64_t)(((k & 1) * Cfg::B_STAGE) >> 4);
-        const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
-        uint32_t acc = k > 0 ? 1u : 0u;
-#pragma unroll
-        for (int ks = 0; ks < CIN / 8; ++ks) {
-          // B descriptor start address is in 16-byte units: K-block ks/4, 32-byte slice ks%4
-          const uint64_t bo = (uint64_t)(((ks >> 2) * Cfg::B_BLK + (ks & 3) * 32) >> 4);
-          tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
-          tc::mma_tf32_ts(d, a_hi + 8 * ks, db_lo + bo, idesc, 1);
-          tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
-          acc = 1;
-        }
-        tc::mma_commit(&empty_bar[stage]);
-      }
+  // Persistent CTA: round r owns the tile slots t < MAXT with tile = blockIdx.x + (r MAXT + t) gridDim.x
+  // (interleaved, so the heavy classes at the end of the plan order spread over all CTAs).
+  int jbase = 0;      // steps issued in earlier rounds: A-stage index and mbarrier phase continue
+  int wcount = 0;     // W[k] stagings so far: weight double-buffer index continues
+  for (int round = 0;; ++round) {
+    const int64_t first_tile = (int64_t)blockIdx.x + (int64_t)round * MAXT * gridDim.x;
+    if (first_tile >= total_tiles) break;
+    int ntiles = (int)((total_tiles - first_tile + gridDim.x - 1) / gridDim.x);
+    if (ntiles > MAXT) ntiles = MAXT;
+    // ---- active step list of the round, k-major (W[k] is staged once per offset and round) ----
+    if (tid < MAXT)
+      tmask_s[tid] = tid < ntiles ? (tile_mask ? tile_mask[first_tile + (int64_t)tid * gridDim.x] & kmask : kmask) : 0u;
+    __syncthreads();
+    if (tid < 256) {
+      const int kk = tid / MAXT, tt = tid % MAXT;
+      const bool on = kk < K && ((tmask_s[tt] >> kk) & 1u);
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) warp_cnt_s[warp] = __popc(bal);
       __syncwarp();
-      if (++t == ntiles) { t = 0; ++k; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 list-building warps only
+      int pos = __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+      for (int w = 0; w < 8; ++w) pos += (w < warp) ? warp_cnt_s[w] : 0;
+      if (on) steps_s[pos] = (uint16_t)((kk << 4) | tt);
+      if (tid == 255) nsteps_s = pos + (on ? 1 : 0);
     }
-  } else {
-    // ================= producer warps (gather + tf32 split + tcgen05.st), later the epilogue ====
-    // TMEM access rule: warp w touches lanes [32 (w%4), +32).  Thread (q = w%4, lane) owns tile row
-    // 32q + lane; the 4 warps of a lane quarter split the C_in input channels into 4 slices.
-    const int q = warp & 3, cs = warp >> 2;
-    const int prow = q * 32 + lane;
-    const int col0 = cs * CPT;                                // my channel slice [col0, col0 + CPT)
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int64_t row_base = tile0 * CT_ROWS;
-    auto load_idx = [&](int k2, int t2) -> int {
-      const int64_t o = row_base + (int64_t)t2 * CT_ROWS + prow;
-      return (k2 < K && o < n_out) ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
-    };
-    auto load_rows = [&](int src, float4* v) {
-      if (src >= 0) {
-        const float4* rp = (const float4*)(in + (int64_t)src * CIN + col0);
+    __syncthreads();
+    const int nsteps = nsteps_s;
+
+    if (warp == CT_THREADS / 32) {
+      // ================= MMA issuer warp =================
+      const uint32_t idesc = tc::idesc_tf32(128, COUT);
+      const uint64_t db0 = tc::smem_desc_sw128(tc::smem_u32(b_base));
+      uint32_t touched = 0;
+      int k_prev = -1, wc = wcount;
+      for (int j = 0; j < nsteps; ++j) {
+        const int jg = jbase + j;
+        const int stage = jg & 1;
+        const int k = steps_s[j] >> 4, t = steps_s[j] & 15;
+        if (k != k_prev) { k_prev = k; ++wc; }             // wc - 1 = index of this offset's staging
+        tc::mbar_wait(&full_bar[stage], (uint32_t)(jg >> 1) & 1u);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t d = tmem_base + (uint32_t)(t * COUT);
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS);
+          const uint32_t a_lo = a_hi + 64;
+          const uint64_t db_hi = db0 + (uint64_t)((((wc - 1) & 1) * Cfg::B_STAGE) >> 4);
+          const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
+          uint32_t acc = (touched >> t) & 1u;
 #pragma unroll
-        for (int i = 0; i < CPT / 4; ++i) v[i] = __ldg(rp + i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < CPT / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    float4 v[CPT / 4], v_next[CPT / 4];
-    int k = 0, t = 0;                         // step j
-    int kc = 0, tc2 = 0;                      // step j + 2
-    auto advance = [&](int& kk, int& tt) { if (++tt == ntiles) { tt = 0; ++kk; } };
-    int src_a = load_idx(0, 0);
-    load_rows(src_a, v);
-    advance(kc, tc2);
-    int src_b = load_idx(kc, tc2);
-    advance(kc, tc2);
-    for (int j = 0; j < total_steps; ++j) {
-      const int stage = j & 1;
-      const int src_c = load_idx(kc, tc2);    // index prefetch distance 2
-      load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
-      // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on the
-      // critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
-      float hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < CPT / 4; ++i) {
-        float4 h4, l4;
-        tc::split_tf32(v[i], h4, l4);
-        hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
-        lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
-      }
-      if (j >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((j >> 1) - 1) & 1u);
-      tc::fence_after_sync();
-      if (t == 0) {
-        // stage W[k]: every MMA of offset k-2 (last reader of this buffer) precedes step j-2's
-        // commit, which the wait above has just observed
-        uint8_t* bh = b_base + (k & 1) * Cfg::B_STAGE;
-        uint8_t* bl = bh + Cfg::B_PLANE;
-        const float* wk = wt + (int64_t)k * COUT * CIN;
-        for (int tt = tid; tt < COUT * KB * 8; tt += CT_THREADS) {
-          int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
-          float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), whi, wlo;
-          tc::split_tf32(w4, whi, wlo);
-          uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
-          *(float4*)(bh + off) = whi;
-          *(float4*)(bl + off) = wlo;
+          for (int ks = 0; ks < CIN / 8; ++ks) {
+            // B descriptor start address is in 16-byte units: K-block ks/4, 32-byte slice ks%4
+            const uint64_t bo = (uint64_t)(((ks >> 2) * Cfg::B_BLK + (ks & 3) * 32) >> 4);
+            tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
+            tc::mma_tf32_ts(d, a_hi + 8 * ks, db_lo + bo, idesc, 1);
+            tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
+            acc = 1;
+          }
+          tc::mma_commit(&empty_bar[stage]);
         }
-        tc::fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        touched |= 1u << t;
       }
-      const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + lane_addr + (uint32_t)col0;
-      if (CPT == 16) {
-        tc::tmem_st16(a_hi, hi);
-        tc::tmem_st16(a_hi + 64, lo);
-      } else {
-        tc::tmem_st8(a_hi, hi);
-        tc::tmem_st8(a_hi + 64, lo);
+    } else {
+      // ================= producer warps (gather + tf32 split + tcgen05.st), later the epilogue ====
+      // TMEM access rule: warp w touches lanes [32 (w%4), +32).  Thread (q = w%4, lane) owns tile row
+      // 32q + lane; the 4 warps of a lane quarter split the C_in input channels into 4 slices.
+      const int q = warp & 3, cs = warp >> 2;
+      const int prow = q * 32 + lane;
+      const int col0 = cs * CPT;                                // my channel slice [col0, col0 + CPT)
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      auto load_idx = [&](int jj) -> int {
+        if (jj >= nsteps) return -1;
+        const int k2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
+        const int64_t o = (first_tile + (int64_t)t2 * gridDim.x) * CT_ROWS + prow;
+        return o < n_out ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
+      };
+      auto load_rows = [&](int src, float4* v) {
+        if (src >= 0) {
+          const float4* rp = (const float4*)(in + (int64_t)src * CIN + col0);
+#pragma unroll
+          for (int i = 0; i < CPT / 4; ++i) v[i] = __ldg(rp + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 v[CPT / 4], v_next[CPT / 4];
+      int src_a = load_idx(0);
+      load_rows(src_a, v);
+      int src_b = load_idx(1);
+      int k_prev = -1, wc = wcount;
+      for (int j = 0; j < nsteps; ++j) {
+        const int jg = jbase + j;
+        const int stage = jg & 1;
+        const int k = steps_s[j] >> 4;
+        const int src_c = load_idx(j + 2);      // index prefetch distance 2
+        load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
+        // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on the
+        // critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < CPT / 4; ++i) {
+          float4 h4, l4;
+          tc::split_tf32(v[i], h4, l4);
+          hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+          lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+        }
+        if (jg >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((jg >> 1) - 1) & 1u);
+        tc::fence_after_sync();
+        if (k != k_prev) {
+          // stage W[k] into buffer (stagings so far) & 1.  Its last readers are the MMAs of the
+          // offset staged two stagings ago; the offset staged in between has at least one step, so
+          // they all precede step jg-2's commit, which the wait above has just observed (a round
+          // boundary drains every MMA).
+          k_prev = k;
+          uint8_t* bh = b_base + (wc & 1) * Cfg::B_STAGE;
+          uint8_t* bl = bh + Cfg::B_PLANE;
+          ++wc;
+          const float* wk = wt + (int64_t)k * COUT * CIN;
+          for (int tt = tid; tt < COUT * KB * 8; tt += CT_THREADS) {
+            int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
+            float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), whi, wlo;
+            tc::split_tf32(w4, whi, wlo);
+            uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
+            *(float4*)(bh + off) = whi;
+            *(float4*)(bl + off) = wlo;
+          }
+          tc::fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
+        }
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + lane_addr + (uint32_t)col0;
+        if (CPT == 16) {
+          tc::tmem_st16(a_hi, hi);
+          tc::tmem_st16(a_hi + 64, lo);
+        } else {
+          tc::tmem_st8(a_hi, hi);
+          tc::tmem_st8(a_hi + 64, lo);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+#pragma unroll
+        for (int i = 0; i < CPT / 4; ++i) v[i] = v_next[i];
+        src_a = src_b;
+        src_b = src_c;
       }
-      tc::tmem_st_wait();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+      // ---- drain: the last commit on each stage ----
+      const int gtot = jbase + nsteps;
+      const int c0 = (gtot + 1) >> 1, c1 = gtot >> 1;
+      if (c0) tc::mbar_wait(&empty_bar[0], (uint32_t)(c0 - 1) & 1u);
+      if (c1) tc::mbar_wait(&empty_bar[1], (uint32_t)(c1 - 1) & 1u);
+      tc::fence_after_sync();
+      // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
+      constexpr int NSLICE = COUT / 16;
+      if (cs < NSLICE) {
+        const int c_base = cs * 16;
+        for (int tt = 0; tt < ntiles; ++tt) {
+          const int64_t pos = (first_tile + (int64_t)tt * gridDim.x) * CT_ROWS + prow;
+          float acc[16];
+          if (tmask_s[tt]) {
+            tc::tmem_ld16(tmem_base + lane_addr + (uint32_t)(tt * COUT + c_base), acc);
+          } else {                              // tile without a single pair: the sum is empty
 #pragma unroll
-      for (int i = 0; i < CPT / 4; ++i) v[i] = v_next[i];
-      src_a = src_b;
-      src_b = src_c;
-      advance(k, t);
-      advance(kc, tc2);
-    }
-    // ---- drain: the last commit on each stage ----
-    const int c0 = (total_steps + 1) >> 1, c1 = total_steps >> 1;
-    if (c0) tc::mbar_wait(&empty_bar[0], (uint32_t)(c0 - 1) & 1u);
-    if (c1) tc::mbar_wait(&empty_bar[1], (uint32_t)(c1 - 1) & 1u);
-    tc::fence_after_sync();
-    // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
-    constexpr int NSLICE = COUT / 16;
-    if (cs < NSLICE) {
-      const int c_base = cs * 16;
-      for (int tt = 0; tt < ntiles; ++tt) {
-        const int64_t o = (tile0 + tt) * CT_ROWS + prow;
-        float acc[16];
-        tc::tmem_ld16(tmem_base + lane_addr + (uint32_t)(tt * COUT + c_base), acc);
-        if (o < n_out) {
-          float* dst = out + o * COUT + c_base;
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+          }
+          if (pos < n_out) {
+            const int64_t o = perm ? (int64_t)__ldg(perm + pos) : pos;
+            float* dst = out + o * COUT + c_base;
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            float4 y = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
-            if (ep.d_scale) {
-              float4 sc = __ldg((const float4*)(ep.d_scale + c_base + e));
-              y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+            for (int e = 0; e < 16; e += 4) {
+              float4 y = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+              if (ep.d_scale) {
+                float4 sc = __ldg((const float4*)(ep.d_scale + c_base + e));
+                y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+              }
+              if (ep.d_shift) {
+                float4 sh = __ldg((const float4*)(ep.d_shift + c_base + e));
+                y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
+              }
+              if (ep.d_residual) {
+                float4 rr = lk_ldg_stream((const float4*)(ep.d_residual + o * COUT + c_base + e));
+                y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+              }
+              if (ep.relu) {
+                y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+              }
+              lk_stg_stream((float4*)(dst + e), y);
             }
-            if (ep.d_shift) {
-              float4 sh = __ldg((const float4*)(ep.d_shift + c_base + e));
-              y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
-            }
-            if (ep.d_residual) {
-              float4 rr = lk_ldg_stream((const float4*)(ep.d_residual + o * COUT + c_base + e));
-              y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
-            }
-            if (ep.relu) {
-              y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-            }
-            lk_stg_stream((float4*)(dst + e), y);
           }
         }
       }
     }
+    // round boundary: every MMA has completed (drain) and every accumulator has been read before
+    // the next round's first MMA overwrites it
+    {
+      int kp = -1;
+      for (int j = 0; j < nsteps; ++j) {        // uniform bookkeeping for all roles
+        const int k = steps_s[j] >> 4;
+        if (k != kp) { kp = k; ++wcount; }
+      }
+    }
+    jbase += nsteps;
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -236,7 +300,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 }
 
 template <int CIN, int COUT>
-static int launch_conv_tc(const float* in, const float* wt, const int* nbr, int64_t n_out, int k,
+static int launch_conv_tc(const float* in, const float* wt, const int* nbr, const int* perm,
+                          const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
   using Cfg = ConvTcCfg<CIN, COUT>;
   static bool attr_set = false;
@@ -246,11 +311,9 @@ static int launch_conv_tc(const float* in, const float* wt, const int* nbr, int6
     attr_set = true;
   }
   int64_t tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
-  int64_t tpc = (tiles + LK_SM_COUNT - 1) / LK_SM_COUNT;     // balance over the 148 SMs ...
-  if (tpc > Cfg::MAX_TILES) tpc = Cfg::MAX_TILES;            // ... within the 512 TMEM columns
-  if (tpc < 1) tpc = 1;
-  int grid = (int)((tiles + tpc - 1) / tpc);
-  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, n_out, k, (int)tpc, ep, out);
+  int grid = (int)(tiles < LK_SM_COUNT ? tiles : LK_SM_COUNT);   // persistent: one CTA per SM
+  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, perm, tile_mask,
+                                                                      n_out, k, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -263,23 +326,32 @@ extern "C" int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_
                               int64_t n_out, int k, int c_in, int c_out, const float* d_bias,
                               float* d_out, lk_stream_t s) {
   lk_conv_epilogue_t ep = {nullptr, d_bias, nullptr, 0, 0};
-  return lk_conv_tc_fwd_ex(d_in, d_wt, d_nbr, n_out, k, c_in, c_out, &ep, d_out, s);
+  return lk_conv_tc_fwd_plan(d_in, d_wt, d_nbr, nullptr, nullptr, n_out, k, c_in, c_out, &ep, d_out, s);
 }
 
 extern "C" int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wt, const int32_t* d_nbr,
                                  int64_t n_out, int k, int c_in, int c_out,
                                  const lk_conv_epilogue_t* epp, float* d_out, lk_stream_t s) {
+  return lk_conv_tc_fwd_plan(d_in, d_wt, d_nbr, nullptr, nullptr, n_out, k, c_in, c_out, epp, d_out, s);
+}
+
+extern "C" int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const int32_t* d_nbr,
+                                   const int32_t* d_perm, const uint32_t* d_tile_mask,
+                                   int64_t n_out, int k, int c_in, int c_out,
+                                   const lk_conv_epilogue_t* epp, float* d_out, lk_stream_t s) {
   lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, 0};
   if (epp) ep = *epp;
-  LK_REQUIRE(n_out >= 0 && k > 0, "lk_conv_tc_fwd: bad sizes");
+  LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32, "lk_conv_tc_fwd: bad sizes (1 <= K <= 32)");
   LK_REQUIRE(lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_fwd: channels must be 32 or 64");
+  LK_REQUIRE((d_perm == nullptr) == (d_tile_mask == nullptr),
+             "lk_conv_tc_fwd: perm and tile_mask come together (lk_conv_plan)");
   if (n_out == 0) return LK_OK;
   LK_REQUIRE(d_in && d_wt && d_nbr && d_out, "lk_conv_tc_fwd: null pointer");
   LK_REQUIRE((uintptr_t)d_in % 16 == 0 && (uintptr_t)d_wt % 16 == 0 && (uintptr_t)d_out % 16 == 0,
              "lk_conv_tc_fwd: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)s;
-  if (c_in == 32 && c_out == 32) return launch_conv_tc<32, 32>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
-  if (c_in == 32 && c_out == 64) return launch_conv_tc<32, 64>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
-  if (c_in == 64 && c_out == 32) return launch_conv_tc<64, 32>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
-  return launch_conv_tc<64, 64>(d_in, d_wt, d_nbr, n_out, k, ep, d_out, st);
+  if (c_in == 32 && c_out == 32) return launch_conv_tc<32, 32>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
+  if (c_in == 32 && c_out == 64) return launch_conv_tc<32, 64>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
+  if (c_in == 64 && c_out == 32) return launch_conv_tc<64, 32>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
+  return launch_conv_tc<64, 64>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
 }

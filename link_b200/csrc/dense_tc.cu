@@ -55,19 +55,26 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
   uint32_t parity = 0;
 
   const int64_t tiles = (n + DT_ROWS - 1) / DT_ROWS;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  // Software pipeline: the global loads of tile i+1 are issued right after tile i's MMAs and stay
+  // in flight (registers) during its MMA wait and LayerNorm epilogue, so a tile costs
+  // max(load latency, MMA + epilogue) instead of their sum.
+  constexpr int NLD = DT_ROWS * KB * 8 / DT_THREADS;
+  float4 ld[NLD];
+  auto load_tile = [&](int64_t tile) {
     const int64_t row0 = tile * DT_ROWS;
-    // ---- stage A (hi/lo): all loads of the tile first (memory-level parallelism), then the
-    //      split + swizzled stores ----
-    constexpr int NLD = DT_ROWS * KB * 8 / DT_THREADS;
-    float4 ld[NLD];
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       int t = tid + i * DT_THREADS;
       int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
       ld[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + row < n) ld[i] = lk_ldg_stream((const float4*)(x + (row0 + row) * C + kb * 32 + chunk * 4));
+      if (tile < tiles && row0 + row < n)
+        ld[i] = lk_ldg_stream((const float4*)(x + (row0 + row) * C + kb * 32 + chunk * 4));
     }
+  };
+  load_tile(blockIdx.x);
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * DT_ROWS;
+    // ---- stage A (hi/lo): split + swizzled stores of the rows loaded one iteration ago ----
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       int t = tid + i * DT_THREADS;
@@ -99,6 +106,7 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
       }
       tc::mma_commit(&mma_bar);
     }
+    load_tile(tile + gridDim.x);          // next tile's rows: in flight during the wait + epilogue
     tc::mbar_wait(&mma_bar, parity);
     parity ^= 1;
     tc::fence_after_sync();

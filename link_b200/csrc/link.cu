@@ -10,11 +10,18 @@
 // voxel and float atomics per element, multiplies back by the counts, gathers r^3 neighbours with
 // a global read-modify-write per neighbour, divides, gathers [N,kC] back to voxels and combines in
 // five more elementwise kernels.  Here the phase p = W.x is recomputed from the integer coordinate
-// in both passes (12 FMAs + one sincos per 4 channels), so the only HBM streams are: read F_in
-// once, read coords + block index twice, write out once; block sums / means are L2 resident.
+// in both passes, so the only HBM streams are: read F_in once, read coords + block index twice,
+// write out once; block sums / means are L2 resident.
 //
-// Thread mapping: a row of C floats is owned by a group of LPR = pow2 >= C/4 lanes, 4 channels
-// (one 128-bit transaction) per lane, so a warp handles G = 32/LPR rows per step.
+// Thread mapping.  A row of C floats is owned by LPR lanes; lane j of the group owns the VPL
+// float4 vectors {i * LPR + j : i < VPL} (channels 4 (i LPR + j) .. +3), so every load instruction
+// of a lane group covers 16 LPR contiguous bytes and a row is fetched with VPL fully coalesced
+// instructions.  For C = 16, 32, 64, 128:  VPL = 4 (16 channels per lane), LPR = C / 16 -- one warp
+// step covers 32 / LPR rows.  (Any other C % 4 == 0: VPL = 1, LPR = pow2 >= C / 4.)  Compared with a
+// 4-channel-per-lane layout this cuts the per-row bookkeeping (index loads, address arithmetic,
+// run-boundary tests) and the LayerNorm shuffle trees 4x, and channel groups
+// (pos.repeat([1, groups]), linkencoder.py:152) fall INSIDE a lane: vectors i and i + IB share
+// their phases, so a lane evaluates only 4 IB sincos per row and reuses them.
 #include "common.cuh"
 
 struct GenDev {
@@ -24,16 +31,16 @@ struct GenDev {
   const float* alpha;
 };
 
-struct LaneGen {       // per-lane kernel-generator state for its 4 channels
-  float w0[4], w1[4], w2[4], al[4];
-};
+// libdevice sincosf kept out of line: inlined into the unrolled row loops its slow path
+// (Payne-Hanek) multiplies the code size ~10x and the kernels become instruction-fetch bound.
+__device__ __noinline__ void accurate_sincos(float p, float* s, float* c) { sincosf(p, s, c); }
 
 // sin and cos of one fp32 phase: two-term Cody-Waite reduction to [-pi, pi] (exact for the
 // |p| < ~1e5 rad that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7) followed by the SFU
 // approximations (sin.approx / cos.approx, max abs error 2^-20.9 on [-pi, pi]).  ~9 instructions
 // instead of ~20 for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
 __device__ __forceinline__ void fast_sincos(float p, bool accurate, float& s, float& c) {
-  if (accurate) { sincosf(p, &s, &c); return; }      // warp-uniform switch
+  if (accurate) { accurate_sincos(p, &s, &c); return; }      // warp-uniform switch
   float k = rintf(p * 0.15915494309189535f);
   float r = fmaf(k, -6.2831855f, p);
   r = fmaf(k, 1.7484555e-7f, r);
@@ -41,137 +48,160 @@ __device__ __forceinline__ void fast_sincos(float p, bool accurate, float& s, fl
   c = __cosf(r);
 }
 
-// Phase, sin and cos of the lane's 4 channels for voxel (x,y,z); the phase follows the operation
-// order of nn.Linear(3, .) [ (x*w0 + y*w1) + z*w2 ] followed by "* alpha" (linkencoder.py:151,165).
-// With channel groups (pos.repeat([1, groups]), linkencoder.py:152) the SH = C/wrows lanes
-// {l0 + j*S} of a row own IDENTICAL phases: each evaluates only N = 4/SH of them (its weights for
-// exactly those were loaded by load_lane_gen_owned) and the rest arrive by shuffle, so the
-// transcendental work per row drops SH-fold.  Must be called by all 32 lanes.
-template <int LPR, int SH, bool COSX>
-__device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen& lg, int4 c, int lane,
-                                          float p[4], float sn[4], float cs[4]) {
-  constexpr int N = 4 / SH;            // phases evaluated by this lane
-  float x = (float)c.x, y = (float)c.y, z = (float)c.z;
-  if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
-  float mp[N], ms[N], mc[N];
+// per-lane kernel-generator state: weights of the NP = 4 IB distinct phases the lane evaluates
+template <int NP>
+struct LaneGen {
+  float w0[NP], w1[NP], w2[NP], al[NP];
+};
+
+// phase slot q = ib * 4 + e  <->  channel 4 (ib * LPR + j) + e  (and every channel congruent to
+// it modulo wrows that the lane owns)
+template <int LPR, int IB>
+__device__ __forceinline__ void load_lane_gen(const GenDev& g, int j, bool active, LaneGen<4 * IB>& lg) {
 #pragma unroll
-  for (int q = 0; q < N; ++q) {
-    float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
-    mp[q] = COSX ? v * lg.al[q] : v;
-    fast_sincos(mp[q], g.accurate != 0, ms[q], mc[q]);
-  }
-  if (SH == 1) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { p[e] = mp[e % N]; sn[e] = ms[e % N]; cs[e] = mc[e % N]; }
-  } else {
-    constexpr int S = LPR / SH;        // lane distance between the copies
-    const int li = lane % LPR, base = lane - li + (li % S);
+  for (int ib = 0; ib < IB; ++ib)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int src = base + (e / N) * S;
-      sn[e] = __shfl_sync(0xffffffffu, ms[e % N], src);
-      cs[e] = __shfl_sync(0xffffffffu, mc[e % N], src);
-      if (COSX) p[e] = __shfl_sync(0xffffffffu, mp[e % N], src);
+      const int q = ib * 4 + e;
+      const int row = active ? (4 * (ib * LPR + j) + e) % g.wrows : 0;
+      lg.w0[q] = active ? __ldg(g.pw + row * 3 + 0) : 0.f;
+      lg.w1[q] = active ? __ldg(g.pw + row * 3 + 1) : 0.f;
+      lg.w2[q] = active ? __ldg(g.pw + row * 3 + 2) : 0.f;
+      lg.al[q] = (active && g.alpha) ? __ldg(g.alpha + row) : 1.f;
     }
-  }
 }
 
-// weights of the phases this lane evaluates: element q <-> channel ch + j*N + q, j = copy index
-template <int LPR, int SH>
-__device__ __forceinline__ void load_lane_gen_owned(const GenDev& g, int lane, int ch, bool active,
-                                                    LaneGen& lg) {
-  constexpr int N = 4 / SH;
-  const int j = (SH == 1) ? 0 : (lane % LPR) / (LPR / SH);
+// Phase, sin and cos of the lane's 4 IB distinct phases for voxel (x,y,z); the phase follows the
+// operation order of nn.Linear(3, .) [ (x*w0 + y*w1) + z*w2 ] followed by "* alpha"
+// (linkencoder.py:151,165).
+template <int NP, bool COSX>
+__device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen<NP>& lg, int cx, int cy, int cz,
+                                          float p[NP], float sn[NP], float cs[NP]) {
+  float x = (float)cx, y = (float)cy, z = (float)cz;
+  if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int row = (active && q < N) ? (ch + j * N + q) % g.wrows : 0;
-    bool on = active && q < N;
-    lg.w0[q] = on ? g.pw[row * 3 + 0] : 0.f;
-    lg.w1[q] = on ? g.pw[row * 3 + 1] : 0.f;
-    lg.w2[q] = on ? g.pw[row * 3 + 2] : 0.f;
-    lg.al[q] = (on && g.alpha) ? g.alpha[row] : 1.f;
+  for (int q = 0; q < NP; ++q) {
+    float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
+    p[q] = COSX ? v * lg.al[q] : v;
+    fast_sincos(p[q], g.accurate != 0, sn[q], cs[q]);
   }
 }
-
-#define PREAGG_ROWS_PER_GROUP 8
-#define PREAGG_UNROLL 2
 
 // ------------------------------------------------------------------ pass 1: block sums
-template <int LPR, int OP, int SH>
-__global__ void __launch_bounds__(256, 4) link_preagg_kernel(const float* __restrict__ fin,
-                                                          const int4* __restrict__ coords,
-                                                          const int* __restrict__ blk, int64_t n,
-                                                          GenDev g, float* sums) {
-  constexpr int G = 32 / LPR;
+// One kernel, two visiting orders:
+//   * segmented (order != NULL; what the block executor uses): voxels are visited in BLOCK order
+//     through the sort permutation -- position i of the sorted sequence is voxel row order[i] in
+//     block row rank[i] (both from lk_sort_unique_ex).  A warp loads 32 PL consecutive pairs with
+//     coalesced loads; every lane group walks RPG consecutive sorted positions (about one whole
+//     block at (3x7)^3) with the row loads of PRE_U voxels in flight, reduces runs of equal block
+//     row in registers -- a warp-level segmented reduction over the variable-length voxel lists
+//     of the blocks -- and issues one vector reduction per run.  Feature rows are still fetched as
+//     whole 4C-byte rows.
+//   * storage order (order == NULL, rank = voxel -> block row): same code with the identity
+//     permutation; LiDAR scans arrive in column order, so runs are ~1 voxel long and the kernel
+//     is bound by the L2 reduction rate (REDG) instead of HBM -- kept for callers without a sort.
+template <int LPR, int VPL, int IB, int OP>
+__global__ void __launch_bounds__(128, 3) link_preagg_kernel(
+    const float* __restrict__ fin, const int4* __restrict__ coords, const int* __restrict__ order,
+    const int* __restrict__ rank, int64_t n, GenDev g, float* sums) {
+  constexpr int G = 32 / LPR;                    // row groups per warp
+  constexpr int RPG = LPR > 8 ? LPR : 8;         // sorted positions walked by one lane group
+  constexpr int PL = RPG / LPR;                  // positions held per lane
   constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
   constexpr bool COSX = (OP == LK_OP_COSX);
+  constexpr int NP = 4 * IB;
+  constexpr int PRE_U = (COSX && VPL > 1) ? 2 : 4;   // rows in flight per lane group (register budget)
+  static_assert(RPG % PRE_U == 0, "batching must divide the span");
   const int lane = threadIdx.x & 31;
   const int grp = lane / LPR;
-  const int ch = (lane % LPR) * 4;
-  const bool active = ch < g.c;
+  const int j = lane % LPR;
+  const bool active = 4 * j < g.c;               // VPL == 1 only: C/4 need not be a power of two
   const int kc = K * g.c;
-  LaneGen lg;
-  load_lane_gen_owned<LPR, SH>(g, lane, ch, active, lg);
+  LaneGen<NP> lg;
+  load_lane_gen<LPR, IB>(g, j, active, lg);
 
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t rows_per_warp = (int64_t)PREAGG_ROWS_PER_GROUP * G;
-  for (int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * rows_per_warp;
-       wbase < n; wbase += warps_total * rows_per_warp) {
-    int64_t r0 = wbase + (int64_t)grp * PREAGG_ROWS_PER_GROUP;
-    int64_t r1 = r0 + PREAGG_ROWS_PER_GROUP;
-    if (r1 > n) r1 = n;
-    float acc[K][4];
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (G * RPG); base < n;
+       base += warps_total * (G * RPG)) {
+    int ord[PL], rk[PL];
+#pragma unroll
+    for (int q = 0; q < PL; ++q) {
+      const int64_t pos = base + (int64_t)lane * PL + q;
+      ord[q] = pos < n ? (order ? __ldg(order + pos) : (int)pos) : 0;
+      rk[q] = pos < n ? __ldg(rank + pos) : -1;
+    }
+    float acc[K][VPL][4];
 #pragma unroll
     for (int q = 0; q < K; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-    int cur = -1;
-    // NB: trip count is warp-uniform (r1 - r0 may be shorter for the last group; `ok` masks it)
-    for (int64_t r = r0; r < r0 + PREAGG_ROWS_PER_GROUP; r += PREAGG_UNROLL) {
-      int b[PREAGG_UNROLL];
-      int4 cc[PREAGG_UNROLL];
-      float4 f[PREAGG_UNROLL];
+      for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int u = 0; u < PREAGG_UNROLL; ++u) {   // all loads of the batch first (MLP)
-        bool ok = r + u < r1;
-        b[u] = ok ? __ldg(blk + r + u) : -1;
-        cc[u] = ok ? __ldg(coords + r + u) : make_int4(0, 0, 0, 0);
-        f[u] = (ok && active) ? lk_ldg_stream((const float4*)(fin + (r + u) * g.c + ch))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
+    int cur = -1;
+#pragma unroll
+    for (int i0 = 0; i0 < RPG; i0 += PRE_U) {
+      int b[PRE_U], cx[PRE_U], cy[PRE_U], cz[PRE_U];
+      float4 f[PRE_U][VPL];
+#pragma unroll
+      for (int u = 0; u < PRE_U; ++u) {          // all row loads of the batch first (MLP)
+        const int ii = i0 + u;
+        const int src = grp * LPR + ii / PL;
+        const int r = __shfl_sync(0xffffffffu, ord[ii % PL], src);
+        b[u] = __shfl_sync(0xffffffffu, rk[ii % PL], src);
+        const bool ok = b[u] >= 0;
+        int4 cc = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
+        cx[u] = cc.x; cy[u] = cc.y; cz[u] = cc.z;
+        const float4* row = (const float4*)(fin + (int64_t)r * g.c) + j;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          f[u][i] = (ok && active) ? lk_ldg_stream(row + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < PREAGG_UNROLL; ++u) {
-        float p[4], sn[4], cs[4];
-        lane_trig<LPR, SH, COSX>(g, lg, cc[u], lane, p, sn, cs);   // all lanes: full-mask shuffles
-        if (b[u] < 0) continue;                    // tail of the batch (or unmapped voxel)
-        if (b[u] != cur) {                         // run boundary: flush the finished block
-          if (cur >= 0 && active) {
+      for (int u = 0; u < PRE_U; ++u) {
+        if (b[u] >= 0) {                         // else: past the end / unmapped voxel
+          float p[NP], sn[NP], cs[NP];
+          lane_trig<NP, COSX>(g, lg, cx[u], cy[u], cz[u], p, sn, cs);
+          if (b[u] != cur) {                     // run boundary: flush the finished block
+            if (cur >= 0 && active) {
+              float* dst = sums + (int64_t)cur * kc + 4 * j;
+#pragma unroll
+              for (int q = 0; q < K; ++q)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i)
+                  lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
+                                make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
+            }
 #pragma unroll
             for (int q = 0; q < K; ++q)
-              lk_red_add_v4(sums + (int64_t)cur * kc + q * g.c + ch,
-                            make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+#pragma unroll
+              for (int i = 0; i < VPL; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
+            cur = b[u];
           }
 #pragma unroll
-          for (int q = 0; q < K; ++q)
+          for (int i = 0; i < VPL; ++i) {
+            const float fv[4] = {f[u][i].x, f[u][i].y, f[u][i].z, f[u][i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-          cur = b[u];
-        }
-        const float fv[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // plane order: cos -> [cos, sin]; sin -> [sin, cos]; cos_x -> [cos, sin, lin]
-          acc[0][e] += fv[e] * (OP == LK_OP_SIN ? sn[e] : cs[e]);
-          acc[1][e] += fv[e] * (OP == LK_OP_SIN ? cs[e] : sn[e]);
-          if (COSX) acc[K - 1][e] += fv[e] * p[e];
+            for (int e = 0; e < 4; ++e) {
+              const int q = (i % IB) * 4 + e;
+              // plane order: cos -> [cos, sin]; sin -> [sin, cos]; cos_x -> [cos, sin, lin]
+              acc[0][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? sn[q] : cs[q]), acc[0][i][e]);
+              acc[1][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? cs[q] : sn[q]), acc[1][i][e]);
+              if (COSX) acc[K - 1][i][e] = fmaf(fv[e], p[q], acc[K - 1][i][e]);
+            }
+          }
         }
       }
     }
     if (cur >= 0 && active) {
+      float* dst = sums + (int64_t)cur * kc + 4 * j;
 #pragma unroll
       for (int q = 0; q < K; ++q)
-        lk_red_add_v4(sums + (int64_t)cur * kc + q * g.c + ch,
-                      make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
+                        make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
     }
   }
 }
@@ -201,6 +231,9 @@ extern "C" int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity
 }
 
 // ------------------------------------------------------------------ pass 2a: window means
+// One warp per block row.  The R neighbour indices are loaded by the first R lanes, the present
+// ones are compacted with a ballot, and only those rows are fetched (a LiDAR block has ~9-12 of
+// its 27 neighbours), four at a time so the L2 loads overlap.
 __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __restrict__ sums,
                                                                const int* __restrict__ counts,
                                                                const int* __restrict__ nbr,
@@ -209,26 +242,49 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
                                                                float* __restrict__ mean) {
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
-  int vpr = kc >> 2;
-  int64_t total = m * vpr;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t / vpr;
-    int j = (int)(t - b * vpr) * 4;
-    const int* nb = nbr + b * R;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float tot = 0.f;
-#pragma unroll 9
-    for (int k = 0; k < R; ++k) {            // branch-free so the R row loads can be in flight
-      int src = __ldg(nb + k);
-      float wgt = src >= 0 ? 1.f : 0.f;
-      src = max(src, 0);
-      float4 v = __ldg((const float4*)(sums + (int64_t)src * kc + j));
-      acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
-      tot += wgt * (float)__ldg(counts + src);
+  const int lane = threadIdx.x & 31;
+  const int vpr = kc >> 2;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < m; b += warps_total) {
+    int src = -1, cnt = 0;
+    if (lane < R) {                              // R <= 32
+      src = __ldg(nbr + b * R + lane);
+      if (src >= 0) cnt = __ldg(counts + src);
     }
-    acc.x /= tot; acc.y /= tot; acc.z /= tot; acc.w /= tot;
-    *(float4*)(mean + b * kc + j) = acc;
+    const unsigned present = __ballot_sync(0xffffffffu, src >= 0);
+    int tot_i = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
+    const float tot = (float)tot_i;
+    for (int v0 = 0; v0 < vpr; v0 += 32) {
+      const int v = v0 + lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned rest = present;
+      while (rest) {                             // warp-uniform loop over the present neighbours
+        int s4[4];
+        bool on[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          on[t] = rest != 0;
+          const int l = on[t] ? __ffs(rest) - 1 : 0;
+          rest &= rest - 1;
+          s4[t] = __shfl_sync(0xffffffffu, src, l);
+        }
+        float4 r4[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          r4[t] = (v < vpr && on[t]) ? __ldg((const float4*)(sums + (int64_t)s4[t] * kc) + v)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc.x += r4[t].x; acc.y += r4[t].y; acc.z += r4[t].z; acc.w += r4[t].w;
+        }
+      }
+      if (v < vpr) {
+        acc.x /= tot; acc.y /= tot; acc.z /= tot; acc.w /= tot;
+        *((float4*)(mean + b * kc) + v) = acc;
+      }
+    }
   }
 }
 
@@ -240,26 +296,38 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <int LPR>
-__device__ __forceinline__ void group_layernorm(float v[4], bool active, float inv_c, const float* gam,
-                                                const float* bet, int ch) {
-  float s = active ? (v[0] + v[1] + v[2] + v[3]) : 0.f;
-  float mean = group_sum<LPR>(s) * inv_c;
-  float d[4], q = 0.f;
+// LayerNorm of one row spread over LPR lanes x VPL vectors (eps 1e-6, biased variance)
+template <int LPR, int VPL>
+__device__ __forceinline__ void group_layernorm(float v[VPL][4], bool active, float inv_c,
+                                                const float* __restrict__ gam,
+                                                const float* __restrict__ bet, int j) {
+  float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) { d[e] = v[e] - mean; q += d[e] * d[e]; }
-  float var = group_sum<LPR>(active ? q : 0.f) * inv_c;
-  float rstd = rsqrtf(var + 1e-6f);
+  for (int i = 0; i < VPL; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  const float mean = group_sum<LPR>(active ? s : 0.f) * inv_c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[i][e] -= mean; q = fmaf(v[i][e], v[i][e], q); }
+  const float var = group_sum<LPR>(active ? q : 0.f) * inv_c;
+  const float rstd = rsqrtf(var + 1e-6f);
   if (active) {
-    float4 gg = __ldg((const float4*)(gam + ch));
-    float4 bb = __ldg((const float4*)(bet + ch));
-    v[0] = d[0] * rstd * gg.x + bb.x; v[1] = d[1] * rstd * gg.y + bb.y;
-    v[2] = d[2] * rstd * gg.z + bb.z; v[3] = d[3] * rstd * gg.w + bb.w;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 gg = __ldg((const float4*)gam + i * LPR + j);
+      const float4 bb = __ldg((const float4*)bet + i * LPR + j);
+      v[i][0] = fmaf(v[i][0] * rstd, gg.x, bb.x); v[i][1] = fmaf(v[i][1] * rstd, gg.y, bb.y);
+      v[i][2] = fmaf(v[i][2] * rstd, gg.z, bb.z); v[i][3] = fmaf(v[i][3] * rstd, gg.w, bb.w);
+    }
   }
 }
 
-template <int LPR, int OP, bool NORM, int SH>
-__global__ void __launch_bounds__(256, 4) link_apply_kernel(
+// Every lane group handles U rows per step with all of their loads in flight together: first the
+// independent ones (block index, coordinate, local_mix row), then the mean rows that depend on
+// the block index.
+template <int LPR, int VPL, int IB, int OP, bool NORM>
+__global__ void __launch_bounds__(128, 3) link_apply_kernel(
     const float* __restrict__ mean, const float* __restrict__ fin, const int4* __restrict__ coords,
     const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
@@ -267,77 +335,93 @@ __global__ void __launch_bounds__(256, 4) link_apply_kernel(
   constexpr int G = 32 / LPR;
   constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
   constexpr bool COSX = (OP == LK_OP_COSX);
+  constexpr int NP = 4 * IB;
+  constexpr int U = (COSX && VPL > 1) ? 1 : 2;        // rows per lane group per step (register budget)
   const int lane = threadIdx.x & 31;
   const int grp = lane / LPR;
-  const int ch = (lane % LPR) * 4;
-  const bool active = ch < g.c;
+  const int j = lane % LPR;
+  const bool active = 4 * j < g.c;
   const int kc = K * g.c;
-  LaneGen lg;
-  load_lane_gen_owned<LPR, SH>(g, lane, ch, active, lg);
+  LaneGen<NP> lg;
+  load_lane_gen<LPR, IB>(g, j, active, lg);
   const float inv_c = 1.0f / (float)g.c;
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t steps = (n + G - 1) / G;
-  // software pipeline: block index, coordinate and local_mix row of the NEXT step are loaded
-  // while the current step computes (the mean-row loads depend on the block index, so without
-  // the prefetch every step pays two dependent memory latencies back to back)
-  int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int b_n = -1;
-  int4 cc_n = make_int4(0, 0, 0, 0);
-  float4 lv_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto prefetch = [&](int64_t st) {
-    int64_t r = st * G + grp;
-    bool ok = st < steps && r < n;
-    b_n = ok ? __ldg(blk + r) : -1;
-    cc_n = ok ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
-    lv_n = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (NORM && ok && active) lv_n = lk_ldg_stream((const float4*)(local + r * g.c + ch));
-  };
-  prefetch(step);
-  for (; step < steps; step += warps_total) {
-    const int64_t r = step * G + grp;
-    const bool ok = r < n;               // NB: whole groups go inactive together; shuffles stay
-    const int b = b_n;                   // inside a group, so no divergence hazard
-    const int4 cc = cc_n;
-    const float4 lv = lv_n;
-    float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0, m2 = m0, f = m0;
-    const bool live = ok && active && b >= 0;
-    if (live) {                          // issue the dependent loads first ...
-      const float* mrow = mean + (int64_t)b * kc + ch;
-      m0 = __ldg((const float4*)mrow);
-      m1 = __ldg((const float4*)(mrow + g.c));
-      if (COSX) {
-        m2 = __ldg((const float4*)(mrow + 2 * g.c));
-        f = lk_ldg_stream((const float4*)(fin + r * g.c + ch));
+  const int64_t steps = (n + G * U - 1) / (G * U);
+  for (int64_t step = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; step < steps;
+       step += warps_total) {
+    int b[U];
+    int4 cc[U];
+    float4 lv[U][VPL], m0[U][VPL], m1[U][VPL];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {          // independent loads of all U rows
+      const int64_t r = (step * U + u) * G + grp;   // NB: whole groups go inactive together;
+      ok[u] = r < n;                                //     shuffles stay inside a group
+      b[u] = ok[u] ? __ldg(blk + r) : -1;
+      cc[u] = ok[u] ? __ldg(coords + r) : make_int4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        lv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NORM && ok[u] && active) lv[u][i] = lk_ldg_stream((const float4*)(local + r * g.c) + i * LPR + j);
       }
     }
-    prefetch(step + warps_total);        // ... then the next step's independent ones
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    float p[4], sn[4], cs[4];
-    lane_trig<LPR, SH, COSX>(g, lg, cc, lane, p, sn, cs);   // all lanes: full-mask shuffles
-    if (live) {
-      const float a0[4] = {m0.x, m0.y, m0.z, m0.w};
-      const float a1[4] = {m1.x, m1.y, m1.z, m1.w};
-      if (OP == LK_OP_SIN) {             // planes [sin, cos]: F[:, :C]*cos - F[:, C:]*sin
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = a0[e] * cs[e] - a1[e] * sn[e];
-      } else {                           // planes [cos, sin]: F[:, :C]*cos + F[:, C:]*sin
+    for (int u = 0; u < U; ++u) {          // dependent loads: the blocks' window means (L2)
+      const bool live = ok[u] && active && b[u] >= 0;
+      const float4* mrow = (const float4*)(mean + (int64_t)(live ? b[u] : 0) * kc) + j;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = a0[e] * cs[e] + a1[e] * sn[e];
-      }
-      if (COSX) {                        // + (mean(F*pos) - F*pos), linkencoder.py:176
-        v[0] += m2.x - f.x * p[0]; v[1] += m2.y - f.y * p[1];
-        v[2] += m2.z - f.z * p[2]; v[3] += m2.w - f.w * p[3];
+      for (int i = 0; i < VPL; ++i) {
+        m0[u][i] = live ? __ldg(mrow + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+        m1[u][i] = live ? __ldg(mrow + (g.c >> 2) + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    if (NORM) {
-      float l[4] = {lv.x, lv.y, lv.z, lv.w};
-      group_layernorm<LPR>(v, active, inv_c, g1, b1, ch);
-      group_layernorm<LPR>(l, active, inv_c, g2, b2, ch);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e] + l[e], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = (step * U + u) * G + grp;
+      const bool live = ok[u] && active && b[u] >= 0;
+      float p[NP], sn[NP], cs[NP];
+      lane_trig<NP, COSX>(g, lg, cc[u].x, cc[u].y, cc[u].z, p, sn, cs);
+      float v[VPL][4];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float a0[4] = {m0[u][i].x, m0[u][i].y, m0[u][i].z, m0[u][i].w};
+        const float a1[4] = {m1[u][i].x, m1[u][i].y, m1[u][i].z, m1[u][i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = (i % IB) * 4 + e;
+          // planes [sin, cos]: F[:, :C]*cos - F[:, C:]*sin;  planes [cos, sin]: ... + ...
+          v[i][e] = (OP == LK_OP_SIN) ? a0[e] * cs[q] - a1[e] * sn[q] : a0[e] * cs[q] + a1[e] * sn[q];
+        }
+        if (COSX) {                        // + (mean(F*pos) - F*pos), linkencoder.py:176
+          float4 m2 = make_float4(0.f, 0.f, 0.f, 0.f), f = m2;
+          if (live) {
+            m2 = __ldg((const float4*)(mean + (int64_t)b[u] * kc + 2 * g.c) + i * LPR + j);
+            f = lk_ldg_stream((const float4*)(fin + r * g.c) + i * LPR + j);
+          }
+          v[i][0] += m2.x - f.x * p[(i % IB) * 4 + 0]; v[i][1] += m2.y - f.y * p[(i % IB) * 4 + 1];
+          v[i][2] += m2.z - f.z * p[(i % IB) * 4 + 2]; v[i][3] += m2.w - f.w * p[(i % IB) * 4 + 3];
+        }
+      }
+      if (NORM) {
+        float l[VPL][4];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          l[i][0] = lv[u][i].x; l[i][1] = lv[u][i].y; l[i][2] = lv[u][i].z; l[i][3] = lv[u][i].w;
+        }
+        group_layernorm<LPR, VPL>(v, active, inv_c, g1, b1, j);
+        group_layernorm<LPR, VPL>(l, active, inv_c, g2, b2, j);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[i][e] = fmaxf(v[i][e] + l[i][e], 0.f);
+      }
+      if (ok[u] && active) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          lk_stg_stream((float4*)(out + r * g.c) + i * LPR + j,
+                        make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+      }
     }
-    if (ok && active)
-      lk_stg_stream((float4*)(out + r * g.c + ch), make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -354,29 +438,74 @@ static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
   return LK_OK;
 }
 
-// number of lanes of a row that own identical phases (channel groups), if the layout allows the
-// shuffle exchange: C/4 a power of two, wrows a multiple of 4, C/wrows in {2,4}
-static int share_of(const GenDev& g, int lpr) {
-  if (lpr * 4 != g.c || g.wrows % 4 != 0 || g.c % g.wrows != 0) return 1;
-  int sh = g.c / g.wrows;
-  return (sh == 2 || sh == 4) ? sh : 1;
-}
-
-static int lpr_of(int c) {
-  int v = c / 4, l = 1;
-  while (l < v) l <<= 1;
-  return l;
-}
-
-#define DISPATCH_LPR(LPRV, MACRO) \
-  switch (LPRV) {                 \
-    case 1: MACRO(1); break;      \
-    case 2: MACRO(2); break;      \
-    case 4: MACRO(4); break;      \
-    case 8: MACRO(8); break;      \
-    case 16: MACRO(16); break;    \
-    default: MACRO(32); break;    \
+// Lane layout of a C-channel row: (LPR lanes, VPL vectors per lane, IB distinct phase blocks per
+// lane).  IB < VPL when the channel groups alias inside a lane: wrows a multiple of 4 LPR.
+struct RowLayout { int lpr, vpl, ib; };
+static RowLayout layout_of(const GenDev& g) {
+  RowLayout L;
+  if (g.c == 16 || g.c == 32 || g.c == 64 || g.c == 128) {
+    L.vpl = 4; L.lpr = g.c / 16;
+    const int span = 4 * L.lpr;            // channels covered by one vector index i
+    const int ib = (g.wrows % span == 0) ? g.wrows / span : 4;
+    L.ib = (ib == 1 || ib == 2) ? ib : 4;
+  } else {
+    L.vpl = 1; L.ib = 1;
+    const int v = g.c / 4;
+    L.lpr = 1;
+    while (L.lpr < v) L.lpr <<= 1;
   }
+  return L;
+}
+
+// MACRO(LPR, VPL, IB) for the layouts that exist
+#define DISPATCH_IB(LPRV, L, MACRO)                  \
+  do {                                               \
+    if (L.ib == 1) MACRO(LPRV, 4, 1);                \
+    else if (L.ib == 2) MACRO(LPRV, 4, 2);           \
+    else MACRO(LPRV, 4, 4);                          \
+  } while (0)
+#define DISPATCH_LAYOUT(L, MACRO)                    \
+  do {                                               \
+    if (L.vpl == 4) {                                \
+      if (L.lpr == 1) DISPATCH_IB(1, L, MACRO);      \
+      else if (L.lpr == 2) DISPATCH_IB(2, L, MACRO); \
+      else if (L.lpr == 4) DISPATCH_IB(4, L, MACRO); \
+      else DISPATCH_IB(8, L, MACRO);                 \
+    } else {                                         \
+      switch (L.lpr) {                               \
+        case 1: MACRO(1, 1, 1); break;               \
+        case 2: MACRO(2, 1, 1); break;               \
+        case 4: MACRO(4, 1, 1); break;               \
+        case 8: MACRO(8, 1, 1); break;               \
+        case 16: MACRO(16, 1, 1); break;             \
+        default: MACRO(32, 1, 1); break;             \
+      }                                              \
+    }                                                \
+  } while (0)
+
+static int launch_preagg(const float* d_fin, const int32_t* d_coords, const int32_t* d_order,
+                         const int32_t* d_rank, int64_t n, const GenDev& g, float* d_sums,
+                         cudaStream_t st) {
+  const RowLayout L = layout_of(g);
+  const int rpg = L.lpr > 8 ? L.lpr : 8;
+  const int64_t per_warp = (int64_t)(32 / L.lpr) * rpg;
+  const int64_t warps = (n + per_warp - 1) / per_warp;
+  const int grid = (int)((warps + 3) / 4);
+#define LAUNCH_PRE_OP(LPRV, VPLV, IBV, O)                                                       \
+  link_preagg_kernel<LPRV, VPLV, IBV, O><<<grid, 128, 0, st>>>(d_fin, (const int4*)d_coords,    \
+                                                               d_order, d_rank, n, g, d_sums)
+#define LAUNCH_PRE(LPRV, VPLV, IBV)                                      \
+  do {                                                                   \
+    if (g.op == LK_OP_COS) LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_COS);    \
+    else if (g.op == LK_OP_SIN) LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_SIN); \
+    else LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_COSX);                     \
+  } while (0)
+  DISPATCH_LAYOUT(L, LAUNCH_PRE);
+#undef LAUNCH_PRE
+#undef LAUNCH_PRE_OP
+  LK_LAUNCHED();
+  return LK_OK;
+}
 
 extern "C" int lk_link_preagg_fwd(const float* d_fin, const int32_t* d_coords, const int32_t* d_blk,
                                   int64_t n, const lk_kernelgen_t* gen, float* d_sums,
@@ -388,41 +517,32 @@ extern "C" int lk_link_preagg_fwd(const float* d_fin, const int32_t* d_coords, c
   LK_REQUIRE(d_fin && d_coords && d_blk && d_sums && n > 0, "lk_link_preagg_fwd: null pointer");
   LK_REQUIRE((uintptr_t)d_fin % 16 == 0 && (uintptr_t)d_sums % 16 == 0,
              "lk_link_preagg_fwd: feature buffers must be 16-byte aligned");
-  int lpr = lpr_of(g.c);
-  int64_t rows_per_warp = (int64_t)PREAGG_ROWS_PER_GROUP * (32 / lpr);
-  int64_t warps = (n + rows_per_warp - 1) / rows_per_warp;
-  int grid = lk_grid(warps * 32, 256, 8);
-  cudaStream_t st = (cudaStream_t)s;
-  const int sh = share_of(g, lpr);
-#define LAUNCH_PRE2(L, O, S) \
-  link_preagg_kernel<L, O, S><<<grid, 256, 0, st>>>(d_fin, (const int4*)d_coords, d_blk, n, g, d_sums)
-#define LAUNCH_PRE1(L, O)                                           \
-  do {                                                              \
-    if (sh == 2 && L >= 2) LAUNCH_PRE2(L, O, (L >= 2 ? 2 : 1));     \
-    else if (sh == 4 && L >= 4) LAUNCH_PRE2(L, O, (L >= 4 ? 4 : 1)); \
-    else LAUNCH_PRE2(L, O, 1);                                      \
-  } while (0)
-#define LAUNCH_PRE(L)                                   \
-  do {                                                  \
-    if (g.op == LK_OP_COS) LAUNCH_PRE1(L, LK_OP_COS);   \
-    else if (g.op == LK_OP_SIN) LAUNCH_PRE1(L, LK_OP_SIN); \
-    else LAUNCH_PRE1(L, LK_OP_COSX);                    \
-  } while (0)
-  DISPATCH_LPR(lpr, LAUNCH_PRE);
-#undef LAUNCH_PRE
-#undef LAUNCH_PRE1
-#undef LAUNCH_PRE2
-  LK_LAUNCHED();
-  return LK_OK;
+  return launch_preagg(d_fin, d_coords, nullptr, d_blk, n, g, d_sums, (cudaStream_t)s);
+}
+
+extern "C" int lk_link_preagg_seg_fwd(const float* d_fin, const int32_t* d_coords,
+                                      const int32_t* d_order, const int32_t* d_sorted_rank,
+                                      int64_t n, const lk_kernelgen_t* gen, float* d_sums,
+                                      lk_stream_t s) {
+  GenDev g;
+  int rc = check_gen(gen, &g, "lk_link_preagg_seg_fwd");
+  if (rc) return rc;
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_fin && d_coords && d_order && d_sorted_rank && d_sums && n > 0,
+             "lk_link_preagg_seg_fwd: null pointer");
+  LK_REQUIRE((uintptr_t)d_fin % 16 == 0 && (uintptr_t)d_sums % 16 == 0,
+             "lk_link_preagg_seg_fwd: feature buffers must be 16-byte aligned");
+  return launch_preagg(d_fin, d_coords, d_order, d_sorted_rank, n, g, d_sums, (cudaStream_t)s);
 }
 
 extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
                                    const int32_t* d_nbr, const int32_t* d_num, int64_t capacity,
                                    int r3, int kc, float* d_mean, lk_stream_t s) {
-  LK_REQUIRE(capacity >= 0 && r3 > 0 && kc > 0 && kc % 4 == 0, "lk_link_window_mean: bad sizes");
+  LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32 && kc > 0 && kc % 4 == 0,
+             "lk_link_window_mean: bad sizes (needs r^3 <= 32)");
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_sums && d_counts && d_nbr && d_num && d_mean, "lk_link_window_mean: null pointer");
-  link_window_mean_kernel<<<lk_grid(capacity * (kc / 4), 256, 8), 256, 0, (cudaStream_t)s>>>(
+  link_window_mean_kernel<<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
       d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean);
   LK_LAUNCHED();
   return LK_OK;
@@ -441,37 +561,29 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
   LK_REQUIRE(g.op != LK_OP_COSX || d_fin, "lk_link_apply_fwd: cos_x needs the input features");
   LK_REQUIRE(!fuse_norm || (d_local && d_g1 && d_b1 && d_g2 && d_b2),
              "lk_link_apply_fwd: fused norms need local features and both LayerNorm parameters");
-  int lpr = lpr_of(g.c);
-  int64_t steps = (n + (32 / lpr) - 1) / (32 / lpr);
-  int grid = lk_grid(steps * 32, 256, 8);
+  const RowLayout L = layout_of(g);
+  const int rows_per_step = (32 / L.lpr) * ((g.op == LK_OP_COSX && L.vpl > 1) ? 1 : 2);
+  const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
+  const int grid = lk_grid(steps * 32, 128, 3);
   cudaStream_t st = (cudaStream_t)s;
-  const int sh = share_of(g, lpr);
-#define LAUNCH_APPLY3(L, O, NRM, S)                                                              \
-  link_apply_kernel<L, O, NRM, S><<<grid, 256, 0, st>>>(d_mean, d_fin, (const int4*)d_coords,    \
-                                                        d_blk, n, g, d_local, d_g1, d_b1, d_g2,  \
-                                                        d_b2, d_out)
-#define LAUNCH_APPLY2N(L, O, NRM)                                       \
-  do {                                                                  \
-    if (sh == 2 && L >= 2) LAUNCH_APPLY3(L, O, NRM, (L >= 2 ? 2 : 1));  \
-    else if (sh == 4 && L >= 4) LAUNCH_APPLY3(L, O, NRM, (L >= 4 ? 4 : 1)); \
-    else LAUNCH_APPLY3(L, O, NRM, 1);                                   \
+#define LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, NRM)                                               \
+  link_apply_kernel<LPRV, VPLV, IBV, O, NRM><<<grid, 128, 0, st>>>(                            \
+      d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
+#define LAUNCH_APPLY_O(LPRV, VPLV, IBV, O)                         \
+  do {                                                             \
+    if (fuse_norm) LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, true);      \
+    else LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, false);               \
   } while (0)
-#define LAUNCH_APPLY2(L, O)                      \
-  do {                                           \
-    if (fuse_norm) LAUNCH_APPLY2N(L, O, true);   \
-    else LAUNCH_APPLY2N(L, O, false);            \
+#define LAUNCH_APPLY(LPRV, VPLV, IBV)                                      \
+  do {                                                                     \
+    if (g.op == LK_OP_COS) LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_COS);     \
+    else if (g.op == LK_OP_SIN) LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_SIN); \
+    else LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_COSX);                      \
   } while (0)
-#define LAUNCH_APPLY(L)                                         \
-  do {                                                          \
-    if (g.op == LK_OP_COS) LAUNCH_APPLY2(L, LK_OP_COS);         \
-    else if (g.op == LK_OP_SIN) LAUNCH_APPLY2(L, LK_OP_SIN);    \
-    else LAUNCH_APPLY2(L, LK_OP_COSX);                          \
-  } while (0)
-  DISPATCH_LPR(lpr, LAUNCH_APPLY);
+  DISPATCH_LAYOUT(L, LAUNCH_APPLY);
 #undef LAUNCH_APPLY
-#undef LAUNCH_APPLY2
-#undef LAUNCH_APPLY2N
-#undef LAUNCH_APPLY3
+#undef LAUNCH_APPLY_O
+#undef LAUNCH_APPLY_ON
   LK_LAUNCHED();
   return LK_OK;
 }

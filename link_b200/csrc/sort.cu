@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(RS_THREADS) uniq_count_kernel(
 __global__ void __launch_bounds__(RS_THREADS) uniq_write_kernel(
     const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, int64_t n,
     const unsigned* __restrict__ tile_base, unsigned long long* __restrict__ uniq,
-    int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg) {
+    int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg,
+    int* __restrict__ rank_sorted) {
   __shared__ unsigned wsum[RS_WARPS];
   int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int64_t i0 = (int64_t)blockIdx.x * RS_TILE + (int64_t)tid * RS_ITEMS;
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(RS_THREADS) uniq_write_kernel(
       }
       if (inverse) inverse[v] = (int)r;
       if (order) order[i] = (int)v;
+      if (rank_sorted) rank_sorted[i] = (int)r;
     }
   }
 }
@@ -413,21 +415,33 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
   int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < RS_WARPS * 257; i += RS_THREADS) (&cnt[0][0])[i] = 0;
 
+  // this thread's keys first: their loads overlap the histogram walk below
+  int64_t wbase_i = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+  unsigned long long key[RS_ITEMS];
+  unsigned val[RS_ITEMS];
+  unsigned short dig[RS_ITEMS];
+  unsigned rank[RS_ITEMS];
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = wbase_i + j * 32 + lane;
+    bool valid = i < n;
+    key[j] = valid ? keys_in[i] : 0ULL;
+    val[j] = valid ? (vals_in ? vals_in[i] : (unsigned)i) : 0u;
+    dig[j] = valid ? (unsigned short)((unsigned)(key[j] >> shift) & 255u) : (unsigned short)256;
+  }
+
   // ---- digit `tid`: elements of this digit in earlier tiles, and in all tiles ----
   unsigned below = 0, total = 0;
-  {
-    int t = 0;
-    for (; t + 4 <= T; t += 4) {
-      unsigned a0 = __ldg(hist + (int64_t)(t + 0) * 256 + tid), a1 = __ldg(hist + (int64_t)(t + 1) * 256 + tid);
-      unsigned a2 = __ldg(hist + (int64_t)(t + 2) * 256 + tid), a3 = __ldg(hist + (int64_t)(t + 3) * 256 + tid);
-      total += a0 + a1 + a2 + a3;
-      below += (t + 0 < (int)blockIdx.x ? a0 : 0u) + (t + 1 < (int)blockIdx.x ? a1 : 0u) +
-               (t + 2 < (int)blockIdx.x ? a2 : 0u) + (t + 3 < (int)blockIdx.x ? a3 : 0u);
-    }
-    for (; t < T; ++t) {
-      unsigned a = __ldg(hist + (int64_t)t * 256 + tid);
-      total += a;
-      below += t < (int)blockIdx.x ? a : 0u;
+  // 16 independent loads per round trip to L2: this column walk is a pure latency chain (T = 59
+  // tiles at the bench size) and sits on the critical path of every pass
+  for (int t = 0; t < T; t += 16) {
+    unsigned a[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] = (t + u < T) ? __ldg(hist + (int64_t)(t + u) * 256 + tid) : 0u;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      total += a[u];
+      below += (t + u < (int)blockIdx.x) ? a[u] : 0u;
     }
   }
   // exclusive scan of `total` over the 256 digits
@@ -444,19 +458,6 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
   for (int w = 0; w < RS_WARPS; ++w) wbase += (w < warp) ? wsum[w] : 0u;
   const unsigned my_base = wbase + (incl - total) + below;      // global base of (digit tid, this tile)
 
-  int64_t wbase_i = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
-  unsigned long long key[RS_ITEMS];
-  unsigned val[RS_ITEMS];
-  unsigned short dig[RS_ITEMS];
-  unsigned rank[RS_ITEMS];
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    int64_t i = wbase_i + j * 32 + lane;
-    bool valid = i < n;
-    key[j] = valid ? keys_in[i] : 0ULL;
-    val[j] = valid ? (vals_in ? vals_in[i] : (unsigned)i) : 0u;
-    dig[j] = valid ? (unsigned short)((unsigned)(key[j] >> shift) & 255u) : (unsigned short)256;
-  }
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     unsigned d = dig[j];
@@ -499,7 +500,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
 __global__ void __launch_bounds__(RS_THREADS) uniq_write_fused_kernel(
     const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, int64_t n,
     const unsigned* __restrict__ tile_heads, int T, unsigned long long* __restrict__ uniq,
-    int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg, int* __restrict__ d_num) {
+    int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg, int* __restrict__ d_num,
+    int* __restrict__ rank_sorted) {
   __shared__ unsigned wsum[RS_WARPS];
   __shared__ unsigned red[2][RS_WARPS];
   __shared__ unsigned tile_base_s;
@@ -568,6 +570,7 @@ __global__ void __launch_bounds__(RS_THREADS) uniq_write_fused_kernel(
       }
       if (inverse) inverse[v] = (int)r;
       if (order) order[i] = (int)v;
+      if (rank_sorted) rank_sorted[i] = (int)r;
     }
   }
 }
@@ -581,10 +584,11 @@ extern "C" int64_t lk_sort_unique_ws_bytes(int64_t n) {
          align256((T + 1) * 4) + align256((n + 1) * 4) + align256(4);
 }
 
-extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
-                              int32_t* d_inverse, int32_t* d_order, int32_t* d_seg,
-                              int32_t* d_counts, int32_t* d_num, void* d_ws, int64_t ws_bytes,
-                              lk_stream_t s) {
+extern "C" int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits,
+                                 uint64_t* d_unique, int32_t* d_inverse, int32_t* d_order,
+                                 int32_t* d_seg, int32_t* d_counts, int32_t* d_num,
+                                 int32_t* d_sorted_rank, void* d_ws, int64_t ws_bytes,
+                                 lk_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   LK_REQUIRE(n >= 0 && n < (1LL << 31), "lk_sort_unique: n out of range");
   LK_REQUIRE(key_bits >= 0 && key_bits <= 64, "lk_sort_unique: key_bits out of range");
@@ -654,13 +658,14 @@ extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, u
   if (fused) {
     uniq_write_fused_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads, T,
                                                       (unsigned long long*)d_unique, d_inverse,
-                                                      d_order, seg, num);
+                                                      d_order, seg, num, d_sorted_rank);
     LK_LAUNCHED();
   } else {
     scan_single_cta_kernel<<<1, 1024, 0, st>>>(tile_heads, T, num, seg, (int)n);
     LK_LAUNCHED();
     uniq_write_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads,
-                                                (unsigned long long*)d_unique, d_inverse, d_order, seg);
+                                                (unsigned long long*)d_unique, d_inverse, d_order, seg,
+                                                d_sorted_rank);
     LK_LAUNCHED();
   }
   if (d_counts) {
@@ -668,4 +673,12 @@ extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, u
     LK_LAUNCHED();
   }
   return LK_OK;
+}
+
+extern "C" int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
+                              int32_t* d_inverse, int32_t* d_order, int32_t* d_seg,
+                              int32_t* d_counts, int32_t* d_num, void* d_ws, int64_t ws_bytes,
+                              lk_stream_t s) {
+  return lk_sort_unique_ex(d_keys, n, key_bits, d_unique, d_inverse, d_order, d_seg, d_counts, d_num,
+                           nullptr, d_ws, ws_bytes, s);
 }

@@ -51,7 +51,10 @@ class BlockIndex:
         bounds = _index.coord_bounds(coords, cache)
         self.spec, self.bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
         keys = _index.pack_keys(coords, self.spec)
-        su = _index.sort_unique(keys, self.bits)
+        su = _index.sort_unique(keys, self.bits, want_order=True)
+        self.order = su.order              # [n] int32  voxel row at each block-sorted position
+        self.sorted_rank = su.sorted_rank  # [n] int32  block row at each block-sorted position
+        self.seg = su.seg                  # [n+1] int32 start of each block's run in `order`
         self.unique_keys = su.unique       # [n] int64, first M valid, ascending == torch.unique order
         self.idx_query = su.inverse        # [n] int32  voxel -> block row
         self.counts = su.counts            # [n] int32, first M valid
@@ -226,10 +229,12 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
     m_hint = bi._m if bi._m is not None else 0      # only for the byte accounting of bench.py
     _capi.check(L.lk_zero_rows(_capi.ptr(sums), _capi.ptr(bi.num), n, k * c, st), 'lk_zero_rows')
     # algorithmic bytes: read F_in + coords + block index once, write the M block-sum rows
+    # (the segmented kernel reads the 4-byte permutation entry in addition: not counted)
     with _capi.timed('lk_link_preagg_fwd', n * (4 * c + 16 + 4) + m_hint * 4 * k * c):
-        _capi.check(L.lk_link_preagg_fwd(_capi.ptr(f_input, torch.float32),
-                                         _capi.ptr(coords, torch.int32), _capi.ptr(bi.idx_query), n,
-                                         C.byref(gen), _capi.ptr(sums), st), 'lk_link_preagg_fwd')
+        _capi.check(L.lk_link_preagg_seg_fwd(_capi.ptr(f_input, torch.float32),
+                                             _capi.ptr(coords, torch.int32), _capi.ptr(bi.order),
+                                             _capi.ptr(bi.sorted_rank), n, C.byref(gen),
+                                             _capi.ptr(sums), st), 'lk_link_preagg_seg_fwd')
     with _capi.timed('lk_link_window_mean', m_hint * (2 * 4 * k * c + 4 * nbr.shape[1] + 4)):
         _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
                                           _capi.ptr(bi.num), n, nbr.shape[1], k * c,
@@ -300,6 +305,16 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     a.d_conv_wt = _capi.ptr(wt)
     a.d_conv_offsets = _capi.ptr(conv_off)
     a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
+    if build:
+        kmap.offsets = conv_off
+    a.build_plan = 0
+    if USE_TENSOR_CORES and c in (32, 64) and conv.kernel_volume <= 32 and kmap._plan is not False:
+        from link_b200.nn.functional import conv as _convmod
+        if kmap._plan is None and _convmod.USE_PLAN:     # the executor fills the plan buffers
+            kmap._plan = kmap.plan_buffers()
+            a.build_plan = 1
+        if kmap._plan:
+            a.d_plan_perm, a.d_plan_nbr, a.d_plan_mask = (_capi.ptr(t) for t in kmap._plan)
     bounds = _index.coord_bounds(coords, st.kmaps)
     spec, bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
     a.keyspec, a.key_bits, a.r3 = spec, bits, r3

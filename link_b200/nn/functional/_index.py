@@ -76,7 +76,7 @@ def unpack_keys(keys: torch.Tensor, n: int, spec: _capi.KeySpec,
 
 class SortUnique:
     """Result of lk_sort_unique: capacity-n buffers + the device scalar `num`."""
-    __slots__ = ('unique', 'inverse', 'order', 'seg', 'counts', 'num', 'n')
+    __slots__ = ('unique', 'inverse', 'order', 'seg', 'counts', 'num', 'n', 'sorted_rank')
 
 
 def sort_unique(keys: torch.Tensor, key_bits: int, want_order: bool = False) -> SortUnique:
@@ -89,15 +89,17 @@ def sort_unique(keys: torch.Tensor, key_bits: int, want_order: bool = False) -> 
     r.counts = torch.empty(n, dtype=torch.int32, device=dev)
     r.order = torch.empty(n, dtype=torch.int32, device=dev) if want_order else None
     r.seg = torch.empty(n + 1, dtype=torch.int32, device=dev) if want_order else None
+    r.sorted_rank = torch.empty(n, dtype=torch.int32, device=dev) if want_order else None
     r.num = torch.empty(1, dtype=torch.int32, device=dev)
     L = _capi.lib()
     ws_bytes = L.lk_sort_unique_ws_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with _capi.timed('lk_sort_unique', n * 12 * 2 * ((int(key_bits) + 7) // 8)):
-        _capi.check(L.lk_sort_unique(_capi.ptr(keys), n, int(key_bits), _capi.ptr(r.unique),
-                                     _capi.ptr(r.inverse), _capi.ptr(r.order), _capi.ptr(r.seg),
-                                     _capi.ptr(r.counts), _capi.ptr(r.num), _capi.ptr(ws), ws_bytes,
-                                     _capi.stream()), 'lk_sort_unique')
+        _capi.check(L.lk_sort_unique_ex(_capi.ptr(keys), n, int(key_bits), _capi.ptr(r.unique),
+                                        _capi.ptr(r.inverse), _capi.ptr(r.order), _capi.ptr(r.seg),
+                                        _capi.ptr(r.counts), _capi.ptr(r.num),
+                                        _capi.ptr(r.sorted_rank), _capi.ptr(ws), ws_bytes,
+                                        _capi.stream()), 'lk_sort_unique_ex')
     return r
 
 

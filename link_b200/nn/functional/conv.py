@@ -37,6 +37,8 @@ class KernelMap:
         self.out_coords = out_coords
         self._inv = None
         self._ref = None
+        self.offsets = None      # int32 [K,3] offsets the map was built with (classes of the plan)
+        self._plan = None        # (perm [n_out], nbr_p [K,n_out], tile_mask [tiles]) or False
 
     @property
     def inv(self) -> torch.Tensor:
@@ -49,6 +51,33 @@ class KernelMap:
                         'lk_kmap_invert')
             self._inv = inv
         return self._inv
+
+    def plan_buffers(self):
+        """Uninitialised buffers of the tile-skipping plan (filled by lk_conv_plan, here or inside
+        the native block executor)."""
+        k, dev = self.nbr.shape[0], self.nbr.device
+        return (torch.empty(self.n_out, dtype=torch.int32, device=dev),
+                torch.empty(k, self.n_out, dtype=torch.int32, device=dev),
+                torch.empty((self.n_out + 127) // 128, dtype=torch.int32, device=dev))
+
+    def plan(self):
+        """Tile-skipping plan of this map for the tensor-core conv (lk_conv_plan), built once and
+        shared by every conv that reuses the map; None when the map is too wide (K > 32)."""
+        if self._plan is None:
+            k = self.nbr.shape[0]
+            if k > 32 or self.n_out == 0 or not USE_PLAN:
+                self._plan = False
+            else:
+                perm, nbr_p, tmask = self.plan_buffers()
+                L = _capi.lib()
+                ws_bytes = L.lk_conv_plan_ws_bytes(self.n_out)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.nbr.device)
+                with _capi.timed('lk_conv_plan', self.n_out * (4 * k * 2 + 8)):
+                    _capi.check(L.lk_conv_plan(_capi.ptr(self.nbr), self.n_out, k, _capi.ptr(self.offsets),
+                                               _capi.ptr(perm), _capi.ptr(nbr_p), _capi.ptr(tmask),
+                                               _capi.ptr(ws), ws_bytes, _capi.stream()), 'lk_conv_plan')
+                self._plan = (perm, nbr_p, tmask)
+        return self._plan or None
 
     def _reference_layout(self):
         if self._ref is None:
@@ -94,11 +123,15 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> Kern
         _capi.check(query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
                           _capi.ptr(table.table), table.capacity, _capi.ptr(nbr), _capi.stream()),
                     'lk_kmap_query')
-    return KernelMap(nbr, coords.shape[0], n_out, out_coords)
+    kmap = KernelMap(nbr, coords.shape[0], n_out, out_coords)
+    kmap.offsets = offsets
+    return kmap
 
 
 # dense / sparse GEMMs on tcgen05 (3xTF32, fp32-level accuracy); '0' selects the FFMA kernel
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
+# tile-skipping plan (lk_conv_plan) for the tensor-core conv; '0' runs every (offset, tile) step
+USE_PLAN = os.environ.get('LINKB200_CONV_PLAN', '1') != '0'
 _tc_supported = {}
 
 
@@ -137,7 +170,7 @@ def _transposed_padded(weight: torch.nn.Parameter, c_pad: int) -> torch.Tensor:
 
 
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
-              relu=False):
+              relu=False, kmap=None):
     """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
     None when its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies).
     epilogue: y = relu?(acc * scale + shift + residual), each part optional."""
@@ -167,11 +200,16 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         weight, c_in, tc_ok = None, 32, True
     if USE_TENSOR_CORES and tc_ok:
         wt = weight_t if weight_t is not None else _transposed(weight)
+        plan = kmap.plan() if kmap is not None else None      # only for the forward map (kmap.nbr)
+        if plan is not None:
+            nbr = plan[1]
         with _capi.timed('lk_conv_fwd', nb):
-            _capi.check(L.lk_conv_tc_fwd_ex(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
-                                            _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out,
-                                            C.byref(ep), _capi.ptr(out), _capi.stream()),
-                        'lk_conv_tc_fwd')
+            _capi.check(L.lk_conv_tc_fwd_plan(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
+                                              _capi.ptr(nbr, torch.int32),
+                                              _capi.ptr(plan[0]) if plan is not None else None,
+                                              _capi.ptr(plan[2]) if plan is not None else None,
+                                              n_out, k, c_in, c_out, C.byref(ep), _capi.ptr(out),
+                                              _capi.stream()), 'lk_conv_tc_fwd_plan')
         return out
     if weight is None:
         weight = weight_t.transpose(1, 2).contiguous()
@@ -192,7 +230,7 @@ class ConvolutionFunction(Function):
         feats = feats.contiguous().float()
         weight = weight.contiguous().float()
         if not transposed:
-            out = _conv_fwd(feats, weight, kmap.nbr, kmap.n_out)
+            out = _conv_fwd(feats, weight, kmap.nbr, kmap.n_out, kmap=kmap)
         else:
             out = _conv_fwd(feats, weight, kmap.inv, kmap.n_in)
         ctx.save_for_backward(feats, weight)
@@ -267,7 +305,7 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
         if kmap is None:
             kmap = build_kernel_map(input, kernel_size, stride, dilation)
             input.kmaps[key] = kmap
-        out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu)
+        out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu, kmap=kmap)
         output = SparseTensor(coords=kmap.out_coords, feats=out,
                               stride=tuple(input.stride[k] * stride[k] for k in range(3)))
     else:

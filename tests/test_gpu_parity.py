@@ -88,6 +88,7 @@ def test_sort_unique_vs_numpy(dev, n, bits):
     assert np.array_equal(su.order.cpu().numpy(), np.argsort(keys, kind='stable'))
     seg = su.seg[:m + 1].cpu().numpy()
     assert seg[0] == 0 and seg[-1] == n and np.array_equal(np.diff(seg), cnt)
+    assert np.array_equal(su.sorted_rank.cpu().numpy(), inv.reshape(-1)[np.argsort(keys, kind='stable')])
 
 
 def test_sort_unique_empty(dev):
@@ -223,6 +224,65 @@ def test_conv_chain_kmaps_and_outputs(dev):
         assert np.array_equal(km[1].cpu().numpy(), g[tag + '_nbsizes']), tag
     for y, k in zip(ys, ['y1', 'y2', 'y3', 'y4', 'y5']):
         np.testing.assert_allclose(y.F.cpu().numpy(), g[k], rtol=RTOL, atol=1e-5, err_msg=k)
+
+
+@pytest.mark.parametrize('n,cin,cout,ksize,stride', [(20_000, 64, 64, 3, 1), (3_000, 32, 64, 3, 1),
+                                                     (130, 64, 32, 3, 1), (9_000, 32, 32, 2, 2),
+                                                     (1, 64, 64, 3, 1)])
+def test_conv_plan_tile_skipping(dev, n, cin, cout, ksize, stride):
+    """lk_conv_plan: perm is a permutation grouped by class, nbr_p / tile_mask are consistent with
+    the kernel map; the planned tensor-core conv equals the unplanned one bit for bit (the plan only
+    moves rows between tiles) and the float64 numpy contraction within fp32 tolerance."""
+    import ctypes as Ct
+    import link_b200.nn.functional as F
+    from link_b200 import SparseTensor, _capi
+    from link_b200.nn.functional.conv import build_kernel_map, _conv_fwd
+    from link_b200.utils.synthetic import kitti_like_voxels, random_voxels
+    if n >= 9_000:
+        c3, _ = kitti_like_voxels(n, seed=3)
+        coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    else:
+        coords = random_voxels(n, 24, seed=n)
+    st = SparseTensor(torch.zeros(len(coords), cin, device=dev), cu(coords, dev), 1)
+    km = build_kernel_map(st, (ksize,) * 3, (stride,) * 3, (1, 1, 1))
+    K, n_out = km.nbr.shape
+    perm, nbr_p, tmask = km.plan()
+    nbr = km.nbr.cpu().numpy()
+    perm_h, nbr_p_h = perm.cpu().numpy(), nbr_p.cpu().numpy()
+    tmask_h = tmask.cpu().numpy().view(np.uint32)
+    assert np.array_equal(np.sort(perm_h), np.arange(n_out))
+    assert np.array_equal(nbr_p_h, nbr[:, perm_h])
+    rowmask = ((nbr >= 0) * (1 << np.arange(K, dtype=np.int64))[:, None]).sum(0)
+    pm = rowmask[perm_h]
+    pad = (-n_out) % 128
+    want_tm = np.bitwise_or.reduce(np.concatenate([pm, np.zeros(pad, np.int64)]).reshape(-1, 128), axis=1)
+    assert np.array_equal(tmask_h.astype(np.int64), want_tm)
+    if K <= 8:
+        cls = pm & 255
+    else:
+        off = km.offsets.cpu().numpy()
+        code = np.zeros(K, np.int64)
+        for a in range(3):
+            code |= (off[:, a] < 0).astype(np.int64) << (2 * a)
+            code |= (off[:, a] > 0).astype(np.int64) << (2 * a + 1)
+        cls = np.bitwise_or.reduce(np.where((nbr[:, perm_h] >= 0), code[:, None], 0), axis=0)
+    assert np.all(np.diff(cls) >= 0), 'rows must be grouped by class'
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(km.n_in, cin, generator=g)
+    w = torch.randn(K, cin, cout, generator=g) / np.sqrt(cin * 4)
+    res = torch.randn(n_out, cout, generator=g)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    xd, wd, rd, sd, hd = (t.to(dev) for t in (x, w, res, scale, shift))
+    planned = _conv_fwd(xd, wd, km.nbr, n_out, None, sd, hd, rd, True, kmap=km)
+    plain = _conv_fwd(xd, wd, km.nbr, n_out, None, sd, hd, rd, True)
+    assert torch.equal(planned, plain)
+    acc = np.zeros((n_out, cout))
+    xn, wn = x.numpy().astype(np.float64), w.numpy().astype(np.float64)
+    for k in range(K):
+        hit = nbr[k] >= 0
+        acc[hit] += xn[nbr[k][hit]] @ wn[k]
+    want = np.maximum(acc * scale.numpy() + shift.numpy() + res.numpy(), 0)
+    np.testing.assert_allclose(planned.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
 
 
 def test_conv_backward_vs_oracle_autograd(dev):
@@ -396,6 +456,56 @@ def test_full_size_scan_properties(dev):
     b = link_aggregate(f2, cc, bi, r, 'cos', w)
     ab = link_aggregate(f1 + 2 * f2, cc, bi, r, 'cos', w)
     np.testing.assert_allclose(ab.cpu().numpy(), (a + 2 * b).cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('op,C,groups', [('cos', 64, 2), ('sin', 32, 1), ('cos_x', 16, 1), ('cos', 128, 4),
+                                         ('cos', 48, 1), ('cos', 8, 1), ('cos_x', 4, 1)])
+@pytest.mark.parametrize('n', [1, 31, 1000, 40_013])
+def test_preagg_segmented_vs_storage_order_vs_numpy(dev, op, C, groups, n):
+    """The two forms of pass 1 (storage order + atomics per LiDAR column; block order through the
+    sort permutation) against a float64 numpy block sum of the weighted planes."""
+    import ctypes as Ct
+    from link_b200 import SparseTensor, _capi
+    from link_b200.elk import block_index, _kernel_gen
+    from link_b200.utils.synthetic import random_voxels
+    coords = random_voxels(n, 40, seed=n + C)
+    n = len(coords)
+    st = SparseTensor(torch.zeros(n, C, device=dev), cu(coords, dev), 1)
+    bi = block_index(st, 3)
+    m = bi.m
+    g = torch.Generator().manual_seed(C)
+    f = torch.randn(n, C, generator=g)
+    w = torch.randn(C // groups, 3, generator=g) * 0.3
+    alpha = torch.rand(C // groups, generator=g) + 0.5 if op == 'cos_x' else None
+    k = 3 if op == 'cos_x' else 2
+    w_d, a_d = w.to(dev), (alpha.to(dev) if alpha is not None else None)   # keep alive: gen holds raw pointers
+    gen = _kernel_gen(op, C, w_d, a_d, 1.0)
+    L, stream = _capi.lib(), _capi.stream()
+    fd = f.to(dev)
+    out = []
+    for seg in (False, True):
+        sums = torch.zeros(n, k * C, device=dev)
+        if seg:
+            _capi.check(L.lk_link_preagg_seg_fwd(_capi.ptr(fd), _capi.ptr(st.C), _capi.ptr(bi.order),
+                                                 _capi.ptr(bi.sorted_rank), n, Ct.byref(gen),
+                                                 _capi.ptr(sums), stream), 'seg')
+        else:
+            _capi.check(L.lk_link_preagg_fwd(_capi.ptr(fd), _capi.ptr(st.C), _capi.ptr(bi.idx_query), n,
+                                             Ct.byref(gen), _capi.ptr(sums), stream), 'storage')
+        out.append(sums[:m].cpu().numpy())
+        assert float(sums[m:].abs().max()) == 0.0 if m < n else True
+    pos = (coords[:, :3].astype(np.float32) @ w.numpy().T.astype(np.float32))
+    if alpha is not None:
+        pos = pos * alpha.numpy()
+    pos = np.tile(pos, (1, groups)).astype(np.float64)
+    fn = f.numpy().astype(np.float64)
+    planes = {'cos': [fn * np.cos(pos), fn * np.sin(pos)], 'sin': [fn * np.sin(pos), fn * np.cos(pos)],
+              'cos_x': [fn * np.cos(pos), fn * np.sin(pos), fn * pos]}[op]
+    want = np.zeros((m, k * C))
+    np.add.at(want, bi.idx_query.cpu().numpy(), np.concatenate(planes, 1))
+    for got in out:
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-5, atol=2e-5)
 
 
 # ------------------------------------------------------------------ dense pre_mix kernels
