@@ -220,14 +220,13 @@ typedef struct {
   float premix_eps;
   int32_t kvol;                  /* kernel volume of local_mix (27) */
   const float* d_conv_w;         /* [kvol,C,C]  local_mix.0.kernel (FFMA path), may be NULL */
-  const float* d_conv_wt;        /* [kvol,C,C]  its per-offset transpose (tensor-core path) */
+  const float* d_conv_wt;        /* packed tensor-core image of the kernel (lk_conv_tc_pack_weights) */
   const int32_t* d_conv_offsets; /* [kvol,3] kernel offsets (already scaled by the tensor stride) */
   int32_t* d_kmap;               /* caller-owned [kvol,n] kernel map of local_mix */
   int32_t build_kmap;            /* 1: build it here (hash -> table -> query) into d_kmap; 0: use it */
   int32_t build_plan;            /* 1: run lk_conv_plan on d_kmap into the three buffers below; 0: use them */
-  int32_t* d_plan_perm;          /* caller-owned tile-skipping plan of the kernel map (lk_conv_plan), */
-  int32_t* d_plan_nbr;           /*   [n], [kvol,n], [ceil(n/128)]; all NULL = run the tensor-core    */
-  uint32_t* d_plan_mask;         /*   conv without a plan                                              */
+  int32_t* d_plan_perm;          /* caller-owned tile-skipping plan of the kernel map (lk_conv_plan): */
+  uint32_t* d_plan_mask;         /*   [n], [ceil(n/128)]; both NULL = tensor-core conv without a plan */
   lk_keyspec_t keyspec;          /* block-key layout (div = block edge) */
   int32_t key_bits;
   int32_t r3;                    /* r^3 */
@@ -296,33 +295,39 @@ typedef struct {
 } lk_conv_epilogue_t;
 int lk_conv_fwd_ex(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out, int k,
                    int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out, lk_stream_t s);
-int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wt, const int32_t* d_nbr, int64_t n_out,
+int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wimg, const int32_t* d_nbr, int64_t n_out,
                       int k, int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
                       lk_stream_t s);
 
 /* Same contraction on the tcgen05 tensor cores (kind::tf32, 3xTF32 split => fp32-level accuracy):
  * weight-stationary persistent CTAs, the accumulators of up to 512/c_out output tiles resident in
- * TMEM, operands gathered into SWIZZLE_128B shared-memory tiles.  Takes the weights TRANSPOSED,
- * d_wt [K, c_out, c_in] (K-major B operand).  lk_conv_tc_supported: c_in, c_out in {32, 64}. */
+ * TMEM, gathered rows written straight into TMEM (A operand), weights fetched as packed images
+ * (d_wimg, see lk_conv_tc_pack_weights).  lk_conv_tc_supported: c_in, c_out in {32, 64}. */
 int lk_conv_tc_supported(int c_in, int c_out);
-int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_t* d_nbr, int64_t n_out,
+int lk_conv_tc_fwd(const float* d_in, const float* d_wimg, const int32_t* d_nbr, int64_t n_out,
                    int k, int c_in, int c_out, const float* d_bias /*or NULL*/, float* d_out,
                    lk_stream_t s);
 /* Tile-skipping plan for lk_conv_tc_fwd_plan (K <= 32).  Output rows are grouped by the signs of
  * the offsets they use (a counting sort on a <= 8-bit class derived from d_offsets int32 [K,3];
  * with K <= 8 or d_offsets == NULL the class is the K-bit presence mask itself), so that 128-row
  * tiles are homogeneous and (offset, tile) steps without a single pair can be skipped.
- * Outputs: d_perm [n_out] plan position -> output row; d_nbr_p [K, n_out] the kernel map in plan
- * order (d_nbr_p[k, i] = d_nbr[k, d_perm[i]]); d_tile_mask [ceil(n_out/128)] bit k set iff some
- * row of the tile has a neighbour at offset k.  Results of the convolution do not depend on the
- * plan (same per-row sums in the same order). */
+ * Outputs: d_perm [n_out] plan position -> output row (tile t = positions [128 t, 128 t + 128));
+ * d_tile_mask [ceil(n_out/128)] bit k set iff some row of the tile has a neighbour at offset k.
+ * Results of the convolution do not depend on the plan (same per-row sums in the same order). */
 int64_t lk_conv_plan_ws_bytes(int64_t n_out);
 int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const int32_t* d_offsets /*or NULL*/,
-                 int32_t* d_perm, int32_t* d_nbr_p, uint32_t* d_tile_mask, void* d_ws,
-                 int64_t ws_bytes, lk_stream_t s);
-/* lk_conv_tc_fwd_ex on a planned kernel map: d_nbr is the plan-order map (d_nbr_p), d_perm and
- * d_tile_mask as produced by lk_conv_plan (both NULL = identity order, no skipping). */
-int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const int32_t* d_nbr,
+                 int32_t* d_perm, uint32_t* d_tile_mask, void* d_ws, int64_t ws_bytes,
+                 lk_stream_t s);
+/* Weights of the tensor-core conv as the kernel consumes them: per offset k one contiguous image
+ * of the shared-memory B operand (tf32 hi plane then lo plane, each [c_in/32] K-blocks of
+ * [c_out rows x 128 bytes] in the SWIZZLE_128B pattern), so that the kernel fetches W[k] with ONE
+ * asynchronous bulk copy.  d_wt [K, c_out, c_in] (per-offset transpose of the module parameter);
+ * d_img: K * 8 * c_in * c_out bytes.  Packed once per weight update (cached by the caller). */
+int lk_conv_tc_pack_weights(const float* d_wt, int k, int c_in, int c_out, float* d_img,
+                            lk_stream_t s);
+/* The tensor-core conv on packed weights, optionally with a plan: d_perm and d_tile_mask as
+ * produced by lk_conv_plan (both NULL = identity order, no skipping). */
+int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wimg, const int32_t* d_nbr,
                         const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
                         int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
                         lk_stream_t s);

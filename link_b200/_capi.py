@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblinkb200.so')
+LIB_PATH = os.environ.get('LINKB200_LIB') or os.path.join(_HERE, 'liblinkb200.so')
 
 _lib = None
 
@@ -42,7 +42,7 @@ class ElkBlockArgs(C.Structure):
                 ('d_premix_b', C.c_void_p), ('premix_eps', C.c_float), ('kvol', C.c_int32),
                 ('d_conv_w', C.c_void_p), ('d_conv_wt', C.c_void_p), ('d_conv_offsets', C.c_void_p),
                 ('d_kmap', C.c_void_p), ('build_kmap', C.c_int32), ('build_plan', C.c_int32),
-                ('d_plan_perm', C.c_void_p), ('d_plan_nbr', C.c_void_p), ('d_plan_mask', C.c_void_p),
+                ('d_plan_perm', C.c_void_p), ('d_plan_mask', C.c_void_p),
                 ('keyspec', KeySpec), ('key_bits', C.c_int32), ('r3', C.c_int32),
                 ('d_block_offsets', C.c_void_p), ('gen', KernelGen),
                 ('d_g1', C.c_void_p), ('d_b1', C.c_void_p), ('d_g2', C.c_void_p), ('d_b2', C.c_void_p),
@@ -92,7 +92,8 @@ PROTOTYPES = {
     'lk_conv_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_plan_ws_bytes': (i64, [i64]),
-    'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, i64, vp]),
+    'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp]),
+    'lk_conv_tc_pack_weights': (i32, [vp, i32, i32, i32, vp, vp]),
     'lk_conv_tc_fwd_plan': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),

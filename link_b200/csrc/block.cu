@@ -88,12 +88,12 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
     LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, s));
   // local_mix
   if (a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt) {
-    if (a->d_plan_perm && a->d_plan_nbr && a->d_plan_mask && a->kvol <= 32) {
+    if (a->d_plan_perm && a->d_plan_mask && a->kvol <= 32) {
       if (a->build_plan)
-        LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_nbr,
-                            a->d_plan_mask, ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
-      LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, a->d_plan_nbr, a->d_plan_perm,
-                                 a->d_plan_mask, n, a->kvol, c, c, nullptr, local, s));
+        LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
+                            ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
+      LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, kmap, a->d_plan_perm, a->d_plan_mask, n,
+                                 a->kvol, c, c, nullptr, local, s));
     } else {
       LK_TRY(lk_conv_tc_fwd(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, nullptr, local, s));
     }

@@ -11,8 +11,7 @@
 //
 //   class kernel   : per row, the K-bit mask of present offsets and its class; class histogram
 //   scatter kernel : perm[position] = row      (class-major order, order inside a class arbitrary)
-//   tile kernel    : nbr_p[k, i] = nbr[k, perm[i]]  (kernel map in plan order, coalesced for the
-//                    conv) and tile_mask[t] = OR of the masks of the tile's rows
+//                    and tile_mask[position / 128] |= mask of the row
 //
 // Output values do not depend on the plan: every output row is still the same sum over k in the
 // same order, only the tile it is computed in changes.  The reference has no counterpart (its
@@ -32,8 +31,12 @@ __global__ void __launch_bounds__(256) plan_class_kernel(const int* __restrict__
                                                          int K, const int* __restrict__ offsets,
                                                          unsigned* __restrict__ rowmask,
                                                          unsigned char* __restrict__ cls,
-                                                         unsigned* __restrict__ hist) {
+                                                         unsigned* __restrict__ hist,
+                                                         unsigned* __restrict__ tile_mask, int tiles) {
   __shared__ unsigned h[256];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tiles;
+       t += (int64_t)gridDim.x * blockDim.x)
+    tile_mask[t] = 0u;                             // OR-accumulated by the scatter kernel
   __shared__ unsigned code[32];
   h[threadIdx.x] = 0;
   if (threadIdx.x < 32) {
@@ -68,7 +71,9 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(const unsigned char* 
                                                            int64_t n_out,
                                                            const unsigned* __restrict__ hist,
                                                            unsigned* __restrict__ cursor,
-                                                           int* __restrict__ perm) {
+                                                           const unsigned* __restrict__ rowmask,
+                                                           int* __restrict__ perm,
+                                                           unsigned* __restrict__ tile_mask) {
   __shared__ unsigned base[256];
   __shared__ unsigned wsum[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,51 +91,41 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(const unsigned char* 
   for (int w = 0; w < 8; ++w) wb += (w < warp) ? wsum[w] : 0u;
   base[tid] = wb + incl - v;
   __syncthreads();
+  // Positions are reserved per (CTA, class): ranks inside the CTA come from shared-memory atomics
+  // and ONE global atomic per class present in the CTA claims the range, so the 64 hot class
+  // cursors see ~10 atomics per CTA instead of one per warp and class.
+  __shared__ unsigned cnt_s[256];
+  __shared__ unsigned cta_base[256];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (n_out + stride - 1) / stride;
-  for (int64_t it = 0; it < rounds; ++it) {       // uniform trip count: match_any needs the full warp
+  for (int64_t it = 0; it < rounds; ++it) {       // uniform trip count (block-wide barriers inside)
+    cnt_s[tid] = 0;
+    __syncthreads();
     const int64_t o = it * stride + blockIdx.x * (int64_t)blockDim.x + tid;
     const bool ok = o < n_out;
-    const unsigned c = ok ? cls[o] : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const int leader = __ffs(peers) - 1;
-    unsigned first = 0;
-    if (lane == leader && ok) first = atomicAdd(&cursor[c], (unsigned)__popc(peers));
-    first = __shfl_sync(0xffffffffu, first, leader);
-    if (ok) perm[base[c] + first + __popc(peers & ((1u << lane) - 1u))] = (int)o;
-  }
-}
-
-__global__ void __launch_bounds__(CP_TILE) plan_tiles_kernel(const int* __restrict__ nbr, int64_t n_out,
-                                                             int K, const int* __restrict__ perm,
-                                                             const unsigned* __restrict__ rowmask,
-                                                             int* __restrict__ nbr_p,
-                                                             unsigned* __restrict__ tile_mask) {
-  __shared__ unsigned wm[CP_TILE / 32];
-  const int64_t i = (int64_t)blockIdx.x * CP_TILE + threadIdx.x;
-  const int row = i < n_out ? perm[i] : -1;
-  unsigned m = row >= 0 ? rowmask[row] : 0u;
-  unsigned wmask = __reduce_or_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = wmask;
-  if (row >= 0) {
-    for (int k = 0; k < K; ++k)
-      nbr_p[(int64_t)k * n_out + i] = (m >> k) & 1u ? __ldg(nbr + (int64_t)k * n_out + row) : -1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t = 0;
-#pragma unroll
-    for (int w = 0; w < CP_TILE / 32; ++w) t |= wm[w];
-    tile_mask[blockIdx.x] = t;
+    const unsigned c = ok ? cls[o] : 0u;
+    const unsigned m = ok ? rowmask[o] : 0u;
+    unsigned r = 0;
+    if (ok) r = atomicAdd(&cnt_s[c], 1u);
+    __syncthreads();
+    if (cnt_s[tid]) cta_base[tid] = base[tid] + atomicAdd(&cursor[tid], cnt_s[tid]);
+    __syncthreads();
+    const unsigned pos = ok ? cta_base[c] + r : 0xFFFFFFFFu;
+    if (ok) perm[pos] = (int)o;
+    // tile masks: one atomicOr per (warp, tile) -- lanes of a warp mostly land in 1-3 tiles
+    const unsigned tile = ok ? pos / CP_TILE : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, tile);
+    const unsigned tm = __reduce_or_sync(peers, m);
+    if (ok && lane == __ffs(peers) - 1) atomicOr(&tile_mask[tile], tm);
   }
 }
 
 extern "C" int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const int32_t* d_offsets,
-                            int32_t* d_perm, int32_t* d_nbr_p, uint32_t* d_tile_mask, void* d_ws,
-                            int64_t ws_bytes, lk_stream_t s) {
+                            int32_t* d_perm, uint32_t* d_tile_mask, void* d_ws, int64_t ws_bytes,
+                            lk_stream_t s) {
   LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32, "lk_conv_plan: needs 1 <= K <= 32");
   if (n_out == 0) return LK_OK;
-  LK_REQUIRE(d_nbr && d_perm && d_nbr_p && d_tile_mask && d_ws, "lk_conv_plan: null pointer");
+  LK_REQUIRE(d_nbr && d_perm && d_tile_mask && d_ws, "lk_conv_plan: null pointer");
   if (ws_bytes < lk_conv_plan_ws_bytes(n_out)) {
     lk_set_error("lk_conv_plan: workspace %lld < %lld bytes", (long long)ws_bytes,
                  (long long)lk_conv_plan_ws_bytes(n_out));
@@ -142,15 +137,13 @@ extern "C" int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const in
   unsigned char* cls = (unsigned char*)p; p += cp_al(n_out);
   unsigned* hist = (unsigned*)p; p += cp_al(256 * 4);
   unsigned* cursor = (unsigned*)p;
+  const int tiles = (int)((n_out + CP_TILE - 1) / CP_TILE);
   LK_CUDA(cudaMemsetAsync(hist, 0, 2 * cp_al(256 * 4), st));
   lk_count_launch();
   const int grid = lk_grid(n_out, 256, 4);
-  plan_class_kernel<<<grid, 256, 0, st>>>(d_nbr, n_out, k, d_offsets, rowmask, cls, hist);
+  plan_class_kernel<<<grid, 256, 0, st>>>(d_nbr, n_out, k, d_offsets, rowmask, cls, hist, d_tile_mask, tiles);
   LK_LAUNCHED();
-  plan_scatter_kernel<<<grid, 256, 0, st>>>(cls, n_out, hist, cursor, d_perm);
-  LK_LAUNCHED();
-  const int tiles = (int)((n_out + CP_TILE - 1) / CP_TILE);
-  plan_tiles_kernel<<<tiles, CP_TILE, 0, st>>>(d_nbr, n_out, k, d_perm, rowmask, d_nbr_p, d_tile_mask);
+  plan_scatter_kernel<<<grid, 256, 0, st>>>(cls, n_out, hist, cursor, rowmask, d_perm, d_tile_mask);
   LK_LAUNCHED();
   return LK_OK;
 }

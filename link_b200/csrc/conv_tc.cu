@@ -28,43 +28,49 @@
 //     -> + residual -> ReLU -> one streaming store per row.
 //
 // No atomics, no temporaries, deterministic, output written exactly once.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
 #define CT_ROWS 128
 #define CT_THREADS 512      // producer threads (16 warps); one more warp issues the MMAs
-#define CT_ACC_COLS 256     // TMEM columns [0,256): accumulators; [256,512): two A stages
+// TMEM: columns [0, 512 - 128 NST) hold the accumulators, the rest NST A stages of 128 columns
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int NST>
 struct ConvTcCfg {
   static constexpr int KB = CIN / 32;                       // 128-byte K-blocks per weight row
   static constexpr uint32_t B_BLK = COUT * 128;             // one [COUT x 32] K-block
   static constexpr uint32_t B_PLANE = KB * B_BLK;           // hi (or lo) plane
   static constexpr uint32_t B_STAGE = 2 * B_PLANE;          // hi + lo
-  static constexpr uint32_t SMEM = 2 * B_STAGE + 1024;      // double-buffered W[k] + alignment slack
-  static constexpr int MAX_TILES = CT_ACC_COLS / COUT;
+  static constexpr int NWB = 6;                             // W[k] ring: prefetched NWB-2 offsets ahead
+  static constexpr uint32_t SMEM = NWB * B_STAGE + 1024;     // weight ring + alignment slack
+  static constexpr int ACC_COLS = 512 - 128 * NST;
+  static constexpr int MAX_TILES = ACC_COLS / COUT;
   static constexpr int A_STAGE_COLS = 128;                  // hi plane at +0, lo plane at +64
   static constexpr int CPT = CIN / 4;                       // input channels per producer thread
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int NST>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
-    const float* __restrict__ in, const float* __restrict__ wt /*[K][COUT][CIN]*/,
-    const int* __restrict__ nbr /*[K][n_out], in plan order when perm != NULL*/,
+    const float* __restrict__ in, const float* __restrict__ wimg /*[K] packed B-operand images*/,
+    const int* __restrict__ nbr /*[K][n_out]*/,
     const int* __restrict__ perm /*[n_out] plan position -> output row, or NULL = identity*/,
     const unsigned* __restrict__ tile_mask /*[tiles] offsets present in each tile, or NULL = all*/,
     int64_t n_out, int K, lk_conv_epilogue_t ep, float* __restrict__ out) {
-  using Cfg = ConvTcCfg<CIN, COUT>;
-  constexpr int KB = Cfg::KB;
+  using Cfg = ConvTcCfg<CIN, COUT, NST>;
   constexpr int CPT = Cfg::CPT;                 // 16 (CIN = 64) or 8 (CIN = 32)
   constexpr int MAXT = Cfg::MAX_TILES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const b_base = smem;
-  __shared__ uint64_t full_bar[2];    // A stage written   (one arrival per producer warp)
-  __shared__ uint64_t empty_bar[2];   // A stage consumed  (tcgen05.commit)
+  __shared__ uint64_t full_bar[NST];  // A stage written   (one arrival per producer warp)
+  __shared__ uint64_t empty_bar[NST]; // A stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint64_t wfull_bar[Cfg::NWB];  // W[k] image landed (bulk copy, complete_tx)
   __shared__ uint16_t steps_s[32 * MAXT];   // active (offset, tile slot) steps of the round: k << 4 | t
+  __shared__ uint8_t klist_s[32];           // distinct offsets of the round, ascending
+  __shared__ int orow_s[MAXT][CT_ROWS];     // output row of every tile-slot row (-1 past the end)
   __shared__ uint32_t tmask_s[MAXT];
   __shared__ int warp_cnt_s[8];
   __shared__ int nsteps_s;
@@ -75,22 +81,28 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    tc::mbar_init(&full_bar[0], CT_THREADS / 32);
-    tc::mbar_init(&full_bar[1], CT_THREADS / 32);
-    tc::mbar_init(&empty_bar[0], 1);
-    tc::mbar_init(&empty_bar[1], 1);
+#pragma unroll
+    for (int b = 0; b < NST; ++b) {
+      tc::mbar_init(&full_bar[b], CT_THREADS / 32);
+      tc::mbar_init(&empty_bar[b], 1);
+    }
+#pragma unroll
+    for (int b = 0; b < Cfg::NWB; ++b) tc::mbar_init(&wfull_bar[b], 1);
     tc::fence_mbar_init();
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_a0 = tmem_base + CT_ACC_COLS;          // A stage s at + s * 128 columns
+  const uint32_t tmem_a0 = tmem_base + Cfg::ACC_COLS;        // A stage s at + s * 128 columns
 
-  // Persistent CTA: round r owns the tile slots t < MAXT with tile = blockIdx.x + (r MAXT + t) gridDim.x
-  // (interleaved, so the heavy classes at the end of the plan order spread over all CTAs).
+  // Persistent CTA: round r owns the tile slots t < MAXT with tile = blockIdx.x + (r MAXT + t) gridDim.x.
+  // Interleaving spreads the heavy classes at the end of the plan order over all CTAs and keeps
+  // the number of rounds per CTA minimal (a round costs ~5 us of set-up, drain and epilogue; work-
+  // balanced CONTIGUOUS ranges share each W[k] between more steps but give the CTAs that own the
+  // light classes 10+ rounds and were 25 % slower end to end).
   int jbase = 0;      // steps issued in earlier rounds: A-stage index and mbarrier phase continue
-  int wcount = 0;     // W[k] stagings so far: weight double-buffer index continues
+  int wcount = 0;     // offsets (W[k] images) consumed so far: weight ring index / phase continue
   for (int round = 0;; ++round) {
     const int64_t first_tile = (int64_t)blockIdx.x + (int64_t)round * MAXT * gridDim.x;
     if (first_tile >= total_tiles) break;
@@ -112,9 +124,48 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       for (int w = 0; w < 8; ++w) pos += (w < warp) ? warp_cnt_s[w] : 0;
       if (on) steps_s[pos] = (uint16_t)((kk << 4) | tt);
       if (tid == 255) nsteps_s = pos + (on ? 1 : 0);
+    } else if (tid < 256 + 32) {
+      uint32_t uni = 0;
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) uni |= tmask_s[t];
+      if ((uni >> lane) & 1u) klist_s[__popc(uni & ((1u << lane) - 1u))] = (uint8_t)lane;
+    }
+    for (int i = tid; i < MAXT * CT_ROWS; i += CT_THREADS + 32) {
+      const int t = i / CT_ROWS, r = i % CT_ROWS;
+      int o = -1;
+      if (t < ntiles) {
+        const int64_t pos = (first_tile + (int64_t)t * gridDim.x) * CT_ROWS + r;
+        if (pos < n_out) o = perm ? __ldg(perm + pos) : (int)pos;
+      }
+      orow_s[t][r] = o;
     }
     __syncthreads();
     const int nsteps = nsteps_s;
+    uint32_t uni_mask = 0;
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) uni_mask |= tmask_s[t];
+    const int nk = __popc(uni_mask);            // distinct offsets of this round
+    // W[k] images arrive by bulk copy into a ring of NWB buffers, NWB-NST offsets ahead of their
+    // use.  Offset number w (global count wcount + local index) lives in buffer w % NWB; the copy
+    // for offset w + NWB - NST is issued when offset w begins and overwrites offset w - NST, all of
+    // whose MMAs are complete: the NST - 1 offsets in between have >= 1 step each and the issuing
+    // thread has just observed the commit of step j - NST (a round boundary drains everything).
+    auto issue_w = [&](int local_idx) {
+      if (local_idx < nk) {
+        const int wg = wcount + local_idx;
+        uint64_t* bar = &wfull_bar[wg % Cfg::NWB];
+        const uint32_t dst = tc::smem_u32(b_base + (wg % Cfg::NWB) * Cfg::B_STAGE);
+        const float* src = wimg + (int64_t)klist_s[local_idx] * (Cfg::B_STAGE / 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(tc::smem_u32(bar)), "r"(Cfg::B_STAGE) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(Cfg::B_STAGE), "r"(tc::smem_u32(bar)) : "memory");
+      }
+    };
+    if (tid == 0) {
+#pragma unroll
+      for (int w = 0; w < Cfg::NWB - NST; ++w) issue_w(w);
+    }
 
     if (warp == CT_THREADS / 32) {
       // ================= MMA issuer warp =================
@@ -124,16 +175,20 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       int k_prev = -1, wc = wcount;
       for (int j = 0; j < nsteps; ++j) {
         const int jg = jbase + j;
-        const int stage = jg & 1;
+        const int stage = jg % NST;
         const int k = steps_s[j] >> 4, t = steps_s[j] & 15;
-        if (k != k_prev) { k_prev = k; ++wc; }             // wc - 1 = index of this offset's staging
-        tc::mbar_wait(&full_bar[stage], (uint32_t)(jg >> 1) & 1u);
+        if (k != k_prev) {                                 // first step of an offset: its W image
+          k_prev = k;
+          tc::mbar_wait(&wfull_bar[wc % Cfg::NWB], (uint32_t)(wc / Cfg::NWB) & 1u);
+          ++wc;                                            // wc - 1 = ring index of this offset
+        }
+        tc::mbar_wait(&full_bar[stage], (uint32_t)(jg / NST) & 1u);
         tc::fence_after_sync();
         if (tc::elect_one()) {
           const uint32_t d = tmem_base + (uint32_t)(t * COUT);
           const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS);
           const uint32_t a_lo = a_hi + 64;
-          const uint64_t db_hi = db0 + (uint64_t)((((wc - 1) & 1) * Cfg::B_STAGE) >> 4);
+          const uint64_t db_hi = db0 + (uint64_t)((((wc - 1) % Cfg::NWB) * Cfg::B_STAGE) >> 4);
           const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
           uint32_t acc = (touched >> t) & 1u;
 #pragma unroll
@@ -161,8 +216,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       auto load_idx = [&](int jj) -> int {
         if (jj >= nsteps) return -1;
         const int k2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
-        const int64_t o = (first_tile + (int64_t)t2 * gridDim.x) * CT_ROWS + prow;
-        return o < n_out ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
+        const int o = orow_s[t2][prow];
+        return o >= 0 ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
       };
       auto load_rows = [&](int src, float4* v) {
         if (src >= 0) {
@@ -174,48 +229,36 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           for (int i = 0; i < CPT / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      float4 v[CPT / 4], v_next[CPT / 4];
-      int src_a = load_idx(0);
-      load_rows(src_a, v);
-      int src_b = load_idx(1);
+      // Register ring of depth 2: the rows of step j are fetched while steps j-2 and j-1 are being
+      // processed (two full steps of lead time cover the L2 gather latency; with one step the
+      // producers sat on the loads), their indices two steps before that.
+      float4 va[CPT / 4], vb[CPT / 4];
+      load_rows(load_idx(0), va);
+      load_rows(load_idx(1), vb);
+      int idx_a = load_idx(2), idx_b = load_idx(3);     // rows of steps 2 / 3, fetched at steps 0 / 1
       int k_prev = -1, wc = wcount;
-      for (int j = 0; j < nsteps; ++j) {
+      auto produce = [&](int j, float4* cur, int& idx_cur) {
         const int jg = jbase + j;
-        const int stage = jg & 1;
+        const int stage = jg % NST;
         const int k = steps_s[j] >> 4;
-        const int src_c = load_idx(j + 2);      // index prefetch distance 2
-        load_rows(src_b, v_next);               // row prefetch distance 1 (in flight during the stores)
         // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on the
         // critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
         float hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < CPT / 4; ++i) {
           float4 h4, l4;
-          tc::split_tf32(v[i], h4, l4);
+          tc::split_tf32(cur[i], h4, l4);
           hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
           lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
         }
-        if (jg >= 2) tc::mbar_wait(&empty_bar[stage], (uint32_t)((jg >> 1) - 1) & 1u);
+        load_rows(idx_cur, cur);                // refill this buffer: rows of step j + 2
+        idx_cur = load_idx(j + 4);              // ... and the index for its next refill
+        if (jg >= NST) tc::mbar_wait(&empty_bar[stage], (uint32_t)((jg / NST) - 1) & 1u);
         tc::fence_after_sync();
-        if (k != k_prev) {
-          // stage W[k] into buffer (stagings so far) & 1.  Its last readers are the MMAs of the
-          // offset staged two stagings ago; the offset staged in between has at least one step, so
-          // they all precede step jg-2's commit, which the wait above has just observed (a round
-          // boundary drains every MMA).
+        if (k != k_prev) {                      // an offset begins: prefetch the one after next
           k_prev = k;
-          uint8_t* bh = b_base + (wc & 1) * Cfg::B_STAGE;
-          uint8_t* bl = bh + Cfg::B_PLANE;
+          if (tid == 0) issue_w(wc - wcount + Cfg::NWB - NST);
           ++wc;
-          const float* wk = wt + (int64_t)k * COUT * CIN;
-          for (int tt = tid; tt < COUT * KB * 8; tt += CT_THREADS) {
-            int chunk = tt & 7, kb = (tt >> 3) % KB, row = tt / (8 * KB);
-            float4 w4 = __ldg((const float4*)(wk + row * CIN + kb * 32 + chunk * 4)), whi, wlo;
-            tc::split_tf32(w4, whi, wlo);
-            uint32_t off = kb * Cfg::B_BLK + tc::sw128_offset(row, chunk);
-            *(float4*)(bh + off) = whi;
-            *(float4*)(bl + off) = wlo;
-          }
-          tc::fence_proxy_async();              // generic-proxy stores -> visible to the tensor core
         }
         const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + lane_addr + (uint32_t)col0;
         if (CPT == 16) {
@@ -229,23 +272,25 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
-#pragma unroll
-        for (int i = 0; i < CPT / 4; ++i) v[i] = v_next[i];
-        src_a = src_b;
-        src_b = src_c;
+      };
+      for (int j = 0; j < nsteps; j += 2) {
+        produce(j, va, idx_a);
+        if (j + 1 < nsteps) produce(j + 1, vb, idx_b);
       }
       // ---- drain: the last commit on each stage ----
       const int gtot = jbase + nsteps;
-      const int c0 = (gtot + 1) >> 1, c1 = gtot >> 1;
-      if (c0) tc::mbar_wait(&empty_bar[0], (uint32_t)(c0 - 1) & 1u);
-      if (c1) tc::mbar_wait(&empty_bar[1], (uint32_t)(c1 - 1) & 1u);
+#pragma unroll
+      for (int b = 0; b < NST; ++b) {
+        const int cb = gtot > b ? (gtot - b + NST - 1) / NST : 0;   // commits seen by stage b so far
+        if (cb) tc::mbar_wait(&empty_bar[b], (uint32_t)(cb - 1) & 1u);
+      }
       tc::fence_after_sync();
       // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
       constexpr int NSLICE = COUT / 16;
       if (cs < NSLICE) {
         const int c_base = cs * 16;
         for (int tt = 0; tt < ntiles; ++tt) {
-          const int64_t pos = (first_tile + (int64_t)tt * gridDim.x) * CT_ROWS + prow;
+          const int orow = orow_s[tt][prow];
           float acc[16];
           if (tmask_s[tt]) {
             tc::tmem_ld16(tmem_base + lane_addr + (uint32_t)(tt * COUT + c_base), acc);
@@ -253,8 +298,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = 0.f;
           }
-          if (pos < n_out) {
-            const int64_t o = perm ? (int64_t)__ldg(perm + pos) : pos;
+          if (orow >= 0) {
+            const int64_t o = orow;
             float* dst = out + o * COUT + c_base;
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
@@ -282,13 +327,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     }
     // round boundary: every MMA has completed (drain) and every accumulator has been read before
     // the next round's first MMA overwrites it
-    {
-      int kp = -1;
-      for (int j = 0; j < nsteps; ++j) {        // uniform bookkeeping for all roles
-        const int k = steps_s[j] >> 4;
-        if (k != kp) { kp = k; ++wcount; }
-      }
-    }
+    wcount += nk;
     jbase += nsteps;
     tc::fence_before_sync();
     __syncthreads();
@@ -299,27 +338,81 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int CIN, int COUT>
-static int launch_conv_tc(const float* in, const float* wt, const int* nbr, const int* perm,
+template <int CIN, int COUT, int NST>
+static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
-  using Cfg = ConvTcCfg<CIN, COUT>;
+  using Cfg = ConvTcCfg<CIN, COUT, NST>;
   static bool attr_set = false;
   if (!attr_set) {
-    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)Cfg::SMEM));
     attr_set = true;
   }
   int64_t tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   int grid = (int)(tiles < LK_SM_COUNT ? tiles : LK_SM_COUNT);   // persistent: one CTA per SM
-  conv_tc_kernel<CIN, COUT><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wt, nbr, perm, tile_mask,
+  conv_tc_kernel<CIN, COUT, NST><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
                                                                       n_out, k, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
 
+// number of TMEM A stages (tuning knob, default 2): 3 stages hide more of the producer <-> MMA
+// handshake latency but leave room for only two accumulator tiles per round at C_out = 64, i.e.
+// twice the rounds; measured slower
+static int conv_tc_stages() {
+  static int nst = 0;
+  if (!nst) {
+    const char* e = getenv("LINKB200_CONV_STAGES");
+    nst = (e && e[0] == '3') ? 3 : 2;
+  }
+  return nst;
+}
+
+template <int CIN, int COUT>
+static int launch_conv_tc(const float* in, const float* wimg, const int* nbr, const int* perm,
+                          const unsigned* tile_mask, int64_t n_out, int k,
+                          const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
+  if (conv_tc_stages() == 2)
+    return launch_conv_tc_n<CIN, COUT, 2>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+  return launch_conv_tc_n<CIN, COUT, 3>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+}
+
 extern "C" int lk_conv_tc_supported(int c_in, int c_out) {
   return (c_in == 32 || c_in == 64) && (c_out == 32 || c_out == 64);
+}
+
+// W[k] [COUT][CIN] -> the kernel's shared-memory image: tf32 hi plane, then lo plane, each CIN/32
+// K-blocks of [COUT rows x 128 B] in the SWIZZLE_128B pattern (one thread per 16-byte chunk)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ wt, int K, int cin,
+                                                           int cout, float* __restrict__ img) {
+  const int kb_n = cin / 32;
+  const int64_t per_k = (int64_t)cout * kb_n * 8;          // 16-byte chunks per plane
+  const int64_t total = (int64_t)K * per_k;
+  const int64_t stage_floats = (int64_t)2 * cin * cout;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / per_k);
+    const int r = (int)(t - (int64_t)k * per_k);
+    const int chunk = r & 7, kb = (r >> 3) % kb_n, row = r / (8 * kb_n);
+    float4 w4 = __ldg((const float4*)(wt + ((int64_t)k * cout + row) * cin + kb * 32 + chunk * 4)), hi, lo;
+    tc::split_tf32(w4, hi, lo);
+    const uint32_t off = (uint32_t)kb * (uint32_t)(cout * 128) + tc::sw128_offset(row, chunk);
+    float* base = img + (int64_t)k * stage_floats;
+    *(float4*)((uint8_t*)base + off) = hi;
+    *(float4*)((uint8_t*)base + (size_t)cin * cout * 4 + off) = lo;
+  }
+}
+
+extern "C" int lk_conv_tc_pack_weights(const float* d_wt, int k, int c_in, int c_out, float* d_img,
+                                       lk_stream_t s) {
+  LK_REQUIRE(k > 0 && lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_pack_weights: channels must be 32 or 64");
+  LK_REQUIRE(d_wt && d_img && (uintptr_t)d_wt % 16 == 0 && (uintptr_t)d_img % 128 == 0,
+             "lk_conv_tc_pack_weights: null or misaligned pointer");
+  pack_weights_kernel<<<lk_grid((int64_t)k * c_out * (c_in / 32) * 8, 256, 4), 256, 0, (cudaStream_t)s>>>(
+      d_wt, k, c_in, c_out, d_img);
+  LK_LAUNCHED();
+  return LK_OK;
 }
 
 extern "C" int lk_conv_tc_fwd(const float* d_in, const float* d_wt, const int32_t* d_nbr,

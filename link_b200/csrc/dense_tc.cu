@@ -37,13 +37,25 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
   if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
   // W [C out][C in] is already "N rows x K contiguous" = K-major B.  8 lanes cover one 128-byte
   // K-block of one row per load instruction (fully coalesced).
-  for (int t = tid; t < C * KB * 8; t += DT_THREADS) {
-    int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
-    float4 v = __ldg((const float4*)(w + (int64_t)row * C + kb * 32 + chunk * 4)), hi, lo;
-    tc::split_tf32(v, hi, lo);
-    uint32_t off = kb * B_BLK + tc::sw128_offset(row, chunk);
-    *(float4*)(b_hi + off) = hi;
-    *(float4*)(b_lo + off) = lo;
+  {
+    constexpr int NW = C * KB * 8 / DT_THREADS;      // all weight loads in flight before the first use
+    float4 wv[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      int t = tid + i * DT_THREADS;
+      int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
+      wv[i] = __ldg((const float4*)(w + (int64_t)row * C + kb * 32 + chunk * 4));
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      int t = tid + i * DT_THREADS;
+      int chunk = t & 7, kb = (t >> 3) % KB, row = t / (8 * KB);
+      float4 hi, lo;
+      tc::split_tf32(wv[i], hi, lo);
+      uint32_t off = kb * B_BLK + tc::sw128_offset(row, chunk);
+      *(float4*)(b_hi + off) = hi;
+      *(float4*)(b_lo + off) = lo;
+    }
   }
   tc::fence_before_sync();
   __syncthreads();

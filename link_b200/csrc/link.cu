@@ -33,14 +33,18 @@ struct GenDev {
 
 // libdevice sincosf kept out of line: inlined into the unrolled row loops its slow path
 // (Payne-Hanek) multiplies the code size ~10x and the kernels become instruction-fetch bound.
-__device__ __noinline__ void accurate_sincos(float p, float* s, float* c) { sincosf(p, s, c); }
+__device__ __noinline__ float2 accurate_sincos(float p) {
+  float s, c;
+  sincosf(p, &s, &c);
+  return make_float2(s, c);
+}
 
 // sin and cos of one fp32 phase: two-term Cody-Waite reduction to [-pi, pi] (exact for the
 // |p| < ~1e5 rad that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7) followed by the SFU
 // approximations (sin.approx / cos.approx, max abs error 2^-20.9 on [-pi, pi]).  ~9 instructions
 // instead of ~20 for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
 __device__ __forceinline__ void fast_sincos(float p, bool accurate, float& s, float& c) {
-  if (accurate) { accurate_sincos(p, &s, &c); return; }      // warp-uniform switch
+  if (accurate) { float2 sc = accurate_sincos(p); s = sc.x; c = sc.y; return; }   // warp-uniform switch
   float k = rintf(p * 0.15915494309189535f);
   float r = fmaf(k, -6.2831855f, p);
   r = fmaf(k, 1.7484555e-7f, r);
@@ -101,7 +105,7 @@ __device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen<NP>& lg
 //     permutation; LiDAR scans arrive in column order, so runs are ~1 voxel long and the kernel
 //     is bound by the L2 reduction rate (REDG) instead of HBM -- kept for callers without a sort.
 template <int LPR, int VPL, int IB, int OP>
-__global__ void __launch_bounds__(128, 3) link_preagg_kernel(
+__global__ void __launch_bounds__(128, VPL >= 4 ? 3 : 5) link_preagg_kernel(
     const float* __restrict__ fin, const int4* __restrict__ coords, const int* __restrict__ order,
     const int* __restrict__ rank, int64_t n, GenDev g, float* sums) {
   constexpr int G = 32 / LPR;                    // row groups per warp
@@ -203,6 +207,136 @@ __global__ void __launch_bounds__(128, 3) link_preagg_kernel(
           lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
                         make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
     }
+  }
+}
+
+
+// ------------------------------------------------------------------ pass 1, shared-memory staged
+// C in {16, 32, 64, 128}.  Same visiting orders as link_preagg_kernel, but the gathered feature
+// rows never sit in registers while they are in flight: a warp issues ALL its row fetches
+// (G x 8 rows = 8 KB, 16 cp.async of 16 bytes per lane, plus the rows' coordinates) straight into
+// its private shared-memory stage right after it has read its 32 (voxel row, block row) pairs, so
+//   * one dependent memory round trip (pairs -> rows) instead of one per register batch,
+//   * ~60 registers per thread -> 24 resident warps per SM x 8 KB = 190 KB of HBM reads in flight
+//     per SM, against the ~45 KB that saturate HBM3e (Little: 6.5 TB/s x ~1 us / 148 SMs).
+// The accumulation then runs out of shared memory (conflict-free 128-bit reads: the LPR lanes of a
+// row read consecutive 16-byte vectors).
+#define PS_RPG 8                         // sorted positions walked by one lane group
+#define PS_WARPS 4
+template <int LPR, int IB, int OP>
+__global__ void __launch_bounds__(PS_WARPS * 32, (IB == 1 && OP != LK_OP_COSX) ? 6 : 4) link_preagg_smem_kernel(
+    const float* __restrict__ fin, const int4* __restrict__ coords, const int* __restrict__ order,
+    const int* __restrict__ rank, int64_t n, GenDev g, float* sums) {
+  constexpr int VPL = 2;
+  constexpr int G = 32 / LPR;                    // row groups per warp
+  constexpr int ROWS = G * PS_RPG;               // rows per warp step (8 KB of features)
+  constexpr int PL = ROWS > 32 ? ROWS / 32 : 1;  // (voxel row, block row) pairs held per lane
+  constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
+  constexpr bool COSX = (OP == LK_OP_COSX);
+  constexpr int NP = 4 * IB;
+  constexpr int ROW_BYTES = 16 * VPL * LPR;      // = 4 C
+  __shared__ __align__(16) uint8_t stage_s[PS_WARPS][ROWS * ROW_BYTES];
+  __shared__ __align__(16) int4 coord_s[PS_WARPS][ROWS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int grp = lane / LPR;
+  const int j = lane % LPR;
+  const int kc = K * g.c;
+  LaneGen<NP> lg;
+  load_lane_gen<LPR, IB>(g, j, true, lg);
+  uint8_t* const stage = stage_s[wib];
+  const uint32_t stage_u = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t coord_u = (uint32_t)__cvta_generic_to_shared(coord_s[wib]);
+
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; base < n;
+       base += warps_total * ROWS) {
+    int ord[PL], rk[PL];
+#pragma unroll
+    for (int q = 0; q < PL; ++q) {
+      const int64_t pos = base + (int64_t)lane * PL + q;
+      const bool ok = pos < n && lane * PL + q < ROWS;
+      ord[q] = ok ? (order ? __ldg(order + pos) : (int)pos) : 0;
+      rk[q] = ok ? __ldg(rank + pos) : -1;
+    }
+    // ---- every fetch of the step in flight at once ----
+#pragma unroll
+    for (int u = 0; u < PS_RPG; ++u) {
+      const int p = grp * PS_RPG + u;                // position inside the warp step
+      const int r = __shfl_sync(0xffffffffu, ord[p % PL], p / PL);
+      const int b = __shfl_sync(0xffffffffu, rk[p % PL], p / PL);
+      if (b >= 0) {
+        const float* src = fin + (int64_t)r * g.c + 4 * j;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                       ::"r"(stage_u + p * ROW_BYTES + (i * LPR + j) * 16), "l"(src + 4 * i * LPR) : "memory");
+        if (j == 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                       ::"r"(coord_u + p * 16), "l"(coords + r) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- segmented reduction over the group's rows, out of shared memory ----
+    float acc[K][VPL][4];
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
+    int cur = -1;
+#pragma unroll
+    for (int u = 0; u < PS_RPG; ++u) {
+      const int p = grp * PS_RPG + u;
+      const int b = __shfl_sync(0xffffffffu, rk[p % PL], p / PL);
+      if (b >= 0) {
+        const int4 cc = *(const int4*)((const uint8_t*)coord_s[wib] + p * 16);
+        float ph[NP], sn[NP], cs[NP];
+        lane_trig<NP, COSX>(g, lg, cc.x, cc.y, cc.z, ph, sn, cs);
+        if (b != cur) {                          // run boundary: flush the finished block
+          if (cur >= 0) {
+            float* dst = sums + (int64_t)cur * kc + 4 * j;
+#pragma unroll
+            for (int q = 0; q < K; ++q)
+#pragma unroll
+              for (int i = 0; i < VPL; ++i)
+                lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
+                              make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
+          }
+#pragma unroll
+          for (int q = 0; q < K; ++q)
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
+          cur = b;
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const float4 f4 = *(const float4*)(stage + p * ROW_BYTES + (i * LPR + j) * 16);
+          const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = (i % IB) * 4 + e;
+            acc[0][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? sn[q] : cs[q]), acc[0][i][e]);
+            acc[1][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? cs[q] : sn[q]), acc[1][i][e]);
+            if (COSX) acc[K - 1][i][e] = fmaf(fv[e], ph[q], acc[K - 1][i][e]);
+          }
+        }
+      }
+    }
+    if (cur >= 0) {
+      float* dst = sums + (int64_t)cur * kc + 4 * j;
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
+                        make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
+    }
+    __syncwarp();                                // the stage is rewritten by the next step
   }
 }
 
@@ -327,7 +461,7 @@ __device__ __forceinline__ void group_layernorm(float v[VPL][4], bool active, fl
 // independent ones (block index, coordinate, local_mix row), then the mean rows that depend on
 // the block index.
 template <int LPR, int VPL, int IB, int OP, bool NORM>
-__global__ void __launch_bounds__(128, 3) link_apply_kernel(
+__global__ void __launch_bounds__(128, VPL >= 4 ? 3 : 5) link_apply_kernel(
     const float* __restrict__ mean, const float* __restrict__ fin, const int4* __restrict__ coords,
     const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
@@ -425,6 +559,7 @@ __global__ void __launch_bounds__(128, 3) link_apply_kernel(
   }
 }
 
+
 // ------------------------------------------------------------------ host side
 static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
   if (!gen || !gen->d_pos_weight || gen->c <= 0 || gen->c % 4 != 0 || gen->c > 128 ||
@@ -441,66 +576,65 @@ static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
 // Lane layout of a C-channel row: (LPR lanes, VPL vectors per lane, IB distinct phase blocks per
 // lane).  IB < VPL when the channel groups alias inside a lane: wrows a multiple of 4 LPR.
 struct RowLayout { int lpr, vpl, ib; };
-static RowLayout layout_of(const GenDev& g) {
-  RowLayout L;
-  if (g.c == 16 || g.c == 32 || g.c == 64 || g.c == 128) {
-    L.vpl = 4; L.lpr = g.c / 16;
-    const int span = 4 * L.lpr;            // channels covered by one vector index i
-    const int ib = (g.wrows % span == 0) ? g.wrows / span : 4;
-    L.ib = (ib == 1 || ib == 2) ? ib : 4;
-  } else {
-    L.vpl = 1; L.ib = 1;
-    const int v = g.c / 4;
-    L.lpr = 1;
-    while (L.lpr < v) L.lpr <<= 1;
-  }
-  return L;
-}
-
-// MACRO(LPR, VPL, IB) for the layouts that exist
-#define DISPATCH_IB(LPRV, L, MACRO)                  \
-  do {                                               \
-    if (L.ib == 1) MACRO(LPRV, 4, 1);                \
-    else if (L.ib == 2) MACRO(LPRV, 4, 2);           \
-    else MACRO(LPRV, 4, 4);                          \
-  } while (0)
-#define DISPATCH_LAYOUT(L, MACRO)                    \
-  do {                                               \
-    if (L.vpl == 4) {                                \
-      if (L.lpr == 1) DISPATCH_IB(1, L, MACRO);      \
-      else if (L.lpr == 2) DISPATCH_IB(2, L, MACRO); \
-      else if (L.lpr == 4) DISPATCH_IB(4, L, MACRO); \
-      else DISPATCH_IB(8, L, MACRO);                 \
-    } else {                                         \
-      switch (L.lpr) {                               \
-        case 1: MACRO(1, 1, 1); break;               \
-        case 2: MACRO(2, 1, 1); break;               \
-        case 4: MACRO(4, 1, 1); break;               \
-        case 8: MACRO(8, 1, 1); break;               \
-        case 16: MACRO(16, 1, 1); break;             \
-        default: MACRO(32, 1, 1); break;             \
-      }                                              \
-    }                                                \
-  } while (0)
 
 static int launch_preagg(const float* d_fin, const int32_t* d_coords, const int32_t* d_order,
                          const int32_t* d_rank, int64_t n, const GenDev& g, float* d_sums,
                          cudaStream_t st) {
-  const RowLayout L = layout_of(g);
+  if (g.c == 16 || g.c == 32 || g.c == 64 || g.c == 128) {
+    // shared-memory staged kernel: 2 vectors per lane, LPR = C / 8 lanes per row
+    const int lpr = g.c / 8, span = 4 * lpr;
+    const int ib = (g.wrows % span == 0 && g.wrows / span == 1) ? 1 : 2;
+    const int64_t rows_per_warp = (int64_t)(32 / lpr) * PS_RPG;
+    const int64_t warps = (n + rows_per_warp - 1) / rows_per_warp;
+    const int grid = (int)((warps + PS_WARPS - 1) / PS_WARPS);
+#define LAUNCH_PS_OP(LPRV, IBV, O)                                                              \
+  link_preagg_smem_kernel<LPRV, IBV, O><<<grid, PS_WARPS * 32, 0, st>>>(                        \
+      d_fin, (const int4*)d_coords, d_order, d_rank, n, g, d_sums)
+#define LAUNCH_PS_IB(LPRV, IBV)                                      \
+  do {                                                               \
+    if (g.op == LK_OP_COS) LAUNCH_PS_OP(LPRV, IBV, LK_OP_COS);       \
+    else if (g.op == LK_OP_SIN) LAUNCH_PS_OP(LPRV, IBV, LK_OP_SIN);  \
+    else LAUNCH_PS_OP(LPRV, IBV, LK_OP_COSX);                        \
+  } while (0)
+#define LAUNCH_PS(LPRV)                       \
+  do {                                        \
+    if (ib == 1) LAUNCH_PS_IB(LPRV, 1);       \
+    else LAUNCH_PS_IB(LPRV, 2);               \
+  } while (0)
+    if (lpr == 2) LAUNCH_PS(2);
+    else if (lpr == 4) LAUNCH_PS(4);
+    else if (lpr == 8) LAUNCH_PS(8);
+    else LAUNCH_PS(16);
+#undef LAUNCH_PS
+#undef LAUNCH_PS_IB
+#undef LAUNCH_PS_OP
+    LK_LAUNCHED();
+    return LK_OK;
+  }
+  RowLayout L;                                   // any other C % 4 == 0: register-staged kernel
+  L.vpl = 1; L.ib = 1; L.lpr = 1;
+  while (L.lpr < g.c / 4) L.lpr <<= 1;
   const int rpg = L.lpr > 8 ? L.lpr : 8;
   const int64_t per_warp = (int64_t)(32 / L.lpr) * rpg;
   const int64_t warps = (n + per_warp - 1) / per_warp;
   const int grid = (int)((warps + 3) / 4);
-#define LAUNCH_PRE_OP(LPRV, VPLV, IBV, O)                                                       \
-  link_preagg_kernel<LPRV, VPLV, IBV, O><<<grid, 128, 0, st>>>(d_fin, (const int4*)d_coords,    \
-                                                               d_order, d_rank, n, g, d_sums)
-#define LAUNCH_PRE(LPRV, VPLV, IBV)                                      \
-  do {                                                                   \
-    if (g.op == LK_OP_COS) LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_COS);    \
-    else if (g.op == LK_OP_SIN) LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_SIN); \
-    else LAUNCH_PRE_OP(LPRV, VPLV, IBV, LK_OP_COSX);                     \
+#define LAUNCH_PRE_OP(LPRV, O)                                                               \
+  link_preagg_kernel<LPRV, 1, 1, O><<<grid, 128, 0, st>>>(d_fin, (const int4*)d_coords,       \
+                                                          d_order, d_rank, n, g, d_sums)
+#define LAUNCH_PRE(LPRV)                                      \
+  do {                                                        \
+    if (g.op == LK_OP_COS) LAUNCH_PRE_OP(LPRV, LK_OP_COS);    \
+    else if (g.op == LK_OP_SIN) LAUNCH_PRE_OP(LPRV, LK_OP_SIN); \
+    else LAUNCH_PRE_OP(LPRV, LK_OP_COSX);                     \
   } while (0)
-  DISPATCH_LAYOUT(L, LAUNCH_PRE);
+  switch (L.lpr) {
+    case 1: LAUNCH_PRE(1); break;
+    case 2: LAUNCH_PRE(2); break;
+    case 4: LAUNCH_PRE(4); break;
+    case 8: LAUNCH_PRE(8); break;
+    case 16: LAUNCH_PRE(16); break;
+    default: LAUNCH_PRE(32); break;
+  }
 #undef LAUNCH_PRE
 #undef LAUNCH_PRE_OP
   LK_LAUNCHED();
@@ -561,26 +695,76 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
   LK_REQUIRE(g.op != LK_OP_COSX || d_fin, "lk_link_apply_fwd: cos_x needs the input features");
   LK_REQUIRE(!fuse_norm || (d_local && d_g1 && d_b1 && d_g2 && d_b2),
              "lk_link_apply_fwd: fused norms need local features and both LayerNorm parameters");
-  const RowLayout L = layout_of(g);
-  const int rows_per_step = (32 / L.lpr) * ((g.op == LK_OP_COSX && L.vpl > 1) ? 1 : 2);
-  const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
-  const int grid = lk_grid(steps * 32, 128, 3);
   cudaStream_t st = (cudaStream_t)s;
-#define LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, NRM)                                               \
-  link_apply_kernel<LPRV, VPLV, IBV, O, NRM><<<grid, 128, 0, st>>>(                            \
+  if (g.c == 16 || g.c == 32 || g.c == 64 || g.c == 128) {
+    // 4 vectors (16 channels) per lane, LPR = C / 16 lanes per row: fewest instructions per row
+    // (LayerNorm trees of log2(LPR) steps); a shared-memory staged variant with 2 vectors per lane
+    // measured no faster (the kernel is issue-bound, ~2 000 thread instructions per row)
+    const int lpr = g.c / 16, span = 4 * lpr;
+    const int ibr = (g.wrows % span == 0) ? g.wrows / span : 4;
+    const int ib = (ibr == 1 || ibr == 2) ? ibr : 4;
+    const int rows_per_step = (32 / lpr) * (g.op == LK_OP_COSX ? 1 : 2);
+    const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
+    const int grid = lk_grid(steps * 32, 128, 3);
+#define LAUNCH_A4_ON(LPRV, IBV, O, NRM)                                                        \
+  link_apply_kernel<LPRV, 4, IBV, O, NRM><<<grid, 128, 0, st>>>(                               \
       d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
-#define LAUNCH_APPLY_O(LPRV, VPLV, IBV, O)                         \
-  do {                                                             \
-    if (fuse_norm) LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, true);      \
-    else LAUNCH_APPLY_ON(LPRV, VPLV, IBV, O, false);               \
+#define LAUNCH_A4_O(LPRV, IBV, O)                           \
+  do {                                                      \
+    if (fuse_norm) LAUNCH_A4_ON(LPRV, IBV, O, true);        \
+    else LAUNCH_A4_ON(LPRV, IBV, O, false);                 \
   } while (0)
-#define LAUNCH_APPLY(LPRV, VPLV, IBV)                                      \
-  do {                                                                     \
-    if (g.op == LK_OP_COS) LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_COS);     \
-    else if (g.op == LK_OP_SIN) LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_SIN); \
-    else LAUNCH_APPLY_O(LPRV, VPLV, IBV, LK_OP_COSX);                      \
+#define LAUNCH_A4_IB(LPRV, IBV)                                       \
+  do {                                                                \
+    if (g.op == LK_OP_COS) LAUNCH_A4_O(LPRV, IBV, LK_OP_COS);         \
+    else if (g.op == LK_OP_SIN) LAUNCH_A4_O(LPRV, IBV, LK_OP_SIN);    \
+    else LAUNCH_A4_O(LPRV, IBV, LK_OP_COSX);                          \
   } while (0)
-  DISPATCH_LAYOUT(L, LAUNCH_APPLY);
+#define LAUNCH_A4(LPRV)                      \
+  do {                                       \
+    if (ib == 1) LAUNCH_A4_IB(LPRV, 1);      \
+    else if (ib == 2) LAUNCH_A4_IB(LPRV, 2); \
+    else LAUNCH_A4_IB(LPRV, 4);              \
+  } while (0)
+    if (lpr == 1) LAUNCH_A4(1);
+    else if (lpr == 2) LAUNCH_A4(2);
+    else if (lpr == 4) LAUNCH_A4(4);
+    else LAUNCH_A4(8);
+#undef LAUNCH_A4
+#undef LAUNCH_A4_IB
+#undef LAUNCH_A4_O
+#undef LAUNCH_A4_ON
+    LK_LAUNCHED();
+    return LK_OK;
+  }
+  RowLayout L;                                   // any other C % 4 == 0: register-staged kernel
+  L.vpl = 1; L.ib = 1; L.lpr = 1;
+  while (L.lpr < g.c / 4) L.lpr <<= 1;
+  const int rows_per_step = (32 / L.lpr) * 2;
+  const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
+  const int grid = lk_grid(steps * 32, 128, 5);
+#define LAUNCH_APPLY_ON(LPRV, O, NRM)                                                          \
+  link_apply_kernel<LPRV, 1, 1, O, NRM><<<grid, 128, 0, st>>>(                                 \
+      d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
+#define LAUNCH_APPLY_O(LPRV, O)                         \
+  do {                                                  \
+    if (fuse_norm) LAUNCH_APPLY_ON(LPRV, O, true);      \
+    else LAUNCH_APPLY_ON(LPRV, O, false);               \
+  } while (0)
+#define LAUNCH_APPLY(LPRV)                                      \
+  do {                                                          \
+    if (g.op == LK_OP_COS) LAUNCH_APPLY_O(LPRV, LK_OP_COS);     \
+    else if (g.op == LK_OP_SIN) LAUNCH_APPLY_O(LPRV, LK_OP_SIN); \
+    else LAUNCH_APPLY_O(LPRV, LK_OP_COSX);                      \
+  } while (0)
+  switch (L.lpr) {
+    case 1: LAUNCH_APPLY(1); break;
+    case 2: LAUNCH_APPLY(2); break;
+    case 4: LAUNCH_APPLY(4); break;
+    case 8: LAUNCH_APPLY(8); break;
+    case 16: LAUNCH_APPLY(16); break;
+    default: LAUNCH_APPLY(32); break;
+  }
 #undef LAUNCH_APPLY
 #undef LAUNCH_APPLY_O
 #undef LAUNCH_APPLY_ON

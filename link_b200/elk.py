@@ -274,7 +274,7 @@ def _pre_mix_fused(pre_mix, x: torch.Tensor) -> torch.Tensor:
 def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, alpha, coord_scale, norm,
                     norm_local) -> torch.Tensor:
     """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
-    from link_b200.nn.functional.conv import KernelMap, _transposed
+    from link_b200.nn.functional.conv import KernelMap, _tc_image
     L = _capi.lib()
     x = st.F.contiguous()
     coords = st.C.contiguous()
@@ -301,7 +301,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     a.kvol = conv.kernel_volume
     w = conv.kernel.detach().contiguous()
     a.d_conv_w = _capi.ptr(w)
-    wt = _transposed(conv.kernel) if USE_TENSOR_CORES else None   # cached on the Parameter
+    wt = _tc_image(conv.kernel) if (USE_TENSOR_CORES and c in (32, 64)) else None   # cached on the Parameter
     a.d_conv_wt = _capi.ptr(wt)
     a.d_conv_offsets = _capi.ptr(conv_off)
     a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
@@ -314,7 +314,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
             kmap._plan = kmap.plan_buffers()
             a.build_plan = 1
         if kmap._plan:
-            a.d_plan_perm, a.d_plan_nbr, a.d_plan_mask = (_capi.ptr(t) for t in kmap._plan)
+            a.d_plan_perm, a.d_plan_mask = (_capi.ptr(t) for t in kmap._plan)
     bounds = _index.coord_bounds(coords, st.kmaps)
     spec, bits = _index.make_keyspec(bounds, (s, s, s), (0, 1, 2, 3))
     a.keyspec, a.key_bits, a.r3 = spec, bits, r3

@@ -38,7 +38,7 @@ class KernelMap:
         self._inv = None
         self._ref = None
         self.offsets = None      # int32 [K,3] offsets the map was built with (classes of the plan)
-        self._plan = None        # (perm [n_out], nbr_p [K,n_out], tile_mask [tiles]) or False
+        self._plan = None        # (perm [n_out], tile_mask [tiles]) or False
 
     @property
     def inv(self) -> torch.Tensor:
@@ -57,7 +57,6 @@ class KernelMap:
         the native block executor)."""
         k, dev = self.nbr.shape[0], self.nbr.device
         return (torch.empty(self.n_out, dtype=torch.int32, device=dev),
-                torch.empty(k, self.n_out, dtype=torch.int32, device=dev),
                 torch.empty((self.n_out + 127) // 128, dtype=torch.int32, device=dev))
 
     def plan(self):
@@ -68,15 +67,15 @@ class KernelMap:
             if k > 32 or self.n_out == 0 or not USE_PLAN:
                 self._plan = False
             else:
-                perm, nbr_p, tmask = self.plan_buffers()
+                perm, tmask = self.plan_buffers()
                 L = _capi.lib()
                 ws_bytes = L.lk_conv_plan_ws_bytes(self.n_out)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.nbr.device)
-                with _capi.timed('lk_conv_plan', self.n_out * (4 * k * 2 + 8)):
+                with _capi.timed('lk_conv_plan', self.n_out * (4 * k + 8)):
                     _capi.check(L.lk_conv_plan(_capi.ptr(self.nbr), self.n_out, k, _capi.ptr(self.offsets),
-                                               _capi.ptr(perm), _capi.ptr(nbr_p), _capi.ptr(tmask),
+                                               _capi.ptr(perm), _capi.ptr(tmask),
                                                _capi.ptr(ws), ws_bytes, _capi.stream()), 'lk_conv_plan')
-                self._plan = (perm, nbr_p, tmask)
+                self._plan = (perm, tmask)
         return self._plan or None
 
     def _reference_layout(self):
@@ -135,20 +134,35 @@ USE_PLAN = os.environ.get('LINKB200_CONV_PLAN', '1') != '0'
 _tc_supported = {}
 
 
-def _transposed(weight: torch.Tensor) -> torch.Tensor:
-    """[K, Cin, Cout] -> contiguous [K, Cout, Cin] (K-major B operand of the tensor-core kernel).
-    For an nn.Parameter the result is cached ON the parameter object (keyed by its version and
-    storage address), so a module's weights are transposed once per update; the cache lives and
-    dies with the parameter, so a recycled address can never alias another tensor's entry."""
-    if not isinstance(weight, torch.nn.Parameter):
-        return weight.detach().transpose(1, 2).contiguous()
-    ver = (weight._version, weight.data_ptr())
-    hit = weight.__dict__.get('_lk_wt')
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    wt = weight.detach().transpose(1, 2).contiguous()
-    weight.__dict__['_lk_wt'] = (ver, wt)
-    return wt
+def _pack(wt: torch.Tensor) -> torch.Tensor:
+    """[K, Cout, Cin] (per-offset transposed weights) -> packed tensor-core image
+    (lk_conv_tc_pack_weights: tf32 hi/lo planes in the SWIZZLE_128B shared-memory layout)."""
+    k, c_out, c_in = wt.shape
+    wt = wt.contiguous().float()
+    img = torch.empty(k * 2 * c_in * c_out, dtype=torch.float32, device=wt.device)
+    _capi.check(_capi.lib().lk_conv_tc_pack_weights(_capi.ptr(wt), k, c_in, c_out, _capi.ptr(img),
+                                                    _capi.stream()), 'lk_conv_tc_pack_weights')
+    return img
+
+
+def _tc_image(weight: torch.Tensor, c_pad: int = 0) -> torch.Tensor:
+    """Packed tensor-core image of a [K, Cin, Cout] kernel (input channels zero-padded to `c_pad`
+    if given).  For an nn.Parameter the image is cached ON the parameter object (keyed by its
+    version and storage address), so a module's weights are packed once per update; the cache lives
+    and dies with the parameter, so a recycled address can never alias another tensor's entry."""
+    cached = isinstance(weight, torch.nn.Parameter)
+    if cached:
+        ver = (weight._version, weight.data_ptr(), c_pad)
+        hit = weight.__dict__.get('_lk_img')
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+    wt = weight.detach().transpose(1, 2)
+    if c_pad and c_pad > weight.shape[1]:
+        wt = torch.nn.functional.pad(wt, (0, c_pad - weight.shape[1]))
+    img = _pack(wt)
+    if cached:
+        weight.__dict__['_lk_img'] = (ver, img)
+    return img
 
 
 def _tc_ok(L, c_in, c_out) -> bool:
@@ -156,17 +170,6 @@ def _tc_ok(L, c_in, c_out) -> bool:
     if ok is None:
         ok = _tc_supported[(c_in, c_out)] = bool(L.lk_conv_tc_supported(c_in, c_out))
     return ok
-
-
-def _transposed_padded(weight: torch.nn.Parameter, c_pad: int) -> torch.Tensor:
-    """[K, Cin, Cout] -> [K, Cout, c_pad] with zero-padded input channels, cached on the parameter."""
-    ver = (weight._version, weight.data_ptr(), c_pad)
-    hit = weight.__dict__.get('_lk_wtp')
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    wt = torch.nn.functional.pad(weight.detach().transpose(1, 2), (0, c_pad - weight.shape[1])).contiguous()
-    weight.__dict__['_lk_wtp'] = (ver, wt)
-    return wt
 
 
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
@@ -196,18 +199,19 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         # narrow input layer (the 4-channel stem): zero-pad C_in to one 32-float K-block and run on
         # the tensor cores; the zero K-columns cost tensor time only (and that pipe has slack)
         feats = torch.nn.functional.pad(feats, (0, 32 - c_in))
-        weight_t = _transposed_padded(weight, 32)
-        weight, c_in, tc_ok = None, 32, True
+        img = _tc_image(weight, 32)
+        c_in, tc_ok = 32, True
+    else:
+        img = None
     if USE_TENSOR_CORES and tc_ok:
-        wt = weight_t if weight_t is not None else _transposed(weight)
+        if img is None:
+            img = _pack(weight_t) if weight_t is not None else _tc_image(weight)
         plan = kmap.plan() if kmap is not None else None      # only for the forward map (kmap.nbr)
-        if plan is not None:
-            nbr = plan[1]
         with _capi.timed('lk_conv_fwd', nb):
-            _capi.check(L.lk_conv_tc_fwd_plan(_capi.ptr(feats, torch.float32), _capi.ptr(wt, torch.float32),
+            _capi.check(L.lk_conv_tc_fwd_plan(_capi.ptr(feats, torch.float32), _capi.ptr(img, torch.float32),
                                               _capi.ptr(nbr, torch.int32),
                                               _capi.ptr(plan[0]) if plan is not None else None,
-                                              _capi.ptr(plan[2]) if plan is not None else None,
+                                              _capi.ptr(plan[1]) if plan is not None else None,
                                               n_out, k, c_in, c_out, C.byref(ep), _capi.ptr(out),
                                               _capi.stream()), 'lk_conv_tc_fwd_plan')
         return out

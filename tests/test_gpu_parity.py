@@ -230,7 +230,7 @@ def test_conv_chain_kmaps_and_outputs(dev):
                                                      (130, 64, 32, 3, 1), (9_000, 32, 32, 2, 2),
                                                      (1, 64, 64, 3, 1)])
 def test_conv_plan_tile_skipping(dev, n, cin, cout, ksize, stride):
-    """lk_conv_plan: perm is a permutation grouped by class, nbr_p / tile_mask are consistent with
+    """lk_conv_plan: perm is a permutation grouped by class, tile_mask is consistent with
     the kernel map; the planned tensor-core conv equals the unplanned one bit for bit (the plan only
     moves rows between tiles) and the float64 numpy contraction within fp32 tolerance."""
     import ctypes as Ct
@@ -246,12 +246,11 @@ def test_conv_plan_tile_skipping(dev, n, cin, cout, ksize, stride):
     st = SparseTensor(torch.zeros(len(coords), cin, device=dev), cu(coords, dev), 1)
     km = build_kernel_map(st, (ksize,) * 3, (stride,) * 3, (1, 1, 1))
     K, n_out = km.nbr.shape
-    perm, nbr_p, tmask = km.plan()
+    perm, tmask = km.plan()
     nbr = km.nbr.cpu().numpy()
-    perm_h, nbr_p_h = perm.cpu().numpy(), nbr_p.cpu().numpy()
+    perm_h = perm.cpu().numpy()
     tmask_h = tmask.cpu().numpy().view(np.uint32)
     assert np.array_equal(np.sort(perm_h), np.arange(n_out))
-    assert np.array_equal(nbr_p_h, nbr[:, perm_h])
     rowmask = ((nbr >= 0) * (1 << np.arange(K, dtype=np.int64))[:, None]).sum(0)
     pm = rowmask[perm_h]
     pad = (-n_out) % 128
@@ -363,7 +362,8 @@ def test_block_forward_composed_and_grads(dev, name):
     o = O.elk_block_forward(f_cpu, g['coords'], int(g['tstride']), p, int(g['s']), int(g['r']),
                             str(g['baseop']), int(g['groups']))
     o.backward(go)
-    np.testing.assert_allclose(feats.grad.cpu().numpy(), f_cpu.grad.numpy(), rtol=2e-3, atol=2e-5)
+    # float atomics in the backward scatter kernels: accumulation order varies run to run
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), f_cpu.grad.numpy(), rtol=2e-3, atol=1e-4)
     ours = dict(blk.named_parameters())
     for k in ['pre_mix.0.weight', 'pos_weight.0.weight', 'local_mix.0.kernel', 'norm.weight']:
         ref = p[k].grad.numpy()
