@@ -296,10 +296,42 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
             d2h = out_host.numel() * 4
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    # ---- reference GPU leg (reported baseline, rank 0, block workload): the reference's own CUDA
+    #      kernels (oracle/_ref/backend_cuda.so) under a restatement of its python glue ----
+    ref_gpu = None
+    if workload == 'block' and rank == 0 and not args.no_cpu_baseline:
+        ref_gpu = reference_gpu_leg(dev, coords_dev[0], feats_dev[0], model, flush)
     return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
             'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,
-            'roof': roof,
+            'roof': roof, 'ref_gpu': ref_gpu,
             'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
+
+
+def reference_gpu_leg(dev, coords, feats, blk, flush, steps=5, warmup=2):
+    try:
+        from oracle import ref_gpu
+        if not ref_gpu.available():
+            return {'unavailable': 'oracle/_ref/backend_cuda.so not built'}
+        p = {k: v.detach() for k, v in blk.state_dict().items()}
+        evs = []
+        with torch.no_grad():
+            for k in range(warmup + steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ref_gpu.elk_block_forward(feats, coords, 1, p, S_BLK, R_BLK, BASEOP, GROUPS)
+                e1.record()
+                if k >= warmup:
+                    evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+        n = coords.shape[0]
+        return {'value': n / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+                'kind': 'reference CUDA kernels (torchsparse-u backend built for sm_100a from /root/reference, '
+                        'oracle/_ref/backend_cuda.so) driven by the restated python glue of oracle/ref_gpu.py; '
+                        'same scan, L2 flushed between steps, CUDA events, median'}
+    except Exception as e:   # a baseline leg must never take the bench line down
+        return {'unavailable': repr(e)[:200]}
 
 
 def preagg_roofline(dev, coords, bounds, blk, nbuf=6, reps=4):
@@ -425,6 +457,8 @@ def main_ours(args):
     }
     if extra is not None:
         line['encoder'] = extra
+    if m.get('ref_gpu'):
+        line['reference_gpu'] = m['ref_gpu']
     if world == 1 and not args.no_cpu_baseline:
         n_s = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
         v, dt, n, cores = run_cpu(args, n_s, 2, 1)

@@ -53,17 +53,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_variant(name: str, defines, verbose: bool = False) -> str:
-    """Tuning aid: liblinkb200_<name>.so with link.cu recompiled under extra -D flags (selected at
-    run time with LINKB200_LIB=<path>); every other object is shared with the main build."""
+def build_variant(name: str, defines, verbose: bool = False, source: str = 'link.cu') -> str:
+    """Tuning aid: liblinkb200_<name>.so with one source recompiled under extra -D flags (selected
+    at run time with LINKB200_LIB=<path>); every other object is shared with the main build."""
     build(verbose=verbose)
-    obj = os.path.join(OBJ, f'link_{name}.o')
-    src = os.path.join(CSRC, 'link.cu')
+    obj = os.path.join(OBJ, f'{source[:-3]}_{name}.o')
+    src = os.path.join(CSRC, source)
     cmd = [NVCC] + FLAGS + [f'-D{d}' for d in defines] + ['-c', src, '-o', obj]
     if verbose:
         print(' '.join(cmd), flush=True)
     subprocess.check_call(cmd)
-    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + '.o') for s in sources() if not s.endswith('link.cu')]
+    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + '.o') for s in sources() if not s.endswith('/' + source)]
     lib = os.path.join(HERE, f'liblinkb200_{name}.so')
     subprocess.check_call([NVCC, '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', lib, obj] + objs)
     return lib

@@ -34,6 +34,9 @@
 #include "tc.cuh"
 
 #define CT_ROWS 128
+#ifndef CT_NWB
+#define CT_NWB 4          // weight ring depth (tuning knob; 6 measured slower than 4)
+#endif
 #define CT_THREADS 512      // producer threads (16 warps); one more warp issues the MMAs
 // TMEM: columns [0, 512 - 128 NST) hold the accumulators, the rest NST A stages of 128 columns
 
@@ -43,7 +46,7 @@ struct ConvTcCfg {
   static constexpr uint32_t B_BLK = COUT * 128;             // one [COUT x 32] K-block
   static constexpr uint32_t B_PLANE = KB * B_BLK;           // hi (or lo) plane
   static constexpr uint32_t B_STAGE = 2 * B_PLANE;          // hi + lo
-  static constexpr int NWB = 6;                             // W[k] ring: prefetched NWB-2 offsets ahead
+  static constexpr int NWB = CT_NWB;                        // W[k] ring: prefetched NWB-NST offsets ahead
   static constexpr uint32_t SMEM = NWB * B_STAGE + 1024;     // weight ring + alignment slack
   static constexpr int ACC_COLS = 512 - 128 * NST;
   static constexpr int MAX_TILES = ACC_COLS / COUT;

@@ -46,6 +46,80 @@ def build(force: bool = False) -> str:
     return OUT
 
 
+OUT_CUDA = os.path.join(HERE, '_ref', 'backend_cuda.so')
+
+
+def build_cuda(force: bool = False, jobs: int = 8) -> str:
+    """The reference's own CUDA backend (pybind_cuda.cpp + every *_cuda.cu + the *_cpu.cpp it also
+    binds), compiled for sm_100a into oracle/_ref/backend_cuda.so.  nvcc cross-compiles here without a
+    GPU; the GPU box only uses the prebuilt file.  torch 2.11 no longer converts
+    `Tensor::type()` to a ScalarType inside AT_DISPATCH_*, so the sources are compiled from a
+    scratch copy under /tmp in which the 9 `x.type()` dispatch arguments read `x.scalar_type()`
+    (convolution_cuda.cu, devoxelize_cuda.cu, voxelize_cuda.cu) -- no other change, nothing copied
+    into the repo."""
+    if not os.path.isdir(REF):
+        return OUT_CUDA if os.path.exists(OUT_CUDA) else ''
+    if not force and os.path.exists(OUT_CUDA):
+        return OUT_CUDA
+    import concurrent.futures as cf
+    import re
+    import shutil
+    import tempfile
+    import torch
+    from torch.utils.cpp_extension import include_paths
+    tmp = tempfile.mkdtemp(prefix='lk_ref_cuda_')
+    src = os.path.join(tmp, 'backend')
+    shutil.copytree(REF, src)
+    for f in glob.glob(os.path.join(src, '*', '*_cuda.cu')):
+        txt = open(f).read()
+        txt2 = re.sub(r'(AT_DISPATCH_FLOATING_TYPES_AND_HALF\(\s*[A-Za-z_]+)\.type\(\)', r'\1.scalar_type()', txt)
+        if txt2 != txt:
+            open(f, 'w').write(txt2)
+    os.makedirs(os.path.dirname(OUT_CUDA), exist_ok=True)
+    tlib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+    incs = ['-I' + os.path.join(HERE, 'shim'), '-I' + sysconfig.get_paths()['include'],
+            '-I/usr/local/cuda/include'] + ['-I' + p for p in include_paths()]
+    defs = ['-DTORCH_EXTENSION_NAME=backend', '-DTORCH_API_INCLUDE_EXTENSION_H',
+            f'-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}']
+    cus = sorted(glob.glob(os.path.join(src, '*', '*_cuda.cu')))
+    cpps = [os.path.join(src, 'pybind_cuda.cpp')] + sorted(glob.glob(os.path.join(src, '*', '*_cpu.cpp')))
+
+    def cc(f):
+        obj = f + '.o'
+        if f.endswith('.cu'):
+            cmd = ['/usr/local/cuda/bin/nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3',
+                   '-std=c++17', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',
+                   '-D__CUDA_NO_HALF_OPERATORS__', '-D__CUDA_NO_HALF_CONVERSIONS__',
+                   '-D__CUDA_NO_HALF2_OPERATORS__'] + defs + incs + ['-c', f, '-o', obj]
+        else:
+            cmd = ['g++', '-O3', '-g0', '-fopenmp', '-fPIC', '-std=c++17'] + defs + incs + ['-c', f, '-o', obj]
+        subprocess.check_call(cmd)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        objs = list(ex.map(cc, cus + cpps))
+    cmd = ['g++', '-shared', '-fopenmp'] + objs + ['-L' + tlib, '-L/usr/local/cuda/lib64', '-ltorch', '-ltorch_cpu',
+                                       '-ltorch_cuda', '-lc10', '-lc10_cuda', '-ltorch_python', '-lcudart',
+                                       '-Wl,-rpath,' + tlib, '-o', OUT_CUDA]
+    subprocess.check_call(cmd)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return OUT_CUDA
+
+
+def load_cuda():
+    """Import oracle/_ref/backend_cuda.so as a module named `backend` (20 reference ops)."""
+    import importlib.machinery
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.exists(OUT_CUDA):
+        raise FileNotFoundError(OUT_CUDA)
+    loader = importlib.machinery.ExtensionFileLoader('backend', OUT_CUDA)
+    spec = importlib.util.spec_from_loader('backend', loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
 def load():
     """Import the built module as `torchsparse.backend` (name the reference's
     python layer expects) without touching /root/reference."""
@@ -63,3 +137,5 @@ def load():
 
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv))
+    if '--cuda' in sys.argv:
+        print(build_cuda(force='--force' in sys.argv))

@@ -505,7 +505,7 @@ def test_preagg_segmented_vs_storage_order_vs_numpy(dev, op, C, groups, n):
     np.add.at(want, bi.idx_query.cpu().numpy(), np.concatenate(planes, 1))
     for got in out:
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-4)
-    np.testing.assert_allclose(out[0], out[1], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-4, atol=1e-4)    # float atomics: order varies
 
 
 # ------------------------------------------------------------------ dense pre_mix kernels
@@ -704,3 +704,28 @@ def test_encoder_training_step(dev):
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_reference_cuda_kernels_vs_oracle_and_ours(dev):
+    """The reference GPU arm of bench.py (the reference's own CUDA kernels from oracle/_ref/backend_cuda.so
+    under the restated python glue) computes the same ELKBlock forward as the CPU oracle and as ours."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip('oracle/_ref/backend_cuda.so not built (needs /root/reference at build time)')
+    from link_b200 import SparseTensor
+    from link_b200.elk import ELKBlock
+    from link_b200.utils.synthetic import random_voxels
+    for baseop, groups, C, s, r in [('cos', 2, 64, 7, 3), ('cos_x', 1, 16, 3, 2)]:
+        coords = random_voxels(6000, 48, seed=7)
+        torch.manual_seed(1)
+        blk = ELKBlock(C, C, groups=groups, baseop=baseop).eval()
+        feats = torch.randn(len(coords), C)
+        sd = {k: v.detach() for k, v in blk.state_dict().items()}
+        want = O.elk_block_forward(feats, coords, 1, sd, s, r, baseop, groups).numpy()
+        blk = blk.to(dev)
+        with torch.no_grad():
+            ref = ref_gpu.elk_block_forward(feats.to(dev), cu(coords, dev), 1,
+                                            {k: v.detach() for k, v in blk.state_dict().items()}, s, r, baseop, groups)
+            ours = blk(SparseTensor(feats.to(dev), cu(coords, dev), 1), s, r).F
+        np.testing.assert_allclose(ref.cpu().numpy(), want, rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(ours.cpu().numpy(), ref.cpu().numpy(), rtol=1e-3, atol=2e-4)
