@@ -204,7 +204,9 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(i, coords, feats):
-        st = SparseTensor(feats, coords, 1)
+        return step_st(i, SparseTensor(feats, coords, 1))
+
+    def step_st(i, st):
         _index.set_coord_bounds(st.kmaps, bounds[i][0], bounds[i][1])
         with torch.no_grad():
             if workload == 'block':
@@ -285,9 +287,10 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        c = coords_host[i].to(dev, non_blocking=True)
-        f = feats_host[i].to(dev, non_blocking=True)
-        out = step(i, c, f)
+        # public API: SparseTensor.from_host uploads the coordinates on the current stream and the
+        # features on a copy stream; the block's index build overlaps the feature upload
+        st = SparseTensor.from_host(feats_host[i], coords_host[i], 1, device=dev)
+        out = step_st(i, st)
         out_host.copy_(out.sum(dim=0), non_blocking=True)
         e1.record()
         if k >= w_e2e:
@@ -299,7 +302,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     # ---- reference GPU leg (reported baseline, rank 0, block workload): the reference's own CUDA
     #      kernels (oracle/_ref/backend_cuda.so) under a restatement of its python glue ----
     ref_gpu = None
-    if workload == 'block' and rank == 0 and not args.no_cpu_baseline:
+    if workload == 'block' and world == 1 and not args.no_cpu_baseline:
         ref_gpu = reference_gpu_leg(dev, coords_dev[0], feats_dev[0], model, flush)
     return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
             'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,

@@ -237,6 +237,10 @@ typedef struct {
   int32_t use_tensor_cores;
   int32_t reserved;
   void* d_ws; int64_t ws_bytes;
+  void* feats_ready;             /* cudaEvent_t or NULL: d_feats is still being uploaded on another
+                                    stream; the executor enqueues all index-only work first and
+                                    makes the stream wait for this event (cudaStreamWaitEvent, no
+                                    host or device synchronisation) before the first feature kernel */
 } lk_elk_block_args_t;
 /* sizeof of the structs above as compiled (0: lk_keyspec_t, 1: lk_kernelgen_t,
  * 2: lk_elk_block_args_t): lets an FFI binding verify its struct layouts at load time. */

@@ -2,10 +2,12 @@
 // a single C-ABI call enqueues the whole kernel sequence on the stream
 //
 //   hash -> table build -> submanifold kernel map        (skipped when the caller passes a map)
+//   conv plan (tile-skipping order of the kernel map)
+//   block keys -> radix sort/unique -> neighbour-block table -> zero sums
+//   -- wait for the features if they are still being uploaded (cudaStreamWaitEvent) --
 //   pre_mix  = LN(x W^T)                                  (tcgen05 / FFMA)
 //   local    = SubM 3^3 conv(x)                           (tcgen05 / FFMA)
-//   block keys -> radix sort/unique -> neighbour-block table
-//   zero sums -> segmented pre-aggregation (block order) -> window mean -> apply (+LN, +LN(local), add, ReLU)
+//   segmented pre-aggregation (block order) -> window mean -> apply (+LN, +LN(local), add, ReLU)
 //
 // so the host pays one FFI crossing and one workspace allocation per block instead of ~27
 // Python-level launches (the reference: ~150-180 launches, >= 4 device syncs, 4 cudaMalloc/Free).
@@ -79,6 +81,30 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
     LK_TRY(lk_kmap_query_subm(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
                               a->d_kmap, s));
   }
+  // ---- index-only work first: it does not read the features, so it overlaps an upload of
+  //      d_feats that is still in flight on another stream (a->feats_ready) ----
+  const bool tc_conv = a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt;
+  const bool planned = tc_conv && a->d_plan_perm && a->d_plan_mask && a->kvol <= 32;
+  if (planned && a->build_plan)
+    LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
+                        ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
+  uint64_t* keys = (uint64_t*)(ws + w.keys);
+  uint64_t* uniq = (uint64_t*)(ws + w.uniq);
+  int32_t* inverse = (int32_t*)(ws + w.inverse);
+  int32_t* counts = (int32_t*)(ws + w.counts);
+  int32_t* num = (int32_t*)(ws + w.num);
+  int32_t* nbr = (int32_t*)(ws + w.nbr);
+  int32_t* order = (int32_t*)(ws + w.order);
+  int32_t* srank = (int32_t*)(ws + w.srank);
+  float* sums = (float*)(ws + w.sums);
+  float* mean = (float*)(ws + w.mean);
+  LK_TRY(lk_pack_keys(a->d_coords, n, &a->keyspec, keys, s));
+  LK_TRY(lk_sort_unique_ex(keys, n, a->key_bits, uniq, inverse, order, nullptr, counts, num, srank,
+                           ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
+  LK_TRY(lk_block_neighbors(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, s));
+  LK_TRY(lk_zero_rows(sums, num, n, kc, s));
+  // ---- feature kernels ----
+  if (a->feats_ready) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)a->feats_ready, 0));
   float* fin = (float*)(ws + w.fin);
   float* local = (float*)(ws + w.local);
   // pre_mix
@@ -87,37 +113,17 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   else
     LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, s));
   // local_mix
-  if (a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt) {
-    if (a->d_plan_perm && a->d_plan_mask && a->kvol <= 32) {
-      if (a->build_plan)
-        LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
-                            ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
+  if (tc_conv) {
+    if (planned)
       LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, kmap, a->d_plan_perm, a->d_plan_mask, n,
                                  a->kvol, c, c, nullptr, local, s));
-    } else {
+    else
       LK_TRY(lk_conv_tc_fwd(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, nullptr, local, s));
-    }
   } else {
     LK_REQUIRE(a->d_conv_w, "lk_elk_block_fwd: FFMA conv needs the untransposed weights");
     LK_TRY(lk_conv_fwd(a->d_feats, a->d_conv_w, kmap, n, a->kvol, c, c, nullptr, local, s));
   }
-  // block index
-  uint64_t* keys = (uint64_t*)(ws + w.keys);
-  uint64_t* uniq = (uint64_t*)(ws + w.uniq);
-  int32_t* inverse = (int32_t*)(ws + w.inverse);
-  int32_t* counts = (int32_t*)(ws + w.counts);
-  int32_t* num = (int32_t*)(ws + w.num);
-  int32_t* nbr = (int32_t*)(ws + w.nbr);
-  LK_TRY(lk_pack_keys(a->d_coords, n, &a->keyspec, keys, s));
-  int32_t* order = (int32_t*)(ws + w.order);
-  int32_t* srank = (int32_t*)(ws + w.srank);
-  LK_TRY(lk_sort_unique_ex(keys, n, a->key_bits, uniq, inverse, order, nullptr, counts, num, srank,
-                           ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
-  LK_TRY(lk_block_neighbors(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, s));
   // linear-kernel aggregation
-  float* sums = (float*)(ws + w.sums);
-  float* mean = (float*)(ws + w.mean);
-  LK_TRY(lk_zero_rows(sums, num, n, kc, s));
   LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, s));
   LK_TRY(lk_link_window_mean(sums, counts, nbr, num, n, a->r3, kc, mean, s));
   LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,

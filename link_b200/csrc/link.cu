@@ -259,12 +259,13 @@ __global__ void __launch_bounds__(PS_WARPS * 32, (IB == 1 && OP != LK_OP_COSX) ?
       rk[q] = ok ? __ldg(rank + pos) : -1;
     }
     // ---- every fetch of the step in flight at once ----
+    int bb[PS_RPG];                                  // block row of each of the group's positions
 #pragma unroll
     for (int u = 0; u < PS_RPG; ++u) {
       const int p = grp * PS_RPG + u;                // position inside the warp step
       const int r = __shfl_sync(0xffffffffu, ord[p % PL], p / PL);
-      const int b = __shfl_sync(0xffffffffu, rk[p % PL], p / PL);
-      if (b >= 0) {
+      bb[u] = __shfl_sync(0xffffffffu, rk[p % PL], p / PL);
+      if (bb[u] >= 0) {
         const float* src = fin + (int64_t)r * g.c + 4 * j;
 #pragma unroll
         for (int i = 0; i < VPL; ++i)
@@ -286,44 +287,43 @@ __global__ void __launch_bounds__(PS_WARPS * 32, (IB == 1 && OP != LK_OP_COSX) ?
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
-    int cur = -1;
+    int cur = bb[0];                                 // positions past the end (b < 0) only trail
 #pragma unroll
     for (int u = 0; u < PS_RPG; ++u) {
       const int p = grp * PS_RPG + u;
-      const int b = __shfl_sync(0xffffffffu, rk[p % PL], p / PL);
-      if (b >= 0) {
-        const int4 cc = *(const int4*)((const uint8_t*)coord_s[wib] + p * 16);
-        float ph[NP], sn[NP], cs[NP];
-        lane_trig<NP, COSX>(g, lg, cc.x, cc.y, cc.z, ph, sn, cs);
-        if (b != cur) {                          // run boundary: flush the finished block
-          if (cur >= 0) {
-            float* dst = sums + (int64_t)cur * kc + 4 * j;
-#pragma unroll
-            for (int q = 0; q < K; ++q)
-#pragma unroll
-              for (int i = 0; i < VPL; ++i)
-                lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
-                              make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
-          }
+      const int b = bb[u];
+      if (b != cur) {                                // run boundary: flush the finished block
+        if (cur >= 0) {
+          float* dst = sums + (int64_t)cur * kc + 4 * j;
 #pragma unroll
           for (int q = 0; q < K; ++q)
 #pragma unroll
             for (int i = 0; i < VPL; ++i)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
-          cur = b;
+              lk_red_add_v4(dst + q * g.c + 4 * i * LPR,
+                            make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]));
         }
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          const float4 f4 = *(const float4*)(stage + p * ROW_BYTES + (i * LPR + j) * 16);
-          const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+        for (int q = 0; q < K; ++q)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int q = (i % IB) * 4 + e;
-            acc[0][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? sn[q] : cs[q]), acc[0][i][e]);
-            acc[1][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? cs[q] : sn[q]), acc[1][i][e]);
-            if (COSX) acc[K - 1][i][e] = fmaf(fv[e], ph[q], acc[K - 1][i][e]);
-          }
+          for (int i = 0; i < VPL; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][i][e] = 0.f;
+        cur = b;
+      }
+      // rows past the end were never fetched: their stage bytes are stale, so they are masked
+      const int4 cc = *(const int4*)((const uint8_t*)coord_s[wib] + p * 16);
+      float ph[NP], sn[NP], cs[NP];
+      lane_trig<NP, COSX>(g, lg, b >= 0 ? cc.x : 0, b >= 0 ? cc.y : 0, b >= 0 ? cc.z : 0, ph, sn, cs);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float4 f4 = *(const float4*)(stage + p * ROW_BYTES + (i * LPR + j) * 16);
+        const float fv[4] = {b >= 0 ? f4.x : 0.f, b >= 0 ? f4.y : 0.f, b >= 0 ? f4.z : 0.f, b >= 0 ? f4.w : 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = (i % IB) * 4 + e;
+          acc[0][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? sn[q] : cs[q]), acc[0][i][e]);
+          acc[1][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? cs[q] : sn[q]), acc[1][i][e]);
+          if (COSX) acc[K - 1][i][e] = fmaf(fv[e], ph[q], acc[K - 1][i][e]);
         }
       }
     }

@@ -276,7 +276,8 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
     from link_b200.nn.functional.conv import KernelMap, _tc_image
     L = _capi.lib()
-    x = st.F.contiguous()
+    x, ready = st.take_feats_event()          # a pending async upload is joined ON THE DEVICE, after
+    x = x.contiguous()                         # the index-only kernels (SparseTensor.from_host)
     coords = st.C.contiguous()
     n, c = x.shape
     dev = x.device
@@ -329,6 +330,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     ws_bytes = L.lk_elk_block_ws_bytes(n, c, a.gen.op, r3, a.kvol, a.build_kmap)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
+    a.feats_ready = ready.cuda_event if ready is not None else None
     _capi.check(L.lk_elk_block_fwd(C.byref(a), _capi.stream()), 'lk_elk_block_fwd')
     return out
 
@@ -337,7 +339,7 @@ def elk_forward_fused(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, 
                       norm, norm_local) -> torch.Tensor:
     """Fused forward of a LinK block given its sub-modules (shared by ELKBlock and TSELKBlock):
     the native executor when available, else one python-level call per kernel."""
-    c = st.F.shape[1]
+    c = st._feats.shape[1]
     if NATIVE_EXECUTOR and _capi.TIMERS is None and c in (16, 32, 64, 128):
         return _forward_native(st, s, r, op=op, pre_mix=pre_mix, conv=conv, pos_weight=pos_weight,
                                alpha=alpha, coord_scale=coord_scale, norm=norm, norm_local=norm_local)
@@ -374,11 +376,11 @@ class ELKBlock(nn.Module):
         self.activate = nn.ReLU(True)
 
     def _needs_grad(self, st: SparseTensor) -> bool:
-        return torch.is_grad_enabled() and (st.F.requires_grad or
+        return torch.is_grad_enabled() and (st._feats.requires_grad or
                                             any(p.requires_grad for p in self.parameters()))
 
     def forward(self, st: SparseTensor, s, r):
-        composed = self._needs_grad(st) or st.F.dtype != torch.float32
+        composed = self._needs_grad(st) or st._feats.dtype != torch.float32   # (no upload join here)
         if not composed:
             if self.baseop == 'cos_x' and self.groups != 1:
                 raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor "

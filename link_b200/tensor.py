@@ -13,16 +13,71 @@ from link_b200.utils import make_ntuple
 
 __all__ = ['SparseTensor', 'PointTensor']
 
+_COPY_STREAMS: Dict[Any, Any] = {}
+
+
+def _copy_stream(device):
+    key = (device.type, device.index)
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return st
+
 
 class SparseTensor:
 
     def __init__(self, feats: torch.Tensor, coords: torch.Tensor,
                  stride: Union[int, Tuple[int, ...]] = 1) -> None:
-        self.feats = feats
+        self._feats = feats
+        self._feats_ready = None       # CUDA event of a pending async upload (from_host), or None
         self.coords = coords
         self.stride = make_ntuple(stride, ndim=3)
         self.cmaps: Dict[Tuple[int, ...], torch.Tensor] = {}
         self.kmaps: Dict[Tuple[Any, ...], Any] = {}
+
+    # `feats` is a plain attribute in the reference; here reading it also joins a pending
+    # asynchronous upload, so every consumer sees complete data without knowing about it.
+    @property
+    def feats(self) -> torch.Tensor:
+        ev = self._feats_ready
+        if ev is not None:
+            torch.cuda.current_stream(self._feats.device).wait_event(ev)
+            self._feats_ready = None
+        return self._feats
+
+    @feats.setter
+    def feats(self, feats: torch.Tensor) -> None:
+        self._feats = feats
+        self._feats_ready = None
+
+    def take_feats_event(self):
+        """(raw feats tensor, pending upload event or None) WITHOUT waiting: for consumers that
+        enqueue index-only work first and wait for the features on the device, in stream order
+        (the native block executor)."""
+        ev, self._feats_ready = self._feats_ready, None
+        return self._feats, ev
+
+    @classmethod
+    def from_host(cls, feats: torch.Tensor, coords: torch.Tensor,
+                  stride: Union[int, Tuple[int, ...]] = 1, device=None) -> 'SparseTensor':
+        """Upload a scan from (pinned) host memory.  The coordinates go first on the current stream;
+        the features -- 16x more bytes at C = 64 -- follow on a dedicated copy stream, so the index
+        build of the first layer (hash grid, kernel map, conv plan, block sort: ~45 % of a LinK
+        block) runs while they are still crossing PCIe.  Consumers join the upload through
+        `feats` / `take_feats_event`."""
+        device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+        main = torch.cuda.current_stream(device)
+        c_dev = coords.to(device, non_blocking=True)
+        f_dev = torch.empty(feats.shape, dtype=feats.dtype, device=device)
+        copy_stream = _copy_stream(device)
+        copy_stream.wait_stream(main)      # f_dev may recycle memory still in use by queued kernels
+        with torch.cuda.stream(copy_stream):
+            f_dev.copy_(feats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        st = cls(f_dev, c_dev, stride)
+        st._feats_ready = ev
+        return st
 
     @property
     def F(self) -> torch.Tensor:

@@ -1,0 +1,123 @@
+"""BASELINE config 5 (active-voxel sweep) and config 4 (detection backbone) on one GPU.
+
+    python scripts/sweep.py [--out gpurun_out/sweep.json] [--quick]
+
+ELKBlock forward (cos, groups=2), N in {10k..500k} x C in {16,64,128} x (r,s) in {(2,3),(3,5),(3,7)},
+synthetic SemanticKITTI-shaped scans, index + kernel maps rebuilt every iteration, L2 flushed
+between iterations, CUDA events, median of 10 after 3 warm-ups.  Then SpMiddleResNetFHDELKv3
+(nuScenes-shaped grid 1440 x 1440 x 40, ~120k voxels, batch 1) forward and forward+backward.
+Prints one JSON line per configuration and writes them all to --out."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from link_b200 import SparseTensor
+from link_b200.elk import ELKBlock
+from link_b200.nn.functional import _index
+from link_b200.utils.synthetic import kitti_like_voxels, lidar_scan
+
+
+def timed(fn, flush, warm=3, reps=10):
+    ts = []
+    for k in range(warm + reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= warm:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default='gpurun_out/sweep.json')
+    ap.add_argument('--quick', action='store_true')
+    a = ap.parse_args()
+    dev = torch.device('cuda:0')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    ns = [10_000, 50_000, 120_000] if a.quick else [10_000, 20_000, 50_000, 120_000, 250_000, 500_000]
+    base = {}
+    for n_t in ns:
+        if n_t <= 125_000:
+            c3, _ = kitti_like_voxels(n_t, seed=1)
+        else:
+            # larger clouds: several independent 125k scans side by side (x offset > scan extent), so the
+            # local structure (voxels per block, neighbours per voxel) stays that of a LiDAR scan
+            parts = []
+            for k in range(n_t // 125_000):
+                if k not in base:
+                    base[k] = kitti_like_voxels(125_000, seed=2 + k)[0]
+                parts.append(base[k] + np.array([[4000 * k, 0, 0]], np.int32))
+            c3 = np.concatenate(parts, 0)
+        coords_h = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+        coords = torch.from_numpy(coords_h).to(dev)
+        lo, hi = coords_h.min(0), coords_h.max(0)
+        n = len(coords_h)
+        for c in (16, 64, 128):
+            torch.manual_seed(0)
+            blk = ELKBlock(c, c, groups=2, baseop='cos').to(dev).eval()
+            feats = torch.randn(n, c, device=dev)
+            for r, s in ((2, 3), (3, 5), (3, 7)):
+                def step():
+                    st = SparseTensor(feats.clone(), coords, 1)
+                    _index.set_coord_bounds(st.kmaps, lo, hi)
+                    with torch.no_grad():
+                        return blk(st, s, r).F
+                ms = timed(step, flush)
+                row = {'workload': 'ELKBlock fwd', 'n': n, 'c': c, 'r': r, 's': s, 'ms': ms,
+                       'voxels_per_s': n / (ms * 1e-3)}
+                print(json.dumps(row), flush=True)
+                rows.append(row)
+    # ---- detection backbone (config 4): nuScenes-shaped grid
+    try:
+        from link_b200.scn import SpMiddleResNetFHDELKv3
+        pts = np.concatenate([lidar_scan(seed=10 + k, beams=32, azimuths=1100) for k in range(10)], 0)
+        rng = [-54, -54, -5, 54, 54, 3]
+        vs = np.array([0.075, 0.075, 0.2])
+        keep = np.all((pts[:, :3] >= rng[:3]) & (pts[:, :3] < rng[3:]), axis=1)
+        ijk = np.floor((pts[keep, :3] - np.array(rng[:3])) / vs).astype(np.int32)      # (x, y, z)
+        ijk = np.unique(ijk, axis=0)
+        ijk = ijk[np.random.default_rng(0).permutation(len(ijk))[:120_000]]
+        idx = np.concatenate([np.zeros((len(ijk), 1), np.int32), ijk[:, ::-1]], 1).astype(np.int32)  # (b, z, y, x)
+        featsd = torch.randn(len(idx), 5, device=dev)
+        torch.manual_seed(0)
+        net = SpMiddleResNetFHDELKv3(num_input_features=5, ds_factor=8).to(dev).eval()
+        idx_d = torch.from_numpy(idx).to(dev)
+
+        def det_fwd():
+            with torch.no_grad():
+                return net(featsd, idx_d, 1, [1440, 1440, 40])[0]
+        ms = timed(det_fwd, flush, warm=2, reps=5)
+        row = {'workload': 'SpMiddleResNetFHDELKv3 fwd (eval, fused)', 'n': len(idx), 'ms': ms,
+               'voxels_per_s': len(idx) / (ms * 1e-3)}
+        print(json.dumps(row), flush=True)
+        rows.append(row)
+        net.train()
+
+        def det_fwd_bwd():
+            f = featsd.clone().requires_grad_(True)
+            out = net(f, idx_d, 1, [1440, 1440, 40])[0]
+            out.square().mean().backward()
+            net.zero_grad(set_to_none=True)
+        ms = timed(det_fwd_bwd, flush, warm=2, reps=5)
+        row = {'workload': 'SpMiddleResNetFHDELKv3 fwd+bwd (train)', 'n': len(idx), 'ms': ms,
+               'voxels_per_s': len(idx) / (ms * 1e-3)}
+        print(json.dumps(row), flush=True)
+        rows.append(row)
+    except Exception as e:   # the sweep above is the point; report rather than hide a failure here
+        print(json.dumps({'workload': 'detection backbone', 'error': repr(e)[:300]}), flush=True)
+    os.makedirs(os.path.dirname(a.out) or '.', exist_ok=True)
+    json.dump(rows, open(a.out, 'w'), indent=0)
+
+
+if __name__ == '__main__':
+    main()

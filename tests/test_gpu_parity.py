@@ -729,3 +729,29 @@ def test_reference_cuda_kernels_vs_oracle_and_ours(dev):
             ours = blk(SparseTensor(feats.to(dev), cu(coords, dev), 1), s, r).F
         np.testing.assert_allclose(ref.cpu().numpy(), want, rtol=1e-3, atol=2e-4)
         np.testing.assert_allclose(ours.cpu().numpy(), ref.cpu().numpy(), rtol=1e-3, atol=2e-4)
+
+
+def test_from_host_async_upload_matches_resident_inputs(dev):
+    """SparseTensor.from_host (coordinates on the current stream, features on a copy stream, joined on
+    the device after the index-only kernels) gives the same block and encoder outputs (up to the
+    run-to-run order of the float reductions that join block sums spanning two lane groups)."""
+    from link_b200 import SparseTensor
+    from link_b200.elk import ELKBlock
+    from link_b200.linkencoder import ELKEncoder
+    from link_b200.utils.synthetic import kitti_like_voxels
+    c3, f4 = kitti_like_voxels(30_000, seed=5)
+    coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    ch = torch.from_numpy(coords).pin_memory()
+    torch.manual_seed(0)
+    blk = ELKBlock(64, 64, groups=2, baseop='cos').to(dev).eval()
+    fh = torch.randn(len(coords), 64).pin_memory()
+    enc = ELKEncoder(num_classes=19, cr=1.0, baseop='cos', r=3, s=7, groups=2).to(dev).eval()
+    f4h = torch.from_numpy(f4.astype(np.float32)).pin_memory()
+    with torch.no_grad():
+        for _ in range(3):       # repeated: the upload buffer recycles memory of earlier steps
+            want = blk(SparseTensor(fh.to(dev), ch.to(dev), 1), 7, 3).F
+            got = blk(SparseTensor.from_host(fh, ch, 1, device=dev), 7, 3).F
+            np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        want = enc(SparseTensor(f4h.to(dev), ch.to(dev), 1))
+        got = enc(SparseTensor.from_host(f4h, ch, 1, device=dev))
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5)
