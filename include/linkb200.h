@@ -335,6 +335,23 @@ int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wimg, const int32_t* d
                         const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
                         int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
                         lk_stream_t s);
+/* Composite index builds (one call = the launches of several entry points above; they exist to
+ * keep the host side off the critical path of the encoder forward).
+ * lk_kmap_build: [hash(d_in_coords) -> table build ->] kernel-map query [-> lk_conv_plan]
+ *   (the kmap branch of F.conv3d, nn/functional/conv.py:103-121).  d_table is caller-owned
+ *   (lk_table_capacity(n_in) * 16 bytes) and reusable by later maps of the same input level with
+ *   build_table = 0; subm = 1 selects the symmetric submanifold query; plan pointers may be NULL.
+ * lk_downsample: output coordinates of a strided conv whose kernel equals its stride
+ *   (F.spdownsample, nn/functional/downsample.py:11-51): packed keys -> radix sort -> unique ->
+ *   unpack; d_out_coords [n,4] with *d_num valid rows in the reference's torch.unique order. */
+int64_t lk_kmap_build_ws_bytes(int64_t n_in, int64_t n_out);
+int lk_kmap_build(const int32_t* d_in_coords, int64_t n_in, const int32_t* d_out_coords, int64_t n_out,
+                  const int32_t* d_offsets, int k, int subm, void* d_table, int64_t capacity,
+                  int build_table, int32_t* d_nbr, int32_t* d_plan_perm, uint32_t* d_plan_mask,
+                  void* d_ws, int64_t ws_bytes, lk_stream_t s);
+int64_t lk_downsample_ws_bytes(int64_t n);
+int lk_downsample(const int32_t* d_coords, int64_t n, const lk_keyspec_t* spec, int key_bits,
+                  int32_t* d_out_coords, int32_t* d_num, void* d_ws, int64_t ws_bytes, lk_stream_t s);
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);

@@ -91,6 +91,10 @@ PROTOTYPES = {
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
+    'lk_kmap_build_ws_bytes': (i64, [i64, i64]),
+    'lk_kmap_build': (i32, [vp, i64, vp, i64, vp, i32, i32, vp, i64, i32, vp, vp, vp, vp, i64, vp]),
+    'lk_downsample_ws_bytes': (i64, [i64]),
+    'lk_downsample': (i32, [vp, i64, C.POINTER(KeySpec), i32, vp, vp, vp, i64, vp]),
     'lk_conv_plan_ws_bytes': (i64, [i64]),
     'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp]),
     'lk_conv_tc_pack_weights': (i32, [vp, i32, i32, i32, vp, vp]),

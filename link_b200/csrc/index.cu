@@ -1,0 +1,83 @@
+// Composite index-build entry points: one C call enqueues what the Python layer otherwise issues
+// as 4-7 separate library calls (each ~15-40 us of interpreter + FFI time, which made the encoder
+// forward host-bound).  No new kernels; nothing here synchronises or allocates.
+//
+//   lk_kmap_build : hash(input coords) -> table build -> kernel-map query [-> tile-skipping plan]
+//                   (reference: the kmap branch of F.conv3d, nn/functional/conv.py:103-121)
+//   lk_downsample : packed (b,x,y,z) keys of floor(coords / stride) -> radix sort -> unique ->
+//                   unpack, count left on the device
+//                   (reference: F.spdownsample, nn/functional/downsample.py:11-51)
+#include "common.cuh"
+
+static inline int64_t ix_al(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+#define LK_TRY(call)                \
+  do {                              \
+    int rc__ = (call);              \
+    if (rc__ != LK_OK) return rc__; \
+  } while (0)
+
+extern "C" int64_t lk_kmap_build_ws_bytes(int64_t n_in, int64_t n_out) {
+  return ix_al(n_in * 8) + ix_al(lk_conv_plan_ws_bytes(n_out));
+}
+
+/* d_table: caller-owned, lk_table_capacity(n_in) * 16 bytes (kept: other maps of the same level
+ * reuse it with build_table = 0). */
+extern "C" int lk_kmap_build(const int32_t* d_in_coords, int64_t n_in, const int32_t* d_out_coords,
+                             int64_t n_out, const int32_t* d_offsets, int k, int subm,
+                             void* d_table, int64_t capacity, int build_table, int32_t* d_nbr,
+                             int32_t* d_plan_perm, uint32_t* d_plan_mask, void* d_ws,
+                             int64_t ws_bytes, lk_stream_t s) {
+  LK_REQUIRE(n_in >= 0 && n_out >= 0 && k > 0, "lk_kmap_build: bad sizes");
+  if (n_out == 0) return LK_OK;
+  LK_REQUIRE(d_in_coords && d_out_coords && d_offsets && d_table && d_nbr && d_ws,
+             "lk_kmap_build: null pointer");
+  if (ws_bytes < lk_kmap_build_ws_bytes(n_in, n_out)) {
+    lk_set_error("lk_kmap_build: workspace %lld < %lld bytes", (long long)ws_bytes,
+                 (long long)lk_kmap_build_ws_bytes(n_in, n_out));
+    return LK_ENOSPC;
+  }
+  char* ws = (char*)d_ws;
+  if (build_table) {
+    int64_t* hash = (int64_t*)ws;
+    LK_TRY(lk_hash(d_in_coords, n_in, hash, s));
+    LK_TRY(lk_table_build(hash, n_in, d_table, capacity, s));
+  }
+  if (subm)
+    LK_TRY(lk_kmap_query_subm(d_out_coords, n_out, d_offsets, k, d_table, capacity, d_nbr, s));
+  else
+    LK_TRY(lk_kmap_query(d_out_coords, n_out, d_offsets, k, d_table, capacity, d_nbr, s));
+  if (d_plan_perm && d_plan_mask && k <= 32)
+    LK_TRY(lk_conv_plan(d_nbr, n_out, k, d_offsets, d_plan_perm, d_plan_mask, ws + ix_al(n_in * 8),
+                        lk_conv_plan_ws_bytes(n_out), s));
+  return LK_OK;
+}
+
+extern "C" int64_t lk_downsample_ws_bytes(int64_t n) {
+  return 2 * ix_al(n * 8) + ix_al(lk_sort_unique_ws_bytes(n));
+}
+
+/* d_out_coords [n,4] (first *d_num rows valid, ascending (b,x,y,z) == torch.unique(dim=0) order of the
+ * reference), d_num device scalar. */
+extern "C" int lk_downsample(const int32_t* d_coords, int64_t n, const lk_keyspec_t* spec, int key_bits,
+                             int32_t* d_out_coords, int32_t* d_num, void* d_ws, int64_t ws_bytes,
+                             lk_stream_t s) {
+  LK_REQUIRE(n >= 0 && spec && d_num, "lk_downsample: bad arguments");
+  if (n == 0) return lk_sort_unique(nullptr, 0, key_bits, nullptr, nullptr, nullptr, nullptr, nullptr, d_num,
+                                    nullptr, 0, s);
+  LK_REQUIRE(d_coords && d_out_coords && d_ws, "lk_downsample: null pointer");
+  if (ws_bytes < lk_downsample_ws_bytes(n)) {
+    lk_set_error("lk_downsample: workspace %lld < %lld bytes", (long long)ws_bytes,
+                 (long long)lk_downsample_ws_bytes(n));
+    return LK_ENOSPC;
+  }
+  char* ws = (char*)d_ws;
+  uint64_t* keys = (uint64_t*)ws;
+  uint64_t* uniq = (uint64_t*)(ws + ix_al(n * 8));
+  void* sws = ws + 2 * ix_al(n * 8);
+  LK_TRY(lk_pack_keys(d_coords, n, spec, keys, s));
+  LK_TRY(lk_sort_unique(keys, n, key_bits, uniq, nullptr, nullptr, nullptr, nullptr, d_num, sws,
+                        lk_sort_unique_ws_bytes(n), s));
+  LK_TRY(lk_unpack_keys(uniq, d_num, n, spec, d_out_coords, s));
+  return LK_OK;
+}

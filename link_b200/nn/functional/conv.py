@@ -106,24 +106,43 @@ def _table_for(input: SparseTensor) -> HashTable:
     return tab
 
 
-def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation) -> KernelMap:
+def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_plan: bool = False) -> KernelMap:
+    """Kernel map of a conv over `input` (the kmap branch of the reference's F.conv3d,
+    conv.py:103-121) through ONE library call (lk_kmap_build: hash -> table -> query [-> plan]);
+    the hash table of the input level is kept in `kmaps` and reused by later maps of that level."""
     coords = input.coords.contiguous()
+    dev = coords.device
     # NB: like the reference (conv.py:105-107) the offsets ignore `dilation`.
-    offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=coords.device)
-    table = _table_for(input)
+    offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=dev)
     out_coords = coords
     if any(s > 1 for s in stride):
         out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
-    k, n_out = offsets.shape[0], out_coords.shape[0]
-    nbr = torch.empty(k, n_out, dtype=torch.int32, device=coords.device)
-    subm = all(s == 1 for s in stride) and k % 2 == 1
-    query = _capi.lib().lk_kmap_query_subm if subm else _capi.lib().lk_kmap_query
-    with _capi.timed('lk_kmap_query', n_out * (16 + 4 * k)):
-        _capi.check(query(_capi.ptr(out_coords), n_out, _capi.ptr(offsets), k,
-                          _capi.ptr(table.table), table.capacity, _capi.ptr(nbr), _capi.stream()),
-                    'lk_kmap_query')
-    kmap = KernelMap(nbr, coords.shape[0], n_out, out_coords)
+    k, n_in, n_out = offsets.shape[0], coords.shape[0], out_coords.shape[0]
+    L = _capi.lib()
+    tkey = ('lk', 'table', input.stride)
+    tab = input.kmaps.get(tkey)
+    build_table = tab is None or tab.n != n_in
+    if build_table:
+        tab = HashTable.__new__(HashTable)
+        tab.n, tab.capacity = n_in, int(L.lk_table_capacity(n_in))
+        tab.table = torch.empty(tab.capacity * 16, dtype=torch.uint8, device=dev)
+        input.kmaps[tkey] = tab
+    nbr = torch.empty(k, n_out, dtype=torch.int32, device=dev)
+    kmap = KernelMap(nbr, n_in, n_out, out_coords)
     kmap.offsets = offsets
+    plan = kmap.plan_buffers() if (want_plan and USE_PLAN and k <= 32 and n_out > 0) else None
+    subm = all(s == 1 for s in stride) and k % 2 == 1
+    ws_bytes = L.lk_kmap_build_ws_bytes(n_in, n_out)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with _capi.timed('lk_kmap_query', n_out * (16 + 4 * k)):
+        _capi.check(L.lk_kmap_build(coords.data_ptr(), n_in, out_coords.data_ptr(), n_out, offsets.data_ptr(),
+                                    k, 1 if subm else 0, tab.table.data_ptr(), tab.capacity,
+                                    1 if build_table else 0, nbr.data_ptr(),
+                                    plan[0].data_ptr() if plan else None,
+                                    plan[1].data_ptr() if plan else None, ws.data_ptr(), ws_bytes,
+                                    _capi.stream()), 'lk_kmap_build')
+    if plan:
+        kmap._plan = plan
     return kmap
 
 
@@ -307,7 +326,8 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
         key = (input.stride, kernel_size, stride, dilation)
         kmap = input.kmaps.get(key)
         if kmap is None:
-            kmap = build_kernel_map(input, kernel_size, stride, dilation)
+            kmap = build_kernel_map(input, kernel_size, stride, dilation,
+                                    want_plan=USE_TENSOR_CORES and w.shape[2] in (32, 64) and w.shape[1] in (4, 32, 64))
             input.kmaps[key] = kmap
         out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu, kmap=kmap)
         output = SparseTensor(coords=kmap.out_coords, feats=out,

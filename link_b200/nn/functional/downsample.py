@@ -2,6 +2,10 @@ from typing import Dict, Optional, Tuple, Union
 
 import torch
 
+import ctypes as C
+
+from link_b200 import _capi
+from link_b200.nn.functional import _index
 from link_b200.nn.functional._index import unique_coords
 from link_b200.nn.utils import get_kernel_offsets
 from link_b200.utils import make_ntuple
@@ -23,8 +27,18 @@ def spdownsample(coords: torch.Tensor, stride: Union[int, Tuple[int, ...]] = 2,
     sample_stride = [stride[k] * tensor_stride[k] for k in range(3)]
     coords = coords.contiguous()
     if all(stride[k] in [1, kernel_size[k]] for k in range(3)):
-        out, _, _ = unique_coords(coords, sample_stride, (3, 0, 1, 2), sample_stride, cache)
-        return out
+        # one library call (pack keys -> radix sort -> unique -> unpack), then the size read-back
+        n = coords.shape[0]
+        bounds = _index.coord_bounds(coords, cache)
+        spec, bits = _index.make_keyspec(bounds, sample_stride, (3, 0, 1, 2), sample_stride)
+        L = _capi.lib()
+        out = torch.empty(n, 4, dtype=torch.int32, device=coords.device)
+        num = torch.empty(1, dtype=torch.int32, device=coords.device)
+        ws_bytes = L.lk_downsample_ws_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=coords.device)
+        _capi.check(L.lk_downsample(_capi.ptr(coords, torch.int32), n, C.byref(spec), bits, out.data_ptr(),
+                                    num.data_ptr(), ws.data_ptr(), ws_bytes, _capi.stream()), 'lk_downsample')
+        return out[:int(num.item())]
     # general case (kernel != stride): expand by the kernel offsets, keep the aligned candidates
     offsets = get_kernel_offsets(kernel_size, tensor_stride, device=coords.device)
     kv = offsets.size(0)
