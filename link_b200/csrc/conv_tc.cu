@@ -35,24 +35,38 @@
 
 #define CT_ROWS 128
 #ifndef CT_NWB
-#define CT_NWB 4          // weight ring depth (tuning knob; 6 measured slower than 4)
+#define CT_NWB 3          // weight ring depth (tuning knob; 3 and 4 measure the same, 6 is slower)
+#endif
+#ifndef CT_GST
+#define CT_GST 3          // gather ring depth at 64 channels per step (3 x 32 KB)
 #endif
 #define CT_THREADS 512      // producer threads (16 warps); one more warp issues the MMAs
 // TMEM: columns [0, 512 - 128 NST) hold the accumulators, the rest NST A stages of 128 columns
 
 template <int CIN, int COUT, int NST>
 struct ConvTcCfg {
-  static constexpr int KB = CIN / 32;                       // 128-byte K-blocks per weight row
+  // C_in = 128 is processed as two K-halves of 64 channels: every real offset k becomes KH = 2
+  // "virtual offsets" (k, h) with their own 64-channel W image and A stage, so the TMEM budget of
+  // an A stage (hi + lo planes = 128 columns) and the step structure stay those of C_in = 64.
+  static constexpr int KH = CIN > 64 ? 2 : 1;
+  static constexpr int CE = CIN / KH;                       // channels per step (32 or 64)
+  static constexpr int KB = CE / 32;                        // 128-byte K-blocks per weight row
   static constexpr uint32_t B_BLK = COUT * 128;             // one [COUT x 32] K-block
   static constexpr uint32_t B_PLANE = KB * B_BLK;           // hi (or lo) plane
-  static constexpr uint32_t B_STAGE = 2 * B_PLANE;          // hi + lo
-  static constexpr int NWB = CT_NWB;                        // W[k] ring: prefetched NWB-NST offsets ahead
-  static constexpr uint32_t SMEM = NWB * B_STAGE + 1024;     // weight ring + alignment slack
+  static constexpr uint32_t B_STAGE = 2 * B_PLANE;          // hi + lo of one virtual offset
+  static constexpr int NWB = B_STAGE > 32768 ? 3 : CT_NWB;  // W ring: prefetched NWB-NST offsets ahead
+  // Gather ring: the rows of the next GST-1 steps are fetched with cp.async into per-thread slots of
+  // shared memory (no registers held while in flight).  0 = register ring of depth 2 (C_out = 128:
+  // the 64 KB weight images leave no room).
+  static constexpr uint32_t G_STAGE = CT_ROWS * CE * 4;     // raw fp32 rows of one step
+  static constexpr int GST = B_STAGE > 32768 ? 0 : (CE == 64 ? CT_GST : 4);
+  static constexpr uint32_t SMEM = NWB * B_STAGE + GST * G_STAGE + 1024;   // + alignment slack
   static constexpr int ACC_COLS = 512 - 128 * NST;
   static constexpr int MAX_TILES = ACC_COLS / COUT;
   static constexpr int A_STAGE_COLS = 128;                  // hi plane at +0, lo plane at +64
-  static constexpr int CPT = CIN / 4;                       // input channels per producer thread
+  static constexpr int CPT = CE / 4;                        // input channels per producer thread
 };
+
 
 template <int CIN, int COUT, int NST>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
@@ -64,6 +78,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   using Cfg = ConvTcCfg<CIN, COUT, NST>;
   constexpr int CPT = Cfg::CPT;                 // 16 (CIN = 64) or 8 (CIN = 32)
   constexpr int MAXT = Cfg::MAX_TILES;
+  constexpr int KH = Cfg::KH, CE = Cfg::CE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const b_base = smem;
@@ -71,16 +86,17 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   __shared__ uint64_t empty_bar[NST]; // A stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
   __shared__ uint64_t wfull_bar[Cfg::NWB];  // W[k] image landed (bulk copy, complete_tx)
-  __shared__ uint16_t steps_s[32 * MAXT];   // active (offset, tile slot) steps of the round: k << 4 | t
-  __shared__ uint8_t klist_s[32];           // distinct offsets of the round, ascending
+  __shared__ uint16_t steps_s[64 * MAXT];   // active (virtual offset, tile slot) steps: kv << 4 | t
+  __shared__ uint8_t klist_s[64];           // distinct virtual offsets of the round, ascending
   __shared__ int orow_s[MAXT][CT_ROWS];     // output row of every tile-slot row (-1 past the end)
   __shared__ uint32_t tmask_s[MAXT];
-  __shared__ int warp_cnt_s[8];
+  __shared__ int warp_cnt_s[16];
   __shared__ int nsteps_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t total_tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   const uint32_t kmask = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
+  const int n32 = (int)n_out;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -115,23 +131,27 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     if (tid < MAXT)
       tmask_s[tid] = tid < ntiles ? (tile_mask ? tile_mask[first_tile + (int64_t)tid * gridDim.x] & kmask : kmask) : 0u;
     __syncthreads();
-    if (tid < 256) {
-      const int kk = tid / MAXT, tt = tid % MAXT;
-      const bool on = kk < K && ((tmask_s[tt] >> kk) & 1u);
+    if (tid < CT_THREADS) {
+      const int kk = tid / MAXT, tt = tid % MAXT;            // kk = virtual offset (k, h) = k KH + h
+      const bool on = kk < K * KH && ((tmask_s[tt] >> (kk / KH)) & 1u);
       const unsigned bal = __ballot_sync(0xffffffffu, on);
       if (lane == 0) warp_cnt_s[warp] = __popc(bal);
       __syncwarp();
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 list-building warps only
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // the 16 list-building warps only
       int pos = __popc(bal & ((1u << lane) - 1u));
 #pragma unroll
-      for (int w = 0; w < 8; ++w) pos += (w < warp) ? warp_cnt_s[w] : 0;
+      for (int w = 0; w < 16; ++w) pos += (w < warp) ? warp_cnt_s[w] : 0;
       if (on) steps_s[pos] = (uint16_t)((kk << 4) | tt);
-      if (tid == 255) nsteps_s = pos + (on ? 1 : 0);
-    } else if (tid < 256 + 32) {
+      if (tid == CT_THREADS - 1) nsteps_s = pos + (on ? 1 : 0);
+    } else {
       uint32_t uni = 0;
 #pragma unroll
       for (int t = 0; t < MAXT; ++t) uni |= tmask_s[t];
-      if ((uni >> lane) & 1u) klist_s[__popc(uni & ((1u << lane) - 1u))] = (uint8_t)lane;
+      if ((uni >> lane) & 1u) {
+        const int base = __popc(uni & ((1u << lane) - 1u)) * KH;
+#pragma unroll
+        for (int h = 0; h < KH; ++h) klist_s[base + h] = (uint8_t)(lane * KH + h);
+      }
     }
     for (int i = tid; i < MAXT * CT_ROWS; i += CT_THREADS + 32) {
       const int t = i / CT_ROWS, r = i % CT_ROWS;
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     uint32_t uni_mask = 0;
 #pragma unroll
     for (int t = 0; t < MAXT; ++t) uni_mask |= tmask_s[t];
-    const int nk = __popc(uni_mask);            // distinct offsets of this round
+    const int nk = __popc(uni_mask) * KH;       // distinct virtual offsets of this round
     // W[k] images arrive by bulk copy into a ring of NWB buffers, NWB-NST offsets ahead of their
     // use.  Offset number w (global count wcount + local index) lives in buffer w % NWB; the copy
     // for offset w + NWB - NST is issued when offset w begins and overwrites offset w - NST, all of
@@ -194,8 +214,9 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           const uint64_t db_hi = db0 + (uint64_t)((((wc - 1) % Cfg::NWB) * Cfg::B_STAGE) >> 4);
           const uint64_t db_lo = db_hi + (uint64_t)(Cfg::B_PLANE >> 4);
           uint32_t acc = (touched >> t) & 1u;
+#ifndef CT_DEBUG_NO_MMA          // timing experiments only (results are wrong): see DESIGN.md 3.3
 #pragma unroll
-          for (int ks = 0; ks < CIN / 8; ++ks) {
+          for (int ks = 0; ks < CE / 8; ++ks) {
             // B descriptor start address is in 16-byte units: K-block ks/4, 32-byte slice ks%4
             const uint64_t bo = (uint64_t)(((ks >> 2) * Cfg::B_BLK + (ks & 3) * 32) >> 4);
             tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
@@ -203,6 +224,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
             tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
             acc = 1;
           }
+#endif
           tc::mma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -218,13 +240,20 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       auto load_idx = [&](int jj) -> int {
         if (jj >= nsteps) return -1;
-        const int k2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
+        const int kv2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
         const int o = orow_s[t2][prow];
-        return o >= 0 ? __ldg(nbr + (int64_t)k2 * n_out + o) : -1;
+        const int src = o >= 0 ? __ldg(nbr + (uint32_t)((kv2 / KH) * n32 + o)) : -1;   // K n_out < 2^31 (host check)
+        // the K-half rides in bit 30 of the (non-negative) row index
+        return (KH > 1 && src >= 0) ? (src | ((kv2 % KH) << 30)) : src;
       };
       auto load_rows = [&](int src, float4* v) {
+#ifdef CT_DEBUG_NO_GATHER
+        src = -1;
+#endif
         if (src >= 0) {
-          const float4* rp = (const float4*)(in + (int64_t)src * CIN + col0);
+          const int half = KH > 1 ? (src >> 30) : 0;
+          if (KH > 1) src &= 0x3FFFFFFF;
+          const float4* rp = (const float4*)(in + (int64_t)src * CIN + half * CE + col0);
 #pragma unroll
           for (int i = 0; i < CPT / 4; ++i) v[i] = __ldg(rp + i);
         } else {
@@ -232,30 +261,12 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           for (int i = 0; i < CPT / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      // Register ring of depth 2: the rows of step j are fetched while steps j-2 and j-1 are being
-      // processed (two full steps of lead time cover the L2 gather latency; with one step the
-      // producers sat on the loads), their indices two steps before that.
-      float4 va[CPT / 4], vb[CPT / 4];
-      load_rows(load_idx(0), va);
-      load_rows(load_idx(1), vb);
-      int idx_a = load_idx(2), idx_b = load_idx(3);     // rows of steps 2 / 3, fetched at steps 0 / 1
       int k_prev = -1, wc = wcount;
-      auto produce = [&](int j, float4* cur, int& idx_cur) {
+      // everything of a step after its rows are in registers (hi/lo split done by the caller)
+      auto publish = [&](int j, const float* hi, const float* lo) {
         const int jg = jbase + j;
         const int stage = jg % NST;
         const int k = steps_s[j] >> 4;
-        // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on the
-        // critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
-        float hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < CPT / 4; ++i) {
-          float4 h4, l4;
-          tc::split_tf32(cur[i], h4, l4);
-          hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
-          lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
-        }
-        load_rows(idx_cur, cur);                // refill this buffer: rows of step j + 2
-        idx_cur = load_idx(j + 4);              // ... and the index for its next refill
         if (jg >= NST) tc::mbar_wait(&empty_bar[stage], (uint32_t)((jg / NST) - 1) & 1u);
         tc::fence_after_sync();
         if (k != k_prev) {                      // an offset begins: prefetch the one after next
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           ++wc;
         }
         const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + lane_addr + (uint32_t)col0;
+#ifndef CT_DEBUG_NO_ST
         if (CPT == 16) {
           tc::tmem_st16(a_hi, hi);
           tc::tmem_st16(a_hi + 64, lo);
@@ -272,13 +284,129 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           tc::tmem_st8(a_hi + 64, lo);
         }
         tc::tmem_st_wait();
+#endif
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
       };
-      for (int j = 0; j < nsteps; j += 2) {
-        produce(j, va, idx_a);
-        if (j + 1 < nsteps) produce(j + 1, vb, idx_b);
+      if constexpr (Cfg::GST > 0) {
+        // ---- shared-memory gather ring with COALESCED row fetches.  Measured: when
+        // every thread fetches its own row quarter, a warp-level 16-byte load touches 32 different
+        // rows = 32 L1TEX tag cycles, 2 048 cycles per step and SM -- the kernel was bound by that,
+        // not by latency or bandwidth.  Here the CE/4 lanes that are adjacent in a warp fetch the
+        // CE/4 consecutive 16-byte chunks of ONE row (cp.async, 2-4 rows = 4 cache lines per
+        // instruction, 8x fewer tag cycles), steps j+1 .. j+GST-1 stay in flight in the ring, and
+        // after a producer-wide named barrier every thread reads the row quarter it has to store
+        // to TMEM (lane = row).  Missing neighbours are zero-filled copies (src-size 0); chunks are
+        // XOR-swizzled by the row so that both access patterns spread over all banks. ----
+        constexpr int GST = Cfg::GST, D = GST - 1;
+        constexpr int NCH = CPT / 4;                    // 16-byte chunks per thread and step
+        constexpr int CH_ROW = CE / 4;                  // chunks per row = lanes per fetched row
+        constexpr int RPP = CT_THREADS / CH_ROW;        // rows fetched per pass by the 512 threads
+        static_assert(RPP * NCH == CT_ROWS, "fetch passes must cover the tile");
+        const uint32_t g_base = tc::smem_u32(b_base + Cfg::NWB * Cfg::B_STAGE);
+        const int f_chunk = tid % CH_ROW, f_row0 = tid / CH_ROW;       // fetch role
+        uint32_t read_off[NCH], fetch_off[NCH];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          read_off[i] = (uint32_t)(prow * (CE * 4) + (((cs * NCH + i) ^ (prow & (CH_ROW - 1))) << 4));
+          const int fr = f_row0 + i * RPP;
+          fetch_off[i] = (uint32_t)(fr * (CE * 4) + ((f_chunk ^ (fr & (CH_ROW - 1))) << 4));
+        }
+        auto load_idx4 = [&](int jj, int* src) {        // neighbour rows of the NCH rows I fetch in step jj
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) src[i] = -1;
+          if (jj < nsteps) {
+            const int kv2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+              const int o = orow_s[t2][f_row0 + i * RPP];
+              const int sr = o >= 0 ? __ldg(nbr + (uint32_t)((kv2 / KH) * n32 + o)) : -1;   // K n_out < 2^31 (host check)
+              src[i] = (KH > 1 && sr >= 0) ? (sr | ((kv2 % KH) << 30)) : sr;
+            }
+          }
+        };
+        int w_slot = 0, r_slot = 0;                     // ring positions of the next fetch / next read
+        auto issue_gather = [&](int jj, const int* src) {   // rows of step jj -> slot jj % GST
+          const uint32_t dst = g_base + (uint32_t)w_slot * Cfg::G_STAGE;
+          w_slot = (w_slot + 1 == GST) ? 0 : w_slot + 1;
+          if (jj < nsteps) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+#ifdef CT_DEBUG_NO_GATHER
+              const int sv = -1;
+#else
+              const int sv = src[i];
+#endif
+              const int half = (KH > 1 && sv >= 0) ? (sv >> 30) : 0;
+              const int row = sv >= 0 ? (KH > 1 ? (sv & 0x3FFFFFFF) : sv) : 0;
+              const float* rp = in + (int64_t)row * CIN + half * CE + 4 * f_chunk;
+              const int nbytes = sv >= 0 ? 16 : 0;      // 0: zero-fill (missing neighbour)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                           ::"r"(dst + fetch_off[i]), "l"(rp), "r"(nbytes) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");   // one group per step, even if empty
+        };
+        int idx_a[NCH], idx_b[NCH];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          load_idx4(d, idx_a);
+          issue_gather(d, idx_a);
+        }
+        load_idx4(D, idx_a);                            // indices of steps j+D, two iterations ahead
+        load_idx4(D + 1, idx_b);
+        auto produce = [&](int j, int* idx_cur) {
+          // my copies of step j (and older) have landed; after the barrier so have everybody's,
+          // and every thread has finished reading step j-1, whose slot the next fetch overwrites
+          asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+          asm volatile("bar.sync 2, 512;" ::: "memory");
+          issue_gather(j + D, idx_cur);
+          load_idx4(j + D + 2, idx_cur);
+          const uint8_t* slot = b_base + Cfg::NWB * Cfg::B_STAGE + (uint32_t)r_slot * Cfg::G_STAGE;
+          r_slot = (r_slot + 1 == GST) ? 0 : r_slot + 1;
+          float hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const float4 v4 = *(const float4*)(slot + read_off[i]);
+            float4 h4, l4;
+            tc::split_tf32(v4, h4, l4);
+            hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+            lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+          }
+          publish(j, hi, lo);
+        };
+        for (int j = 0; j < nsteps; j += 2) {
+          produce(j, idx_a);
+          if (j + 1 < nsteps) produce(j + 1, idx_b);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        // ---- register ring of depth 2: the rows of step j are fetched while steps j-2 and j-1 are
+        // being processed, their indices two steps before that ----
+        float4 va[CPT / 4], vb[CPT / 4];
+        load_rows(load_idx(0), va);
+        load_rows(load_idx(1), vb);
+        int idx_a = load_idx(2), idx_b = load_idx(3);     // rows of steps 2 / 3, fetched at steps 0 / 1
+        auto produce = [&](int j, float4* cur, int& idx_cur) {
+          // split BEFORE waiting for the stage: after the wake-up only the TMEM stores remain on
+          // the critical path  commit(j-2) -> tcgen05.st -> full(j) -> MMA(j)
+          float hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < CPT / 4; ++i) {
+            float4 h4, l4;
+            tc::split_tf32(cur[i], h4, l4);
+            hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+            lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+          }
+          load_rows(idx_cur, cur);                // refill this buffer: rows of step j + 2
+          idx_cur = load_idx(j + 4);              // ... and the index for its next refill
+          publish(j, hi, lo);
+        };
+        for (int j = 0; j < nsteps; j += 2) {
+          produce(j, va, idx_a);
+          if (j + 1 < nsteps) produce(j + 1, vb, idx_b);
+        }
       }
       // ---- drain: the last commit on each stage ----
       const int gtot = jbase + nsteps;
@@ -290,8 +418,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
       tc::fence_after_sync();
       // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
       constexpr int NSLICE = COUT / 16;
-      if (cs < NSLICE) {
-        const int c_base = cs * 16;
+      for (int sl = cs; sl < NSLICE; sl += 4) {
+        const int c_base = sl * 16;
         for (int tt = 0; tt < ntiles; ++tt) {
           const int orow = orow_s[tt][prow];
           float acc[16];
@@ -376,40 +504,46 @@ template <int CIN, int COUT>
 static int launch_conv_tc(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
-  if (conv_tc_stages() == 2)
-    return launch_conv_tc_n<CIN, COUT, 2>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
-  return launch_conv_tc_n<CIN, COUT, 3>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+#ifdef CT_WITH_3_STAGES
+  if (conv_tc_stages() == 3)
+    return launch_conv_tc_n<CIN, COUT, 3>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+#endif
+  (void)conv_tc_stages;
+  return launch_conv_tc_n<CIN, COUT, 2>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
 }
 
 extern "C" int lk_conv_tc_supported(int c_in, int c_out) {
-  return (c_in == 32 || c_in == 64) && (c_out == 32 || c_out == 64);
+  return (c_in == 32 || c_in == 64 || c_in == 128) && (c_out == 32 || c_out == 64 || c_out == 128);
 }
 
-// W[k] [COUT][CIN] -> the kernel's shared-memory image: tf32 hi plane, then lo plane, each CIN/32
+// W[k] [COUT][CIN] -> the kernel's shared-memory images: one per virtual offset (k, h) (h = K-half
+// of 64 channels when CIN = 128, else a single half): tf32 hi plane, then lo plane, each CE/32
 // K-blocks of [COUT rows x 128 B] in the SWIZZLE_128B pattern (one thread per 16-byte chunk)
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ wt, int K, int cin,
                                                            int cout, float* __restrict__ img) {
-  const int kb_n = cin / 32;
-  const int64_t per_k = (int64_t)cout * kb_n * 8;          // 16-byte chunks per plane
-  const int64_t total = (int64_t)K * per_k;
-  const int64_t stage_floats = (int64_t)2 * cin * cout;
+  const int kh = cin > 64 ? 2 : 1, ce = cin / kh;
+  const int kb_n = ce / 32;
+  const int64_t per_v = (int64_t)cout * kb_n * 8;          // 16-byte chunks per plane and virtual offset
+  const int64_t total = (int64_t)K * kh * per_v;
+  const int64_t stage_floats = (int64_t)2 * ce * cout;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(t / per_k);
-    const int r = (int)(t - (int64_t)k * per_k);
+    const int kv = (int)(t / per_v);
+    const int r = (int)(t - (int64_t)kv * per_v);
+    const int k = kv / kh, h = kv % kh;
     const int chunk = r & 7, kb = (r >> 3) % kb_n, row = r / (8 * kb_n);
-    float4 w4 = __ldg((const float4*)(wt + ((int64_t)k * cout + row) * cin + kb * 32 + chunk * 4)), hi, lo;
+    float4 w4 = __ldg((const float4*)(wt + ((int64_t)k * cout + row) * cin + h * ce + kb * 32 + chunk * 4)), hi, lo;
     tc::split_tf32(w4, hi, lo);
     const uint32_t off = (uint32_t)kb * (uint32_t)(cout * 128) + tc::sw128_offset(row, chunk);
-    float* base = img + (int64_t)k * stage_floats;
+    float* base = img + (int64_t)kv * stage_floats;
     *(float4*)((uint8_t*)base + off) = hi;
-    *(float4*)((uint8_t*)base + (size_t)cin * cout * 4 + off) = lo;
+    *(float4*)((uint8_t*)base + (size_t)ce * cout * 4 + off) = lo;
   }
 }
 
 extern "C" int lk_conv_tc_pack_weights(const float* d_wt, int k, int c_in, int c_out, float* d_img,
                                        lk_stream_t s) {
-  LK_REQUIRE(k > 0 && lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_pack_weights: channels must be 32 or 64");
+  LK_REQUIRE(k > 0 && lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_pack_weights: channels must be 32, 64 or 128");
   LK_REQUIRE(d_wt && d_img && (uintptr_t)d_wt % 16 == 0 && (uintptr_t)d_img % 128 == 0,
              "lk_conv_tc_pack_weights: null or misaligned pointer");
   pack_weights_kernel<<<lk_grid((int64_t)k * c_out * (c_in / 32) * 8, 256, 4), 256, 0, (cudaStream_t)s>>>(
@@ -437,8 +571,8 @@ extern "C" int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const i
                                    const lk_conv_epilogue_t* epp, float* d_out, lk_stream_t s) {
   lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, 0};
   if (epp) ep = *epp;
-  LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32, "lk_conv_tc_fwd: bad sizes (1 <= K <= 32)");
-  LK_REQUIRE(lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_fwd: channels must be 32 or 64");
+  LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32 && n_out * k < (1LL << 31), "lk_conv_tc_fwd: bad sizes (1 <= K <= 32, K n_out < 2^31)");
+  LK_REQUIRE(lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_fwd: channels must be 32, 64 or 128");
   LK_REQUIRE((d_perm == nullptr) == (d_tile_mask == nullptr),
              "lk_conv_tc_fwd: perm and tile_mask come together (lk_conv_plan)");
   if (n_out == 0) return LK_OK;
@@ -446,8 +580,18 @@ extern "C" int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const i
   LK_REQUIRE((uintptr_t)d_in % 16 == 0 && (uintptr_t)d_wt % 16 == 0 && (uintptr_t)d_out % 16 == 0,
              "lk_conv_tc_fwd: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)s;
-  if (c_in == 32 && c_out == 32) return launch_conv_tc<32, 32>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
-  if (c_in == 32 && c_out == 64) return launch_conv_tc<32, 64>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
-  if (c_in == 64 && c_out == 32) return launch_conv_tc<64, 32>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
-  return launch_conv_tc<64, 64>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st);
+#define LK_CONV_TC_CASE(CI, CO) \
+  if (c_in == CI && c_out == CO) return launch_conv_tc<CI, CO>(d_in, d_wt, d_nbr, d_perm, d_tile_mask, n_out, k, ep, d_out, st)
+  LK_CONV_TC_CASE(32, 32);
+  LK_CONV_TC_CASE(32, 64);
+  LK_CONV_TC_CASE(32, 128);
+  LK_CONV_TC_CASE(64, 32);
+  LK_CONV_TC_CASE(64, 64);
+  LK_CONV_TC_CASE(64, 128);
+  LK_CONV_TC_CASE(128, 32);
+  LK_CONV_TC_CASE(128, 64);
+  LK_CONV_TC_CASE(128, 128);
+#undef LK_CONV_TC_CASE
+  lk_set_error("lk_conv_tc_fwd: unsupported channel combination");
+  return LK_EINVAL;
 }

@@ -302,14 +302,14 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     a.kvol = conv.kernel_volume
     w = conv.kernel.detach().contiguous()
     a.d_conv_w = _capi.ptr(w)
-    wt = _tc_image(conv.kernel) if (USE_TENSOR_CORES and c in (32, 64)) else None   # cached on the Parameter
+    wt = _tc_image(conv.kernel) if (USE_TENSOR_CORES and c in (32, 64, 128)) else None   # cached on the Parameter
     a.d_conv_wt = _capi.ptr(wt)
     a.d_conv_offsets = _capi.ptr(conv_off)
     a.d_kmap, a.build_kmap = _capi.ptr(kmap.nbr), 1 if build else 0
     if build:
         kmap.offsets = conv_off
     a.build_plan = 0
-    if USE_TENSOR_CORES and c in (32, 64) and conv.kernel_volume <= 32 and kmap._plan is not False:
+    if USE_TENSOR_CORES and c in (32, 64, 128) and conv.kernel_volume <= 32 and kmap._plan is not False:
         from link_b200.nn.functional import conv as _convmod
         if kmap._plan is None and _convmod.USE_PLAN:     # the executor fills the plan buffers
             kmap._plan = kmap.plan_buffers()

@@ -327,7 +327,7 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
         kmap = input.kmaps.get(key)
         if kmap is None:
             kmap = build_kernel_map(input, kernel_size, stride, dilation,
-                                    want_plan=USE_TENSOR_CORES and w.shape[2] in (32, 64) and w.shape[1] in (4, 32, 64))
+                                    want_plan=USE_TENSOR_CORES and w.shape[2] in (32, 64, 128) and w.shape[1] in (4, 32, 64, 128))
             input.kmaps[key] = kmap
         out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu, kmap=kmap)
         output = SparseTensor(coords=kmap.out_coords, feats=out,
