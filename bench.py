@@ -254,7 +254,6 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     t_wall1 = time.time()
     launches = _capi.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    clocks = sampler.finish(t_wall0, t_wall1) if with_clocks else None
     # ---- instrumented pass: same steps with one python-level call per kernel, CUDA events around
     #      each library call on the launching stream (per-kernel times for `kernels`/`roofline`) ----
     _capi.TIMERS = {}
@@ -299,6 +298,9 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
             d2h = out_host.numel() * 4
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    # clocks / throttle reasons sampled under load over all timed loops of this workload (device-resident,
+    # instrumented, roofline and end-to-end passes): the device-resident loop alone lasts a few ms
+    clocks = sampler.finish(t_wall0, time.time()) if with_clocks else None
     # ---- reference GPU leg (reported baseline, rank 0, block workload): the reference's own CUDA
     #      kernels (oracle/_ref/backend_cuda.so) under a restatement of its python glue ----
     ref_gpu = None

@@ -58,7 +58,11 @@ int lk_kernel_hash(const int32_t* d_coords, int64_t n, const int32_t* d_offsets,
  * insert, query_cpu.cpp:22-26).  Keys must not equal -1 (the empty marker); sphash
  * outputs are 60-bit non-negative.
  * ---------------------------------------------------------------------------------- */
-int64_t lk_table_capacity(int64_t n);                 /* slots; bytes = 16 * slots */
+int64_t lk_table_capacity(int64_t n);
+/* lk_hash + lk_table_build in one launch: the keys are the FNV hashes of d_coords [n,4], computed on
+ * the fly (same table contents). */
+int lk_table_build_coords(const int32_t* d_coords, int64_t n, void* d_table, int64_t capacity,
+                          lk_stream_t s);                 /* slots; bytes = 16 * slots */
 int lk_table_build(const int64_t* d_keys, int64_t n, void* d_table, int64_t capacity,
                    lk_stream_t s);                    /* value of key i is i */
 /* d_out[i] = value of d_queries[i] or -1 (the reference returns value+1 / 0 and python
@@ -130,6 +134,11 @@ int64_t lk_sort_unique_ws_bytes(int64_t n);
 int lk_sort_unique(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t* d_unique,
                    int32_t* d_inverse, int32_t* d_order, int32_t* d_seg, int32_t* d_counts,
                    int32_t* d_num, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+/* lk_pack_keys + lk_sort_unique_ex with the key packing fused into the first histogram launch. */
+int lk_sort_unique_coords(const int32_t* d_coords, const lk_keyspec_t* spec, int64_t n, int key_bits,
+                          uint64_t* d_unique, int32_t* d_inverse, int32_t* d_order, int32_t* d_seg,
+                          int32_t* d_counts, int32_t* d_num, int32_t* d_sorted_rank, void* d_ws,
+                          int64_t ws_bytes, lk_stream_t s);
 /* Same, plus d_sorted_rank[n] (may be NULL): rank of the key at each SORTED position, i.e.
  * d_sorted_rank[i] == d_inverse[d_order[i]] (the block row of the i-th voxel in block order;
  * feeds the segmented pre-aggregation, lk_link_preagg_seg_fwd). */
@@ -149,6 +158,11 @@ int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits, uint64_t*
 int lk_block_neighbors(const uint64_t* d_unique, const int32_t* d_num, int64_t capacity,
                        const lk_keyspec_t* spec, const int32_t* d_offsets, int r3,
                        int32_t* d_nbr, lk_stream_t s);
+/* Same, and the first M rows of d_zero [capacity, row_floats] are cleared in the same launch
+ * (lk_zero_rows fused: the block-sum buffer of the pre-aggregation). */
+int lk_block_neighbors_zero(const uint64_t* d_unique, const int32_t* d_num, int64_t capacity,
+                            const lk_keyspec_t* spec, const int32_t* d_offsets, int r3,
+                            int32_t* d_nbr, float* d_zero, int row_floats, lk_stream_t s);
 
 #define LK_OP_COS 0   /* planes [cos, sin]           linkencoder.py:150-162 */
 #define LK_OP_SIN 1   /* planes [sin, cos]           linkencoder.py:135-148 */
@@ -193,6 +207,11 @@ int lk_link_preagg_seg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords
 int lk_link_window_mean(const float* d_sums, const int32_t* d_counts, const int32_t* d_nbr,
                         const int32_t* d_num, int64_t capacity, int r3, int kc, float* d_mean,
                         lk_stream_t s);
+/* Pass 2a with the block populations given as segment starts (n[b] = d_seg[b+1] - d_seg[b], the
+ * d_seg output of lk_sort_unique*), which saves the separate counts pass. */
+int lk_link_window_mean_seg(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
+                            const int32_t* d_num, int64_t capacity, int r3, int kc, float* d_mean,
+                            lk_stream_t s);
 /* Pass 2b: per voxel combine with its own phase.  Writes d_out [n,C]:
  *   fuse_norm == 0 : pre-LayerNorm value (linkencoder.py:162 / 148 / 176)
  *   fuse_norm == 1 : relu(LN(value; g1,b1) + LN(local; g2,b2)), eps 1e-6

@@ -59,6 +59,7 @@ PROTOTYPES = {
     'lk_kernel_hash': (i32, [vp, i64, vp, i32, vp, vp]),
     'lk_table_capacity': (i64, [i64]),
     'lk_table_build': (i32, [vp, i64, vp, i64, vp]),
+    'lk_table_build_coords': (i32, [vp, i64, vp, i64, vp]),
     'lk_table_query': (i32, [vp, i64, vp, i64, vp, vp]),
     'lk_hash_div': (i32, [vp, i64, i32, vp, vp]),
     'lk_table_query_div': (i32, [vp, i64, i32, vp, i64, vp, vp]),
@@ -74,10 +75,13 @@ PROTOTYPES = {
     'lk_sort_unique': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'lk_sort_unique_ex': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'lk_block_neighbors': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, i32, vp, vp]),
+    'lk_block_neighbors_zero': (i32, [vp, vp, i64, C.POINTER(KeySpec), vp, i32, vp, vp, i32, vp]),
+    'lk_sort_unique_coords': (i32, [vp, C.POINTER(KeySpec), i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'lk_zero_rows': (i32, [vp, vp, i64, i32, vp]),
     'lk_link_preagg_fwd': (i32, [vp, vp, vp, i64, C.POINTER(KernelGen), vp, vp]),
     'lk_link_preagg_seg_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), vp, vp]),
     'lk_link_window_mean': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
+    'lk_link_window_mean_seg': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
     'lk_abi_sizeof': (i32, [i32]),

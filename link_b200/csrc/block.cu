@@ -3,7 +3,8 @@
 //
 //   hash -> table build -> submanifold kernel map        (skipped when the caller passes a map)
 //   conv plan (tile-skipping order of the kernel map)
-//   block keys -> radix sort/unique -> neighbour-block table -> zero sums
+//   block keys + radix sort/unique (key packing fused into the first pass) -> neighbour-block table
+//   (+ zeroing of the block sums in the same launch)
 //   -- wait for the features if they are still being uploaded (cudaStreamWaitEvent) --
 //   pre_mix  = LN(x W^T)                                  (tcgen05 / FFMA)
 //   local    = SubM 3^3 conv(x)                           (tcgen05 / FFMA)
@@ -17,7 +18,7 @@
 static inline int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct BlockWs {
-  int64_t hash, table, kmap, plan_ws, fin, local, keys, uniq, inverse, order, srank, counts, num, nbr, sums, mean, sort_ws, total;
+  int64_t table, kmap, plan_ws, fin, local, uniq, inverse, order, srank, seg, num, nbr, sums, mean, sort_ws, total;
   int64_t table_cap;
 };
 
@@ -26,18 +27,16 @@ static BlockWs plan(int64_t n, int c, int kc, int r3, int kvol, bool need_kmap, 
   int64_t o = 0;
   const int64_t cp_bytes = need_plan ? al256(lk_conv_plan_ws_bytes(n)) : 0;
   w.table_cap = lk_table_capacity(n);
-  w.hash = o;    o += need_kmap ? al256(n * 8) : 0;
   w.table = o;   o += need_kmap ? al256(w.table_cap * 16) : 0;
   w.kmap = o;
   w.plan_ws = o; o += cp_bytes;
   w.fin = o;     o += al256(n * c * 4);
   w.local = o;   o += al256(n * c * 4);
-  w.keys = o;    o += al256(n * 8);
   w.uniq = o;    o += al256(n * 8);
   w.inverse = o; o += al256(n * 4);
   w.order = o;   o += al256(n * 4);
   w.srank = o;   o += al256(n * 4);
-  w.counts = o;  o += al256(n * 4);
+  w.seg = o;     o += al256((n + 1) * 4);
   w.num = o;     o += 256;
   w.nbr = o;     o += al256(n * (int64_t)r3 * 4);
   w.sums = o;    o += al256(n * (int64_t)kc * 4);
@@ -75,9 +74,7 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   char* ws = (char*)a->d_ws;
   const int32_t* kmap = a->d_kmap;
   if (need_kmap) {
-    int64_t* hash = (int64_t*)(ws + w.hash);
-    LK_TRY(lk_hash(a->d_coords, n, hash, s));
-    LK_TRY(lk_table_build(hash, n, ws + w.table, w.table_cap, s));
+    LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, s));
     LK_TRY(lk_kmap_query_subm(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
                               a->d_kmap, s));
   }
@@ -88,21 +85,18 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   if (planned && a->build_plan)
     LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
                         ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
-  uint64_t* keys = (uint64_t*)(ws + w.keys);
   uint64_t* uniq = (uint64_t*)(ws + w.uniq);
   int32_t* inverse = (int32_t*)(ws + w.inverse);
-  int32_t* counts = (int32_t*)(ws + w.counts);
+  int32_t* seg = (int32_t*)(ws + w.seg);
   int32_t* num = (int32_t*)(ws + w.num);
   int32_t* nbr = (int32_t*)(ws + w.nbr);
   int32_t* order = (int32_t*)(ws + w.order);
   int32_t* srank = (int32_t*)(ws + w.srank);
   float* sums = (float*)(ws + w.sums);
   float* mean = (float*)(ws + w.mean);
-  LK_TRY(lk_pack_keys(a->d_coords, n, &a->keyspec, keys, s));
-  LK_TRY(lk_sort_unique_ex(keys, n, a->key_bits, uniq, inverse, order, nullptr, counts, num, srank,
-                           ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
-  LK_TRY(lk_block_neighbors(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, s));
-  LK_TRY(lk_zero_rows(sums, num, n, kc, s));
+  LK_TRY(lk_sort_unique_coords(a->d_coords, &a->keyspec, n, a->key_bits, uniq, inverse, order, seg,
+                               nullptr, num, srank, ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
+  LK_TRY(lk_block_neighbors_zero(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, sums, kc, s));
   // ---- feature kernels ----
   if (a->feats_ready) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)a->feats_ready, 0));
   float* fin = (float*)(ws + w.fin);
@@ -125,7 +119,7 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   }
   // linear-kernel aggregation
   LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, s));
-  LK_TRY(lk_link_window_mean(sums, counts, nbr, num, n, a->r3, kc, mean, s));
+  LK_TRY(lk_link_window_mean_seg(sums, seg, nbr, num, n, a->r3, kc, mean, s));
   LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,
                            a->d_g2, a->d_b2, a->d_out, s));
   return LK_OK;

@@ -103,6 +103,40 @@ __global__ void __launch_bounds__(256) table_query_kernel(const int64_t* __restr
     out[i] = table_find(table, mask, (unsigned long long)q[i]);
 }
 
+// same table, keys hashed on the fly from the coordinates (saves the hash array round trip and a launch)
+__global__ void __launch_bounds__(256) table_insert_coords_kernel(const int4* __restrict__ coords,
+                                                                  int64_t n, Slot* table, uint64_t mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = coords[i];
+    unsigned long long key = (unsigned long long)lk_fnv4(c.x, c.y, c.z, c.w);
+    uint64_t s = slot_of(key, mask);
+    while (true) {
+      unsigned long long prev = atomicCAS(&table[s].key, LK_EMPTY, key);
+      if (prev == LK_EMPTY || prev == key) {
+        atomicMin(&table[s].val, (unsigned int)i);
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+
+extern "C" int lk_table_build_coords(const int32_t* d_coords, int64_t n, void* d_table, int64_t capacity,
+                                     lk_stream_t s) {
+  LK_REQUIRE(d_table && capacity >= 2 * n && (capacity & (capacity - 1)) == 0 && n >= 0,
+             "lk_table_build_coords: capacity must be a power of two >= 2n");
+  LK_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)capacity * sizeof(Slot), (cudaStream_t)s));
+  lk_count_launch();
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_coords, "lk_table_build_coords: null coords");
+  table_insert_coords_kernel<<<lk_grid(n, 256, 8), 256, 0, (cudaStream_t)s>>>((const int4*)d_coords, n,
+                                                                             (Slot*)d_table,
+                                                                             (uint64_t)capacity - 1);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 extern "C" int64_t lk_table_capacity(int64_t n) {
   int64_t cap = 1024;
   while (cap < 2 * n) cap <<= 1;

@@ -38,11 +38,7 @@ extern "C" int lk_kmap_build(const int32_t* d_in_coords, int64_t n_in, const int
     return LK_ENOSPC;
   }
   char* ws = (char*)d_ws;
-  if (build_table) {
-    int64_t* hash = (int64_t*)ws;
-    LK_TRY(lk_hash(d_in_coords, n_in, hash, s));
-    LK_TRY(lk_table_build(hash, n_in, d_table, capacity, s));
-  }
+  if (build_table) LK_TRY(lk_table_build_coords(d_in_coords, n_in, d_table, capacity, s));
   if (subm)
     LK_TRY(lk_kmap_query_subm(d_out_coords, n_out, d_offsets, k, d_table, capacity, d_nbr, s));
   else

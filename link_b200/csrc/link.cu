@@ -368,6 +368,8 @@ extern "C" int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity
 // One warp per block row.  The R neighbour indices are loaded by the first R lanes, the present
 // ones are compacted with a ballot, and only those rows are fetched (a LiDAR block has ~9-12 of
 // its 27 neighbours), four at a time so the L2 loads overlap.
+// SEG: `counts` holds the segment starts of the sorted voxel sequence (n[b] = seg[b+1] - seg[b])
+template <bool SEG>
 __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __restrict__ sums,
                                                                const int* __restrict__ counts,
                                                                const int* __restrict__ nbr,
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
     int src = -1, cnt = 0;
     if (lane < R) {                              // R <= 32
       src = __ldg(nbr + b * R + lane);
-      if (src >= 0) cnt = __ldg(counts + src);
+      if (src >= 0) cnt = SEG ? __ldg(counts + src + 1) - __ldg(counts + src) : __ldg(counts + src);
     }
     const unsigned present = __ballot_sync(0xffffffffu, src >= 0);
     int tot_i = cnt;
@@ -676,8 +678,21 @@ extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
              "lk_link_window_mean: bad sizes (needs r^3 <= 32)");
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_sums && d_counts && d_nbr && d_num && d_mean, "lk_link_window_mean: null pointer");
-  link_window_mean_kernel<<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
+  link_window_mean_kernel<false><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
       d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_link_window_mean_seg(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
+                                       const int32_t* d_num, int64_t capacity, int r3, int kc,
+                                       float* d_mean, lk_stream_t s) {
+  LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32 && kc > 0 && kc % 4 == 0,
+             "lk_link_window_mean_seg: bad sizes (needs r^3 <= 32)");
+  if (capacity == 0) return LK_OK;
+  LK_REQUIRE(d_sums && d_seg && d_nbr && d_num && d_mean, "lk_link_window_mean_seg: null pointer");
+  link_window_mean_kernel<true><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
+      d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean);
   LK_LAUNCHED();
   return LK_OK;
 }

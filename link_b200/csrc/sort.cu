@@ -115,10 +115,17 @@ extern "C" int lk_unpack_keys(const uint64_t* d_keys, const int32_t* d_count, in
 // offset coordinate and binary-searching the (L1/L2 resident) key array.
 __global__ void __launch_bounds__(256) block_neighbors_kernel(
     const unsigned long long* __restrict__ uniq, const int* __restrict__ d_num, int64_t capacity,
-    KeySpecDev sp, const int* __restrict__ offsets, int R, int* __restrict__ nbr) {
+    KeySpecDev sp, const int* __restrict__ offsets, int R, int* __restrict__ nbr,
+    float4* __restrict__ zero_buf, int zero_row_vec) {
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
   int64_t total = m * R;
+  if (zero_buf) {            // optional: clear the first M rows of the block-sum buffer in the same launch
+    const int64_t zt = m * zero_row_vec;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < zt;
+         t += (int64_t)gridDim.x * blockDim.x)
+      zero_buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = t / R;
@@ -158,7 +165,23 @@ extern "C" int lk_block_neighbors(const uint64_t* d_unique, const int32_t* d_num
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_unique && d_num && d_offsets && d_nbr && r3 > 0, "lk_block_neighbors: bad arguments");
   block_neighbors_kernel<<<lk_grid(capacity * r3, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      (const unsigned long long*)d_unique, d_num, capacity, sp, d_offsets, r3, d_nbr);
+      (const unsigned long long*)d_unique, d_num, capacity, sp, d_offsets, r3, d_nbr, nullptr, 0);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_block_neighbors_zero(const uint64_t* d_unique, const int32_t* d_num, int64_t capacity,
+                                       const lk_keyspec_t* spec, const int32_t* d_offsets, int r3,
+                                       int32_t* d_nbr, float* d_zero, int row_floats, lk_stream_t s) {
+  KeySpecDev sp;
+  LK_REQUIRE(spec && make_spec(spec, &sp) >= 0, "lk_block_neighbors_zero: invalid key spec");
+  if (capacity == 0) return LK_OK;
+  LK_REQUIRE(d_unique && d_num && d_offsets && d_nbr && r3 > 0 && d_zero && row_floats > 0 &&
+                 row_floats % 4 == 0 && (uintptr_t)d_zero % 16 == 0,
+             "lk_block_neighbors_zero: bad arguments");
+  block_neighbors_kernel<<<lk_grid(capacity * r3, 256, 8), 256, 0, (cudaStream_t)s>>>(
+      (const unsigned long long*)d_unique, d_num, capacity, sp, d_offsets, r3, d_nbr, (float4*)d_zero,
+      row_floats / 4);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -405,6 +428,30 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_tm_kernel(
   hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];   // tile-major
 }
 
+// first pass of a sort that starts from coordinates: pack the keys (stored for the scatter passes)
+// and build the tile histograms of digit 0 in one launch
+__global__ void __launch_bounds__(RS_THREADS) radix_pack_hist_tm_kernel(
+    const int4* __restrict__ coords, int64_t n, KeySpecDev sp, unsigned long long* __restrict__ keys,
+    unsigned* __restrict__ hist) {
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    int64_t i = base + j * RS_THREADS + threadIdx.x;
+    if (i < n) {
+      int4 c = coords[i];
+      unsigned long long k = pack_fields(sp, lk_floordiv(c.x, sp.div[0]), lk_floordiv(c.y, sp.div[1]),
+                                         lk_floordiv(c.z, sp.div[2]), c.w);
+      keys[i] = k;
+      atomicAdd(&h[(unsigned)k & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];   // tile-major
+}
+
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
     const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
     unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out, int64_t n,
@@ -584,11 +631,34 @@ extern "C" int64_t lk_sort_unique_ws_bytes(int64_t n) {
          align256((T + 1) * 4) + align256((n + 1) * 4) + align256(4);
 }
 
+static int sort_unique_impl(const uint64_t* d_keys, const int32_t* d_coords, const lk_keyspec_t* spec,
+                            int64_t n, int key_bits, uint64_t* d_unique, int32_t* d_inverse,
+                            int32_t* d_order, int32_t* d_seg, int32_t* d_counts, int32_t* d_num,
+                            int32_t* d_sorted_rank, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+
 extern "C" int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits,
                                  uint64_t* d_unique, int32_t* d_inverse, int32_t* d_order,
                                  int32_t* d_seg, int32_t* d_counts, int32_t* d_num,
                                  int32_t* d_sorted_rank, void* d_ws, int64_t ws_bytes,
                                  lk_stream_t s) {
+  return sort_unique_impl(d_keys, nullptr, nullptr, n, key_bits, d_unique, d_inverse, d_order, d_seg,
+                          d_counts, d_num, d_sorted_rank, d_ws, ws_bytes, s);
+}
+
+extern "C" int lk_sort_unique_coords(const int32_t* d_coords, const lk_keyspec_t* spec, int64_t n,
+                                     int key_bits, uint64_t* d_unique, int32_t* d_inverse,
+                                     int32_t* d_order, int32_t* d_seg, int32_t* d_counts,
+                                     int32_t* d_num, int32_t* d_sorted_rank, void* d_ws,
+                                     int64_t ws_bytes, lk_stream_t s) {
+  LK_REQUIRE(spec && (d_coords || n == 0), "lk_sort_unique_coords: null coords/spec");
+  return sort_unique_impl(nullptr, d_coords, spec, n, key_bits, d_unique, d_inverse, d_order, d_seg,
+                          d_counts, d_num, d_sorted_rank, d_ws, ws_bytes, s);
+}
+
+static int sort_unique_impl(const uint64_t* d_keys, const int32_t* d_coords, const lk_keyspec_t* spec,
+                            int64_t n, int key_bits, uint64_t* d_unique, int32_t* d_inverse,
+                            int32_t* d_order, int32_t* d_seg, int32_t* d_counts, int32_t* d_num,
+                            int32_t* d_sorted_rank, void* d_ws, int64_t ws_bytes, lk_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   LK_REQUIRE(n >= 0 && n < (1LL << 31), "lk_sort_unique: n out of range");
   LK_REQUIRE(key_bits >= 0 && key_bits <= 64, "lk_sort_unique: key_bits out of range");
@@ -597,7 +667,9 @@ extern "C" int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits
     if (d_seg) { LK_CUDA(cudaMemsetAsync(d_seg, 0, 4, st)); lk_count_launch(); }
     return LK_OK;
   }
-  LK_REQUIRE(d_keys && d_ws, "lk_sort_unique: null keys/workspace");
+  LK_REQUIRE((d_keys || d_coords) && d_ws, "lk_sort_unique: null keys/workspace");
+  KeySpecDev spd;
+  if (d_coords) LK_REQUIRE(make_spec(spec, &spd) >= 0, "lk_sort_unique_coords: invalid key spec");
   if (ws_bytes < lk_sort_unique_ws_bytes(n)) {
     lk_set_error("lk_sort_unique: workspace %lld < %lld bytes", (long long)ws_bytes,
                  (long long)lk_sort_unique_ws_bytes(n));
@@ -621,13 +693,23 @@ extern "C" int lk_sort_unique_ex(const uint64_t* d_keys, int64_t n, int key_bits
   unsigned long long* kout = ka;
   unsigned* vout = va;
   const bool fused = T <= RS_MAX_FUSED_TILES;
+  if (d_coords) {            // keys are packed into kb by the first kernel (fused with the histogram
+    kin = kb;                // when the fused path applies); the first scatter then reads kb, writes ka
+    if (!fused) {
+      pack_keys_kernel<<<lk_grid(n, 256, 8), 256, 0, st>>>((const int4*)d_coords, n, spd, kb);
+      LK_LAUNCHED();
+    }
+  }
   if (fused) {
     const int64_t hsz = 256 * (int64_t)T;          // one [T][256] matrix per pass
     if (passes > 1) {
       LK_CUDA(cudaMemsetAsync(hist + hsz, 0, (size_t)(passes - 1) * hsz * sizeof(unsigned), st));
       lk_count_launch();
     }
-    radix_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, 0, hist);
+    if (d_coords)
+      radix_pack_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>((const int4*)d_coords, n, spd, kb, hist);
+    else
+      radix_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, 0, hist);
     LK_LAUNCHED();
     for (int pss = 0; pss < passes; ++pss) {
       radix_scatter_fused_kernel<<<T, RS_THREADS, 0, st>>>(

@@ -757,3 +757,60 @@ def test_from_host_async_upload_matches_resident_inputs(dev):
         want = enc(SparseTensor(f4h.to(dev), ch.to(dev), 1))
         got = enc(SparseTensor.from_host(f4h, ch, 1, device=dev))
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_index_entry_points_match_their_parts(dev):
+    """lk_sort_unique_coords == lk_pack_keys + lk_sort_unique_ex, lk_table_build_coords == lk_hash +
+    lk_table_build, lk_block_neighbors_zero / lk_link_window_mean_seg == their unfused forms."""
+    import ctypes as Ct
+    from link_b200 import _capi
+    from link_b200.nn.functional import _index
+    from link_b200.nn.functional.hash import sphash
+    from link_b200.nn.functional.query import HashTable
+    from link_b200.nn.utils import get_kernel_offsets
+    from link_b200.utils.synthetic import random_voxels
+    L, st = _capi.lib(), _capi.stream()
+    for n in (1, 2049, 30_000):
+        coords_h = random_voxels(n, 60, seed=n, batch=2)
+        coords = cu(coords_h, dev)
+        n2 = coords.shape[0]
+        spec, bits = _index.make_keyspec(_index.coord_bounds(coords), (3, 3, 3), (0, 1, 2, 3))
+        a = _index.sort_unique(_index.pack_keys(coords, spec), bits, want_order=True)
+        b_unique = torch.empty(n2, dtype=torch.int64, device=dev)
+        b_inv, b_ord, b_srank = (torch.empty(n2, dtype=torch.int32, device=dev) for _ in range(3))
+        b_seg = torch.empty(n2 + 1, dtype=torch.int32, device=dev)
+        b_num = torch.empty(1, dtype=torch.int32, device=dev)
+        ws_bytes = L.lk_sort_unique_ws_bytes(n2)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _capi.check(L.lk_sort_unique_coords(_capi.ptr(coords), Ct.byref(spec), n2, bits, _capi.ptr(b_unique),
+                                            _capi.ptr(b_inv), _capi.ptr(b_ord), _capi.ptr(b_seg), None,
+                                            _capi.ptr(b_num), _capi.ptr(b_srank), _capi.ptr(ws), ws_bytes, st),
+                    'lk_sort_unique_coords')
+        m = int(a.num.item())
+        assert int(b_num.item()) == m
+        assert torch.equal(b_unique[:m], a.unique[:m]) and torch.equal(b_inv, a.inverse)
+        assert torch.equal(b_ord, a.order) and torch.equal(b_srank, a.sorted_rank)
+        assert torch.equal(b_seg[:m + 1], a.seg[:m + 1])
+        # table from coordinates == table from hashes
+        t_ref = HashTable(sphash(coords))
+        tab = torch.empty(t_ref.capacity * 16, dtype=torch.uint8, device=dev)
+        _capi.check(L.lk_table_build_coords(_capi.ptr(coords), n2, _capi.ptr(tab), t_ref.capacity, st), 'tbc')
+        assert torch.equal(tab, t_ref.table)
+        # neighbours + zeroing, window mean from segment starts
+        offs = get_kernel_offsets(3, 1, 1, device=dev)
+        nbr_a = torch.full((n2, 27), -7, dtype=torch.int32, device=dev)
+        nbr_b = torch.full((n2, 27), -7, dtype=torch.int32, device=dev)
+        zbuf = torch.ones(n2, 8, device=dev)
+        _capi.check(L.lk_block_neighbors(_capi.ptr(a.unique), _capi.ptr(a.num), n2, Ct.byref(spec), _capi.ptr(offs),
+                                         27, _capi.ptr(nbr_a), st), 'bn')
+        _capi.check(L.lk_block_neighbors_zero(_capi.ptr(a.unique), _capi.ptr(a.num), n2, Ct.byref(spec),
+                                              _capi.ptr(offs), 27, _capi.ptr(nbr_b), _capi.ptr(zbuf), 8, st), 'bnz')
+        assert torch.equal(nbr_a, nbr_b)
+        assert float(zbuf[:m].abs().sum()) == 0.0 and (m == n2 or float(zbuf[m:].min()) == 1.0)
+        sums = torch.randn(n2, 8, device=dev)
+        mean_a, mean_b = torch.empty(n2, 8, device=dev), torch.empty(n2, 8, device=dev)
+        _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(a.counts), _capi.ptr(nbr_a), _capi.ptr(a.num),
+                                          n2, 27, 8, _capi.ptr(mean_a), st), 'wm')
+        _capi.check(L.lk_link_window_mean_seg(_capi.ptr(sums), _capi.ptr(a.seg), _capi.ptr(nbr_a), _capi.ptr(a.num),
+                                              n2, 27, 8, _capi.ptr(mean_b), st), 'wms')
+        assert torch.equal(mean_a[:m], mean_b[:m])
