@@ -371,6 +371,20 @@ int lk_kmap_build(const int32_t* d_in_coords, int64_t n_in, const int32_t* d_out
 int64_t lk_downsample_ws_bytes(int64_t n);
 int lk_downsample(const int32_t* d_coords, int64_t n, const lk_keyspec_t* spec, int key_bits,
                   int32_t* d_out_coords, int32_t* d_num, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+/* ------------------------------------------------------------------------------------
+ * Voxelisation front-end of the detection pipeline: points -> voxels with the exact semantics of
+ * det3d/ops/point_cloud/point_cloud_ops.py:112-183 (`points_to_voxel`, reverse_index=True): voxel
+ * ids in order of first appearance, at most max_voxels voxels, the first max_points points of a
+ * voxel in point order, coordinates (z, y, x).  voxel_size[3] / coors_range[6] are HOST arrays
+ * (float32, like the numpy arguments of the reference).  d_voxels [max_voxels, max_points, ndim]
+ * (rows of existing voxels fully written, zero padded), d_coors [max_voxels, 3], d_num_points
+ * [max_voxels], d_voxel_num device scalar.  Deterministic (two stable radix sorts, no atomics).
+ * ---------------------------------------------------------------------------------- */
+int64_t lk_points_to_voxel_ws_bytes(int64_t n);
+int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* voxel_size,
+                       const float* coors_range, int max_points, int max_voxels, float* d_voxels,
+                       int32_t* d_coors, int32_t* d_num_points, int32_t* d_voxel_num, void* d_ws,
+                       int64_t ws_bytes, lk_stream_t s);
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);

@@ -99,6 +99,8 @@ PROTOTYPES = {
     'lk_kmap_build': (i32, [vp, i64, vp, i64, vp, i32, i32, vp, i64, i32, vp, vp, vp, vp, i64, vp]),
     'lk_downsample_ws_bytes': (i64, [i64]),
     'lk_downsample': (i32, [vp, i64, C.POINTER(KeySpec), i32, vp, vp, vp, i64, vp]),
+    'lk_points_to_voxel_ws_bytes': (i64, [i64]),
+    'lk_points_to_voxel': (i32, [vp, i64, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     'lk_conv_plan_ws_bytes': (i64, [i64]),
     'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp]),
     'lk_conv_tc_pack_weights': (i32, [vp, i32, i32, i32, vp, vp]),

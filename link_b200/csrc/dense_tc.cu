@@ -127,12 +127,20 @@ __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
 #pragma unroll
     for (int c0 = 0; c0 < C; c0 += 16)
       tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v + c0);
-    float s = 0.f;
+    // LayerNorm with 8 independent partial sums (a 64-term dependent chain costs 64 x 4 cycles on a
+    // kernel that runs only 2 warps per scheduler)
+    float ps[8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) s += v[c];
-    float mean = s / (float)C, q = 0.f;
+    for (int k = 0; k < 8; ++k) ps[k] = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { v[c] -= mean; q += v[c] * v[c]; }
+    for (int c = 0; c < C; ++c) ps[c & 7] += v[c];
+    const float s = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+    const float mean = s / (float)C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ps[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { v[c] -= mean; ps[c & 7] = fmaf(v[c], v[c], ps[c & 7]); }
+    const float q = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
     float rstd = 1.0f / sqrtf(q / (float)C + eps);
     int64_t r = row0 + tid;
     if (r < n) {

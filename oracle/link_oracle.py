@@ -526,3 +526,42 @@ def initial_voxelize(pF: torch.Tensor, pC: torch.Tensor, init_res, after_res):
     vc = torch.round(spvoxelize(fl, idx, counts)).int()
     vf = spvoxelize(pF, idx, counts)
     return vf, vc.numpy(), idx, counts
+
+
+# --------------------------------------------------------------------------
+# detection voxelisation front-end
+# --------------------------------------------------------------------------
+def points_to_voxel(points: np.ndarray, voxel_size, coors_range, max_points=35, reverse_index=True,
+                    max_voxels=20000):
+    """det3d/ops/point_cloud/point_cloud_ops.py:8-56 / 112-183 restated without the sequential
+    loop: a point is kept iff floor((p - lo) / vs) is inside round((hi - lo) / vs) (float32
+    arithmetic, like the reference's numpy float32 arrays); voxels are numbered by first appearance,
+    the first `max_voxels` exist; each keeps its first `max_points` points in point order."""
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    vs = np.asarray(voxel_size, dtype=np.float32)
+    cr = np.asarray(coors_range, dtype=np.float32)
+    gs = np.round((cr[3:] - cr[:3]) / vs).astype(np.int32)
+    c = np.floor((points[:, :3] - cr[:3]) / vs)                      # float32
+    ok = np.all((c >= 0) & (c < gs), axis=1)
+    ci = c[ok].astype(np.int64)
+    idx = np.nonzero(ok)[0]
+    key = (ci[:, 2] * gs[1] + ci[:, 1]) * gs[0] + ci[:, 0]
+    uq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    vid_of_cell = np.empty(len(uq), np.int64)
+    vid_of_cell[np.argsort(first, kind='stable')] = np.arange(len(uq))
+    vid = vid_of_cell[inv.reshape(-1)]
+    m = min(len(uq), max_voxels)
+    voxels = np.zeros((m, max_points, points.shape[1]), np.float32)
+    coors = np.zeros((m, 3), np.int32)
+    num = np.zeros(m, np.int32)
+    order = np.argsort(vid, kind='stable')                            # points grouped by voxel, in point order
+    vs_sorted = vid[order]
+    start = np.searchsorted(vs_sorted, np.arange(m))
+    rank = np.arange(len(order)) - start[np.minimum(vs_sorted, m - 1)] if m else np.zeros(0, np.int64)
+    keep = (vs_sorted < m) & (rank < max_points)
+    voxels[vs_sorted[keep], rank[keep]] = points[idx[order[keep]]]
+    np.add.at(num, vs_sorted[keep], 1)
+    cell_first = ci[first]                                            # (x, y, z) of each cell
+    sel = vid_of_cell < m
+    coors[vid_of_cell[sel]] = cell_first[sel][:, ::-1] if reverse_index else cell_first[sel]
+    return voxels, coors, num

@@ -795,7 +795,11 @@ def test_fused_index_entry_points_match_their_parts(dev):
         t_ref = HashTable(sphash(coords))
         tab = torch.empty(t_ref.capacity * 16, dtype=torch.uint8, device=dev)
         _capi.check(L.lk_table_build_coords(_capi.ptr(coords), n2, _capi.ptr(tab), t_ref.capacity, st), 'tbc')
-        assert torch.equal(tab, t_ref.table)
+        # (slot placement under collisions depends on insertion order: compare look-ups, not bytes)
+        q = torch.cat([sphash(coords), sphash(coords + 1000)])
+        got = torch.empty_like(q)
+        _capi.check(L.lk_table_query(_capi.ptr(q), q.shape[0], _capi.ptr(tab), t_ref.capacity, _capi.ptr(got), st), 'tq')
+        assert torch.equal(got, t_ref.query(q)) and torch.equal(got[:n2], torch.arange(n2, device=dev))
         # neighbours + zeroing, window mean from segment starts
         offs = get_kernel_offsets(3, 1, 1, device=dev)
         nbr_a = torch.full((n2, 27), -7, dtype=torch.int32, device=dev)
@@ -814,3 +818,34 @@ def test_fused_index_entry_points_match_their_parts(dev):
         _capi.check(L.lk_link_window_mean_seg(_capi.ptr(sums), _capi.ptr(a.seg), _capi.ptr(nbr_a), _capi.ptr(a.num),
                                               n2, 27, 8, _capi.ptr(mean_b), st), 'wms')
         assert torch.equal(mean_a[:m], mean_b[:m])
+
+
+def test_points_to_voxel_bit_exact(dev):
+    """GPU points_to_voxel == the reference's numba loop (golden fixture) and == the oracle on a
+    larger cloud with rejected points, the voxel cap and the per-voxel point cap all active."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_points_golden import cloud
+    from link_b200.ops import points_to_voxel
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'points.npz'))
+    pts = cloud(seed=7)
+    for tag in ('a', 'b'):
+        mp, mv = (int(x) for x in g[f'{tag}_cfg'])
+        v, c, n = points_to_voxel(cu(pts, dev), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], mp, True, mv)
+        assert np.array_equal(c.cpu().numpy(), g[f'{tag}_coors']) and np.array_equal(n.cpu().numpy(), g[f'{tag}_num'])
+        vh = v.cpu().numpy()
+        assert np.array_equal(vh[:len(g[f'{tag}_voxels'])], g[f'{tag}_voxels'])
+        assert np.array_equal(vh.astype(np.float64).sum(axis=(1, 2)), g[f'{tag}_voxel_sum'])
+    big = cloud(seed=11, n=300_000)
+    for mp, mv, rev in [(10, 120_000, True), (3, 500, False), (1, 1, True)]:
+        want = O.points_to_voxel(big, [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], mp, rev, mv)
+        got = points_to_voxel(cu(big, dev), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], mp, rev, mv)
+        for a, b in zip(got, want):
+            assert np.array_equal(a.cpu().numpy(), b)
+    # every point rejected / empty input
+    far = np.full((100, 5), 1000.0, np.float32)
+    v, c, n = points_to_voxel(cu(far, dev), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, True, 100)
+    assert v.shape[0] == 0 and c.shape[0] == 0 and n.shape[0] == 0
+    v, c, n = points_to_voxel(torch.zeros(0, 5, device=dev), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, True, 100)
+    assert v.shape[0] == 0
