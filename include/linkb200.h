@@ -256,6 +256,10 @@ typedef struct {
   int32_t use_tensor_cores;
   int32_t reserved;
   void* d_ws; int64_t ws_bytes;
+  int32_t single_stream;         /* 0 (default): the sort / pre-aggregation chain runs on a library-owned
+                                    side stream next to the kernel-map / conv chain (fork/join by
+                                    events); 1: everything on the caller's stream */
+  int32_t reserved1;
   void* feats_ready;             /* cudaEvent_t or NULL: d_feats is still being uploaded on another
                                     stream; the executor enqueues all index-only work first and
                                     makes the stream wait for this event (cudaStreamWaitEvent, no

@@ -13,6 +13,8 @@
 // so the host pays one FFI crossing and one workspace allocation per block instead of ~27
 // Python-level launches (the reference: ~150-180 launches, >= 4 device syncs, 4 cudaMalloc/Free).
 // Nothing here synchronises or allocates: the caller provides one workspace arena.
+#include <mutex>
+
 #include "common.cuh"
 
 static inline int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
@@ -57,6 +59,28 @@ extern "C" int64_t lk_elk_block_ws_bytes(int64_t n, int c, int op, int r3, int k
     if (rc__ != LK_OK) return rc__; \
   } while (0)
 
+// side stream + fork/join events of the two-chain schedule, created once per device on first use
+// (the only CUDA objects the library owns; no memory is allocated, nothing is synchronised)
+struct BlockSide {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static BlockSide* block_side() {
+  static BlockSide sides[64];
+  static bool made[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!made[dev]) {
+    if (cudaStreamCreateWithFlags(&sides[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&sides[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&sides[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    made[dev] = true;
+  }
+  return &sides[dev];
+}
+
 extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   LK_REQUIRE(a && a->n >= 0 && a->d_coords && a->d_feats && a->d_out && a->d_ws,
              "lk_elk_block_fwd: null argument");
@@ -73,18 +97,8 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   }
   char* ws = (char*)a->d_ws;
   const int32_t* kmap = a->d_kmap;
-  if (need_kmap) {
-    LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, s));
-    LK_TRY(lk_kmap_query_subm(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
-                              a->d_kmap, s));
-  }
-  // ---- index-only work first: it does not read the features, so it overlaps an upload of
-  //      d_feats that is still in flight on another stream (a->feats_ready) ----
   const bool tc_conv = a->use_tensor_cores && lk_conv_tc_supported(c, c) && a->d_conv_wt;
   const bool planned = tc_conv && a->d_plan_perm && a->d_plan_mask && a->kvol <= 32;
-  if (planned && a->build_plan)
-    LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
-                        ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
   uint64_t* uniq = (uint64_t*)(ws + w.uniq);
   int32_t* inverse = (int32_t*)(ws + w.inverse);
   int32_t* seg = (int32_t*)(ws + w.seg);
@@ -94,19 +108,47 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   int32_t* srank = (int32_t*)(ws + w.srank);
   float* sums = (float*)(ws + w.sums);
   float* mean = (float*)(ws + w.mean);
-  LK_TRY(lk_sort_unique_coords(a->d_coords, &a->keyspec, n, a->key_bits, uniq, inverse, order, seg,
-                               nullptr, num, srank, ws + w.sort_ws, lk_sort_unique_ws_bytes(n), s));
-  LK_TRY(lk_block_neighbors_zero(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, sums, kc, s));
-  // ---- feature kernels ----
-  if (a->feats_ready) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)a->feats_ready, 0));
   float* fin = (float*)(ws + w.fin);
   float* local = (float*)(ws + w.local);
-  // pre_mix
+
+  // Two independent chains meet only in the last kernel, so they are enqueued on two streams:
+  //   main : hash table -> kernel map -> conv plan -> [features ready] -> local_mix conv
+  //   side : block keys + sort/unique -> neighbour table + zero -> [features ready] -> pre_mix ->
+  //          pre-aggregation -> window mean
+  //   join : apply (+ both LayerNorms, add, ReLU)
+  // The index kernels of both chains are small, latency-bound grids (59-1184 CTAs of work that
+  // leave most of the 148 SMs idle), so running the chains side by side hides one of them almost
+  // completely.  Fork and join are stream-ordered events: no host or device synchronisation, and
+  // still CUDA-graph capturable.
+  lk_stream_t side = s;
+  BlockSide* bs = a->single_stream ? nullptr : block_side();
+  if (bs) {
+    side = (lk_stream_t)bs->stream;
+    LK_CUDA(cudaEventRecord(bs->fork, (cudaStream_t)s));
+    LK_CUDA(cudaStreamWaitEvent(bs->stream, bs->fork, 0));
+  }
+  // ---- side chain ----
+  LK_TRY(lk_sort_unique_coords(a->d_coords, &a->keyspec, n, a->key_bits, uniq, inverse, order, seg,
+                               nullptr, num, srank, ws + w.sort_ws, lk_sort_unique_ws_bytes(n), side));
+  LK_TRY(lk_block_neighbors_zero(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, sums, kc, side));
+  if (a->feats_ready) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)side, (cudaEvent_t)a->feats_ready, 0));
   if (a->use_tensor_cores && (c == 32 || c == 64))
-    LK_TRY(lk_linear_ln_tc_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, s));
+    LK_TRY(lk_linear_ln_tc_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, side));
   else
-    LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, s));
-  // local_mix
+    LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, side));
+  LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, side));
+  LK_TRY(lk_link_window_mean_seg(sums, seg, nbr, num, n, a->r3, kc, mean, side));
+  if (bs) LK_CUDA(cudaEventRecord(bs->join, bs->stream));
+  // ---- main chain ----
+  if (need_kmap) {
+    LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, s));
+    LK_TRY(lk_kmap_query_subm(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
+                              a->d_kmap, s));
+  }
+  if (planned && a->build_plan)
+    LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,
+                        ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
+  if (a->feats_ready && bs) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)a->feats_ready, 0));
   if (tc_conv) {
     if (planned)
       LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, kmap, a->d_plan_perm, a->d_plan_mask, n,
@@ -117,9 +159,8 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
     LK_REQUIRE(a->d_conv_w, "lk_elk_block_fwd: FFMA conv needs the untransposed weights");
     LK_TRY(lk_conv_fwd(a->d_feats, a->d_conv_w, kmap, n, a->kvol, c, c, nullptr, local, s));
   }
-  // linear-kernel aggregation
-  LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, s));
-  LK_TRY(lk_link_window_mean_seg(sums, seg, nbr, num, n, a->r3, kc, mean, s));
+  // ---- join ----
+  if (bs) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, bs->join, 0));
   LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,
                            a->d_g2, a->d_b2, a->d_out, s));
   return LK_OK;

@@ -36,6 +36,8 @@ ACCURATE_TRIG = os.environ.get('LINKB200_ACCURATE_TRIG', '0') == '1'
 # 1 (default): one lk_elk_block_fwd call per block; 0: one python-level call per kernel
 NATIVE_EXECUTOR = os.environ.get('LINKB200_NATIVE_EXECUTOR', '1') != '0'
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
+# 1: keep the whole block on the caller's stream (default 0: two-chain schedule inside the executor)
+SINGLE_STREAM = os.environ.get('LINKB200_SINGLE_STREAM', '0') == '1'
 
 
 class BlockIndex:
@@ -331,6 +333,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
     a.feats_ready = ready.cuda_event if ready is not None else None
+    a.single_stream = 1 if SINGLE_STREAM else 0
     _capi.check(L.lk_elk_block_fwd(C.byref(a), _capi.stream()), 'lk_elk_block_fwd')
     return out
 
