@@ -13,6 +13,8 @@
 // so the host pays one FFI crossing and one workspace allocation per block instead of ~27
 // Python-level launches (the reference: ~150-180 launches, >= 4 device syncs, 4 cudaMalloc/Free).
 // Nothing here synchronises or allocates: the caller provides one workspace arena.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -73,7 +75,12 @@ static BlockSide* block_side() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
   if (!made[dev]) {
-    if (cudaStreamCreateWithFlags(&sides[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // lowest priority: when both chains have work ready, the CTAs of the conv (critical path) go first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char* pe = getenv("LINKB200_SIDE_PRIORITY");
+    const int prio = (pe && pe[0] == '0') ? 0 : prio_lo;
+    if (cudaStreamCreateWithPriority(&sides[dev].stream, cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&sides[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&sides[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     made[dev] = true;

@@ -164,23 +164,26 @@ def _pack(wt: torch.Tensor) -> torch.Tensor:
     return img
 
 
-def _tc_image(weight: torch.Tensor, c_pad: int = 0) -> torch.Tensor:
-    """Packed tensor-core image of a [K, Cin, Cout] kernel (input channels zero-padded to `c_pad`
-    if given).  For an nn.Parameter the image is cached ON the parameter object (keyed by its
-    version and storage address), so a module's weights are packed once per update; the cache lives
-    and dies with the parameter, so a recycled address can never alias another tensor's entry."""
-    cached = isinstance(weight, torch.nn.Parameter)
-    if cached:
-        ver = (weight._version, weight.data_ptr(), c_pad)
-        hit = weight.__dict__.get('_lk_img')
+def _tc_image(weight: torch.Tensor, c_pad: int = 0, c_pad_out: int = 0, cache_on=None) -> torch.Tensor:
+    """Packed tensor-core image of a [K, Cin, Cout] kernel (input / output channels zero-padded to
+    `c_pad` / `c_pad_out` if given).  The image is cached ON the parameter object it derives from
+    (`weight` itself when it is an nn.Parameter, else `cache_on`), keyed by its version and storage
+    address, so a module's weights are packed once per update; the cache lives and dies with the
+    parameter, so a recycled address can never alias another tensor's entry."""
+    holder = weight if isinstance(weight, torch.nn.Parameter) else cache_on
+    if holder is not None:
+        ver = (holder._version, holder.data_ptr(), c_pad, c_pad_out)
+        hit = holder.__dict__.get('_lk_img')
         if hit is not None and hit[0] == ver:
             return hit[1]
-    wt = weight.detach().transpose(1, 2)
-    if c_pad and c_pad > weight.shape[1]:
-        wt = torch.nn.functional.pad(wt, (0, c_pad - weight.shape[1]))
+    wt = weight.detach().transpose(1, 2)                      # [K, Cout, Cin]
+    pad_in = max(c_pad - weight.shape[1], 0) if c_pad else 0
+    pad_out = max(c_pad_out - weight.shape[2], 0) if c_pad_out else 0
+    if pad_in or pad_out:
+        wt = torch.nn.functional.pad(wt, (0, pad_in, 0, pad_out))
     img = _pack(wt)
-    if cached:
-        weight.__dict__['_lk_img'] = (ver, img)
+    if holder is not None:
+        holder.__dict__['_lk_img'] = (ver, img)
     return img
 
 
@@ -191,49 +194,76 @@ def _tc_ok(L, c_in, c_out) -> bool:
     return ok
 
 
+def _pad_to_tc(c: int) -> int:
+    """Smallest tensor-core channel count >= c (0 if none)."""
+    for t in (32, 64, 128):
+        if c <= t:
+            return t
+    return 0
+
+
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
-              relu=False, kmap=None):
+              relu=False, kmap=None, cache_on=None):
     """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
     None when its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies).
-    epilogue: y = relu?(acc * scale + shift + residual), each part optional."""
+    epilogue: y = relu?(acc * scale + shift + residual), each part optional.  `cache_on`: the
+    nn.Parameter that `weight` is a view of (its packed image is cached there)."""
     if weight is not None:
         k, c_in, c_out = weight.shape
     else:
         k, c_out, c_in = weight_t.shape
     if feats.shape[1] != c_in:
         raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
-    out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
     L = _capi.lib()
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
-    tc_ok = _tc_ok(L, c_in, c_out)
-    ep = _capi.ConvEpilogue()
-    ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
-    ep.d_residual = _capi.ptr(residual)
-    ep.relu = 1 if relu else 0
     if residual is not None:
-        assert residual.shape == out.shape and residual.dtype == torch.float32
-    if (USE_TENSOR_CORES and not tc_ok and weight is not None and c_in < 32 and c_in % 4 == 0
-            and _tc_ok(L, 32, c_out) and isinstance(weight, torch.nn.Parameter)):
-        # narrow input layer (the 4-channel stem): zero-pad C_in to one 32-float K-block and run on
-        # the tensor cores; the zero K-columns cost tensor time only (and that pipe has slack)
-        feats = torch.nn.functional.pad(feats, (0, 32 - c_in))
-        img = _tc_image(weight, 32)
-        c_in, tc_ok = 32, True
-    else:
-        img = None
-    if USE_TENSOR_CORES and tc_ok:
-        if img is None:
-            img = _pack(weight_t) if weight_t is not None else _tc_image(weight)
+        assert residual.shape == (n_out, c_out) and residual.dtype == torch.float32
+    if USE_TENSOR_CORES and k <= 32 and _pad_to_tc(c_in) and _pad_to_tc(c_out):
+        # tensor-core kernel; channel counts other than 32 / 64 / 128 (the 4-channel stem, the 5- and
+        # 16-channel layers of the detection backbone) are zero-padded to the next supported size:
+        # the padded K-columns / output columns cost tensor time only, and the FFMA kernel that
+        # would serve them otherwise is ~5x slower at every size
+        ci, co = _pad_to_tc(c_in), _pad_to_tc(c_out)
+        if ci != c_in:
+            feats = torch.nn.functional.pad(feats, (0, ci - c_in))
+        if weight_t is not None:
+            wt = weight_t
+            if ci != c_in or co != c_out:
+                wt = torch.nn.functional.pad(wt, (0, ci - c_in, 0, co - c_out))
+            img = _pack(wt)
+        else:
+            img = _tc_image(weight, ci if ci != c_in else 0, co if co != c_out else 0, cache_on=cache_on)
+        fuse_tail = co == c_out               # residual / ReLU stay in the epilogue unless C_out is padded
+        ep = _capi.ConvEpilogue()
+        if co != c_out:
+            scale = torch.nn.functional.pad(scale, (0, co - c_out), value=1.0) if scale is not None else None
+            shift = torch.nn.functional.pad(shift, (0, co - c_out)) if shift is not None else None
+        ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
+        ep.d_residual = _capi.ptr(residual) if fuse_tail else None
+        ep.relu = 1 if (relu and (fuse_tail or residual is None)) else 0
+        out = torch.empty(n_out, co, dtype=torch.float32, device=feats.device)
         plan = kmap.plan() if kmap is not None else None      # only for the forward map (kmap.nbr)
         with _capi.timed('lk_conv_fwd', nb):
             _capi.check(L.lk_conv_tc_fwd_plan(_capi.ptr(feats, torch.float32), _capi.ptr(img, torch.float32),
                                               _capi.ptr(nbr, torch.int32),
                                               _capi.ptr(plan[0]) if plan is not None else None,
                                               _capi.ptr(plan[1]) if plan is not None else None,
-                                              n_out, k, c_in, c_out, C.byref(ep), _capi.ptr(out),
+                                              n_out, k, ci, co, C.byref(ep), _capi.ptr(out),
                                               _capi.stream()), 'lk_conv_tc_fwd_plan')
+        if not fuse_tail:
+            out = out[:, :c_out]
+            if residual is not None:
+                out = out + residual
+                if relu:
+                    out = torch.relu_(out)
+            out = out.contiguous()
         return out
+    out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
+    ep = _capi.ConvEpilogue()
+    ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
+    ep.d_residual = _capi.ptr(residual)
+    ep.relu = 1 if relu else 0
     if weight is None:
         weight = weight_t.transpose(1, 2).contiguous()
     with _capi.timed('lk_conv_fwd', nb):
@@ -327,7 +357,7 @@ def conv_bn_act(input: SparseTensor, conv, bn=None, relu: bool = False,
         kmap = input.kmaps.get(key)
         if kmap is None:
             kmap = build_kernel_map(input, kernel_size, stride, dilation,
-                                    want_plan=USE_TENSOR_CORES and w.shape[2] in (32, 64, 128) and w.shape[1] in (4, 32, 64, 128))
+                                    want_plan=USE_TENSOR_CORES and w.shape[0] <= 32 and w.shape[1] <= 128 and w.shape[2] <= 128)
             input.kmaps[key] = kmap
         out = _conv_fwd(feats, w, kmap.nbr, kmap.n_out, None, scale, shift, residual, relu, kmap=kmap)
         output = SparseTensor(coords=kmap.out_coords, feats=out,

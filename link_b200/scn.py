@@ -100,7 +100,7 @@ class _SparseConvBase(nn.Module):
                 b = self.bias.detach()
                 shift = b if shift is None else shift + (b * scale if scale is not None else b)
             feats = _conv_fwd(x.features.contiguous().float(), w, kmap.nbr, kmap.n_out, None, scale,
-                              shift, residual, relu)
+                              shift, residual, relu, kmap=kmap, cache_on=self.weight)
         else:
             feats = ConvolutionFunction.apply(x.features, w, kmap, False)
             if self.bias is not None:
@@ -134,6 +134,7 @@ class SubMConv3d(_SparseConvBase):
             _capi.check(fn(_capi.ptr(coords), n, _capi.ptr(taps), k, _capi.ptr(table.table),
                            table.capacity, _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
             kmap = KernelMap(nbr, n, n, coords)
+            kmap.offsets = taps                      # classes of the tile-skipping plan
             x.indice_dict[key] = kmap
         return kmap
 
@@ -177,6 +178,7 @@ class SparseConv3d(_SparseConvBase):
                                               _capi.ptr(table.table), table.capacity,
                                               _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
         kmap = KernelMap(nbr, coords.shape[0], n_out, q)
+        kmap.offsets = taps
         return self._run(x, kmap, out_indices, out_shape, **epilogue)
 
 

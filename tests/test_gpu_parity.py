@@ -230,7 +230,9 @@ def test_conv_chain_kmaps_and_outputs(dev):
                                                      (130, 64, 32, 3, 1), (9_000, 32, 32, 2, 2),
                                                      (1, 64, 64, 3, 1), (9_000, 128, 128, 3, 1),
                                                      (2_000, 64, 128, 3, 1), (2_500, 128, 32, 2, 2),
-                                                     (700, 128, 64, 3, 1), (300, 32, 128, 3, 1)])
+                                                     (700, 128, 64, 3, 1), (300, 32, 128, 3, 1),
+                                                     (4_000, 16, 16, 3, 1), (3_000, 5, 16, 3, 1),
+                                                     (2_000, 16, 32, 3, 1), (1_500, 48, 24, 2, 2)])   # padded to 32/64
 def test_conv_plan_tile_skipping(dev, n, cin, cout, ksize, stride):
     """lk_conv_plan: perm is a permutation grouped by class, tile_mask is consistent with
     the kernel map; the planned tensor-core conv equals the unplanned one bit for bit (the plan only
