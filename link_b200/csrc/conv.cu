@@ -163,10 +163,24 @@ extern "C" int lk_conv_fwd_ex(const float* d_in, const float* d_w, const int32_t
 // [c_in, c_out] tile in registers and flushes once with vector reductions.
 #define CW_THREADS 256
 #define CW_MAX_ITEMS 16
+// grad_w[k] = sum over the pairs (i -> o) of offset k of  in[i]^T gout[o].
+// One CTA owns offset k and a chunk of output rows.  Per 256 candidate rows the present pairs are
+// compacted (ballot + prefix) into a shared list, then processed 32 pairs at a time: the 32 input
+// rows and 32 grad rows are staged in shared memory with coalesced 128-bit loads and every thread
+// accumulates its [1 x 4] patches of the C_in x C_out product from there (the `a` operand is a
+// warp broadcast, the grad vectors are consecutive: no bank conflicts).  The previous version
+// walked the rows one by one with dependent global loads (7.7 ms per conv at N = 108k, C = 64-128).
+#define CW_TR 32
 __global__ void __launch_bounds__(CW_THREADS) conv_bwd_weight_kernel(
     const float* __restrict__ in, const float* __restrict__ gout, const int* __restrict__ nbr,
     int64_t n_out, int c_in, int c_out, float* gw) {
+  extern __shared__ float4 cw_smem[];
+  float* a_s = (float*)cw_smem;                      // [CW_TR][c_in]
+  float* g_s = a_s + CW_TR * c_in;                   // [CW_TR][c_out]
+  __shared__ int list_i[CW_THREADS], list_o[CW_THREADS];
+  __shared__ int wcnt[CW_THREADS / 32];
   const int k = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vpr = c_out >> 2;                       // float4 per weight row
   const int items = (c_in * vpr + CW_THREADS - 1) / CW_THREADS;
   float4 acc[CW_MAX_ITEMS];
@@ -174,20 +188,62 @@ __global__ void __launch_bounds__(CW_THREADS) conv_bwd_weight_kernel(
   for (int q = 0; q < CW_MAX_ITEMS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t per = (n_out + gridDim.y - 1) / gridDim.y;
   int64_t o0 = (int64_t)blockIdx.y * per, o1 = min(n_out, o0 + per);
-  for (int64_t o = o0; o < o1; ++o) {
-    int i = __ldg(nbr + (int64_t)k * n_out + o);    // uniform across the CTA
-    if (i < 0) continue;
+  const int va = c_in >> 2;                          // float4 per input row (c_in % 4 == 0 checked on the host)
+  for (int64_t base = o0; base < o1; base += CW_THREADS) {
+    // ---- compact the present pairs of 256 candidate rows ----
+    const int64_t o = base + tid;
+    const int i = (o < o1) ? __ldg(nbr + (int64_t)k * n_out + o) : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, i >= 0);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int pos = __popc(bal & ((1u << lane) - 1u)), total = 0;
 #pragma unroll
-    for (int q = 0; q < CW_MAX_ITEMS; ++q) {
-      if (q < items) {
-        int e = q * CW_THREADS + threadIdx.x;
-        if (e < c_in * vpr) {
-          int ci = e / vpr, cv = (e % vpr) * 4;
-          float a = __ldg(in + (int64_t)i * c_in + ci);
-          float4 g = __ldg((const float4*)(gout + o * c_out + cv));
-          acc[q].x += a * g.x; acc[q].y += a * g.y; acc[q].z += a * g.z; acc[q].w += a * g.w;
+    for (int w = 0; w < CW_THREADS / 32; ++w) {
+      pos += (w < warp) ? wcnt[w] : 0;
+      total += wcnt[w];
+    }
+    if (i >= 0) { list_i[pos] = i; list_o[pos] = (int)(o - o0); }
+    __syncthreads();
+    // ---- 32 pairs at a time ----
+    for (int p0 = 0; p0 < total; p0 += CW_TR) {
+      const int np = min(CW_TR, total - p0);
+      if ((c_in & 3) == 0) {
+        for (int t = tid; t < CW_TR * va; t += CW_THREADS) {
+          const int r = t / va, v = t - r * va;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < np) x = __ldg((const float4*)(in + (int64_t)list_i[p0 + r] * c_in) + v);
+          ((float4*)a_s)[r * va + v] = x;
+        }
+      } else {                                         // odd channel counts (the 5-channel detection stem)
+        for (int t = tid; t < CW_TR * c_in; t += CW_THREADS) {
+          const int r = t / c_in, cch = t - r * c_in;
+          a_s[t] = r < np ? __ldg(in + (int64_t)list_i[p0 + r] * c_in + cch) : 0.f;
         }
       }
+      for (int t = tid; t < CW_TR * vpr; t += CW_THREADS) {
+        const int r = t / vpr, v = t - r * vpr;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < np) x = __ldg((const float4*)(gout + (o0 + list_o[p0 + r]) * c_out) + v);
+        ((float4*)g_s)[r * vpr + v] = x;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < CW_MAX_ITEMS; ++q) {
+        if (q < items) {
+          const int e = q * CW_THREADS + tid;
+          if (e < c_in * vpr) {
+            const int ci = e / vpr, cv = e % vpr;
+#pragma unroll 8
+            for (int r = 0; r < CW_TR; ++r) {
+              const float a = a_s[r * c_in + ci];
+              const float4 g = ((const float4*)g_s)[r * vpr + cv];
+              acc[q].x = fmaf(a, g.x, acc[q].x); acc[q].y = fmaf(a, g.y, acc[q].y);
+              acc[q].z = fmaf(a, g.z, acc[q].z); acc[q].w = fmaf(a, g.w, acc[q].w);
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 #pragma unroll
@@ -214,12 +270,13 @@ extern "C" int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const 
   lk_count_launch();
   if (n_out == 0) return LK_OK;
   LK_REQUIRE(d_in && d_gout && d_nbr, "lk_conv_bwd_weight: null pointer");
-  int splits = (2 * LK_SM_COUNT + k - 1) / k;
+  int splits = (4 * LK_SM_COUNT + k - 1) / k;
   if (splits < 1) splits = 1;
   int64_t max_splits = (n_out + 255) / 256;
   if (splits > max_splits) splits = (int)max_splits;
   dim3 grid((unsigned)k, (unsigned)splits);
-  conv_bwd_weight_kernel<<<grid, CW_THREADS, 0, st>>>(d_in, d_gout, d_nbr, n_out, c_in, c_out, d_gw);
+  const size_t smem = (size_t)CW_TR * (c_in + c_out) * sizeof(float);      // <= 32 KB
+  conv_bwd_weight_kernel<<<grid, CW_THREADS, smem, st>>>(d_in, d_gout, d_nbr, n_out, c_in, c_out, d_gw);
   LK_LAUNCHED();
   return LK_OK;
 }
