@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(CW_THREADS) conv_bwd_weight_kernel(
   for (int q = 0; q < CW_MAX_ITEMS; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t per = (n_out + gridDim.y - 1) / gridDim.y;
   int64_t o0 = (int64_t)blockIdx.y * per, o1 = min(n_out, o0 + per);
-  const int va = c_in >> 2;                          // float4 per input row (c_in % 4 == 0 checked on the host)
+  const int va = c_in >> 2;                          // float4 per input row
+  const bool quad = (c_in & 3) == 0;                 // 4 x 4 register patches (else scalar input channels)
+  const int ca = c_in >> 2;
+  const int items4 = (ca * vpr + CW_THREADS - 1) / CW_THREADS;
   for (int64_t base = o0; base < o1; base += CW_THREADS) {
     // ---- compact the present pairs of 256 candidate rows ----
     const int64_t o = base + tid;
@@ -227,6 +230,30 @@ __global__ void __launch_bounds__(CW_THREADS) conv_bwd_weight_kernel(
         ((float4*)g_s)[r * vpr + v] = x;
       }
       __syncthreads();
+      if (quad) {
+        // 4 x 4 register patches: one 128-bit read of 4 input channels and one of 4 grad channels
+        // feed 16 FMAs (the scalar path below needs a shared-memory read per 4 FMAs)
+#pragma unroll
+        for (int q = 0; q < CW_MAX_ITEMS / 4; ++q) {
+          if (q < items4) {
+            const int e = q * CW_THREADS + tid;
+            if (e < ca * vpr) {
+              const int cg = e / vpr, cv = e % vpr;
+#pragma unroll 8
+              for (int r = 0; r < CW_TR; ++r) {
+                const float4 a4 = ((const float4*)a_s)[r * ca + cg];
+                const float4 g = ((const float4*)g_s)[r * vpr + cv];
+                float4& c0 = acc[4 * q + 0]; float4& c1 = acc[4 * q + 1];
+                float4& c2 = acc[4 * q + 2]; float4& c3 = acc[4 * q + 3];
+                c0.x = fmaf(a4.x, g.x, c0.x); c0.y = fmaf(a4.x, g.y, c0.y); c0.z = fmaf(a4.x, g.z, c0.z); c0.w = fmaf(a4.x, g.w, c0.w);
+                c1.x = fmaf(a4.y, g.x, c1.x); c1.y = fmaf(a4.y, g.y, c1.y); c1.z = fmaf(a4.y, g.z, c1.z); c1.w = fmaf(a4.y, g.w, c1.w);
+                c2.x = fmaf(a4.z, g.x, c2.x); c2.y = fmaf(a4.z, g.y, c2.y); c2.z = fmaf(a4.z, g.z, c2.z); c2.w = fmaf(a4.z, g.w, c2.w);
+                c3.x = fmaf(a4.w, g.x, c3.x); c3.y = fmaf(a4.w, g.y, c3.y); c3.z = fmaf(a4.w, g.z, c3.z); c3.w = fmaf(a4.w, g.w, c3.w);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int q = 0; q < CW_MAX_ITEMS; ++q) {
         if (q < items) {
@@ -243,16 +270,32 @@ __global__ void __launch_bounds__(CW_THREADS) conv_bwd_weight_kernel(
           }
         }
       }
+      }
       __syncthreads();
     }
   }
+  if (quad) {
 #pragma unroll
-  for (int q = 0; q < CW_MAX_ITEMS; ++q) {
-    if (q < items) {
-      int e = q * CW_THREADS + threadIdx.x;
-      if (e < c_in * vpr) {
-        int ci = e / vpr, cv = (e % vpr) * 4;
-        lk_red_add_v4(gw + ((int64_t)k * c_in + ci) * c_out + cv, acc[q]);
+    for (int q = 0; q < CW_MAX_ITEMS / 4; ++q) {
+      if (q < items4) {
+        const int e = q * CW_THREADS + threadIdx.x;
+        if (e < ca * vpr) {
+          const int cg = e / vpr, cv = (e % vpr) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            lk_red_add_v4(gw + ((int64_t)k * c_in + 4 * cg + i) * c_out + cv, acc[4 * q + i]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < CW_MAX_ITEMS; ++q) {
+      if (q < items) {
+        int e = q * CW_THREADS + threadIdx.x;
+        if (e < c_in * vpr) {
+          int ci = e / vpr, cv = (e % vpr) * 4;
+          lk_red_add_v4(gw + ((int64_t)k * c_in + ci) * c_out + cv, acc[q]);
+        }
       }
     }
   }

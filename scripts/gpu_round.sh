@@ -16,4 +16,4 @@ PY
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err; cut -c1-200 gpurun_out/${tag}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-encoder --no-cpu-baseline > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"link_|conv_tc|linear_ln|kmap_query|plan_|radix|uniq|table_insert|block_neighbors" -s 60 -c 20 -f -o gpurun_out/${tag}_full python bench.py --steps 2 --warmup 3 --no-encoder --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1; tail -2 gpurun_out/${tag}_ncu.log
-timeout 600 python scripts/sweep.py --out gpurun_out/${tag}_sweep.json > gpurun_out/${tag}_sweep.log 2>&1; tail -3 gpurun_out/${tag}_sweep.log | cut -c1-200
+
