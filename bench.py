@@ -62,7 +62,8 @@ def block_params(seed=0):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # captures (profiles/), keyed by kernel; None = not captured for this build.
-NCU_TRAFFIC = {'link_preagg_smem_kernel': 40.68e6}   # profiles/r01_ncu_full_v3.md (two launches: 41.64 / 39.72 MB read, <1 KB written)
+NCU_TRAFFIC = {'link_preagg_smem_kernel': 40.68e6,   # profiles/r01_ncu_full_v3.md (two launches: 41.64 / 39.72 MB read, <1 KB written)
+               'link_preagg_ring_kernel': None}
 
 
 def workload_name(args, n):
@@ -355,22 +356,42 @@ def preagg_roofline(dev, coords, bounds, blk, nbuf=6, reps=4):
     sums = torch.zeros(n, 2 * C_BLOCK, device=dev)
     L, stream = _capi.lib(), _capi.stream()
 
-    def launch(i):
+    def launch(i, stream):
         _capi.check(L.lk_link_preagg_seg_fwd(_capi.ptr(bufs[i % nbuf]), _capi.ptr(coords),
                                              _capi.ptr(bi.order), _capi.ptr(bi.sorted_rank), n,
                                              C.byref(gen), _capi.ptr(sums), stream), 'preagg')
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / (nbuf * reps)
+
     for i in range(nbuf):
-        launch(i)
+        launch(i, stream)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(nbuf * reps):
-        launch(i)
-    e1.record()
-    torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / (nbuf * reps)
+    # (a) launched one by one from python: each ctypes call costs ~10 us of host time, about the
+    #     duration of the kernel, so this figure is partly the host's launch rate
+    us_py = timed(lambda: [launch(i, stream) for i in range(nbuf * reps)])
+    # (b) the same launches captured once into a CUDA graph and replayed: the device-side duration
+    #     per launch (launch latency of back-to-back dependent kernels still included)
+    us, how = us_py, 'python launches'
+    try:
+        gr, cap = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.graph(gr, stream=cap):
+            cs = _capi.stream()
+            for i in range(nbuf * reps):
+                launch(i, cs)
+        gr.replay()
+        torch.cuda.synchronize()
+        us, how = min(timed(gr.replay) for _ in range(3)), 'CUDA-graph replay'
+    except Exception as e:                                       # keep the bench line; say what happened
+        how = f'python launches (graph capture failed: {type(e).__name__})'
     nbytes = n * (4 * C_BLOCK + 16 + 4) + m * 4 * 2 * C_BLOCK     # F_in + coords + block idx + M sums
-    return {'avg_us': us, 'bytes': float(nbytes), 'launches': nbuf * reps, 'm': m,
+    return {'avg_us': us, 'python_launch_avg_us': us_py, 'how': how, 'bytes': float(nbytes),
+            'launches': nbuf * reps, 'm': m,
             'inputs': f'{nbuf} rotating [N,{C_BLOCK}] fp32 feature buffers ({nbuf * n * C_BLOCK * 4 / 1e6:.0f} MB > L2)'}
 
 
@@ -437,14 +458,17 @@ def main_ours(args):
         r = m['roof']
         gbs = r['bytes'] / (r['avg_us'] * 1e-6) / 1e9
         instep = kern.get('lk_link_preagg_fwd', {})
-        roof = {'kernel': 'link_preagg_smem_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak,
+        roof = {'kernel': 'link_preagg_ring_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
-                'traffic': NCU_TRAFFIC.get('link_preagg_smem_kernel'),
+                'traffic': NCU_TRAFFIC.get('link_preagg_ring_kernel'),
                 'algorithmic_bytes_per_launch': r['bytes'], 'avg_us': r['avg_us'],
+                'python_launch_avg_us': r['python_launch_avg_us'],
                 'in_step_avg_us': instep.get('avg_us'),
-                'note': f"{r['launches']} back-to-back launches of the kernel alone on its stream over "
-                        f"{r['inputs']}, CUDA events around the batch; in_step_avg_us = the same kernel "
-                        'inside the step (events around the single python-level call, includes launch latency)'}
+                'note': f"{r['launches']} back-to-back launches of the kernel alone over {r['inputs']}, "
+                        f"timed by {r['how']} with CUDA events around the batch; python_launch_avg_us = the "
+                        'same launches issued one by one from python (host-paced: ~10 us per ctypes call); '
+                        'in_step_avg_us = the same kernel inside the step (events around the single '
+                        'python-level call, includes launch latency)'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
         'warmup': m['warmup'], 'ms_per_step': dev_ms / steps, 'higher_is_better': True,

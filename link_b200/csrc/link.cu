@@ -22,6 +22,8 @@
 // run-boundary tests) and the LayerNorm shuffle trees 4x, and channel groups
 // (pos.repeat([1, groups]), linkencoder.py:152) fall INSIDE a lane: vectors i and i + IB share
 // their phases, so a lane evaluates only 4 IB sincos per row and reuses them.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct GenDev {
@@ -37,19 +39,6 @@ __device__ __noinline__ float2 accurate_sincos(float p) {
   float s, c;
   sincosf(p, &s, &c);
   return make_float2(s, c);
-}
-
-// sin and cos of one fp32 phase: two-term Cody-Waite reduction to [-pi, pi] (exact for the
-// |p| < ~1e5 rad that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7) followed by the SFU
-// approximations (sin.approx / cos.approx, max abs error 2^-20.9 on [-pi, pi]).  ~9 instructions
-// instead of ~20 for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
-__device__ __forceinline__ void fast_sincos(float p, bool accurate, float& s, float& c) {
-  if (accurate) { float2 sc = accurate_sincos(p); s = sc.x; c = sc.y; return; }   // warp-uniform switch
-  float k = rintf(p * 0.15915494309189535f);
-  float r = fmaf(k, -6.2831855f, p);
-  r = fmaf(k, 1.7484555e-7f, r);
-  s = __sinf(r);
-  c = __cosf(r);
 }
 
 // per-lane kernel-generator state: weights of the NP = 4 IB distinct phases the lane evaluates
@@ -75,19 +64,52 @@ __device__ __forceinline__ void load_lane_gen(const GenDev& g, int j, bool activ
     }
 }
 
-// Phase, sin and cos of the lane's 4 IB distinct phases for voxel (x,y,z); the phase follows the
-// operation order of nn.Linear(3, .) [ (x*w0 + y*w1) + z*w2 ] followed by "* alpha"
-// (linkencoder.py:151,165).
+// Phase, sin and cos of the lane's 4 IB distinct phases, SFU form (no accuracy switch inside the
+// phase loop).  Per phase: two-term Cody-Waite reduction to [-pi, pi] (exact for the |p| < ~1e5 rad
+// that voxel grids produce: fl(2pi) = 2pi + 1.7484555e-7), the quotient rounded to nearest by the
+// 1.5 * 2^23 trick (FFMA + FADD on the FMA pipe instead of FMUL + FRND on the conversion pipe), then
+// sin.approx / cos.approx (max abs error 2^-20.9 on [-pi, pi]).  ~10 instructions instead of ~20
+// for sincosf; the 5e-7 absolute error is two orders below the parity tolerance.
 template <int NP, bool COSX>
-__device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen<NP>& lg, int cx, int cy, int cz,
-                                          float p[NP], float sn[NP], float cs[NP]) {
+__device__ __forceinline__ void lane_trig_sfu(const GenDev& g, const LaneGen<NP>& lg, int cx, int cy, int cz,
+                                              float p[NP], float sn[NP], float cs[NP]) {
   float x = (float)cx, y = (float)cy, z = (float)cz;
   if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
     float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
     p[q] = COSX ? v * lg.al[q] : v;
-    fast_sincos(p[q], g.accurate != 0, sn[q], cs[q]);
+    const float t = fmaf(p[q], 0.15915494309189535f, 12582912.f);   // 1.5 * 2^23: rounds to an integer
+    const float k = t - 12582912.f;
+    float r = fmaf(k, -6.2831855f, p[q]);
+    r = fmaf(k, 1.7484555e-7f, r);
+#ifdef PR_DEBUG_NOTRIG                               // timing experiments only (results are wrong)
+    sn[q] = r; cs[q] = k;
+#else
+    sn[q] = __sinf(r);
+    cs[q] = __cosf(r);
+#endif
+  }
+}
+
+// Phase, sin and cos of the lane's 4 IB distinct phases for voxel (x,y,z); the phase follows the
+// operation order of nn.Linear(3, .) [ (x*w0 + y*w1) + z*w2 ] followed by "* alpha"
+// (linkencoder.py:151,165).
+template <int NP, bool COSX>
+__device__ __forceinline__ void lane_trig(const GenDev& g, const LaneGen<NP>& lg, int cx, int cy, int cz,
+                                          float p[NP], float sn[NP], float cs[NP]) {
+  if (!g.accurate) {                             // warp-uniform: one test per row, not one per phase
+    lane_trig_sfu<NP, COSX>(g, lg, cx, cy, cz, p, sn, cs);
+    return;
+  }
+  float x = (float)cx, y = (float)cy, z = (float)cz;
+  if (COSX) { x = x / g.coord_scale; y = y / g.coord_scale; z = z / g.coord_scale; }
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    float v = fmaf(z, lg.w2[q], fmaf(y, lg.w1[q], x * lg.w0[q]));
+    p[q] = COSX ? v * lg.al[q] : v;
+    const float2 sc = accurate_sincos(p[q]);
+    sn[q] = sc.x; cs[q] = sc.y;
   }
 }
 
@@ -340,6 +362,194 @@ __global__ void __launch_bounds__(PS_WARPS * 32, (IB == 1 && OP != LK_OP_COSX) ?
   }
 }
 
+// ------------------------------------------------------------------ pass 1, balanced ring
+// Same arithmetic and visiting order as link_preagg_smem_kernel, scheduled differently:
+//   * every lane group owns ONE contiguous range of q sorted positions, q = ceil(n / resident lane
+//     groups), so the whole grid is resident in a single wave and all warps finish together for any
+//     n (the one-step-per-warp kernel above runs 934 CTAs on 888 slots at n = 119k: a second wave
+//     of 46 CTAs that costs a full latency chain);
+//   * a warp streams its range through a ring of PR_STAGES chunks (PR_RC rows per lane group and
+//     chunk): the row fetches of the next chunk(s) are in flight while chunk c is reduced, and the
+//     (voxel row, block row) pairs are prefetched one more chunk ahead, so the pair -> row
+//     dependency is paid once per warp, not once per step;
+//   * leaner inner loop: SFU trig without the per-phase accuracy switch, block rows handed over
+//     through shared memory, rows past the end skipped, not masked.
+// Measured (B200, n = 119 325, C = 64, cos, CUDA-graph replay of 56 launches over 8 rotating
+// feature buffers; scripts/preagg_ab.py, gpurun_out r01p3/r01p4): one-step-per-warp kernel 11.4 us;
+// ring 3 stages x 4 rows 10.0 us, 2 x 4 9.2, 4 x 4 10.4, 2 x 8 10.3, 3 x 2 9.0, 2 x 2 8.9-9.3
+// (default), 2 x 1 9.6; 24 instead of 16 warps per SM +0.3 us.  Small chunks win: the tail after
+// the last fetch lands is one chunk of arithmetic.  Timing experiments (results wrong by
+// construction): without the trig 9.5 us, without the reductions ~10 us (unchanged), without the
+// feature fetch 7.4 us, without fetch and coordinates 6.4 us, without any of them 6.3 us -- the
+// skeleton (launch, pair loads, ring hand-over) is 2/3 of the kernel; the 30.5 MB feature gather
+// adds ~3 us.
+#ifndef PR_STAGES
+#define PR_STAGES 2
+#endif
+#ifndef PR_WARPS
+#define PR_WARPS 4
+#endif
+#ifndef PR_RC
+#define PR_RC 2                            // rows per lane group and chunk
+#endif
+#ifndef PR_MINB
+#define PR_MINB 4                          // resident CTAs per SM the register budget is capped for
+#endif
+template <int LPR>
+struct RingCfg {
+  static constexpr int G = 32 / LPR;                 // lane groups (rows side by side) per warp
+  static constexpr int RC = LPR < PR_RC ? LPR : PR_RC;   // rows per lane group and chunk
+  static constexpr int CR = G * RC;                  // rows per warp chunk (<= 32: one pair per lane)
+  static constexpr int ROW_BYTES = 32 * LPR;         // = 4 C
+  static constexpr int SLOT = CR * ROW_BYTES + CR * 16 + CR * 4;   // rows | coords | block rows
+  static constexpr int SMEM = PR_WARPS * PR_STAGES * SLOT;
+};
+
+#ifdef PR_DEBUG_NORED                                // timing experiments only (results are wrong)
+#define PR_RED(p, v) do { if ((v).x == 123.456f) lk_red_add_v4(p, v); } while (0)
+#else
+#define PR_RED(p, v) lk_red_add_v4(p, v)
+#endif
+template <int LPR, int IB, int OP>
+__global__ void __launch_bounds__(PR_WARPS * 32, PR_MINB) link_preagg_ring_kernel(
+    const float* __restrict__ fin, const int4* __restrict__ coords, const int* __restrict__ order,
+    const int* __restrict__ rank, int64_t n, int q, GenDev g, float* sums) {
+  using Cfg = RingCfg<LPR>;
+  constexpr int VPL = 2;
+  constexpr int G = Cfg::G, RC = Cfg::RC, CR = Cfg::CR, ROW_BYTES = Cfg::ROW_BYTES, SLOT = Cfg::SLOT;
+  constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
+  constexpr bool COSX = (OP == LK_OP_COSX);
+  constexpr int NP = 4 * IB;
+  extern __shared__ __align__(16) uint8_t ring_s[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int grp = lane / LPR;
+  const int j = lane % LPR;
+  const int kc = K * g.c;
+  uint8_t* const wbase = ring_s + (size_t)wib * (PR_STAGES * SLOT);
+  const uint32_t wbase_u = (uint32_t)__cvta_generic_to_shared(wbase);
+  const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_g * G * (int64_t)q >= n) return;          // whole warp past the end (no CTA-wide barriers below)
+  LaneGen<NP> lg;
+  load_lane_gen<LPR, IB>(g, j, true, lg);
+  const int nchunks = (q + RC - 1) / RC;
+  // the pair this lane fetches for a chunk: lane -> (group lane / RC, row lane % RC of the chunk)
+  const int pg = lane / RC, pu = lane % RC;
+  const int64_t pbase = (warp_g * G + pg) * (int64_t)q + pu;
+
+  auto load_pair = [&](int c, int& o, int& r) {
+    const int off = c * RC + pu;
+    const int64_t pos = pbase + (int64_t)c * RC;
+    const bool ok = lane < CR && off < q && pos < n;
+    o = ok ? (order ? __ldg(order + pos) : (int)pos) : 0;
+    r = ok ? __ldg(rank + pos) : -1;
+  };
+  auto issue = [&](int c, int o, int r) {
+    const uint32_t slot_u = wbase_u + (c % PR_STAGES) * SLOT;
+#pragma unroll
+    for (int u = 0; u < RC; ++u) {
+      const int p = grp * RC + u;                    // row of the warp chunk
+      const int ro = __shfl_sync(0xffffffffu, o, p);
+      const int rb = __shfl_sync(0xffffffffu, r, p);
+      if (rb >= 0) {
+        const float* src = fin + (int64_t)ro * g.c + 4 * j;
+#ifndef PR_DEBUG_NOFETCH                             // timing experiments only (results are wrong)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                       ::"r"(slot_u + p * ROW_BYTES + (i * LPR + j) * 16), "l"(src + 4 * i * LPR) : "memory");
+#endif
+#ifndef PR_DEBUG_NOCOORD
+        if (j == 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                       ::"r"(slot_u + CR * ROW_BYTES + p * 16), "l"(coords + ro) : "memory");
+#endif
+      }
+    }
+    if (lane < CR)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(slot_u + CR * ROW_BYTES + CR * 16 + lane * 4), "r"(r) : "memory");
+  };
+
+  // ---- prologue: pairs of the first PR_STAGES chunks at once, rows of the first PR_STAGES - 1 ----
+  int po[PR_STAGES], pr[PR_STAGES];
+#pragma unroll
+  for (int c = 0; c < PR_STAGES; ++c) load_pair(c, po[c], pr[c]);
+#pragma unroll
+  for (int c = 0; c < PR_STAGES - 1; ++c) {
+    if (c < nchunks) issue(c, po[c], pr[c]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int o_n = po[PR_STAGES - 1], r_n = pr[PR_STAGES - 1];
+
+  float acc[K][VPL][4];
+#pragma unroll
+  for (int qq = 0; qq < K; ++qq)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[qq][i][e] = 0.f;
+  int cur = -1;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int cn = c + PR_STAGES - 1;
+    if (cn < nchunks) issue(cn, o_n, r_n);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    load_pair(cn + 1, o_n, r_n);                     // consumed by the next iteration's issue
+    asm volatile("cp.async.wait_group %0;" ::"n"(PR_STAGES - 1) : "memory");
+    __syncwarp();
+    const uint8_t* slot = wbase + (c % PR_STAGES) * SLOT;
+#pragma unroll
+    for (int u = 0; u < RC; ++u) {
+      const int p = grp * RC + u;
+      const int b = *(const int*)(slot + CR * ROW_BYTES + CR * 16 + p * 4);
+      if (b >= 0) {                                  // else: past the end of the range / of the input
+        if (b != cur) {                              // run boundary: flush the finished block
+          if (cur >= 0) {
+            float* dst = sums + (int64_t)cur * kc + 4 * j;
+#pragma unroll
+            for (int qq = 0; qq < K; ++qq)
+#pragma unroll
+              for (int i = 0; i < VPL; ++i)
+                PR_RED(dst + qq * g.c + 4 * i * LPR,
+                              make_float4(acc[qq][i][0], acc[qq][i][1], acc[qq][i][2], acc[qq][i][3]));
+          }
+#pragma unroll
+          for (int qq = 0; qq < K; ++qq)
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[qq][i][e] = 0.f;
+          cur = b;
+        }
+        const int4 cc = *(const int4*)(slot + CR * ROW_BYTES + p * 16);
+        float ph[NP], sn[NP], cs[NP];
+        lane_trig_sfu<NP, COSX>(g, lg, cc.x, cc.y, cc.z, ph, sn, cs);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const float4 f4 = *(const float4*)(slot + p * ROW_BYTES + (i * LPR + j) * 16);
+          const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qq = (i % IB) * 4 + e;
+            acc[0][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? sn[qq] : cs[qq]), acc[0][i][e]);
+            acc[1][i][e] = fmaf(fv[e], (OP == LK_OP_SIN ? cs[qq] : sn[qq]), acc[1][i][e]);
+            if (COSX) acc[K - 1][i][e] = fmaf(fv[e], ph[qq], acc[K - 1][i][e]);
+          }
+        }
+      }
+    }
+    __syncwarp();                                    // the slot is refilled by the next iteration
+  }
+  if (cur >= 0) {
+    float* dst = sums + (int64_t)cur * kc + 4 * j;
+#pragma unroll
+    for (int qq = 0; qq < K; ++qq)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        PR_RED(dst + qq * g.c + 4 * i * LPR,
+                      make_float4(acc[qq][i][0], acc[qq][i][1], acc[qq][i][2], acc[qq][i][3]));
+  }
+}
+
 // zero the first *d_num rows of a [capacity, row_floats] buffer (block sums are allocated for the
 // worst case M = N but only the M live rows are ever touched)
 __global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p,
@@ -579,13 +789,75 @@ static int check_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
 // lane).  IB < VPL when the channel groups alias inside a lane: wrows a multiple of 4 LPR.
 struct RowLayout { int lpr, vpl, ib; };
 
+// Balanced ring kernel: the grid is sized to the resident capacity (occupancy query, cached per
+// instantiation) and every lane group gets q = ceil(n / lane groups) consecutive sorted positions.
+template <int LPR, int IB, int OP>
+static int launch_ring(const float* d_fin, const int32_t* d_coords, const int32_t* d_order,
+                       const int32_t* d_rank, int64_t n, const GenDev& g, float* d_sums,
+                       cudaStream_t st) {
+  using Cfg = RingCfg<LPR>;
+  auto kern = link_preagg_ring_kernel<LPR, IB, OP>;
+  static int ctas_per_sm = 0;                        // 0: not configured yet, < 0: configuration failed
+  if (ctas_per_sm == 0) {
+    int occ = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PR_WARPS * 32, Cfg::SMEM) != cudaSuccess ||
+        occ < 1) {
+      ctas_per_sm = -1;
+      (void)cudaGetLastError();
+    } else {
+      ctas_per_sm = occ;
+    }
+  }
+  LK_REQUIRE(ctas_per_sm > 0, "lk_link_preagg: cannot configure the ring kernel (shared memory %d bytes)",
+             Cfg::SMEM);
+  static const int q_env = [] {
+    const char* e = getenv("LINKB200_PREAGG_Q");     // tuning knob: positions per lane group
+    return e ? atoi(e) : 0;
+  }();
+  const int64_t groups_cap = (int64_t)LK_SM_COUNT * ctas_per_sm * PR_WARPS * Cfg::G;
+  int64_t q = (n + groups_cap - 1) / groups_cap;
+  if (q < 8) q = 8;
+  if (q_env > 0 && q_env >= q) q = q_env;
+  const int64_t groups = (n + q - 1) / q;
+  const int grid = (int)((groups + (int64_t)Cfg::G * PR_WARPS - 1) / ((int64_t)Cfg::G * PR_WARPS));
+  kern<<<grid, PR_WARPS * 32, Cfg::SMEM, st>>>(d_fin, (const int4*)d_coords, d_order, d_rank, n, (int)q, g, d_sums);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 static int launch_preagg(const float* d_fin, const int32_t* d_coords, const int32_t* d_order,
                          const int32_t* d_rank, int64_t n, const GenDev& g, float* d_sums,
                          cudaStream_t st) {
   if (g.c == 16 || g.c == 32 || g.c == 64 || g.c == 128) {
-    // shared-memory staged kernel: 2 vectors per lane, LPR = C / 8 lanes per row
+    // shared-memory staged kernels: 2 vectors per lane, LPR = C / 8 lanes per row
     const int lpr = g.c / 8, span = 4 * lpr;
     const int ib = (g.wrows % span == 0 && g.wrows / span == 1) ? 1 : 2;
+    static const int use_ring = [] {
+      const char* e = getenv("LINKB200_PREAGG");     // tuning knob: "smem" = one step per warp
+      return !(e && e[0] == 's');
+    }();
+    if (use_ring && !g.accurate) {
+      int rc = LK_EINVAL;
+#define RING_IB(LPRV, IBV)                                                                        \
+  do {                                                                                            \
+    if (g.op == LK_OP_COS) rc = launch_ring<LPRV, IBV, LK_OP_COS>(d_fin, d_coords, d_order, d_rank, n, g, d_sums, st);      \
+    else if (g.op == LK_OP_SIN) rc = launch_ring<LPRV, IBV, LK_OP_SIN>(d_fin, d_coords, d_order, d_rank, n, g, d_sums, st); \
+    else rc = launch_ring<LPRV, IBV, LK_OP_COSX>(d_fin, d_coords, d_order, d_rank, n, g, d_sums, st);                       \
+  } while (0)
+#define RING(LPRV)                   \
+  do {                               \
+    if (ib == 1) RING_IB(LPRV, 1);   \
+    else RING_IB(LPRV, 2);           \
+  } while (0)
+      if (lpr == 2) RING(2);
+      else if (lpr == 4) RING(4);
+      else if (lpr == 8) RING(8);
+      else RING(16);
+#undef RING
+#undef RING_IB
+      return rc;
+    }
     const int64_t rows_per_warp = (int64_t)(32 / lpr) * PS_RPG;
     const int64_t warps = (n + rows_per_warp - 1) / rows_per_warp;
     const int grid = (int)((warps + PS_WARPS - 1) / PS_WARPS);

@@ -512,6 +512,45 @@ def test_preagg_segmented_vs_storage_order_vs_numpy(dev, op, C, groups, n):
     np.testing.assert_allclose(out[0], out[1], rtol=1e-4, atol=1e-4)    # float atomics: order varies
 
 
+@pytest.mark.parametrize('op,C,groups,s', [('cos', 64, 2, 7), ('cos_x', 64, 1, 3), ('sin', 16, 1, 5),
+                                           ('cos', 128, 2, 3), ('cos', 32, 2, 2)])
+def test_preagg_ring_long_ranges(dev, op, C, groups, s):
+    """Balanced ring kernel at sizes where every lane group walks several chunks (q > 8 sorted
+    positions per group, last chunk partial) and block runs straddle chunk, group and warp
+    boundaries: float64 numpy block sums, rows >= M untouched, and batch > 1."""
+    import ctypes as Ct
+    from link_b200 import SparseTensor, _capi
+    from link_b200.elk import block_index, _kernel_gen
+    from link_b200.utils.synthetic import random_voxels
+    coords = random_voxels(90_001, 80, seed=C + s, batch=2)
+    n = len(coords)
+    st = SparseTensor(torch.zeros(n, C, device=dev), cu(coords, dev), 1)
+    bi = block_index(st, s)
+    m = bi.m
+    g = torch.Generator().manual_seed(C)
+    f = torch.randn(n, C, generator=g)
+    w = torch.randn(C // groups, 3, generator=g) * 0.1
+    alpha = torch.rand(C // groups, generator=g) + 0.5 if op == 'cos_x' else None
+    k = 3 if op == 'cos_x' else 2
+    w_d, a_d = w.to(dev), (alpha.to(dev) if alpha is not None else None)
+    gen = _kernel_gen(op, C, w_d, a_d, 1.0)
+    L, stream = _capi.lib(), _capi.stream()
+    sums = torch.zeros(n, k * C, device=dev)
+    _capi.check(L.lk_link_preagg_seg_fwd(_capi.ptr(f.to(dev)), _capi.ptr(st.C), _capi.ptr(bi.order),
+                                         _capi.ptr(bi.sorted_rank), n, Ct.byref(gen), _capi.ptr(sums), stream), 'seg')
+    assert m < n and float(sums[m:].abs().max()) == 0.0
+    pos = (coords[:, :3].astype(np.float32) @ w.numpy().T.astype(np.float32))
+    if alpha is not None:
+        pos = pos * alpha.numpy()
+    pos = np.tile(pos, (1, groups)).astype(np.float64)
+    fn = f.numpy().astype(np.float64)
+    planes = {'cos': [fn * np.cos(pos), fn * np.sin(pos)], 'sin': [fn * np.sin(pos), fn * np.cos(pos)],
+              'cos_x': [fn * np.cos(pos), fn * np.sin(pos), fn * pos]}[op]
+    want = np.zeros((m, k * C))
+    np.add.at(want, bi.idx_query.cpu().numpy(), np.concatenate(planes, 1))
+    np.testing.assert_allclose(sums[:m].cpu().numpy(), want, rtol=1e-4, atol=1e-3)
+
+
 # ------------------------------------------------------------------ dense pre_mix kernels
 @pytest.mark.parametrize('c,tcore', [(16, False), (32, False), (64, False), (128, False),
                                      (32, True), (64, True)])
