@@ -63,7 +63,7 @@ def block_params(seed=0):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # captures (profiles/), keyed by kernel; None = not captured for this build.
 NCU_TRAFFIC = {'link_preagg_smem_kernel': 40.68e6,   # profiles/r01_ncu_full_v3.md (two launches: 41.64 / 39.72 MB read, <1 KB written)
-               'link_preagg_ring_kernel': None}
+               'link_preagg_ring_kernel': 41.62e6}   # profiles/r01_ncu_full_v8.md (41.62 MB read, 3.6 KB written)
 
 
 def workload_name(args, n):
