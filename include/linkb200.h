@@ -194,11 +194,14 @@ int lk_link_preagg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords,
                        const lk_kernelgen_t* gen, float* d_sums, lk_stream_t s);
 /* Pass 1, segmented form (the one the block executor uses): voxels are visited in BLOCK order
  * through the sort permutation (d_order[i] = voxel row at sorted position i, d_sorted_rank[i] =
- * its block row; both from lk_sort_unique_ex), so every lane group walks 16 consecutive sorted
- * positions = 1-2 whole blocks, reduces them in registers (a warp-level segmented reduction over
- * the variable-length voxel lists of the blocks) and issues one vector reduction per block it
- * touches: ~8x fewer L2 atomics than the storage-order form, and a block that lies inside one
- * lane group's span is summed in a fixed order (deterministic).  d_sums must be zeroed. */
+ * its block row; both from lk_sort_unique_ex).  Every lane group walks one contiguous range of
+ * sorted positions (sized so that the whole grid is resident in one wave), reduces runs of equal
+ * block row in registers (a warp-level segmented reduction over the variable-length voxel lists of
+ * the blocks) and issues one vector reduction per block it touches: ~8x fewer L2 atomics than the
+ * storage-order form, and a block that lies inside one lane group's range is summed in a fixed
+ * order (deterministic).  d_sums must be zeroed.  Environment knobs (tuning only):
+ * LINKB200_PREAGG=smem selects the previous one-step-per-warp kernel, LINKB200_PREAGG_Q=<q> raises
+ * the range length per lane group. */
 int lk_link_preagg_seg_fwd(const float* d_fin /*[n,C]*/, const int32_t* d_coords,
                            const int32_t* d_order, const int32_t* d_sorted_rank, int64_t n,
                            const lk_kernelgen_t* gen, float* d_sums, lk_stream_t s);
