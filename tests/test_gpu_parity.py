@@ -800,6 +800,35 @@ def test_from_host_async_upload_matches_resident_inputs(dev):
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+def test_from_host_back_to_back_uploads_do_not_race(dev):
+    """from_host never makes the copy stream wait for the compute stream (the upload of scan i+1
+    overlaps the processing of scan i; the upload buffer is owned by the copy stream and marked
+    as used by the compute stream).  Ten steps issued without any host synchronisation, with
+    DIFFERENT features per step and the results kept on the device: every step must equal the
+    resident-input result of its own features."""
+    from link_b200 import SparseTensor
+    from link_b200.elk import ELKBlock
+    from link_b200.utils.synthetic import kitti_like_voxels
+    c3, _ = kitti_like_voxels(30_000, seed=7)
+    coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    ch = torch.from_numpy(coords).pin_memory()
+    cd = ch.to(dev)
+    torch.manual_seed(1)
+    blk = ELKBlock(64, 64, groups=2, baseop='cos').to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    fhs = [torch.randn(len(coords), 64, generator=g).pin_memory() for _ in range(4)]
+    with torch.no_grad():
+        wants = [blk(SparseTensor(f.to(dev), cd.clone(), 1), 7, 3).F.clone() for f in fhs]
+        torch.cuda.synchronize()
+        gots = []
+        for k in range(10):
+            gots.append(blk(SparseTensor.from_host(fhs[k % 4], ch, 1, device=dev), 7, 3).F.sum(dim=0))
+        torch.cuda.synchronize()
+    for k, got in enumerate(gots):
+        want = wants[k % 4].sum(dim=0)
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
 def test_fused_index_entry_points_match_their_parts(dev):
     """lk_sort_unique_coords == lk_pack_keys + lk_sort_unique_ex, lk_table_build_coords == lk_hash +
     lk_table_build, lk_block_neighbors_zero / lk_link_window_mean_seg == their unfused forms."""
