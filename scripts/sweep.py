@@ -113,8 +113,33 @@ def main():
                'voxels_per_s': len(idx) / (ms * 1e-3)}
         print(json.dumps(row), flush=True)
         rows.append(row)
+        # ---- full detector of config 4: reader -> backbone -> RPN -> CenterHead + losses, fwd+bwd
+        from link_b200.centerpoint import NUSC_TASKS, build_nusc_centerpoint
+        torch.manual_seed(0)
+        det = build_nusc_centerpoint(backbone=net).to(dev).train()
+        g = torch.Generator().manual_seed(1)
+        n_pts = torch.randint(1, 11, (len(idx),), generator=g)
+        voxels = (torch.randn(len(idx), 10, 5, generator=g) * (torch.arange(10)[None, :, None] < n_pts[:, None, None])).to(dev)
+        example = {'voxels': voxels, 'num_points': n_pts.to(dev), 'coordinates': idx_d, 'batch_size': 1,
+                   'shape': [np.array([1440, 1440, 40])], 'hm': [], 'ind': [], 'mask': [], 'cat': [], 'anno_box': []}
+        for t in NUSC_TASKS:                       # CenterPoint targets: 180 x 180 heat maps, <= 500 objects
+            k = len(t['class_names'])
+            example['hm'].append((torch.rand(1, k, 180, 180, generator=g) ** 4).to(dev))
+            example['ind'].append(torch.randint(0, 180 * 180, (1, 500), generator=g).to(dev))
+            example['mask'].append((torch.rand(1, 500, generator=g) < 0.1).to(torch.uint8).to(dev))
+            example['cat'].append(torch.randint(0, k, (1, 500), generator=g).to(dev))
+            example['anno_box'].append(torch.randn(1, 500, 10, generator=g).to(dev))
+
+        def detector_fwd_bwd():
+            sum(det(example, return_loss=True)['loss']).backward()
+            det.zero_grad(set_to_none=True)
+        ms = timed(detector_fwd_bwd, flush, warm=2, reps=5)
+        row = {'workload': 'CenterPoint detector (VFE + SpMiddleResNetFHDELKv3 + RPN + CenterHead + losses) fwd+bwd',
+               'n': len(idx), 'ms': ms, 'voxels_per_s': len(idx) / (ms * 1e-3)}
+        print(json.dumps(row), flush=True)
+        rows.append(row)
     except Exception as e:   # the sweep above is the point; report rather than hide a failure here
-        print(json.dumps({'workload': 'detection backbone', 'error': repr(e)[:300]}), flush=True)
+        print(json.dumps({'workload': 'detection backbone / detector', 'error': repr(e)[:300]}), flush=True)
     os.makedirs(os.path.dirname(a.out) or '.', exist_ok=True)
     json.dump(rows, open(a.out, 'w'), indent=0)
 
