@@ -277,49 +277,28 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     roof = None
     if workload == 'block':
         roof = preagg_roofline(dev, coords_dev[0], bounds[0], model)
-    # ---- end-to-end loops: pinned host buffers -> H2D -> step -> D2H of a per-channel checksum --
-    # public API: SparseTensor.from_host uploads the coordinates on the current stream and the
-    # features on a copy stream; the block's index build overlaps the feature upload, and the
-    # upload of scan i+1 overlaps the processing of scan i.
+    # ---- end-to-end loop: pinned host buffers -> H2D -> step -> D2H of a per-channel checksum --
     h2d = d2h = 0
+    e2e_evs = []
     out_host = torch.empty(C_BLOCK if workload == 'block' else 19, dtype=torch.float32).pin_memory()
-
-    def e2e_step(i):
-        st = SparseTensor.from_host(feats_host[i], coords_host[i], 1, device=dev)
-        out = step_st(i, st)
-        out_host.copy_(out.sum(dim=0), non_blocking=True)
-
     w_e2e = min(3, warmup)
-    # (a) latency: one scan at a time (device idle and L2 flushed before each), events per step
-    lat_evs = []
     for k in range(w_e2e + steps):
         i = k % 2
         flush.zero_()
-        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        e2e_step(i)
+        # public API: SparseTensor.from_host uploads the coordinates on the current stream and the
+        # features on a copy stream; the block's index build overlaps the feature upload
+        st = SparseTensor.from_host(feats_host[i], coords_host[i], 1, device=dev)
+        out = step_st(i, st)
+        out_host.copy_(out.sum(dim=0), non_blocking=True)
         e1.record()
         if k >= w_e2e:
-            lat_evs.append((e0, e1))
+            e2e_evs.append((e0, e1))
+            h2d = coords_host[i].numel() * 4 + feats_host[i].numel() * 4
+            d2h = out_host.numel() * 4
     barrier()
-    e2e_latency_ms = sum(a.elapsed_time(b) for a, b in lat_evs) / steps
-    # (b) throughput (the e2e value): the same calls back to back, one event pair around the whole
-    #     loop; every step's inputs arrive from the host inside the timed region (they were never
-    #     on the device, so there is no L2 state to flush), every step's result is read back
-    for k in range(w_e2e):
-        e2e_step(k % 2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(steps):
-        i = k % 2
-        e2e_step(i)
-        h2d = coords_host[i].numel() * 4 + feats_host[i].numel() * 4
-        d2h = out_host.numel() * 4
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
     # clocks / throttle reasons sampled under load over all timed loops of this workload (device-resident,
     # instrumented, roofline and end-to-end passes): the device-resident loop alone lasts a few ms
     clocks = sampler.finish(t_wall0, time.time()) if with_clocks else None
@@ -330,7 +309,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         ref_gpu = reference_gpu_leg(dev, coords_dev[0], feats_dev[0], model, flush)
     return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
             'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,
-            'roof': roof, 'ref_gpu': ref_gpu, 'e2e_latency_ms': e2e_latency_ms,
+            'roof': roof, 'ref_gpu': ref_gpu,
             'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
 
 
@@ -499,13 +478,7 @@ def main_ours(args):
                    'parallelism': f'{world} independent frame streams (no data-path collective)'},
         'clocks': m['clocks'],
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'],
-                'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps,
-                'latency_ms_per_step': m['e2e_latency_ms'],
-                'note': 'value: SparseTensor.from_host (pinned host buffers) -> module call -> D2H of a '
-                        'per-channel checksum, steps issued back to back, one CUDA-event pair around the '
-                        'loop (the upload of scan i+1 overlaps the processing of scan i; inputs arrive from '
-                        'the host every step, nothing to flush); latency_ms_per_step: the same call on an '
-                        'idle device with L2 flushed, events per step (rank 0)'},
+                'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps},
         'gpu_launches': m['launches'],
         'host_enqueue_ms_per_step': m['host_enqueue_ms'],
         'roofline': roof,

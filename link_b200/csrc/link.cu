@@ -797,18 +797,24 @@ static int launch_ring(const float* d_fin, const int32_t* d_coords, const int32_
                        cudaStream_t st) {
   using Cfg = RingCfg<LPR>;
   auto kern = link_preagg_ring_kernel<LPR, IB, OP>;
-  static int ctas_per_sm = 0;                        // 0: not configured yet, < 0: configuration failed
-  if (ctas_per_sm == 0) {
+  // per-device cache (function attributes and occupancy belong to the device's context);
+  // 0: not configured yet, < 0: configuration failed.  Racing first calls compute the same value.
+  static int ctas_cache[64];
+  int dev = 0;
+  LK_CUDA(cudaGetDevice(&dev));
+  LK_REQUIRE(dev >= 0 && dev < 64, "lk_link_preagg: device ordinal %d out of range", dev);
+  if (ctas_cache[dev] == 0) {
     int occ = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PR_WARPS * 32, Cfg::SMEM) != cudaSuccess ||
         occ < 1) {
-      ctas_per_sm = -1;
+      ctas_cache[dev] = -1;
       (void)cudaGetLastError();
     } else {
-      ctas_per_sm = occ;
+      ctas_cache[dev] = occ;
     }
   }
+  const int ctas_per_sm = ctas_cache[dev];
   LK_REQUIRE(ctas_per_sm > 0, "lk_link_preagg: cannot configure the ring kernel (shared memory %d bytes)",
              Cfg::SMEM);
   static const int q_env = [] {

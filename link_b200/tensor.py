@@ -64,23 +64,17 @@ class SparseTensor:
         the features -- 16x more bytes at C = 64 -- follow on a dedicated copy stream, so the index
         build of the first layer (hash grid, kernel map, conv plan, block sort: ~45 % of a LinK
         block) runs while they are still crossing PCIe.  Consumers join the upload through
-        `feats` / `take_feats_event`.
-
-        The feature buffer is allocated ON the copy stream (its reuse is ordered by that stream) and
-        marked as used by the current stream (`record_stream`: the allocator hands the memory out
-        again only after the consumers queued there have finished), so the copy stream never waits
-        for the compute stream: the upload of scan i+1 crosses PCIe while scan i is still being
-        processed."""
+        `feats` / `take_feats_event`."""
         device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
         main = torch.cuda.current_stream(device)
         c_dev = coords.to(device, non_blocking=True)
+        f_dev = torch.empty(feats.shape, dtype=feats.dtype, device=device)
         copy_stream = _copy_stream(device)
+        copy_stream.wait_stream(main)      # f_dev may recycle memory still in use by queued kernels
         with torch.cuda.stream(copy_stream):
-            f_dev = torch.empty(feats.shape, dtype=feats.dtype, device=device)
             f_dev.copy_(feats, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        f_dev.record_stream(main)
         st = cls(f_dev, c_dev, stride)
         st._feats_ready = ev
         return st

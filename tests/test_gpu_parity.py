@@ -845,11 +845,10 @@ def test_from_host_async_upload_matches_resident_inputs(dev):
 
 
 def test_from_host_back_to_back_uploads_do_not_race(dev):
-    """from_host never makes the copy stream wait for the compute stream (the upload of scan i+1
-    overlaps the processing of scan i; the upload buffer is owned by the copy stream and marked
-    as used by the compute stream).  Ten steps issued without any host synchronisation, with
-    DIFFERENT features per step and the results kept on the device: every step must equal the
-    resident-input result of its own features."""
+    """Ten from_host + block steps issued without any host synchronisation, with DIFFERENT features
+    per step and the results kept on the device: the upload buffers recycle memory of earlier
+    steps while those may still be queued, so every step must equal the resident-input result of
+    its own features."""
     from link_b200 import SparseTensor
     from link_b200.elk import ELKBlock
     from link_b200.utils.synthetic import kitti_like_voxels
