@@ -13,10 +13,12 @@ with `strict=True`:
   * SepHead, CenterHead      detection/det3d/models/bbox_heads/center_head.py:67-293
   * FastFocalLoss, RegLoss   detection/det3d/models/losses/centernet_loss.py:6-54
   * VoxelNet                 detection/det3d/models/detectors/voxelnet.py:10-66 (extract_feat / forward)
+  * CenterHead.predict, circle_nms   center_head.py:296-515, det3d/core/utils/circle_nms_jit.py:4-28
 
 Parity: tests/test_centerpoint_cpu.py loads reference-generated weights + outputs
 (tests/golden/centerpoint.npz, made by tests/golden/make_centerpoint_golden.py from the unmodified
-reference classes) and compares forward outputs and losses.
+reference classes) and compares forward outputs, losses, the input gradient and the decoded /
+NMS-filtered detections.
 """
 import copy
 import math
@@ -27,7 +29,7 @@ import torch
 import torch.nn.functional as tF
 from torch import nn
 
-__all__ = ['VoxelFeatureExtractorV3', 'RPN', 'SepHead', 'CenterHead', 'FastFocalLoss', 'RegLoss',
+__all__ = ['VoxelFeatureExtractorV3', 'RPN', 'SepHead', 'CenterHead', 'FastFocalLoss', 'RegLoss', 'circle_nms',
            'VoxelNet', 'NUSC_TASKS', 'NUSC_COMMON_HEADS', 'NUSC_CODE_WEIGHTS', 'build_nusc_centerpoint']
 
 
@@ -186,6 +188,57 @@ class FastFocalLoss(nn.Module):
         return -(pos + neg) / n_pos
 
 
+class _Cfg:
+    """Attribute + `.get` access over a plain dict or a det3d Config (test_cfg is read both ways)."""
+
+    def __init__(self, obj):
+        self._o = obj
+
+    def get(self, key, default=None):
+        o = self._o
+        if isinstance(o, dict):
+            v = o.get(key, default)
+        else:
+            v = getattr(o, key, default)
+        return _Cfg(v) if isinstance(v, dict) else v
+
+    def __getattr__(self, key):
+        v = self.get(key, _Cfg)
+        if v is _Cfg:
+            raise AttributeError(key)
+        return v
+
+
+def circle_nms(centers: torch.Tensor, scores: torch.Tensor, thresh: float, post_max_size: int = 83,
+               block: int = 2048) -> torch.Tensor:
+    """Greedy NMS by squared centre distance (det3d/core/utils/circle_nms_jit.py:4-28: a box is
+    dropped when a kept, higher-scoring box lies within `thresh` in SQUARED distance), on the
+    device without a sequential loop over boxes: with boxes sorted by score, `keep[j] = not
+    any_{i<j}(keep[i] and close[i, j])` has a unique solution; starting from keep = all and
+    re-evaluating the right-hand side reaches it after as many sweeps as the longest suppression
+    chain (each sweep is one masked reduction over the pairwise matrix, built in row blocks).
+    Returns indices into the input, highest score first, at most `post_max_size`."""
+    n = centers.shape[0]
+    if n == 0:
+        return torch.zeros(0, dtype=torch.long, device=centers.device)
+    order = torch.argsort(scores, descending=True)
+    c = centers[order]
+    keep = torch.ones(n, dtype=torch.bool, device=centers.device)
+    rank = torch.arange(n, device=centers.device)
+    for _ in range(n):
+        supp = torch.zeros_like(keep)
+        for r0 in range(0, n, block):
+            d = c[r0:r0 + block, None, :] - c[None, :, :]
+            close = (d[..., 0] ** 2 + d[..., 1] ** 2) <= thresh                  # [rows, n]
+            earlier = rank[r0:r0 + block, None] < rank[None, :]
+            supp |= (close & earlier & keep[r0:r0 + block, None]).any(dim=0)
+        new_keep = ~supp
+        if bool((new_keep == keep).all()):
+            break
+        keep = new_keep
+    return order[keep][:post_max_size]
+
+
 class CenterHead(nn.Module):
     """Shared 3x3 conv + one SepHead per task group (heat map + reg / height / dim / rot / vel)."""
 
@@ -246,6 +299,107 @@ class CenterHead(nn.Module):
                 merged[k].append(v)
         return merged
 
+    @torch.no_grad()
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        """Decode the head outputs into boxes `(x, y, z, w, l, h, [vx, vy], yaw)`, threshold, NMS, merge
+        the task groups (center_head.py:296-515).  `test_cfg.circular_nms=True` uses the on-device
+        `circle_nms`; rotated-IoU NMS (`rotate_nms_pcdet`, the iou3d CUDA op) is not
+        built."""
+        cfg = _Cfg(test_cfg)
+        double_flip = cfg.get('double_flip', False)
+        hm0 = preds_dicts[0]['hm']
+        center_range = cfg.post_center_limit_range
+        if len(center_range) > 0:
+            center_range = torch.tensor(center_range, dtype=hm0.dtype, device=hm0.device)
+        rets, metas = [], []
+        for task_id, preds in enumerate(preds_dicts):
+            p = {k: v.permute(0, 2, 3, 1).contiguous() for k, v in preds.items()}          # N H W C
+            batch = p['hm'].shape[0]
+            if double_flip:
+                # groups of 4: original, y -> -y, x -> -x, both; bring the maps back to the original frame
+                assert batch % 4 == 0, batch
+                batch //= 4
+                for k, v in p.items():
+                    _, h, w, ch = v.shape
+                    v = v.reshape(batch, 4, h, w, ch).clone()
+                    v[:, 1] = torch.flip(v[:, 1], dims=[1])
+                    v[:, 2] = torch.flip(v[:, 2], dims=[2])
+                    v[:, 3] = torch.flip(v[:, 3], dims=[1, 2])
+                    p[k] = v
+            if 'metadata' not in example or len(example['metadata']) == 0:
+                meta = [None] * batch
+            else:
+                meta = example['metadata'][:4 * batch:4] if double_flip else example['metadata']
+            hm, dim = torch.sigmoid(p['hm']), torch.exp(p['dim'])
+            rot_s, rot_c = p['rot'][..., 0:1].clone(), p['rot'][..., 1:2].clone()
+            reg, hei = p['reg'].clone(), p['height']
+            vel = p['vel'].clone() if 'vel' in p else None
+            if double_flip:
+                hm, hei, dim = hm.mean(dim=1), hei.mean(dim=1), dim.mean(dim=1)
+                reg[:, 1, ..., 1] = 1 - reg[:, 1, ..., 1]                 # y -> -y: offset_y -> 1 - offset_y
+                reg[:, 2, ..., 0] = 1 - reg[:, 2, ..., 0]
+                reg[:, 3, ..., 0] = 1 - reg[:, 3, ..., 0]
+                reg[:, 3, ..., 1] = 1 - reg[:, 3, ..., 1]
+                reg = reg.mean(dim=1)
+                rot_c[:, 1] *= -1                                          # theta -> pi - theta
+                rot_s[:, 2] *= -1                                          # theta -> -theta
+                rot_s[:, 3] *= -1
+                rot_c[:, 3] *= -1
+                rot_c, rot_s = rot_c.mean(dim=1), rot_s.mean(dim=1)
+                if vel is not None:
+                    vel[:, 1, ..., 1] *= -1
+                    vel[:, 2, ..., 0] *= -1
+                    vel[:, 3] *= -1
+                    vel = vel.mean(dim=1)
+            rot = torch.atan2(rot_s, rot_c)
+            b, h, w, n_cls = hm.shape
+            ys, xs = torch.meshgrid(torch.arange(h, device=hm.device), torch.arange(w, device=hm.device), indexing='ij')
+            xs = xs.reshape(1, -1, 1).to(hm) + reg.reshape(b, h * w, 2)[:, :, 0:1]
+            ys = ys.reshape(1, -1, 1).to(hm) + reg.reshape(b, h * w, 2)[:, :, 1:2]
+            xs = xs * cfg.out_size_factor * cfg.voxel_size[0] + cfg.pc_range[0]
+            ys = ys * cfg.out_size_factor * cfg.voxel_size[1] + cfg.pc_range[1]
+            parts = [xs, ys, hei.reshape(b, h * w, 1), dim.reshape(b, h * w, 3)]
+            if vel is not None:
+                parts.append(vel.reshape(b, h * w, 2))
+            parts.append(rot.reshape(b, h * w, 1))
+            metas.append(meta)
+            if cfg.get('per_class_nms', False):
+                raise NotImplementedError('per_class_nms')                 # the reference silently skips the task
+            rets.append(self.post_processing(torch.cat(parts, dim=2), hm.reshape(b, h * w, n_cls), cfg,
+                                             center_range, task_id))
+        out = []
+        for i in range(len(rets[0])):
+            ret = {}
+            for k in ('box3d_lidar', 'scores'):
+                ret[k] = torch.cat([r[i][k] for r in rets])
+            first = 0
+            for j, n_cls in enumerate(self.num_classes):                  # task-local labels -> global class ids
+                rets[j][i]['label_preds'] += first
+                first += n_cls
+            ret['label_preds'] = torch.cat([r[i]['label_preds'] for r in rets])
+            ret['metadata'] = metas[0][i]
+            out.append(ret)
+        return out
+
+
+    @torch.no_grad()
+    def post_processing(self, batch_box_preds, batch_hm, test_cfg, post_center_range, task_id):
+        cfg = test_cfg if isinstance(test_cfg, _Cfg) else _Cfg(test_cfg)
+        if not cfg.get('circular_nms', False):
+            raise NotImplementedError('rotated-IoU NMS (rotate_nms_pcdet) is not built: set test_cfg.circular_nms=True')
+        if cfg.get('tt_rotation', 0) != 0:
+            raise NotImplementedError('tt_rotation')
+        results = []
+        for box_preds, hm_preds in zip(batch_box_preds, batch_hm):
+            scores, labels = torch.max(hm_preds, dim=-1)
+            mask = scores > cfg.score_threshold
+            mask &= (box_preds[..., :3] >= post_center_range[:3]).all(1) & (box_preds[..., :3] <= post_center_range[3:]).all(1)
+            box_preds, scores, labels = box_preds[mask], scores[mask], labels[mask]
+            sel = circle_nms(box_preds[:, :2], scores, thresh=cfg.min_radius[task_id],
+                             post_max_size=cfg.nms.nms_post_max_size)
+            results.append({'box3d_lidar': box_preds[sel], 'scores': scores[sel], 'label_preds': labels[sel]})
+        return results
+
 
 class VoxelNet(nn.Module):
     """reader -> sparse backbone -> neck -> head, the single-stage CenterPoint detector of config 4.
@@ -277,7 +431,9 @@ class VoxelNet(nn.Module):
         preds, _ = self.bbox_head(x)
         if return_loss:
             return self.bbox_head.loss(example, preds, self.test_cfg)
-        return preds
+        if self.test_cfg is None:                  # no post-processing configured: the raw head maps
+            return preds
+        return self.bbox_head.predict(example, preds, self.test_cfg)
 
 
 # nuScenes task grouping and head layout of the reference config

@@ -57,14 +57,13 @@ def import_reference():
     for name in ('det3d.core.box_torch_ops', 'det3d.core.bbox.box_np_ops', 'det3d.models.builder',
                  'det3d.utils.dist.dist_common'):
         _pkg(name)
-    nms = _pkg('det3d.core.utils.circle_nms_jit')
-    nms.circle_nms = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError)
     trainer = _pkg('det3d.torchie.trainer')
     trainer.load_checkpoint = lambda *a, **k: None
     reg = _pkg('det3d.models.registry')
     reg.HEADS = reg.NECKS = reg.READERS = _Registry()
     # real sources
     _load('det3d.torchie.cnn', 'torchie/cnn/weight_init.py')
+    _load('det3d.core.utils.circle_nms_jit', 'core/utils/circle_nms_jit.py')      # numba
     _load('det3d.core.utils.center_utils', 'core/utils/center_utils.py')
     misc = _load('det3d.models.utils_misc', 'models/utils/misc.py')
     norm = _load('det3d.models.utils_norm', 'models/utils/norm.py')
@@ -85,6 +84,18 @@ COMMON = {'reg': (2, 2), 'height': (1, 2), 'dim': (3, 2), 'rot': (2, 2), 'vel': 
 CODE_W = [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0]
 RPN_CFG = dict(layer_nums=[2, 1], ds_layer_strides=[1, 2], ds_num_filters=[8, 16], us_layer_strides=[1, 2],
                us_num_filters=[8, 8], num_input_features=12)
+TEST_CFG = dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], circular_nms=True, min_radius=[4, 12],
+                nms=dict(nms_pre_max_size=1000, nms_post_max_size=83, nms_iou_threshold=0.2), score_threshold=0.1,
+                pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])
+
+
+class AttrDict(dict):
+    """Attribute access like det3d's Config (test_cfg.nms.nms_post_max_size, test_cfg.get(...))."""
+    def __getattr__(self, k):
+        v = self[k]
+        return AttrDict(v) if isinstance(v, dict) else v
+
+
 HEAD_CFG = dict(in_channels=16, tasks=TASKS, dataset='nuscenes', weight=0.25, code_weights=CODE_W,
                 common_heads=COMMON, share_conv_channel=8, dcn_head=False)
 
@@ -151,6 +162,24 @@ def main():
             if mode == 'train':                                  # backward check: d(sum of task losses)/d(BEV input)
                 sum(losses['loss']).backward()
                 out['train_grad_bev'] = x_in.grad.numpy()
+    # ---- predict: decode + circle NMS (the reference's numba circle_nms), plain and double-flip ----
+    # (the train-mode pass above updated the BN running statistics: back to the stored weights)
+    neck.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in out.items() if k.startswith('rpn/')})
+    ch.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in out.items() if k.startswith('head/')})
+    neck.eval(); ch.eval()
+    g = torch.Generator().manual_seed(11)
+    bev4 = torch.randn(4, 12, 20, 24, generator=g)
+    out['bev4'] = bev4.numpy()
+    for tag, x_in, cfg in (('plain', bev4, dict(TEST_CFG)), ('flip', bev4, dict(TEST_CFG, double_flip=True))):
+        with torch.no_grad():
+            preds, _ = ch(neck(x_in))
+            dets = ch.predict({}, preds, AttrDict(cfg))
+        out[f'pred_{tag}_n'] = np.array(len(dets))
+        for i, d in enumerate(dets):
+            out[f'pred_{tag}_{i}_boxes'] = d['box3d_lidar'].numpy()
+            out[f'pred_{tag}_{i}_scores'] = d['scores'].numpy()
+            out[f'pred_{tag}_{i}_labels'] = d['label_preds'].numpy()
+        print(tag, [len(d['scores']) for d in dets])
     np.savez_compressed(os.path.join(HERE, 'centerpoint.npz'), **out)
     print(len(out), 'arrays;', 'eval loss', out['eval_loss'], 'train loss', out['train_loss'])
 
