@@ -29,6 +29,8 @@ import torch
 import torch.nn.functional as tF
 from torch import nn
 
+from link_b200.iou3d import rotate_nms_pcdet
+
 __all__ = ['VoxelFeatureExtractorV3', 'RPN', 'SepHead', 'CenterHead', 'FastFocalLoss', 'RegLoss', 'circle_nms',
            'VoxelNet', 'NUSC_TASKS', 'NUSC_COMMON_HEADS', 'NUSC_CODE_WEIGHTS', 'build_nusc_centerpoint']
 
@@ -303,8 +305,7 @@ class CenterHead(nn.Module):
     def predict(self, example, preds_dicts, test_cfg, **kwargs):
         """Decode the head outputs into boxes `(x, y, z, w, l, h, [vx, vy], yaw)`, threshold, NMS, merge
         the task groups (center_head.py:296-515).  `test_cfg.circular_nms=True` uses the on-device
-        `circle_nms`; rotated-IoU NMS (`rotate_nms_pcdet`, the iou3d CUDA op) is not
-        built."""
+        `circle_nms`, otherwise the rotated-IoU NMS of link_b200/iou3d.py (`rotate_nms_pcdet`)."""
         cfg = _Cfg(test_cfg)
         double_flip = cfg.get('double_flip', False)
         hm0 = preds_dicts[0]['hm']
@@ -385,8 +386,6 @@ class CenterHead(nn.Module):
     @torch.no_grad()
     def post_processing(self, batch_box_preds, batch_hm, test_cfg, post_center_range, task_id):
         cfg = test_cfg if isinstance(test_cfg, _Cfg) else _Cfg(test_cfg)
-        if not cfg.get('circular_nms', False):
-            raise NotImplementedError('rotated-IoU NMS (rotate_nms_pcdet) is not built: set test_cfg.circular_nms=True')
         if cfg.get('tt_rotation', 0) != 0:
             raise NotImplementedError('tt_rotation')
         results = []
@@ -395,8 +394,13 @@ class CenterHead(nn.Module):
             mask = scores > cfg.score_threshold
             mask &= (box_preds[..., :3] >= post_center_range[:3]).all(1) & (box_preds[..., :3] <= post_center_range[3:]).all(1)
             box_preds, scores, labels = box_preds[mask], scores[mask], labels[mask]
-            sel = circle_nms(box_preds[:, :2], scores, thresh=cfg.min_radius[task_id],
-                             post_max_size=cfg.nms.nms_post_max_size)
+            if cfg.get('circular_nms', False):
+                sel = circle_nms(box_preds[:, :2], scores, thresh=cfg.min_radius[task_id],
+                                 post_max_size=cfg.nms.nms_post_max_size)
+            else:
+                sel = rotate_nms_pcdet(box_preds[:, [0, 1, 2, 3, 4, 5, -1]].float(), scores.float(),
+                                       thresh=cfg.nms.nms_iou_threshold, pre_maxsize=cfg.nms.nms_pre_max_size,
+                                       post_max_size=cfg.nms.nms_post_max_size)
             results.append({'box3d_lidar': box_preds[sel], 'scores': scores[sel], 'label_preds': labels[sel]})
         return results
 

@@ -139,3 +139,44 @@ if __name__ == '__main__':
     print(build(force='--force' in sys.argv))
     if '--cuda' in sys.argv:
         print(build_cuda(force='--force' in sys.argv))
+
+
+IOU3D_SRC = '/root/reference/detection/det3d/ops/iou3d_nms/src/iou3d_cpu.cpp'
+OUT_IOU3D = os.path.join(HERE, '_ref', 'iou3d_cpu_ref.so')
+
+
+def build_iou3d(force: bool = False) -> str:
+    """The reference's own CPU rotated-BEV-IoU (det3d/ops/iou3d_nms/src/iou3d_cpu.cpp, the CPU twin
+    of the iou3d_nms CUDA kernels), compiled in place with g++ plus oracle/bind/iou3d_bind.cpp (our
+    pybind stub: the reference's own binding file also binds the CUDA entry points).  The source
+    marks its Point methods `__device__` although it is a .cpp: that macro is defined away."""
+    if not os.path.exists(IOU3D_SRC):
+        return OUT_IOU3D if os.path.exists(OUT_IOU3D) else ''
+    if not force and os.path.exists(OUT_IOU3D):
+        return OUT_IOU3D
+    import torch
+    from torch.utils.cpp_extension import include_paths
+    os.makedirs(os.path.dirname(OUT_IOU3D), exist_ok=True)
+    tlib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+    cmd = ['g++', '-O2', '-g0', '-shared', '-fPIC', '-std=c++17', '-w', '-D__device__=',
+           '-DTORCH_EXTENSION_NAME=iou3d_cpu_ref', '-DTORCH_API_INCLUDE_EXTENSION_H',
+           f'-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}',
+           '-I' + sysconfig.get_paths()['include'], '-I/usr/local/cuda/include']
+    cmd += ['-I' + p for p in include_paths()]
+    cmd += [IOU3D_SRC, os.path.join(HERE, 'bind', 'iou3d_bind.cpp'), '-L' + tlib, '-ltorch', '-ltorch_cpu', '-lc10',
+            '-ltorch_python', '-Wl,-rpath,' + tlib, '-o', OUT_IOU3D]
+    print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return OUT_IOU3D
+
+
+def load_iou3d():
+    import importlib.util
+    path = build_iou3d()
+    if not path:
+        return None
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    spec = importlib.util.spec_from_file_location('iou3d_cpu_ref', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
