@@ -52,3 +52,66 @@ def test_two_rank_sharding_and_reduction():
 def test_single_process_is_identity():
     assert reduce_throughput(3.5, 7.0) == (3.5, 7.0)
     assert shard_frames(5, 0, 1) == [0, 1, 2, 3, 4]
+
+
+def _ddp_worker(rank, world, port, out):
+    """Training-side N>1 plumbing: frames shard over ranks, the ONLY collective is DDP's
+    gradient all-reduce.  The dense CenterPoint head runs on CPU, so gloo can exercise it here."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from link_b200.centerpoint import RPN, CenterHead
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)                                     # same initial weights on every rank
+    tasks = [dict(num_class=1, class_names=['car'])]
+    net = torch.nn.Sequential(
+        RPN(layer_nums=[1], ds_layer_strides=[1], ds_num_filters=[8], us_layer_strides=[1], us_num_filters=[8],
+            num_input_features=4))
+    head = CenterHead(in_channels=8, tasks=tasks, code_weights=[1.0] * 8, common_heads={'reg': (2, 2), 'height': (1, 2),
+                      'dim': (3, 2), 'rot': (2, 2)}, share_conv_channel=8)
+
+    class Both(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net, self.head = net, head
+
+        def forward(self, x):
+            return self.head(self.net(x))[0]
+
+    def loss_of(model, frame):
+        g = torch.Generator().manual_seed(frame_seed(0, frame))
+        x = torch.randn(1, 4, 8, 8, generator=g)
+        ex = {'hm': [torch.rand(1, 1, 8, 8, generator=g) ** 4], 'ind': [torch.randint(0, 64, (1, 5), generator=g)],
+              'mask': [torch.ones(1, 5, dtype=torch.uint8)], 'cat': [torch.zeros(1, 5, dtype=torch.long)],
+              'anno_box': [torch.randn(1, 5, 10, generator=g)]}
+        return sum(head.loss(ex, model(x), None)['loss'])
+
+    both = Both()
+    ddp = DDP(both)
+    frames = shard_frames(2, rank, world)                    # one frame per rank
+    loss_of(ddp, frames[0]).backward()
+    grads = torch.cat([p.grad.flatten() for p in both.parameters()])
+    # single-process reference: mean of the two frames' gradients from the same initial weights
+    torch.manual_seed(0)
+    ref = Both()
+    ref.load_state_dict(both.state_dict())
+    ref.zero_grad()
+    ((loss_of(ref, 0) + loss_of(ref, 1)) / 2).backward()
+    want = torch.cat([p.grad.flatten() for p in ref.parameters()])
+    if rank == 0:
+        out.put((float((grads - want).abs().max()), float(want.abs().max())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_ddp_gradients_equal_mean_over_frames():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, scale = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert scale > 0 and err <= 1e-5 * max(1.0, scale)
