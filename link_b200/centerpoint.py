@@ -32,7 +32,8 @@ from torch import nn
 from link_b200.iou3d import rotate_nms_pcdet
 
 __all__ = ['VoxelFeatureExtractorV3', 'RPN', 'SepHead', 'CenterHead', 'FastFocalLoss', 'RegLoss', 'circle_nms',
-           'VoxelNet', 'NUSC_TASKS', 'NUSC_COMMON_HEADS', 'NUSC_CODE_WEIGHTS', 'build_nusc_centerpoint']
+           'VoxelNet', 'NUSC_TASKS', 'NUSC_COMMON_HEADS', 'NUSC_CODE_WEIGHTS', 'NUSC_TEST_CFG',
+           'build_nusc_centerpoint']
 
 
 class VoxelFeatureExtractorV3(nn.Module):
@@ -452,10 +453,17 @@ NUSC_TASKS: List[Dict] = [
 ]
 NUSC_COMMON_HEADS: Dict[str, Tuple[int, int]] = {'reg': (2, 2), 'height': (1, 2), 'dim': (3, 2), 'rot': (2, 2), 'vel': (2, 2)}
 NUSC_CODE_WEIGHTS: Sequence[float] = (1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2, 1.0, 1.0)
+# test_cfg of the same config (lines 68-82); out_size_factor = get_downsample_factor(model) = 8
+NUSC_TEST_CFG: Dict = dict(
+    post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], max_per_img=500,
+    nms=dict(use_rotate_nms=True, use_multi_class_nms=False, nms_pre_max_size=1000, nms_post_max_size=83,
+             nms_iou_threshold=0.2),
+    score_threshold=0.1, pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])
 
 
-def build_nusc_centerpoint(backbone=None) -> VoxelNet:
-    """The model dict of the reference config as modules (random init)."""
+def build_nusc_centerpoint(backbone=None, test_cfg=None) -> VoxelNet:
+    """The model dict of the reference config as modules (random init).  Pass `test_cfg=NUSC_TEST_CFG`
+    to get decoded, NMS-filtered detections from `forward(example, return_loss=False)`."""
     if backbone is None:
         from link_b200.scn import SpMiddleResNetFHDELKv3
         backbone = SpMiddleResNetFHDELKv3(num_input_features=5, ds_factor=8)
@@ -466,4 +474,5 @@ def build_nusc_centerpoint(backbone=None) -> VoxelNet:
                  us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256),
         bbox_head=CenterHead(in_channels=512, tasks=NUSC_TASKS, dataset='nuscenes', weight=0.25,
                              code_weights=list(NUSC_CODE_WEIGHTS), common_heads=dict(NUSC_COMMON_HEADS),
-                             share_conv_channel=64, dcn_head=False))
+                             share_conv_channel=64, dcn_head=False),
+        test_cfg=test_cfg)

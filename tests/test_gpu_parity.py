@@ -763,37 +763,6 @@ def test_centerpoint_detector_training_step(dev):
     assert len(preds) == len(NUSC_TASKS) and preds[0]['hm'].shape == (B, 1, H // 8, W // 8)
 
 
-def test_rotated_iou_and_predict_on_device(dev):
-    """SURVEY §8f row 4 on the GPU: rotated BEV IoU against the reference-generated fixture, rotated NMS
-    (selection may differ from the CPU-generated one only through IoUs within float noise of the
-    threshold), and CenterHead.predict end to end with both NMS flavours on device tensors."""
-    import os
-    from link_b200.centerpoint import CenterHead, NUSC_COMMON_HEADS, NUSC_TASKS, NUSC_CODE_WEIGHTS
-    from link_b200.iou3d import boxes_iou_bev, rotate_nms_pcdet
-    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'iou3d.npz')))
-    iou = boxes_iou_bev(cu(g['a'], dev), cu(g['b'], dev))
-    np.testing.assert_allclose(iou.cpu().numpy(), g['iou'], rtol=1e-3, atol=1e-4)
-    sel = rotate_nms_pcdet(cu(g['nms_boxes'], dev), cu(g['nms_scores'], dev), 0.2, pre_maxsize=300, post_max_size=83)
-    want = set(g['nms_t02'].tolist())
-    assert sel.device.type == 'cuda' and len(set(sel.tolist()) & want) >= 0.95 * len(want)
-    torch.manual_seed(0)
-    head = CenterHead(in_channels=32, tasks=NUSC_TASKS, code_weights=list(NUSC_CODE_WEIGHTS),
-                      common_heads=dict(NUSC_COMMON_HEADS), share_conv_channel=16).to(dev).eval()
-    cfg = dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], min_radius=[4, 12, 10, 1, 0.85, 0.175],
-               nms=dict(nms_pre_max_size=1000, nms_post_max_size=83, nms_iou_threshold=0.2), score_threshold=0.1,
-               pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])
-    with torch.no_grad():
-        preds, _ = head(torch.randn(2, 32, 24, 24, device=dev))
-        for circular in (True, False):
-            dets = head.predict({}, [dict(p) for p in preds], dict(cfg, circular_nms=circular))
-            assert len(dets) == 2
-            for d in dets:
-                assert d['box3d_lidar'].device.type == 'cuda' and d['box3d_lidar'].shape[1] == 9
-                assert d['scores'].shape == d['label_preds'].shape and len(d['scores']) <= 83 * len(NUSC_TASKS)
-                assert torch.isfinite(d['box3d_lidar']).all()
-                assert len(d['label_preds']) == 0 or 0 <= int(d['label_preds'].min()) <= int(d['label_preds'].max()) <= 9
-
-
 def test_encoder_training_step(dev):
     """fwd + bwd + SGD through ELKEncoder in training mode (BatchNorm batch statistics, composed
     LinK blocks, sparse-conv backward kernels): finite gradients on every parameter the forward
@@ -1021,3 +990,35 @@ def test_points_to_voxel_bit_exact(dev):
     assert v.shape[0] == 0 and c.shape[0] == 0 and n.shape[0] == 0
     v, c, n = points_to_voxel(torch.zeros(0, 5, device=dev), [0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3], 10, True, 100)
     assert v.shape[0] == 0
+
+
+# ------------------------------------------------------------------ SURVEY 8f row 4 (last: first GPU run pending)
+def test_rotated_iou_and_predict_on_device(dev):
+    """SURVEY §8f row 4 on the GPU: rotated BEV IoU against the reference-generated fixture, rotated NMS
+    (selection may differ from the CPU-generated one only through IoUs within float noise of the
+    threshold), and CenterHead.predict end to end with both NMS flavours on device tensors."""
+    import os
+    from link_b200.centerpoint import CenterHead, NUSC_COMMON_HEADS, NUSC_TASKS, NUSC_CODE_WEIGHTS
+    from link_b200.iou3d import boxes_iou_bev, rotate_nms_pcdet
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'iou3d.npz')))
+    iou = boxes_iou_bev(cu(g['a'], dev), cu(g['b'], dev))
+    np.testing.assert_allclose(iou.cpu().numpy(), g['iou'], rtol=1e-3, atol=1e-4)
+    sel = rotate_nms_pcdet(cu(g['nms_boxes'], dev), cu(g['nms_scores'], dev), 0.2, pre_maxsize=300, post_max_size=83)
+    want = set(g['nms_t02'].tolist())
+    assert sel.device.type == 'cuda' and len(set(sel.tolist()) & want) >= 0.95 * len(want)
+    torch.manual_seed(0)
+    head = CenterHead(in_channels=32, tasks=NUSC_TASKS, code_weights=list(NUSC_CODE_WEIGHTS),
+                      common_heads=dict(NUSC_COMMON_HEADS), share_conv_channel=16).to(dev).eval()
+    cfg = dict(post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], min_radius=[4, 12, 10, 1, 0.85, 0.175],
+               nms=dict(nms_pre_max_size=1000, nms_post_max_size=83, nms_iou_threshold=0.2), score_threshold=0.1,
+               pc_range=[-54, -54], out_size_factor=8, voxel_size=[0.075, 0.075])
+    with torch.no_grad():
+        preds, _ = head(torch.randn(2, 32, 24, 24, device=dev))
+        for circular in (True, False):
+            dets = head.predict({}, [dict(p) for p in preds], dict(cfg, circular_nms=circular))
+            assert len(dets) == 2
+            for d in dets:
+                assert d['box3d_lidar'].device.type == 'cuda' and d['box3d_lidar'].shape[1] == 9
+                assert d['scores'].shape == d['label_preds'].shape and len(d['scores']) <= 83 * len(NUSC_TASKS)
+                assert torch.isfinite(d['box3d_lidar']).all()
+                assert len(d['label_preds']) == 0 or 0 <= int(d['label_preds'].min()) <= int(d['label_preds'].max()) <= 9
