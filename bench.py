@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--voxels', type=int, default=120_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-encoder', action='store_true', help='skip the extra encoder measurement')
+    ap.add_argument('--e2e-ring', action='store_true', help='e2e loop through tensor.UploadRing (staging ring), one event pair around the loop')
     return ap.parse_args()
 
 
@@ -299,6 +300,24 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
             d2h = out_host.numel() * 4
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    e2e_ring = None
+    if getattr(args, 'e2e_ring', False):
+        # same calls through a caller-owned staging ring, issued back to back, ONE event pair around
+        # the loop: the upload of scan i+1 overlaps the processing of scan i
+        from link_b200.tensor import UploadRing
+        ring = UploadRing(max(n_vox), feats_host[0].shape[1], device=dev, depth=2)
+        for k in range(w_e2e):
+            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1)).sum(dim=0), non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t_h = time.perf_counter()
+        for k in range(steps):
+            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1)).sum(dim=0), non_blocking=True)
+        host_ms = (time.perf_counter() - t_h) * 1e3 / steps
+        e1.record()
+        barrier()
+        e2e_ring = {'ms_per_step': e0.elapsed_time(e1) / steps, 'host_enqueue_ms_per_step': host_ms}
     # clocks / throttle reasons sampled under load over all timed loops of this workload (device-resident,
     # instrumented, roofline and end-to-end passes): the device-resident loop alone lasts a few ms
     clocks = sampler.finish(t_wall0, time.time()) if with_clocks else None
@@ -309,7 +328,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         ref_gpu = reference_gpu_leg(dev, coords_dev[0], feats_dev[0], model, flush)
     return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
             'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,
-            'roof': roof, 'ref_gpu': ref_gpu,
+            'roof': roof, 'ref_gpu': ref_gpu, 'e2e_ring': e2e_ring,
             'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
 
 
@@ -481,6 +500,7 @@ def main_ours(args):
                 'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps},
         'gpu_launches': m['launches'],
         'host_enqueue_ms_per_step': m['host_enqueue_ms'],
+        'e2e_ring': m.get('e2e_ring'),
         'roofline': roof,
         'kernels': kern,
     }

@@ -395,6 +395,17 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);
+/* ------------------------------------------------------------------------------------
+ * Rotated bird's-eye-view IoU of 3D boxes (x, y, z, dx, dy, dz, heading): d_out [n, m] =
+ * IoU(d_a[i], d_b[j]).  Replaces iou3d_nms_cuda.boxes_iou_bev_gpu / the IoU inside nms_gpu
+ * (detection/det3d/ops/iou3d_nms/src/iou3d_nms_kernel.cu:236-414, iou3d_nms_api.cpp:11-16).
+ * lk_boxes_iou_bev_hostcheck evaluates the SAME __host__ __device__ arithmetic on host arrays: a
+ * test hook that pins the kernel's arithmetic to the reference's iou3d_cpu.cpp fixture without a
+ * GPU -- not a fallback.
+ * ---------------------------------------------------------------------------------- */
+int lk_boxes_iou_bev(const float* d_a, int64_t n, const float* d_b, int64_t m, float* d_out,
+                     lk_stream_t s);
+int lk_boxes_iou_bev_hostcheck(const float* a, int64_t n, const float* b, int64_t m, float* out);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,8 @@ PROTOTYPES = {
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
+    'lk_boxes_iou_bev': (i32, [vp, i64, vp, i64, vp, vp]),
+    'lk_boxes_iou_bev_hostcheck': (i32, [vp, i64, vp, i64, vp]),
 }
 
 

@@ -105,6 +105,12 @@ def boxes_iou_bev(boxes_a: torch.Tensor, boxes_b: torch.Tensor, block: int = 256
     out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=a.device)
     if a.shape[0] == 0 or b.shape[0] == 0:
         return out
+    if a.is_cuda:                                   # fused kernel: one thread per pair (csrc/iou3d.cu)
+        from link_b200 import _capi
+        a, b = a.contiguous(), b.contiguous()
+        _capi.check(_capi.lib().lk_boxes_iou_bev(_capi.ptr(a), a.shape[0], _capi.ptr(b), b.shape[0], _capi.ptr(out),
+                                                 _capi.stream()), 'lk_boxes_iou_bev')
+        return out
     area_b = (b[:, 3] * b[:, 4])[None, :]
     for r0 in range(0, a.shape[0], block):
         blk = a[r0:r0 + block]

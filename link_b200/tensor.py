@@ -11,7 +11,7 @@ import torch
 
 from link_b200.utils import make_ntuple
 
-__all__ = ['SparseTensor', 'PointTensor']
+__all__ = ['SparseTensor', 'PointTensor', 'UploadRing']
 
 _COPY_STREAMS: Dict[Any, Any] = {}
 
@@ -154,3 +154,52 @@ class PointTensor:
         tensor = PointTensor(self.F + other.F, self.C, self.idx_query, self.weights)
         tensor.additional_features = self.additional_features
         return tensor
+
+
+class UploadRing:
+    """Caller-owned staging ring for a stream of scans arriving from pinned host memory: the feature
+    upload of scan i+1 crosses PCIe while scan i is still being processed, without going through
+    the caching allocator (a `record_stream`-managed buffer is never ready for reuse while the host
+    runs ahead of the device, so every upload would pay a `cudaMalloc`).
+
+    `depth` device buffers of `capacity` rows are reused round-robin.  Contract: everything that
+    consumes the SparseTensor returned by `upload()` must be ENQUEUED on the current stream before
+    the next `upload()` call, and the returned tensors alias ring memory that is overwritten
+    `depth` uploads later (clone what must live longer).  Ordering is by events only: upload i
+    waits (on the copy stream) for the compute-stream event recorded at the start of upload
+    i - depth + 1, which is after the consumers of upload i - depth were enqueued."""
+
+    def __init__(self, capacity: int, channels: int, device=None, depth: int = 2, dtype=torch.float32):
+        assert depth >= 2 and capacity > 0 and channels > 0
+        self.device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+        self.depth = depth
+        self._feats = [torch.empty(capacity, channels, dtype=dtype, device=self.device) for _ in range(depth)]
+        self._coords = [torch.empty(capacity, 4, dtype=torch.int32, device=self.device) for _ in range(depth)]
+        self._issued = []                # compute-stream events, one per upload() call (last `depth` kept)
+        self._count = 0
+
+    def upload(self, feats: torch.Tensor, coords: torch.Tensor, stride: Union[int, Tuple[int, ...]] = 1) -> 'SparseTensor':
+        n = feats.shape[0]
+        assert n <= self._feats[0].shape[0] and coords.shape[0] == n, 'scan larger than the ring capacity'
+        main = torch.cuda.current_stream(self.device)
+        copy_stream = _copy_stream(self.device)
+        slot = self._count % self.depth
+        mark = torch.cuda.Event()
+        mark.record(main)                # everything enqueued so far (consumers of earlier uploads) precedes it
+        self._issued.append(mark)
+        if len(self._issued) > self.depth:
+            self._issued.pop(0)
+        if self._count >= self.depth:
+            # the slot was last used by upload count - depth; its consumers were enqueued before upload
+            # count - depth + 1 started, i.e. before the oldest event still held
+            copy_stream.wait_event(self._issued[0])
+        f_dev, c_dev = self._feats[slot][:n], self._coords[slot][:n]
+        c_dev.copy_(coords, non_blocking=True)                   # small: on the compute stream, needed first
+        with torch.cuda.stream(copy_stream):
+            f_dev.copy_(feats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        self._count += 1
+        st = SparseTensor(f_dev, c_dev, stride)
+        st._feats_ready = ev
+        return st

@@ -872,6 +872,34 @@ def test_from_host_back_to_back_uploads_do_not_race(dev):
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-3)
 
 
+def test_upload_ring_back_to_back(dev):
+    """UploadRing: twelve scans of different sizes and features streamed through a depth-2 ring with
+    no host synchronisation; every result equals the resident-input result of its own scan."""
+    from link_b200 import SparseTensor
+    from link_b200.tensor import UploadRing
+    from link_b200.elk import ELKBlock
+    from link_b200.utils.synthetic import kitti_like_voxels
+    scans = []
+    g = torch.Generator().manual_seed(3)
+    for seed, nv in ((7, 30_000), (8, 22_000), (9, 27_000)):
+        c3, _ = kitti_like_voxels(nv, seed=seed)
+        coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+        scans.append((torch.from_numpy(coords).pin_memory(), torch.randn(len(coords), 64, generator=g).pin_memory()))
+    torch.manual_seed(1)
+    blk = ELKBlock(64, 64, groups=2, baseop='cos').to(dev).eval()
+    ring = UploadRing(max(len(c) for c, _ in scans), 64, device=dev, depth=2)
+    with torch.no_grad():
+        wants = [blk(SparseTensor(f.to(dev), c.to(dev), 1), 7, 3).F.sum(dim=0) for c, f in scans]
+        torch.cuda.synchronize()
+        gots = []
+        for k in range(12):
+            c, f = scans[k % 3]
+            gots.append(blk(ring.upload(f, c, 1), 7, 3).F.sum(dim=0))
+        torch.cuda.synchronize()
+    for k, got in enumerate(gots):
+        np.testing.assert_allclose(got.cpu().numpy(), wants[k % 3].cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
 def test_fused_index_entry_points_match_their_parts(dev):
     """lk_sort_unique_coords == lk_pack_keys + lk_sort_unique_ex, lk_table_build_coords == lk_hash +
     lk_table_build, lk_block_neighbors_zero / lk_link_window_mean_seg == their unfused forms."""

@@ -55,3 +55,16 @@ def test_nms_fixed_point_equals_sequential_greedy():
     chain[torch.arange(63), torch.arange(1, 64)] = True            # i suppresses i+1: the longest possible chain
     assert nms_fixed_point(chain).tolist() == [i % 2 == 0 for i in range(64)]
     assert rotate_nms(torch.zeros(0, 7), torch.zeros(0), 0.5).numel() == 0
+
+
+def test_kernel_arithmetic_on_host_matches_reference(gold):
+    """csrc/iou3d.cu evaluates pairs with a __host__ __device__ function; the host instantiation
+    (lk_boxes_iou_bev_hostcheck, a test hook) is held to the reference fixture here, the device
+    instantiation in the GPU suite."""
+    from link_b200 import _capi
+    a = np.ascontiguousarray(gold['a'], np.float32)
+    b = np.ascontiguousarray(gold['b'], np.float32)
+    out = np.zeros((len(a), len(b)), np.float32)
+    _capi.check(_capi.lib().lk_boxes_iou_bev_hostcheck(a.ctypes.data, len(a), b.ctypes.data, len(b), out.ctypes.data), 'hostcheck')
+    np.testing.assert_allclose(out, gold['iou'], rtol=1e-5, atol=2e-6)
+    assert np.array_equal(out > 0, gold['iou'] > 0)
