@@ -88,9 +88,11 @@ def test_block_120k_cos_3x7_vs_reference_cuda_and_oracle(dev):
     order u, i.e. an error of order u * |F| per term in cos(p_i - p_j).  The window mean averages those
     errors, the LayerNorm re-scales the mean to unit variance, so the per-element output error is of
     order u with a tail of a few u on rows whose pre-norm variance is small (measured here for the
-    fp32 oracle against float64: max 2.3 u, p99.9 0.7 u).  Stated bound: |ours - other| <= 8 u
-    elementwise, 99.9 % of the elements <= 3 u; and our error against float64 is held to at most 2x
-    the reference CUDA arm's own error against float64 (p99.9 and max)."""
+    fp32 oracle against float64: max 2.3 u, p99.9 0.7 u).  Two fp32 implementations that evaluate
+    the SAME fp32 phase differ far less (measured on B200, profiles/r02_parity_histograms.txt:
+    ours - reference CUDA max 2.2e-5 = 0.09 u, p99.9 9e-6).  Stated bound: |ours - other| <= 0.5 u
+    elementwise, 99.9 % of the elements <= 0.1 u; and our error against float64 is held to at most
+    1.25x the reference CUDA arm's own error against float64 (p99.9 and max)."""
     from link_b200 import SparseTensor
     from link_b200.elk import ELKBlock
     from link_b200.utils.synthetic import kitti_like_voxels
@@ -113,7 +115,7 @@ def test_block_120k_cos_3x7_vs_reference_cuda_and_oracle(dev):
     e_ours = _hist('ours - float64      ', ours - exact)
     e_orc = _hist('oracle(fp32) - f64  ', want - exact)
     d_orc = _hist('ours - oracle(fp32) ', ours - want)
-    assert d_orc.max() <= 8 * u and np.quantile(d_orc, 0.999) <= 3 * u
+    assert d_orc.max() <= 0.5 * u and np.quantile(d_orc, 0.999) <= 0.1 * u
     if ref_gpu.available():
         with torch.no_grad():
             ref = ref_gpu.elk_block_forward(feats.to(dev), cu(coords, dev), 1,
@@ -121,9 +123,9 @@ def test_block_120k_cos_3x7_vs_reference_cuda_and_oracle(dev):
                                             s, r, 'cos', groups).cpu().numpy()
         e_ref = _hist('reference CUDA - f64', ref - exact)
         d_ref = _hist('ours - reference CUDA', ours - ref)
-        assert d_ref.max() <= 8 * u and np.quantile(d_ref, 0.999) <= 3 * u
-        assert np.quantile(e_ours, 0.999) <= 2 * np.quantile(e_ref, 0.999) + 1e-5
-        assert e_ours.max() <= 2 * e_ref.max() + 1e-5
+        assert d_ref.max() <= 0.5 * u and np.quantile(d_ref, 0.999) <= 0.1 * u
+        assert np.quantile(e_ours, 0.999) <= 1.25 * np.quantile(e_ref, 0.999) + 1e-5
+        assert e_ours.max() <= 1.25 * e_ref.max() + 1e-5
     else:
         assert np.quantile(e_ours, 0.999) <= 2 * np.quantile(e_orc, 0.999) + 1e-5
 
