@@ -225,6 +225,44 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
                       const float* d_g1, const float* d_b1, const float* d_g2,
                       const float* d_b2, float* d_out, lk_stream_t s);
 
+/* Passes 2a + 2b as ONE block-centric kernel (C in {16, 32, 64, 128}; lk_link_window_apply_supported):
+ * one warp per block reduces the window row (the r^3 neighbour block sums / populations, read from
+ * L2) and applies it to the block's voxels, which are contiguous in the sorted sequence
+ * (d_seg [M+1] segment starts, d_order [n] voxel row per sorted position; both from
+ * lk_sort_unique_ex).  Replaces lk_link_window_mean + lk_link_apply_fwd (aux_to_voxel,
+ * utils.py:61-84 + linkencoder.py:162,178-181): no [M,kC] mean round trip, one launch less.
+ * d_mean_out [cap, k*C] / d_tot_out [cap] (optional, may be NULL): the window means and window
+ * populations, kept for the backward pass. */
+int lk_link_window_apply_supported(int c);
+int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
+                             const int32_t* d_order, const int32_t* d_num, int64_t capacity, int r3,
+                             const float* d_fin /*cos_x only, else NULL*/, const int32_t* d_coords,
+                             const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
+                             const float* d_g1, const float* d_b1, const float* d_g2,
+                             const float* d_b2, float* d_out, float* d_mean_out, float* d_tot_out,
+                             lk_stream_t s);
+/* Hand-written backward of the linear-kernel path with the fused norms (ops cos / sin, C in
+ * {16, 32, 64, 128}); replaces autograd through devoxelize_backward (devoxelize_cuda.cu:38-59, float
+ * atomics), the [N,kC] index/cat temporaries and voxelize_backward (voxelize_cuda.cu:28-42):
+ *   lk_link_bwd_norm : recomputes the pre-norm value from the saved window means, both LayerNorms
+ *     and the ReLU mask per voxel; writes d_dy [n,C] (gradient of the pre-norm value), d_dlocal
+ *     [n,C] (gradient of local_mix.F), d_gsum [cap, 2C] = (block sums of the weighted d_dy) / T, and
+ *     ADDS (dgamma1, dbeta1, dgamma2, dbeta2) into d_dparam [4,C] (caller zeroes it);
+ *   lk_link_bwd_apply: sums d_gsum over the TRANSPOSED neighbourhood (d_nbr_t: the neighbour table
+ *     of the negated offsets; equal to d_nbr for odd r), writes d_dfin [n,C] (gradient of F_input)
+ *     and ADDS the gradient of pos_weight into d_dw [wrows,3] (caller zeroes it).
+ * One warp owns a block, so the block sums need no atomics and are deterministic. */
+int lk_link_bwd_norm(const float* d_mean, const float* d_tot, const int32_t* d_seg,
+                     const int32_t* d_order, const int32_t* d_num, int64_t capacity,
+                     const int32_t* d_coords, const lk_kernelgen_t* gen, const float* d_local,
+                     const float* d_dout, const float* d_g1, const float* d_b1, const float* d_g2,
+                     const float* d_b2, float* d_dy, float* d_dlocal, float* d_gsum, float* d_dparam,
+                     lk_stream_t s);
+int lk_link_bwd_apply(const float* d_gsum, const float* d_mean, const int32_t* d_nbr_t,
+                      const int32_t* d_seg, const int32_t* d_order, const int32_t* d_num,
+                      int64_t capacity, int r3, const int32_t* d_coords, const lk_kernelgen_t* gen,
+                      const float* d_fin, const float* d_dy, float* d_dfin, float* d_dw, lk_stream_t s);
+
 /* ------------------------------------------------------------------------------------
  * Native executor: one call enqueues the whole fused ELKBlock forward
  * (linkencoder.py:124-185): [hash -> table -> kernel map] -> pre_mix (Linear+LN) -> local_mix

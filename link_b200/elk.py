@@ -38,6 +38,11 @@ NATIVE_EXECUTOR = os.environ.get('LINKB200_NATIVE_EXECUTOR', '1') != '0'
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 # 1: keep the whole block on the caller's stream (default 0: two-chain schedule inside the executor)
 SINGLE_STREAM = os.environ.get('LINKB200_SINGLE_STREAM', '0') == '1'
+# 1 (default): window mean + apply as one block-centric kernel; 0: the two-kernel form
+USE_WINDOW_APPLY = os.environ.get('LINKB200_WINDOW_APPLY', '1') != '0'
+# 1 (default): training runs the fused forward + hand-written backward (cos / sin, C in {16,32,64,128});
+# 0: the reference's op sequence on differentiable voxelize / devoxelize kernels
+FUSED_BACKWARD = os.environ.get('LINKB200_FUSED_BACKWARD', '1') != '0'
 
 
 class BlockIndex:
@@ -90,6 +95,24 @@ class BlockIndex:
                 _capi.ptr(self.unique_keys), _capi.ptr(self.num), self.n, C.byref(self.spec),
                 _capi.ptr(offsets), R, _capi.ptr(nbr), _capi.stream()), 'lk_block_neighbors')
             self._nbr[r] = nbr
+        return nbr
+
+
+    def neighbors_t(self, r: int) -> torch.Tensor:
+        """Neighbour table of the TRANSPOSED relation {b : b' in N(b)} (used by the backward pass):
+        the table of the negated offsets; for odd r the offset set is symmetric and this is
+        `neighbors(r)` itself (up to the column order, which the window sum does not depend on)."""
+        if r % 2 == 1:
+            return self.neighbors(r)
+        nbr = self._nbr.get(-r)
+        if nbr is None:
+            offsets = (-get_kernel_offsets(r, 1, 1, device=self.unique_keys.device)).contiguous()
+            R = offsets.shape[0]
+            nbr = torch.empty(self.n, R, dtype=torch.int32, device=self.unique_keys.device)
+            _capi.check(_capi.lib().lk_block_neighbors(
+                _capi.ptr(self.unique_keys), _capi.ptr(self.num), self.n, C.byref(self.spec),
+                _capi.ptr(offsets), R, _capi.ptr(nbr), _capi.stream()), 'lk_block_neighbors')
+            self._nbr[-r] = nbr
         return nbr
 
 
@@ -209,12 +232,15 @@ def _kernel_gen(op: str, c: int, pos_weight: torch.Tensor, alpha: Optional[torch
 def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, r: int, op: str,
                    pos_weight: torch.Tensor, alpha: Optional[torch.Tensor] = None,
                    coord_scale: float = 1.0, local: Optional[torch.Tensor] = None,
-                   norm: Optional[Tuple[torch.Tensor, ...]] = None) -> torch.Tensor:
+                   norm: Optional[Tuple[torch.Tensor, ...]] = None,
+                   save: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """Fused kernel generator + block pre-aggregation + outer-block reuse + combine.
 
     f_input [N,C] fp32 (output of pre_mix), coords int32 [N,4].  Returns the pre-LayerNorm value
     of linkencoder.py:162/148/176, or, when `local` [N,C] and `norm` = (g1, b1, g2, b2) are
-    given, relu(LN(value) + LN(local)) of linkencoder.py:178-181.  Forward only."""
+    given, relu(LN(value) + LN(local)) of linkencoder.py:178-181.  Forward only (the differentiable
+    form is `LinkAggregateFunction`); `save` = (mean [n,kC], tot [n]) buffers that receive the window
+    means / populations the backward pass needs."""
     n, c = f_input.shape
     f_input = f_input.contiguous()
     coords = coords.contiguous()
@@ -225,7 +251,6 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
     L, st = _capi.lib(), _capi.stream()
     dev = f_input.device
     sums = torch.empty(n, k * c, dtype=torch.float32, device=dev)
-    mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
     out = torch.empty(n, c, dtype=torch.float32, device=dev)
     nbr = bi.neighbors(r)
     m_hint = bi._m if bi._m is not None else 0      # only for the byte accounting of bench.py
@@ -237,17 +262,29 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
                                              _capi.ptr(coords, torch.int32), _capi.ptr(bi.order),
                                              _capi.ptr(bi.sorted_rank), n, C.byref(gen),
                                              _capi.ptr(sums), st), 'lk_link_preagg_seg_fwd')
-    with _capi.timed('lk_link_window_mean', m_hint * (2 * 4 * k * c + 4 * nbr.shape[1] + 4)):
-        _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
-                                          _capi.ptr(bi.num), n, nbr.shape[1], k * c,
-                                          _capi.ptr(mean), st), 'lk_link_window_mean')
     fuse = 1 if (local is not None and norm is not None) else 0
     g1 = b1 = g2 = b2 = None
     if fuse:
         local = local.contiguous()
         g1, b1, g2, b2 = (t.detach().contiguous().float() for t in norm)
-    # read coords + block index (+ local, + F_in for cos_x) once, the M mean rows, write out
+    # read coords + block index (+ local, + F_in for cos_x) once, the M block-sum rows, write out
     nb = n * (16 + 4 + 4 * c * (1 + fuse + (1 if op == 'cos_x' else 0))) + m_hint * 4 * k * c
+    if USE_WINDOW_APPLY and L.lk_link_window_apply_supported(c):
+        # passes 2a + 2b as one block-centric kernel (no [M,kC] mean round trip)
+        with _capi.timed('lk_link_window_apply_fwd', nb + m_hint * (4 * nbr.shape[1] + 8)):
+            _capi.check(L.lk_link_window_apply_fwd(
+                _capi.ptr(sums), _capi.ptr(nbr), _capi.ptr(bi.seg), _capi.ptr(bi.order), _capi.ptr(bi.num), n,
+                nbr.shape[1], _capi.ptr(f_input), _capi.ptr(coords), C.byref(gen), fuse,
+                _capi.ptr(local) if fuse else None, _capi.ptr(g1), _capi.ptr(b1), _capi.ptr(g2), _capi.ptr(b2),
+                _capi.ptr(out), _capi.ptr(save[0]) if save else None, _capi.ptr(save[1]) if save else None, st),
+                'lk_link_window_apply_fwd')
+        return out
+    assert save is None
+    mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
+    with _capi.timed('lk_link_window_mean', m_hint * (2 * 4 * k * c + 4 * nbr.shape[1] + 4)):
+        _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
+                                          _capi.ptr(bi.num), n, nbr.shape[1], k * c,
+                                          _capi.ptr(mean), st), 'lk_link_window_mean')
     with _capi.timed('lk_link_apply_fwd', nb):
         _capi.check(L.lk_link_apply_fwd(_capi.ptr(mean), _capi.ptr(f_input), _capi.ptr(coords),
                                         _capi.ptr(bi.idx_query), n, C.byref(gen), fuse,
@@ -255,6 +292,59 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
                                         _capi.ptr(b1), _capi.ptr(g2), _capi.ptr(b2), _capi.ptr(out),
                                         st), 'lk_link_apply_fwd')
     return out
+
+
+class LinkAggregateFunction(torch.autograd.Function):
+    """Differentiable linear-kernel path with the fused norms:
+    out = relu(LN(window_mean_combine(f_input)) + LN(local))  (linkencoder.py:150-162, 178-181),
+    gradients for f_input, local, pos_weight and both LayerNorms by the hand-written backward
+    kernels (lk_link_bwd_norm / lk_link_bwd_apply).  The reference reaches the
+    same gradients through autograd over cat / spvoxelize / spdevoxelize / index
+    (devoxelize.py:75-98, voxelize.py:33-56)."""
+
+    @staticmethod
+    def forward(ctx, f_input, local, pos_weight, g1, b1, g2, b2, coords, bi, r, op):
+        n, c = f_input.shape
+        k = 2
+        dev = f_input.device
+        f_input = f_input.contiguous().float()
+        local = local.contiguous().float()
+        mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
+        tot = torch.empty(n, dtype=torch.float32, device=dev)
+        out = link_aggregate(f_input, coords, bi, r, op, pos_weight, None, 1.0, local, (g1, b1, g2, b2),
+                             save=(mean, tot))
+        ctx.save_for_backward(f_input, local, pos_weight.detach().contiguous().float(), g1, b1, g2, b2, mean,
+                              tot, coords)
+        ctx.bi, ctx.r, ctx.op = bi, r, op
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f_input, local, pw, g1, b1, g2, b2, mean, tot, coords = ctx.saved_tensors
+        bi, r, op = ctx.bi, ctx.r, ctx.op
+        n, c = f_input.shape
+        dev = f_input.device
+        dout = dout.contiguous().float()
+        L, st = _capi.lib(), _capi.stream()
+        gen = _kernel_gen(op, c, pw, None, 1.0)
+        g1c, b1c, g2c, b2c = (t.detach().contiguous().float() for t in (g1, b1, g2, b2))
+        dy = torch.empty_like(f_input)
+        dlocal = torch.empty_like(f_input)
+        gsum = torch.empty(n, 2 * c, dtype=torch.float32, device=dev)
+        dparam = torch.zeros(4, c, dtype=torch.float32, device=dev)
+        _capi.check(L.lk_link_bwd_norm(
+            _capi.ptr(mean), _capi.ptr(tot), _capi.ptr(bi.seg), _capi.ptr(bi.order), _capi.ptr(bi.num), n,
+            _capi.ptr(coords), C.byref(gen), _capi.ptr(local), _capi.ptr(dout), _capi.ptr(g1c), _capi.ptr(b1c),
+            _capi.ptr(g2c), _capi.ptr(b2c), _capi.ptr(dy), _capi.ptr(dlocal), _capi.ptr(gsum), _capi.ptr(dparam),
+            st), 'lk_link_bwd_norm')
+        nbr_t = bi.neighbors_t(r)
+        dfin = torch.empty_like(f_input)
+        dw = torch.zeros_like(pw)
+        _capi.check(L.lk_link_bwd_apply(
+            _capi.ptr(gsum), _capi.ptr(mean), _capi.ptr(nbr_t), _capi.ptr(bi.seg), _capi.ptr(bi.order),
+            _capi.ptr(bi.num), n, nbr_t.shape[1], _capi.ptr(coords), C.byref(gen), _capi.ptr(f_input),
+            _capi.ptr(dy), _capi.ptr(dfin), _capi.ptr(dw), st), 'lk_link_bwd_apply')
+        return dfin, dlocal, dw, dparam[0], dparam[1], dparam[2], dparam[3], None, None, None, None
 
 
 def _pre_mix_fused(pre_mix, x: torch.Tensor) -> torch.Tensor:
@@ -397,7 +487,18 @@ class ELKBlock(nn.Module):
                                      alpha=getattr(self, 'alpha', None), coord_scale=scale,
                                      norm=self.norm, norm_local=self.norm_local)
             return st          # like aux_to_voxel, the input tensor object carries the result
-        return self._forward_composed(st, self.pre_mix(st.F), self.local_mix(st), s, r)
+        F_input, local_mix = self.pre_mix(st.F), self.local_mix(st)
+        c = self.inc
+        if (FUSED_BACKWARD and self.baseop in ('cos', 'sin') and st._feats.dtype == torch.float32
+                and _capi.lib().lk_link_window_apply_supported(c)):
+            # training: fused forward + hand-written backward of the linear-kernel path; pre_mix and
+            # local_mix stay autograd nodes of their own (dense Linear+LayerNorm, sparse conv)
+            st.F = LinkAggregateFunction.apply(
+                F_input, local_mix.F, self.pos_weight[0].weight, self.norm.weight, self.norm.bias,
+                self.norm_local.weight, self.norm_local.bias, st.C.contiguous(), block_index(st, s), r,
+                self.baseop)
+            return st
+        return self._forward_composed(st, F_input, local_mix, s, r)
 
     def _forward_composed(self, st, F_input, local_mix, s, r):
         """The reference's op sequence (linkencoder.py:135-183) on differentiable kernels."""

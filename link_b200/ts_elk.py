@@ -121,6 +121,15 @@ class TSELKBlock(nn.Module):
                                          alpha=None, coord_scale=1.0, norm=self.norm,
                                          norm_local=self.norm_local)
             return st
+        if (needs_grad and elk.FUSED_BACKWARD and self.baseop in ('sin', 'cos') and st.F.dtype == torch.float32
+                and self.inc in (16, 32, 64, 128)):
+            # training: fused forward + hand-written backward of the linear-kernel path
+            F_input, local_mix = self.pre_mix(st.F), self.local_mix(st)
+            st.F = elk.LinkAggregateFunction.apply(
+                F_input, local_mix.F, self._phase_rows(), self.norm.weight, self.norm.bias,
+                self.norm_local.weight, self.norm_local.bias, st.C.contiguous(), elk.block_index(st, stride), 3,
+                self.baseop)
+            return st
         return self._forward_composed(st, stride)
 
     def _forward_composed(self, st: SparseTensor, stride):
