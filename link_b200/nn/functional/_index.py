@@ -11,26 +11,70 @@ import torch
 from link_b200 import _capi
 
 BOUNDS_KEY = ('lk', 'bounds')
+# LINKB200_CHECK_BOUNDS=1: verify seeded / derived bounds against the tensor on the host (one sync)
+import os as _os
+CHECK_BOUNDS = _os.environ.get('LINKB200_CHECK_BOUNDS', '0') == '1'
+
+
+def _tkey(coords: torch.Tensor):
+    return ('lk', 'bounds', coords.data_ptr(), coords.shape[0])
+
+
+def _exact_bounds(coords: torch.Tensor):
+    if coords.shape[0] == 0:
+        return ((0, 0, 0, 0), (0, 0, 0, 0))
+    mm = torch.stack([coords.min(dim=0).values, coords.max(dim=0).values]).cpu().tolist()
+    return (tuple(int(v) for v in mm[0]), tuple(int(v) for v in mm[1]))
 
 
 def coord_bounds(coords: torch.Tensor, cache: Optional[Dict] = None):
-    """(lo[4], hi[4]) python ints of an int32 [N,4] coordinate tensor.  With `cache` (a
-    SparseTensor.kmaps dict) the bounds of the family's finest level are reused: every derived
-    level (floor to stride multiples, floor-div into blocks) stays inside them."""
-    if cache is not None and BOUNDS_KEY in cache:
-        return cache[BOUNDS_KEY]
-    if coords.shape[0] == 0:
-        b = ((0, 0, 0, 0), (0, 0, 0, 0))
+    """(lo[4], hi[4]) python ints of an int32 [N,4] coordinate tensor.
+
+    With `cache` (a SparseTensor.kmaps dict) bounds are remembered PER COORDINATE TENSOR (keyed by
+    storage address and length).  Levels that our own ops derive (strided convs) get their bounds
+    analytically from the parent's (`register_floored_bounds`), so a forward pass pays one 8-int
+    read-back for the input scan and none for the derived levels.  The family's seed entry
+    (`set_coord_bounds`, or the first tensor measured) is bound to the first tensor that asks for it
+    and is never applied to a different, unregistered tensor: derived coordinates may lie outside
+    the finest level's bounds (aligned outputs of a k != stride downsample above `hi`, floors below
+    `lo` when a block edge is not a multiple of the tensor stride), and a field outside its key
+    range would alias silently."""
+    if cache is None:
+        return _exact_bounds(coords)
+    key = _tkey(coords)
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    seed = cache.get(BOUNDS_KEY)
+    if seed is not None and len(seed) == 2:          # pre-seeded, not bound yet: this is the input scan
+        b = (seed[0], seed[1])
+        cache[BOUNDS_KEY] = (seed[0], seed[1], key)
     else:
-        mm = torch.stack([coords.min(dim=0).values, coords.max(dim=0).values]).cpu().tolist()
-        b = (tuple(int(v) for v in mm[0]), tuple(int(v) for v in mm[1]))
-    if cache is not None:
-        cache[BOUNDS_KEY] = b
+        b = _exact_bounds(coords)
+        if seed is None:
+            cache[BOUNDS_KEY] = (b[0], b[1], key)
+    if CHECK_BOUNDS:
+        ex = _exact_bounds(coords)
+        if any(ex[0][a] < b[0][a] or ex[1][a] > b[1][a] for a in range(4)):
+            raise RuntimeError(f'coordinate bounds {b} do not contain the tensor\'s range {ex}')
+    cache[key] = b
     return b
 
 
 def set_coord_bounds(cache: Dict, lo: Sequence[int], hi: Sequence[int]) -> None:
+    """Pre-seed the bounds of the input scan (a dataset property the loader knows): the first
+    coordinate tensor of the family that needs bounds takes them without a device read-back."""
     cache[BOUNDS_KEY] = (tuple(int(v) for v in lo), tuple(int(v) for v in hi))
+
+
+def register_floored_bounds(cache: Optional[Dict], child: torch.Tensor, parent_bounds, step: Sequence[int]) -> None:
+    """Bounds of coordinates derived as floor(c / step) * step from a tensor with `parent_bounds`."""
+    if cache is None:
+        return
+    lo, hi = parent_bounds
+    st = [int(v) for v in step] + [1]
+    cache[_tkey(child)] = (tuple((lo[a] // st[a]) * st[a] for a in range(4)),
+                           tuple((hi[a] // st[a]) * st[a] for a in range(4)))
 
 
 def make_keyspec(bounds, div: Sequence[int], order: Sequence[int], mul: Sequence[int] = (1, 1, 1),

@@ -38,7 +38,9 @@ def spdownsample(coords: torch.Tensor, stride: Union[int, Tuple[int, ...]] = 2,
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=coords.device)
         _capi.check(L.lk_downsample(_capi.ptr(coords, torch.int32), n, C.byref(spec), bits, out.data_ptr(),
                                     num.data_ptr(), ws.data_ptr(), ws_bytes, _capi.stream()), 'lk_downsample')
-        return out[:int(num.item())]
+        out = out[:int(num.item())]
+        _index.register_floored_bounds(cache, out, bounds, sample_stride)
+        return out
     # general case (kernel != stride): expand by the kernel offsets, keep the aligned candidates
     offsets = get_kernel_offsets(kernel_size, tensor_stride, device=coords.device)
     kv = offsets.size(0)
