@@ -226,16 +226,17 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
                       const float* d_b2, float* d_out, lk_stream_t s);
 
 /* Passes 2a + 2b as ONE block-centric kernel (C in {16, 32, 64, 128}; lk_link_window_apply_supported):
- * one warp per block reduces the window row (the r^3 neighbour block sums / populations, read from
- * L2) and applies it to the block's voxels, which are contiguous in the sorted sequence
- * (d_seg [M+1] segment starts, d_order [n] voxel row per sorted position; both from
- * lk_sort_unique_ex).  Replaces lk_link_window_mean + lk_link_apply_fwd (aux_to_voxel,
+ * a warp walks chunks of 32 consecutive positions of the block-sorted voxel sequence (d_order [n]
+ * voxel row, d_sorted_rank [n] block row per sorted position, d_seg [M+1] segment starts; all from
+ * lk_sort_unique_ex), reduces the window row (the r^3 neighbour block sums / populations, read from
+ * L2) of every block the chunk touches and applies it to that block's voxels in the chunk.  Replaces lk_link_window_mean + lk_link_apply_fwd (aux_to_voxel,
  * utils.py:61-84 + linkencoder.py:162,178-181): no [M,kC] mean round trip, one launch less.
  * d_mean_out [cap, k*C] / d_tot_out [cap] (optional, may be NULL): the window means and window
  * populations, kept for the backward pass. */
 int lk_link_window_apply_supported(int c);
 int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                             const int32_t* d_order, const int32_t* d_num, int64_t capacity, int r3,
+                             const int32_t* d_order, const int32_t* d_sorted_rank, const int32_t* d_num,
+                             int64_t capacity /* = n voxels */, int r3,
                              const float* d_fin /*cos_x only, else NULL*/, const int32_t* d_coords,
                              const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
                              const float* d_g1, const float* d_b1, const float* d_g2,

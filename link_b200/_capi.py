@@ -86,7 +86,7 @@ PROTOTYPES = {
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
     'lk_link_window_apply_supported': (i32, [i32]),
-    'lk_link_window_apply_fwd': (i32, [vp, vp, vp, vp, vp, i64, i32, vp, vp, C.POINTER(KernelGen), i32, vp, vp, vp,
+    'lk_link_window_apply_fwd': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, C.POINTER(KernelGen), i32, vp, vp, vp,
                                        vp, vp, vp, vp, vp, vp]),
     'lk_link_bwd_norm': (i32, [vp, vp, vp, vp, vp, i64, vp, C.POINTER(KernelGen), vp, vp, vp, vp, vp, vp, vp, vp,
                                vp, vp, vp]),

@@ -176,7 +176,7 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   // ---- join ----
   if (bs) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, bs->join, 0));
   if (use_wa)
-    LK_TRY(lk_link_window_apply_fwd(sums, nbr, seg, order, num, n, a->r3, fin, a->d_coords, &a->gen, 1, local,
+    LK_TRY(lk_link_window_apply_fwd(sums, nbr, seg, order, srank, num, n, a->r3, fin, a->d_coords, &a->gen, 1, local,
                                     a->d_g1, a->d_b1, a->d_g2, a->d_b2, a->d_out, nullptr, nullptr, s));
   else
     LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,

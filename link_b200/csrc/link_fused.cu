@@ -228,6 +228,190 @@ __global__ void __launch_bounds__(WA_WARPS * 32, 2) link_window_apply_kernel(
   }
 }
 
+// ------------------------------------------------------------------ forward, chunk-centric
+// Same arithmetic, different work decomposition: a warp item is a CHUNK of 32 consecutive sorted
+// positions (uniform work for any block-size distribution; the block-centric kernel above is bound by
+// its longest blocks -- 117 voxels = 30 dependent steps on the bench scan -- and by one exposed memory
+// round trip per 4-voxel step).  Per chunk:
+//   * the 32 (voxel row, block row) pairs are read coalesced (prefetched one chunk ahead), the voxels'
+//     coordinates are gathered into registers (lane l <-> position l) and their local_mix / F_in rows
+//     are staged in shared memory with cp.async: ONE gather round trip per 32 voxels;
+//   * the blocks of the chunk are consecutive block rows rank[first] .. rank[last]; for each, the warp
+//     reduces the window row (header prefetched one block ahead) and applies it to the block's
+//     positions inside the chunk (a ballot gives the lane range).  A block that straddles chunks is
+//     reduced once per chunk it touches (+ N/32 window rows at most, bit-identical results).
+#define CA_WARPS 4
+template <int LPR, bool NORM, bool COSX>
+struct ChunkCfg {
+  static constexpr int C = 8 * LPR;
+  static constexpr int K = COSX ? 3 : 2;
+  static constexpr int ROW = C * 4;                                  // bytes per feature row
+  static constexpr int STAGE = ((NORM ? 1 : 0) + (COSX ? 1 : 0)) * 32 * ROW;
+  static constexpr int AROW = K * C * 4;
+  static constexpr int PER_WARP = STAGE + AROW;
+  static constexpr int SMEM = CA_WARPS * PER_WARP;
+};
+
+template <int LPR, int IB, int OP, bool NORM>
+__global__ void __launch_bounds__(CA_WARPS * 32, 4) link_chunk_apply_kernel(
+    const float4* __restrict__ sums, const int* __restrict__ nbr, const int* __restrict__ seg,
+    const int* __restrict__ order, const int* __restrict__ rank, int64_t n, int R,
+    const float* __restrict__ fin, const int4* __restrict__ coords, GenDev g,
+    const float* __restrict__ local, const float* __restrict__ g1, const float* __restrict__ b1,
+    const float* __restrict__ g2, const float* __restrict__ b2, float* __restrict__ out,
+    float4* __restrict__ mean_out, float* __restrict__ tot_out) {
+  constexpr bool COSX = (OP == LK_OP_COSX);
+  using Cfg = ChunkCfg<LPR, NORM, COSX>;
+  constexpr int K = Cfg::K, C = Cfg::C, C4 = C / 4, KC4 = K * C4;
+  constexpr int NV = (KC4 + 31) / 32;
+  constexpr int CH = NV == 1 ? 8 : 4;
+  constexpr int G = 32 / LPR;
+  constexpr int NP = 4 * IB;
+  extern __shared__ __align__(16) uint8_t chunk_s[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int grp = lane / LPR, j = lane % LPR;
+  uint8_t* const wbase = chunk_s + (size_t)wib * Cfg::PER_WARP;
+  const uint32_t wbase_u = (uint32_t)__cvta_generic_to_shared(wbase);
+  float4* const arow = (float4*)(wbase + Cfg::STAGE);
+  const uint8_t* const st_local = wbase;                              // [32][C] floats (NORM)
+  const uint8_t* const st_fin = wbase + (NORM ? 32 * Cfg::ROW : 0);   // [32][C] floats (COSX)
+  const int64_t nitems = (n + 31) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= nitems) return;
+  LaneGen<NP> lg;
+  load_lane_gen<LPR, IB>(g, j, true, lg);
+  const float inv_c = 1.0f / (float)C;
+
+  auto load_pair = [&](int64_t it, int& o, int& r) {
+    const int64_t pos = it * 32 + lane;
+    const bool ok = it < nitems && pos < n;
+    o = ok ? __ldg(order + pos) : -1;
+    r = ok ? __ldg(rank + pos) : -1;
+  };
+  int ord, rk, ord_n, rk_n;
+  load_pair(item, ord, rk);
+
+  for (; item < nitems; item += warps_total) {
+    load_pair(item + warps_total, ord_n, rk_n);                        // next chunk's pairs
+    // ---- gather: coordinates into registers, rows into the shared-memory stage ----
+    const int4 cc = ord >= 0 ? __ldg(coords + ord) : make_int4(0, 0, 0, 0);
+    if (NORM || COSX) {
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {                                  // 32 / G row groups
+        const int row = t * G + grp;
+        const int src = __shfl_sync(0xffffffffu, ord, row);
+        if (src >= 0) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t dst = wbase_u + row * Cfg::ROW + (i * LPR + j) * 16;
+            if (NORM)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                           ::"r"(dst), "l"(local + (int64_t)src * C + 4 * (i * LPR + j)) : "memory");
+            if (COSX)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                           ::"r"(dst + (NORM ? 32 * Cfg::ROW : 0)), "l"(fin + (int64_t)src * C + 4 * (i * LPR + j)) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const unsigned have = __ballot_sync(0xffffffffu, rk >= 0);
+    const int b_first = __shfl_sync(0xffffffffu, rk, 0);
+    const int b_last = __shfl_sync(0xffffffffu, rk, 31 - __clz(have));
+    int src = lane < R ? __ldg(nbr + (int64_t)b_first * R + lane) : -1;
+    bool staged = !(NORM || COSX);
+
+    for (int b = b_first; b <= b_last; ++b) {
+      const int src_next = (b < b_last && lane < R) ? __ldg(nbr + (int64_t)(b + 1) * R + lane) : -1;
+      int cnt = 0;
+      if (src >= 0) cnt = __ldg(seg + src + 1) - __ldg(seg + src);
+      const unsigned present = __ballot_sync(0xffffffffu, src >= 0);
+      float4 acc[NV];
+      window_row<KC4, NV, CH>(sums, src, present, lane, acc);
+      int tot_i = cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
+      const float tot = (float)tot_i;
+#pragma unroll
+      for (int w = 0; w < NV; ++w) {
+        const int v = lane + 32 * w;
+        if (v < KC4) {
+          float4 a = acc[w];
+          a.x /= tot; a.y /= tot; a.z /= tot; a.w /= tot;
+          arow[v] = a;
+          if (mean_out) mean_out[(int64_t)b * KC4 + v] = a;
+        }
+      }
+      if (tot_out && lane == 0) tot_out[b] = tot;
+      if (!staged) {                                                   // the stage is first read below
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        staged = true;
+      }
+      __syncwarp();
+      float4 A[K][2];
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) A[q][i] = arow[q * C4 + i * LPR + j];
+      const unsigned mine = __ballot_sync(0xffffffffu, rk == b);
+      const int lo = __ffs(mine) - 1, hi = lo + __popc(mine);          // the block's positions in this chunk
+
+      for (int t = lo; t < hi; t += G) {
+        const int row = t + grp;
+        const bool ok = row < hi;
+        const int rl = row & 31;
+        const int dst = __shfl_sync(0xffffffffu, ord, rl);
+        const int cx = __shfl_sync(0xffffffffu, cc.x, rl), cy = __shfl_sync(0xffffffffu, cc.y, rl),
+                  cz = __shfl_sync(0xffffffffu, cc.z, rl);
+        float p[NP], sn[NP], cs[NP];
+        lane_trig<NP, COSX>(g, lg, cx, cy, cz, p, sn, cs);
+        float v[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float a0[4] = {A[0][i].x, A[0][i].y, A[0][i].z, A[0][i].w};
+          const float a1[4] = {A[1][i].x, A[1][i].y, A[1][i].z, A[1][i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = (i % IB) * 4 + e;
+            v[i][e] = (OP == LK_OP_SIN) ? a0[e] * cs[q] - a1[e] * sn[q] : a0[e] * cs[q] + a1[e] * sn[q];
+          }
+          if (COSX) {                              // + (mean(F p) - F p), linkencoder.py:176
+            const float4 m2 = A[K - 1][i];
+            const float4 f = ok ? *(const float4*)(st_fin + rl * Cfg::ROW + (i * LPR + j) * 16) : f4zero();
+            v[i][0] += m2.x - f.x * p[(i % IB) * 4 + 0]; v[i][1] += m2.y - f.y * p[(i % IB) * 4 + 1];
+            v[i][2] += m2.z - f.z * p[(i % IB) * 4 + 2]; v[i][3] += m2.w - f.w * p[(i % IB) * 4 + 3];
+          }
+        }
+        if (NORM) {
+          float l[2][4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float4 lv = ok ? *(const float4*)(st_local + rl * Cfg::ROW + (i * LPR + j) * 16) : f4zero();
+            l[i][0] = lv.x; l[i][1] = lv.y; l[i][2] = lv.z; l[i][3] = lv.w;
+          }
+          group_layernorm<LPR, 2>(v, true, inv_c, g1, b1, j);
+          group_layernorm<LPR, 2>(l, true, inv_c, g2, b2, j);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[i][e] = fmaxf(v[i][e] + l[i][e], 0.f);
+        }
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            lk_stg_stream((float4*)(out + (int64_t)dst * C) + i * LPR + j,
+                          make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+        }
+      }
+      __syncwarp();                                // arow is rewritten by the next block
+      src = src_next;
+    }
+    __syncwarp();                                  // the stage is refilled by the next chunk
+    ord = ord_n; rk = rk_n;
+  }
+}
+
 // ------------------------------------------------------------------ backward
 // plane weights of the two-plane ops (forward: g_q = F u_q(p), y = sum_q A_q w_q(p)):
 //   cos: u = (cos, sin), w = (cos,  sin)      sin: u = (sin, cos), w = (cos, -sin)
@@ -620,10 +804,47 @@ static int launch_window_apply(const float* d_sums, const int32_t* d_nbr, const 
   return LK_OK;
 }
 
+template <int LPR, int IB, int OP, bool NORM>
+static int launch_chunk_apply(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
+                              const int32_t* d_order, const int32_t* d_rank, int64_t n, int r3,
+                              const float* d_fin, const int32_t* d_coords, const GenDev& g,
+                              const float* d_local, const float* g1, const float* b1, const float* g2,
+                              const float* b2, float* d_out, float* d_mean, float* d_tot, cudaStream_t st) {
+  using Cfg = ChunkCfg<LPR, NORM, OP == LK_OP_COSX>;
+  auto kern = link_chunk_apply_kernel<LPR, IB, OP, NORM>;
+  static int cache[64];
+  int dev = 0;
+  LK_CUDA(cudaGetDevice(&dev));
+  LK_REQUIRE(dev >= 0 && dev < 64, "lk_link_window_apply_fwd: device ordinal %d out of range", dev);
+  if (cache[dev] == 0) {
+    int occ = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CA_WARPS * 32, Cfg::SMEM) != cudaSuccess || occ < 1) {
+      cache[dev] = -1;
+      (void)cudaGetLastError();
+    } else {
+      cache[dev] = occ;
+    }
+  }
+  LK_REQUIRE(cache[dev] > 0, "lk_link_window_apply_fwd: cannot configure the chunk kernel (shared memory %d bytes)", Cfg::SMEM);
+  // all warps resident; every warp gets the same number of chunks (k = ceil(chunks / resident warps))
+  const int64_t nitems = (n + 31) / 32;
+  const int64_t warp_cap = (int64_t)LK_SM_COUNT * cache[dev] * CA_WARPS;
+  const int64_t k = (nitems + warp_cap - 1) / warp_cap;
+  const int64_t warps = (nitems + k - 1) / k;
+  const int grid = (int)((warps + CA_WARPS - 1) / CA_WARPS);
+  kern<<<grid, CA_WARPS * 32, Cfg::SMEM, st>>>((const float4*)d_sums, d_nbr, d_seg, d_order, d_rank, n, r3, d_fin,
+                                               (const int4*)d_coords, g, d_local, g1, b1, g2, b2, d_out,
+                                               (float4*)d_mean, d_tot);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 extern "C" int lk_link_window_apply_supported(int c) { return c == 16 || c == 32 || c == 64 || c == 128; }
 
 extern "C" int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                                        const int32_t* d_order, const int32_t* d_num, int64_t capacity,
+                                        const int32_t* d_order, const int32_t* d_sorted_rank,
+                                        const int32_t* d_num, int64_t capacity,
                                         int r3, const float* d_fin, const int32_t* d_coords,
                                         const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
                                         const float* d_g1, const float* d_b1, const float* d_g2,
@@ -635,7 +856,7 @@ extern "C" int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nb
   LK_REQUIRE(lk_link_window_apply_supported(g.c), "lk_link_window_apply_fwd: C must be 16, 32, 64 or 128");
   LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32, "lk_link_window_apply_fwd: bad sizes (needs r^3 <= 32)");
   if (capacity == 0) return LK_OK;
-  LK_REQUIRE(d_sums && d_nbr && d_seg && d_order && d_num && d_coords && d_out,
+  LK_REQUIRE(d_sums && d_nbr && d_seg && d_order && d_sorted_rank && d_num && d_coords && d_out,
              "lk_link_window_apply_fwd: null pointer");
   LK_REQUIRE(g.op != LK_OP_COSX || d_fin, "lk_link_window_apply_fwd: cos_x needs the input features");
   LK_REQUIRE(!fuse_norm || (d_local && d_g1 && d_b1 && d_g2 && d_b2),
@@ -646,6 +867,30 @@ extern "C" int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nb
   cudaStream_t st = (cudaStream_t)s;
   const int lpr = g.c / 8, span = 4 * lpr;
   const int ib = (g.wrows % span == 0 && g.wrows / span == 1) ? 1 : 2;
+  static const bool by_block = [] {
+    const char* e = getenv("LINKB200_WINDOW_APPLY");     // tuning knob: "block" = one warp per block
+    return e && e[0] == 'b';
+  }();
+  if (!by_block) {
+#define CA_ARGS d_sums, d_nbr, d_seg, d_order, d_sorted_rank, capacity, r3, d_fin, d_coords, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out, d_mean_out, d_tot_out, st
+#define CA_N(LPRV, IBV, O)                                                     \
+  (fuse_norm ? launch_chunk_apply<LPRV, IBV, O, true>(CA_ARGS)                 \
+             : launch_chunk_apply<LPRV, IBV, O, false>(CA_ARGS))
+#define CA_O(LPRV, IBV)                                                        \
+  (g.op == LK_OP_COS ? CA_N(LPRV, IBV, LK_OP_COS)                              \
+                     : g.op == LK_OP_SIN ? CA_N(LPRV, IBV, LK_OP_SIN) : CA_N(LPRV, IBV, LK_OP_COSX))
+#define CA_I(LPRV) (ib == 1 ? CA_O(LPRV, 1) : CA_O(LPRV, 2))
+    switch (lpr) {
+      case 2: return CA_I(2);
+      case 4: return CA_I(4);
+      case 8: return CA_I(8);
+      default: return CA_I(16);
+    }
+#undef CA_I
+#undef CA_O
+#undef CA_N
+#undef CA_ARGS
+  }
 #define WA_ARGS d_sums, d_nbr, d_seg, d_order, d_num, capacity, r3, d_fin, d_coords, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out, d_mean_out, d_tot_out, st
 #define WA_N(LPRV, IBV, O)                                                      \
   (fuse_norm ? launch_window_apply<LPRV, IBV, O, true>(WA_ARGS)                 \

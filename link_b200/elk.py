@@ -273,8 +273,8 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
         # passes 2a + 2b as one block-centric kernel (no [M,kC] mean round trip)
         with _capi.timed('lk_link_window_apply_fwd', nb + m_hint * (4 * nbr.shape[1] + 8)):
             _capi.check(L.lk_link_window_apply_fwd(
-                _capi.ptr(sums), _capi.ptr(nbr), _capi.ptr(bi.seg), _capi.ptr(bi.order), _capi.ptr(bi.num), n,
-                nbr.shape[1], _capi.ptr(f_input), _capi.ptr(coords), C.byref(gen), fuse,
+                _capi.ptr(sums), _capi.ptr(nbr), _capi.ptr(bi.seg), _capi.ptr(bi.order), _capi.ptr(bi.sorted_rank),
+                _capi.ptr(bi.num), n, nbr.shape[1], _capi.ptr(f_input), _capi.ptr(coords), C.byref(gen), fuse,
                 _capi.ptr(local) if fuse else None, _capi.ptr(g1), _capi.ptr(b1), _capi.ptr(g2), _capi.ptr(b2),
                 _capi.ptr(out), _capi.ptr(save[0]) if save else None, _capi.ptr(save[1]) if save else None, st),
                 'lk_link_window_apply_fwd')

@@ -386,7 +386,7 @@ def elk_block_forward(feats: torch.Tensor, coords, tensor_stride, p: Dict[str, t
     loc = TF.layer_norm(local, (C,), p['norm_local.weight'], p['norm_local.bias'], 1e-6)
     out = torch.relu(new + loc)
     if return_parts:
-        return out, dict(F_input=F_input, local=local, pos=pos, pre_norm=pre_norm,
+        return out, dict(F_input=F_input, local=local, pos=pos, pre_norm=pre_norm, pre_act=new + loc,
                          small_C=small_C, idx=idx, counts=counts)
     return out
 

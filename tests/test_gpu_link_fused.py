@@ -93,7 +93,11 @@ def test_fused_backward_vs_oracle_autograd_and_composed(dev, op, C, groups, s, r
     # oracle (CPU autograd)
     p = {k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
     f_cpu = feats.clone().requires_grad_(True)
-    o = O.elk_block_forward(f_cpu, coords, 1, p, s, r, op, groups)
+    o, parts = O.elk_block_forward(f_cpu, coords, 1, p, s, r, op, groups, return_parts=True)
+    # elements whose pre-activation is within float noise of 0 may land on either side of the ReLU in two
+    # fp32 implementations (a flipped mask changes the gradient of the whole row and, through the 3^3 conv,
+    # of its neighbours): they receive no incoming gradient, so the comparison is mask-independent
+    go = go * (parts['pre_act'].detach().abs() > 1e-3)
     o.backward(go)
     blk = blk.to(dev).train()
 
