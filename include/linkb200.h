@@ -215,6 +215,11 @@ int lk_link_window_mean(const float* d_sums, const int32_t* d_counts, const int3
 int lk_link_window_mean_seg(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
                             const int32_t* d_num, int64_t capacity, int r3, int kc, float* d_mean,
                             lk_stream_t s);
+/* lk_link_window_mean_seg that also writes the window populations T[b] = sum of the neighbour blocks'
+ * voxel counts as floats (d_tot [M], may be NULL): kept with d_mean for the backward pass. */
+int lk_link_window_mean_tot(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
+                            const int32_t* d_num, int64_t capacity, int r3, int kc, float* d_mean,
+                            float* d_tot, lk_stream_t s);
 /* Pass 2b: per voxel combine with its own phase.  Writes d_out [n,C]:
  *   fuse_norm == 0 : pre-LayerNorm value (linkencoder.py:162 / 148 / 176)
  *   fuse_norm == 1 : relu(LN(value; g1,b1) + LN(local; g2,b2)), eps 1e-6
@@ -225,23 +230,6 @@ int lk_link_apply_fwd(const float* d_mean, const float* d_fin /*cos_x only, else
                       const float* d_g1, const float* d_b1, const float* d_g2,
                       const float* d_b2, float* d_out, lk_stream_t s);
 
-/* Passes 2a + 2b as ONE block-centric kernel (C in {16, 32, 64, 128}; lk_link_window_apply_supported):
- * a warp walks chunks of 32 consecutive positions of the block-sorted voxel sequence (d_order [n]
- * voxel row, d_sorted_rank [n] block row per sorted position, d_seg [M+1] segment starts; all from
- * lk_sort_unique_ex), reduces the window row (the r^3 neighbour block sums / populations, read from
- * L2) of every block the chunk touches and applies it to that block's voxels in the chunk.  Replaces lk_link_window_mean + lk_link_apply_fwd (aux_to_voxel,
- * utils.py:61-84 + linkencoder.py:162,178-181): no [M,kC] mean round trip, one launch less.
- * d_mean_out [cap, k*C] / d_tot_out [cap] (optional, may be NULL): the window means and window
- * populations, kept for the backward pass. */
-int lk_link_window_apply_supported(int c);
-int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                             const int32_t* d_order, const int32_t* d_sorted_rank, const int32_t* d_num,
-                             int64_t capacity /* = n voxels */, int r3,
-                             const float* d_fin /*cos_x only, else NULL*/, const int32_t* d_coords,
-                             const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
-                             const float* d_g1, const float* d_b1, const float* d_g2,
-                             const float* d_b2, float* d_out, float* d_mean_out, float* d_tot_out,
-                             lk_stream_t s);
 /* Hand-written backward of the linear-kernel path with the fused norms (ops cos / sin, C in
  * {16, 32, 64, 128}); replaces autograd through devoxelize_backward (devoxelize_cuda.cu:38-59, float
  * atomics), the [N,kC] index/cat temporaries and voxelize_backward (voxelize_cuda.cu:28-42):
@@ -253,6 +241,7 @@ int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const in
  *     of the negated offsets; equal to d_nbr for odd r), writes d_dfin [n,C] (gradient of F_input)
  *     and ADDS the gradient of pos_weight into d_dw [wrows,3] (caller zeroes it).
  * One warp owns a block, so the block sums need no atomics and are deterministic. */
+int lk_link_bwd_supported(int c);
 int lk_link_bwd_norm(const float* d_mean, const float* d_tot, const int32_t* d_seg,
                      const int32_t* d_order, const int32_t* d_num, int64_t capacity,
                      const int32_t* d_coords, const lk_kernelgen_t* gen, const float* d_local,

@@ -85,9 +85,8 @@ PROTOTYPES = {
     'lk_link_window_mean_seg': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
     'lk_link_apply_fwd': (i32, [vp, vp, vp, vp, i64, C.POINTER(KernelGen), i32, vp, vp, vp, vp,
                                 vp, vp, vp]),
-    'lk_link_window_apply_supported': (i32, [i32]),
-    'lk_link_window_apply_fwd': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, C.POINTER(KernelGen), i32, vp, vp, vp,
-                                       vp, vp, vp, vp, vp, vp]),
+    'lk_link_bwd_supported': (i32, [i32]),
+    'lk_link_window_mean_tot': (i32, [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]),
     'lk_link_bwd_norm': (i32, [vp, vp, vp, vp, vp, i64, vp, C.POINTER(KernelGen), vp, vp, vp, vp, vp, vp, vp, vp,
                                vp, vp, vp]),
     'lk_link_bwd_apply': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, C.POINTER(KernelGen), vp, vp, vp, vp, vp]),

@@ -144,14 +144,7 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   else
     LK_TRY(lk_linear_ln_fwd(a->d_feats, a->d_premix_w, a->d_premix_g, a->d_premix_b, a->premix_eps, n, c, fin, side));
   LK_TRY(lk_link_preagg_seg_fwd(fin, a->d_coords, order, srank, n, &a->gen, sums, side));
-  // passes 2a + 2b: one block-centric kernel after the join (default), or window mean on the side
-  // chain + per-voxel apply (LINKB200_WINDOW_APPLY=0)
-  static const bool fused_wa = [] {
-    const char* e = getenv("LINKB200_WINDOW_APPLY");
-    return !(e && e[0] == '0');
-  }();
-  const bool use_wa = fused_wa && lk_link_window_apply_supported(c);
-  if (!use_wa) LK_TRY(lk_link_window_mean_seg(sums, seg, nbr, num, n, a->r3, kc, mean, side));
+  LK_TRY(lk_link_window_mean_seg(sums, seg, nbr, num, n, a->r3, kc, mean, side));
   if (bs) LK_CUDA(cudaEventRecord(bs->join, bs->stream));
   // ---- main chain ----
   if (need_kmap) {
@@ -175,12 +168,8 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   }
   // ---- join ----
   if (bs) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, bs->join, 0));
-  if (use_wa)
-    LK_TRY(lk_link_window_apply_fwd(sums, nbr, seg, order, srank, num, n, a->r3, fin, a->d_coords, &a->gen, 1, local,
-                                    a->d_g1, a->d_b1, a->d_g2, a->d_b2, a->d_out, nullptr, nullptr, s));
-  else
-    LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,
-                             a->d_g2, a->d_b2, a->d_out, s));
+  LK_TRY(lk_link_apply_fwd(mean, fin, a->d_coords, inverse, n, &a->gen, 1, local, a->d_g1, a->d_b1,
+                           a->d_g2, a->d_b2, a->d_out, s));
   return LK_OK;
 }
 

@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
                                                                const int* __restrict__ nbr,
                                                                const int* __restrict__ d_num,
                                                                int64_t capacity, int R, int kc,
-                                                               float* __restrict__ mean) {
+                                                               float* __restrict__ mean,
+                                                               float* __restrict__ tot_out) {
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
   const int lane = threadIdx.x & 31;
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
     const float tot = (float)tot_i;
+    if (tot_out && lane == 0) tot_out[b] = tot;
     for (int v0 = 0; v0 < vpr; v0 += 32) {
       const int v = v0 + lane;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -552,11 +554,19 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
 
 // ------------------------------------------------------------------ pass 2b: combine (+ norms)
 
+// (AP_MINB, AP_U) = (4, 1): 128 registers, 16 warps / SM, 36.0 us for the block chain vs 38.7 us at the
+// round-1 setting (3, 2) (168 registers); (4, 2), (5, 2), (6, 1) spill and measure 42-48 us.
 // Every lane group handles U rows per step with all of their loads in flight together: first the
 // independent ones (block index, coordinate, local_mix row), then the mean rows that depend on
 // the block index.
+#ifndef AP_MINB
+#define AP_MINB 4                          // resident CTAs per SM the register budget is capped for
+#endif
+#ifndef AP_U
+#define AP_U 1                             // rows per lane group and step
+#endif
 template <int LPR, int VPL, int IB, int OP, bool NORM>
-__global__ void __launch_bounds__(128, VPL >= 4 ? 3 : 5) link_apply_kernel(
+__global__ void __launch_bounds__(128, VPL >= 4 ? AP_MINB : 5) link_apply_kernel(
     const float* __restrict__ mean, const float* __restrict__ fin, const int4* __restrict__ coords,
     const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
@@ -565,7 +575,7 @@ __global__ void __launch_bounds__(128, VPL >= 4 ? 3 : 5) link_apply_kernel(
   constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
   constexpr bool COSX = (OP == LK_OP_COSX);
   constexpr int NP = 4 * IB;
-  constexpr int U = (COSX && VPL > 1) ? 1 : 2;        // rows per lane group per step (register budget)
+  constexpr int U = (COSX && VPL > 1) ? 1 : AP_U;     // rows per lane group per step (register budget)
   const int lane = threadIdx.x & 31;
   const int grp = lane / LPR;
   const int j = lane % LPR;
@@ -829,7 +839,20 @@ extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_sums && d_counts && d_nbr && d_num && d_mean, "lk_link_window_mean: null pointer");
   link_window_mean_kernel<false><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean);
+      d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean, nullptr);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
+extern "C" int lk_link_window_mean_tot(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
+                                       const int32_t* d_num, int64_t capacity, int r3, int kc,
+                                       float* d_mean, float* d_tot, lk_stream_t s) {
+  LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32 && kc > 0 && kc % 4 == 0,
+             "lk_link_window_mean_seg: bad sizes (needs r^3 <= 32)");
+  if (capacity == 0) return LK_OK;
+  LK_REQUIRE(d_sums && d_seg && d_nbr && d_num && d_mean, "lk_link_window_mean_seg: null pointer");
+  link_window_mean_kernel<true><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
+      d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean, d_tot);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -837,14 +860,7 @@ extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
 extern "C" int lk_link_window_mean_seg(const float* d_sums, const int32_t* d_seg, const int32_t* d_nbr,
                                        const int32_t* d_num, int64_t capacity, int r3, int kc,
                                        float* d_mean, lk_stream_t s) {
-  LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32 && kc > 0 && kc % 4 == 0,
-             "lk_link_window_mean_seg: bad sizes (needs r^3 <= 32)");
-  if (capacity == 0) return LK_OK;
-  LK_REQUIRE(d_sums && d_seg && d_nbr && d_num && d_mean, "lk_link_window_mean_seg: null pointer");
-  link_window_mean_kernel<true><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean);
-  LK_LAUNCHED();
-  return LK_OK;
+  return lk_link_window_mean_tot(d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean, nullptr, s);
 }
 
 extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const int32_t* d_coords,
@@ -868,9 +884,9 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
     const int lpr = g.c / 16, span = 4 * lpr;
     const int ibr = (g.wrows % span == 0) ? g.wrows / span : 4;
     const int ib = (ibr == 1 || ibr == 2) ? ibr : 4;
-    const int rows_per_step = (32 / lpr) * (g.op == LK_OP_COSX ? 1 : 2);
+    const int rows_per_step = (32 / lpr) * (g.op == LK_OP_COSX ? 1 : AP_U);
     const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
-    const int grid = lk_grid(steps * 32, 128, 3);
+    const int grid = lk_grid(steps * 32, 128, AP_MINB);
 #define LAUNCH_A4_ON(LPRV, IBV, O, NRM)                                                        \
   link_apply_kernel<LPRV, 4, IBV, O, NRM><<<grid, 128, 0, st>>>(                               \
       d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)

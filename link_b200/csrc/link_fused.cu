@@ -1,32 +1,27 @@
-// Outer-block reuse + combine as ONE block-centric kernel (reference: aux_to_voxel,
-// segmentation/core/models/utils.py:61-84, and the combine / norms of ELKBlock.forward,
-// segmentation/core/models/semantic_kitti/linkencoder.py:162, 178-181), and the hand-written
-// backward of the whole linear-kernel path (reference: autograd through
-// devoxelize_cuda.cu:38-59, voxelize_cuda.cu:28-42, devoxelize.py:75-98).
+// Hand-written backward of the linear-kernel path with the fused norms (reference:
+// autograd through index / devoxelize_backward (devoxelize_cuda.cu:38-59, float atomics) / the [N,kC]
+// cat temporaries / voxelize_backward (voxelize_cuda.cu:28-42); glue devoxelize.py:75-98).
 //
-//   forward  link_window_apply : per block b   A[b] = (sum_{b' in N(b)} S[b']) / (sum n[b'])
-//                                per voxel i   y_i  = A_c[b] cos p_i + A_s[b] sin p_i (+ A_l - F p)
-//                                              out_i = relu(LN(y_i) + LN(local_i))          [NORM]
-//   backward link_bwd_norm     : per voxel i   recompute y_i, both LayerNorms, the ReLU mask ->
-//                                              dy_i, dlocal_i, d(gamma, beta) of both norms
-//                                per block b   G[b] = (sum_{i in b} [dy_i cos p_i, dy_i sin p_i]) / T[b]
-//            link_bwd_apply    : per block b'  dS[b'] = sum_{b in N^T(b')} G[b]
-//                                per voxel j   dF_j = dS_c cos p_j + dS_s sin p_j
-//                                              dp_j = F_j (-sin p_j dS_c + cos p_j dS_s)
-//                                                     + dy_j (-A_c sin p_j + A_s cos p_j)
-//                                              dW  += dp_j x_j^T   (summed over the channel groups)
+//   forward (link.cu)  : S[b] = sum_{i in b} F_i {u_0, u_1}(p_i);  A[b] = (sum_{b' in N(b)} S[b']) / T[b];
+//                        y_i = A_0 w_0(p_i) + A_1 w_1(p_i);  out_i = relu(LN(y_i) + LN(local_i))
+//   link_bwd_norm      : per voxel i   recompute y_i, both LayerNorms, the ReLU mask ->
+//                                      dy_i, dlocal_i, d(gamma, beta) of both norms
+//                        per block b   G[b] = (sum_{i in b} [dy_i w_0(p_i), dy_i w_1(p_i)]) / T[b]
+//   link_bwd_apply     : per block b'  dS[b'] = sum_{b in N^T(b')} G[b]
+//                        per voxel j   dF_j = dS_0 u_0(p_j) + dS_1 u_1(p_j)
+//                                      dp_j = F_j (dS_0 u_0'(p_j) + dS_1 u_1'(p_j)) + dy_j (A_0 w_0'(p_j) + A_1 w_1'(p_j))
+//                                      dW  += dp_j x_j^T   (summed over the channel groups)
 //
 // One warp owns one block at a time (blocks are visited round-robin, M is read from the device).
-// The window row (kC floats) is reduced by the whole warp -- lane v owns float4 v of the row, so a
+// The window row (2C floats) is reduced by the whole warp -- lane v owns float4 v of the row, so a
 // neighbour row is one fully coalesced 128-bit load per lane -- and handed to the voxel phase
-// through shared memory; the voxels of the block are contiguous in the sorted sequence
-// (seg / order from lk_sort_unique_ex), LPR = C/8 lanes own a row (two float4 each), 32/LPR voxels
-// side by side.  The separate window-mean kernel and its [M,kC] round trip are gone, block sums /
-// means never leave L2, and because a block belongs to exactly one warp the backward block sums
-// need no atomics and are deterministic.
-// Latency: the block header (neighbour row, segment bounds) is prefetched two blocks ahead and the
-// first 32 entries of the sort permutation one block ahead, so per block one dependent round trip
-// (neighbour rows + the first voxel batch, issued together) is exposed.
+// through shared memory; the voxels of a block are contiguous in the sorted sequence (seg / order
+// from lk_sort_unique_ex), LPR = C/8 lanes own a row (two float4 each), 32/LPR voxels side by side.
+// Because a block belongs to exactly one warp the backward block sums need no atomics and are
+// deterministic.  (A forward kernel of the same shape -- window mean + apply fused, block- and
+// chunk-centric -- was measured and dropped: 32 / 49 us against 6.5 + 9.1 / 6.5 + 19.2 us for the
+// two-kernel form at N = 119k, C = 64; these kernels are issue-bound, not bound by the [M,kC] round
+// trip the fusion saves.  profiles/r02_path_fused_ab.txt.)
 #include <stdlib.h>
 
 #include "link_common.cuh"
@@ -68,347 +63,6 @@ __device__ __forceinline__ void window_row(const float4* __restrict__ rows, int 
     for (int t = 0; t < CH; ++t)
 #pragma unroll
       for (int w = 0; w < NV; ++w) f4add(acc[w], r_[t][w]);
-  }
-}
-
-// per-voxel inputs of one lane (voxel row, coordinate, and the rows only some variants read)
-template <bool WITH_LOCAL, bool WITH_FIN>
-struct VoxIn {
-  int r, cx, cy, cz;
-  float4 lv[WITH_LOCAL ? 2 : 1], fv[WITH_FIN ? 2 : 1];
-};
-
-// ------------------------------------------------------------------ forward
-template <int LPR, int IB, int OP, bool NORM>
-__global__ void __launch_bounds__(WA_WARPS * 32, 2) link_window_apply_kernel(
-    const float4* __restrict__ sums, const int* __restrict__ nbr, const int* __restrict__ seg,
-    const int* __restrict__ order, const int* __restrict__ d_num, int64_t capacity, int R,
-    const float* __restrict__ fin, const int4* __restrict__ coords, GenDev g,
-    const float* __restrict__ local, const float* __restrict__ g1, const float* __restrict__ b1,
-    const float* __restrict__ g2, const float* __restrict__ b2, float* __restrict__ out,
-    float4* __restrict__ mean_out, float* __restrict__ tot_out) {
-  constexpr bool COSX = (OP == LK_OP_COSX);
-  constexpr int K = COSX ? 3 : 2;
-  constexpr int C = 8 * LPR, C4 = C / 4, KC4 = K * C4;
-  constexpr int NV = (KC4 + 31) / 32;
-  constexpr int CH = NV == 1 ? 8 : 4;
-  constexpr int G = 32 / LPR;                      // voxels side by side in a warp
-  constexpr int NP = 4 * IB;
-  __shared__ float4 arow_s[WA_WARPS][KC4];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int grp = lane / LPR, j = lane % LPR;
-  int64_t m = *d_num;
-  if (m > capacity) m = capacity;
-  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= m) return;
-  LaneGen<NP> lg;
-  load_lane_gen<LPR, IB>(g, j, true, lg);
-  const float inv_c = 1.0f / (float)C;
-
-  // software pipeline over blocks: header (neighbour row, segment bounds) two blocks ahead, first
-  // chunk of the sort permutation one block ahead
-  int src0 = -1, s00, s01, src1 = -1, s10 = 0, s11 = 0, ord0;
-  src0 = lane < R ? __ldg(nbr + b * R + lane) : -1;
-  s00 = __ldg(seg + b);
-  s01 = __ldg(seg + b + 1);
-  if (b + warps_total < m) {
-    src1 = lane < R ? __ldg(nbr + (b + warps_total) * R + lane) : -1;
-    s10 = __ldg(seg + b + warps_total);
-    s11 = __ldg(seg + b + warps_total + 1);
-  }
-  ord0 = s00 + lane < s01 ? __ldg(order + s00 + lane) : -1;
-
-  for (; b < m; b += warps_total) {
-    // ---- prefetch: header of block b + 2W, permutation chunk of block b + W ----
-    int src2 = -1, s20 = 0, s21 = 0, ord1 = -1;
-    if (b + 2 * warps_total < m) {
-      src2 = lane < R ? __ldg(nbr + (b + 2 * warps_total) * R + lane) : -1;
-      s20 = __ldg(seg + b + 2 * warps_total);
-      s21 = __ldg(seg + b + 2 * warps_total + 1);
-    }
-    if (b + warps_total < m) ord1 = s10 + lane < s11 ? __ldg(order + s10 + lane) : -1;
-
-    // ---- window population (issued with the first neighbour rows: both depend only on src0) ----
-    int cnt = 0;
-    if (src0 >= 0) cnt = __ldg(seg + src0 + 1) - __ldg(seg + src0);
-    const unsigned present = __ballot_sync(0xffffffffu, src0 >= 0);
-    const int nvox = s01 - s00;
-
-    // ---- first voxel batch: loads issued before the window row is reduced ----
-    int myord = ord0;
-    VoxIn<NORM, COSX> cur, nxt;
-    auto load_batch = [&](VoxIn<NORM, COSX>& d, int t0) {   // t0: offset inside the current 32-position chunk
-      d.r = __shfl_sync(0xffffffffu, myord, (t0 + grp) & 31);
-      const int4 c4 = d.r >= 0 ? __ldg(coords + d.r) : make_int4(0, 0, 0, 0);
-      d.cx = c4.x; d.cy = c4.y; d.cz = c4.z;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (NORM) d.lv[i] = d.r >= 0 ? lk_ldg_stream((const float4*)(local + (int64_t)d.r * C) + i * LPR + j) : f4zero();
-        if (COSX) d.fv[i] = d.r >= 0 ? lk_ldg_stream((const float4*)(fin + (int64_t)d.r * C) + i * LPR + j) : f4zero();
-      }
-    };
-    load_batch(cur, 0);
-    nxt = cur;
-
-    // ---- window row -> shared memory ----
-    float4 acc[NV];
-    window_row<KC4, NV, CH>(sums, src0, present, lane, acc);
-    int tot_i = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
-    const float tot = (float)tot_i;
-#pragma unroll
-    for (int w = 0; w < NV; ++w) {
-      const int v = lane + 32 * w;
-      if (v < KC4) {
-        float4 a = acc[w];
-        a.x /= tot; a.y /= tot; a.z /= tot; a.w /= tot;
-        arow_s[wib][v] = a;
-        if (mean_out) mean_out[b * KC4 + v] = a;
-      }
-    }
-    if (tot_out && lane == 0) tot_out[b] = tot;
-    __syncwarp();
-    float4 A[K][2];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) A[q][i] = arow_s[wib][q * C4 + i * LPR + j];
-
-    // ---- voxels of the block, G side by side; batch t + G is in flight while batch t is computed ----
-    for (int t = 0; t < nvox; t += G) {
-      const int tn = t + G;
-      if (tn < nvox) {                             // crossing a 32-position chunk reloads the permutation entries
-        if ((tn & 31) == 0) myord = s00 + tn + lane < s01 ? __ldg(order + s00 + tn + lane) : -1;
-        load_batch(nxt, tn & 31);
-      }
-      float v[2][4];
-      float p[NP], sn[NP], cs[NP];
-      lane_trig<NP, COSX>(g, lg, cur.cx, cur.cy, cur.cz, p, sn, cs);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float a0[4] = {A[0][i].x, A[0][i].y, A[0][i].z, A[0][i].w};
-        const float a1[4] = {A[1][i].x, A[1][i].y, A[1][i].z, A[1][i].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int q = (i % IB) * 4 + e;
-          v[i][e] = (OP == LK_OP_SIN) ? a0[e] * cs[q] - a1[e] * sn[q] : a0[e] * cs[q] + a1[e] * sn[q];
-        }
-        if (COSX) {                                // + (mean(F p) - F p), linkencoder.py:176
-          const float4 m2 = A[K - 1][i], f = cur.fv[i];
-          v[i][0] += m2.x - f.x * p[(i % IB) * 4 + 0]; v[i][1] += m2.y - f.y * p[(i % IB) * 4 + 1];
-          v[i][2] += m2.z - f.z * p[(i % IB) * 4 + 2]; v[i][3] += m2.w - f.w * p[(i % IB) * 4 + 3];
-        }
-      }
-      if (NORM) {
-        float l[2][4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          l[i][0] = cur.lv[i].x; l[i][1] = cur.lv[i].y; l[i][2] = cur.lv[i].z; l[i][3] = cur.lv[i].w;
-        }
-        group_layernorm<LPR, 2>(v, true, inv_c, g1, b1, j);
-        group_layernorm<LPR, 2>(l, true, inv_c, g2, b2, j);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[i][e] = fmaxf(v[i][e] + l[i][e], 0.f);
-      }
-      if (cur.r >= 0) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          lk_stg_stream((float4*)(out + (int64_t)cur.r * C) + i * LPR + j,
-                        make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
-      }
-      cur = nxt;
-    }
-    __syncwarp();                                  // arow_s is rewritten by the next block
-    src0 = src1; s00 = s10; s01 = s11; ord0 = ord1;
-    src1 = src2; s10 = s20; s11 = s21;
-  }
-}
-
-// ------------------------------------------------------------------ forward, chunk-centric
-// Same arithmetic, different work decomposition: a warp item is a CHUNK of 32 consecutive sorted
-// positions (uniform work for any block-size distribution; the block-centric kernel above is bound by
-// its longest blocks -- 117 voxels = 30 dependent steps on the bench scan -- and by one exposed memory
-// round trip per 4-voxel step).  Per chunk:
-//   * the 32 (voxel row, block row) pairs are read coalesced (prefetched one chunk ahead), the voxels'
-//     coordinates are gathered into registers (lane l <-> position l) and their local_mix / F_in rows
-//     are staged in shared memory with cp.async: ONE gather round trip per 32 voxels;
-//   * the blocks of the chunk are consecutive block rows rank[first] .. rank[last]; for each, the warp
-//     reduces the window row (header prefetched one block ahead) and applies it to the block's
-//     positions inside the chunk (a ballot gives the lane range).  A block that straddles chunks is
-//     reduced once per chunk it touches (+ N/32 window rows at most, bit-identical results).
-#define CA_WARPS 4
-template <int LPR, bool NORM, bool COSX>
-struct ChunkCfg {
-  static constexpr int C = 8 * LPR;
-  static constexpr int K = COSX ? 3 : 2;
-  static constexpr int ROW = C * 4;                                  // bytes per feature row
-  static constexpr int STAGE = ((NORM ? 1 : 0) + (COSX ? 1 : 0)) * 32 * ROW;
-  static constexpr int AROW = K * C * 4;
-  static constexpr int PER_WARP = STAGE + AROW;
-  static constexpr int SMEM = CA_WARPS * PER_WARP;
-};
-
-template <int LPR, int IB, int OP, bool NORM>
-__global__ void __launch_bounds__(CA_WARPS * 32, 4) link_chunk_apply_kernel(
-    const float4* __restrict__ sums, const int* __restrict__ nbr, const int* __restrict__ seg,
-    const int* __restrict__ order, const int* __restrict__ rank, int64_t n, int R,
-    const float* __restrict__ fin, const int4* __restrict__ coords, GenDev g,
-    const float* __restrict__ local, const float* __restrict__ g1, const float* __restrict__ b1,
-    const float* __restrict__ g2, const float* __restrict__ b2, float* __restrict__ out,
-    float4* __restrict__ mean_out, float* __restrict__ tot_out) {
-  constexpr bool COSX = (OP == LK_OP_COSX);
-  using Cfg = ChunkCfg<LPR, NORM, COSX>;
-  constexpr int K = Cfg::K, C = Cfg::C, C4 = C / 4, KC4 = K * C4;
-  constexpr int NV = (KC4 + 31) / 32;
-  constexpr int CH = NV == 1 ? 8 : 4;
-  constexpr int G = 32 / LPR;
-  constexpr int NP = 4 * IB;
-  extern __shared__ __align__(16) uint8_t chunk_s[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int grp = lane / LPR, j = lane % LPR;
-  uint8_t* const wbase = chunk_s + (size_t)wib * Cfg::PER_WARP;
-  const uint32_t wbase_u = (uint32_t)__cvta_generic_to_shared(wbase);
-  float4* const arow = (float4*)(wbase + Cfg::STAGE);
-  const uint8_t* const st_local = wbase;                              // [32][C] floats (NORM)
-  const uint8_t* const st_fin = wbase + (NORM ? 32 * Cfg::ROW : 0);   // [32][C] floats (COSX)
-  const int64_t nitems = (n + 31) >> 5;
-  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (item >= nitems) return;
-  LaneGen<NP> lg;
-  load_lane_gen<LPR, IB>(g, j, true, lg);
-  const float inv_c = 1.0f / (float)C;
-
-  auto load_pair = [&](int64_t it, int& o, int& r) {
-    const int64_t pos = it * 32 + lane;
-    const bool ok = it < nitems && pos < n;
-    o = ok ? __ldg(order + pos) : -1;
-    r = ok ? __ldg(rank + pos) : -1;
-  };
-  int ord, rk, ord_n, rk_n;
-  load_pair(item, ord, rk);
-
-  for (; item < nitems; item += warps_total) {
-    load_pair(item + warps_total, ord_n, rk_n);                        // next chunk's pairs
-    // ---- gather: coordinates into registers, rows into the shared-memory stage ----
-    const int4 cc = ord >= 0 ? __ldg(coords + ord) : make_int4(0, 0, 0, 0);
-    if (NORM || COSX) {
-#pragma unroll
-      for (int t = 0; t < LPR; ++t) {                                  // 32 / G row groups
-        const int row = t * G + grp;
-        const int src = __shfl_sync(0xffffffffu, ord, row);
-        if (src >= 0) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t dst = wbase_u + row * Cfg::ROW + (i * LPR + j) * 16;
-            if (NORM)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                           ::"r"(dst), "l"(local + (int64_t)src * C + 4 * (i * LPR + j)) : "memory");
-            if (COSX)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                           ::"r"(dst + (NORM ? 32 * Cfg::ROW : 0)), "l"(fin + (int64_t)src * C + 4 * (i * LPR + j)) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    const unsigned have = __ballot_sync(0xffffffffu, rk >= 0);
-    const int b_first = __shfl_sync(0xffffffffu, rk, 0);
-    const int b_last = __shfl_sync(0xffffffffu, rk, 31 - __clz(have));
-    int src = lane < R ? __ldg(nbr + (int64_t)b_first * R + lane) : -1;
-    bool staged = !(NORM || COSX);
-
-    for (int b = b_first; b <= b_last; ++b) {
-      const int src_next = (b < b_last && lane < R) ? __ldg(nbr + (int64_t)(b + 1) * R + lane) : -1;
-      int cnt = 0;
-      if (src >= 0) cnt = __ldg(seg + src + 1) - __ldg(seg + src);
-      const unsigned present = __ballot_sync(0xffffffffu, src >= 0);
-      float4 acc[NV];
-      window_row<KC4, NV, CH>(sums, src, present, lane, acc);
-      int tot_i = cnt;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
-      const float tot = (float)tot_i;
-#pragma unroll
-      for (int w = 0; w < NV; ++w) {
-        const int v = lane + 32 * w;
-        if (v < KC4) {
-          float4 a = acc[w];
-          a.x /= tot; a.y /= tot; a.z /= tot; a.w /= tot;
-          arow[v] = a;
-          if (mean_out) mean_out[(int64_t)b * KC4 + v] = a;
-        }
-      }
-      if (tot_out && lane == 0) tot_out[b] = tot;
-      if (!staged) {                                                   // the stage is first read below
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        staged = true;
-      }
-      __syncwarp();
-      float4 A[K][2];
-#pragma unroll
-      for (int q = 0; q < K; ++q)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) A[q][i] = arow[q * C4 + i * LPR + j];
-      const unsigned mine = __ballot_sync(0xffffffffu, rk == b);
-      const int lo = __ffs(mine) - 1, hi = lo + __popc(mine);          // the block's positions in this chunk
-
-      for (int t = lo; t < hi; t += G) {
-        const int row = t + grp;
-        const bool ok = row < hi;
-        const int rl = row & 31;
-        const int dst = __shfl_sync(0xffffffffu, ord, rl);
-        const int cx = __shfl_sync(0xffffffffu, cc.x, rl), cy = __shfl_sync(0xffffffffu, cc.y, rl),
-                  cz = __shfl_sync(0xffffffffu, cc.z, rl);
-        float p[NP], sn[NP], cs[NP];
-        lane_trig<NP, COSX>(g, lg, cx, cy, cz, p, sn, cs);
-        float v[2][4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float a0[4] = {A[0][i].x, A[0][i].y, A[0][i].z, A[0][i].w};
-          const float a1[4] = {A[1][i].x, A[1][i].y, A[1][i].z, A[1][i].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int q = (i % IB) * 4 + e;
-            v[i][e] = (OP == LK_OP_SIN) ? a0[e] * cs[q] - a1[e] * sn[q] : a0[e] * cs[q] + a1[e] * sn[q];
-          }
-          if (COSX) {                              // + (mean(F p) - F p), linkencoder.py:176
-            const float4 m2 = A[K - 1][i];
-            const float4 f = ok ? *(const float4*)(st_fin + rl * Cfg::ROW + (i * LPR + j) * 16) : f4zero();
-            v[i][0] += m2.x - f.x * p[(i % IB) * 4 + 0]; v[i][1] += m2.y - f.y * p[(i % IB) * 4 + 1];
-            v[i][2] += m2.z - f.z * p[(i % IB) * 4 + 2]; v[i][3] += m2.w - f.w * p[(i % IB) * 4 + 3];
-          }
-        }
-        if (NORM) {
-          float l[2][4];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float4 lv = ok ? *(const float4*)(st_local + rl * Cfg::ROW + (i * LPR + j) * 16) : f4zero();
-            l[i][0] = lv.x; l[i][1] = lv.y; l[i][2] = lv.z; l[i][3] = lv.w;
-          }
-          group_layernorm<LPR, 2>(v, true, inv_c, g1, b1, j);
-          group_layernorm<LPR, 2>(l, true, inv_c, g2, b2, j);
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[i][e] = fmaxf(v[i][e] + l[i][e], 0.f);
-        }
-        if (ok) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            lk_stg_stream((float4*)(out + (int64_t)dst * C) + i * LPR + j,
-                          make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
-        }
-      }
-      __syncwarp();                                // arow is rewritten by the next block
-      src = src_next;
-    }
-    __syncwarp();                                  // the stage is refilled by the next chunk
-    ord = ord_n; rk = rk_n;
   }
 }
 
@@ -787,129 +441,7 @@ static int fused_grid(Kern kern, int64_t capacity, int* cache) {
   return (int)(grid < 1 ? 1 : grid);
 }
 
-template <int LPR, int IB, int OP, bool NORM>
-static int launch_window_apply(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                               const int32_t* d_order, const int32_t* d_num, int64_t capacity, int r3,
-                               const float* d_fin, const int32_t* d_coords, const GenDev& g,
-                               const float* d_local, const float* g1, const float* b1, const float* g2,
-                               const float* b2, float* d_out, float* d_mean, float* d_tot, cudaStream_t st) {
-  static int cache[64];
-  auto kern = link_window_apply_kernel<LPR, IB, OP, NORM>;
-  const int grid = fused_grid(kern, capacity, cache);
-  LK_REQUIRE(grid > 0, "lk_link_window_apply_fwd: cannot query the device");
-  kern<<<grid, WA_WARPS * 32, 0, st>>>((const float4*)d_sums, d_nbr, d_seg, d_order, d_num, capacity, r3, d_fin,
-                                       (const int4*)d_coords, g, d_local, g1, b1, g2, b2, d_out,
-                                       (float4*)d_mean, d_tot);
-  LK_LAUNCHED();
-  return LK_OK;
-}
-
-template <int LPR, int IB, int OP, bool NORM>
-static int launch_chunk_apply(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                              const int32_t* d_order, const int32_t* d_rank, int64_t n, int r3,
-                              const float* d_fin, const int32_t* d_coords, const GenDev& g,
-                              const float* d_local, const float* g1, const float* b1, const float* g2,
-                              const float* b2, float* d_out, float* d_mean, float* d_tot, cudaStream_t st) {
-  using Cfg = ChunkCfg<LPR, NORM, OP == LK_OP_COSX>;
-  auto kern = link_chunk_apply_kernel<LPR, IB, OP, NORM>;
-  static int cache[64];
-  int dev = 0;
-  LK_CUDA(cudaGetDevice(&dev));
-  LK_REQUIRE(dev >= 0 && dev < 64, "lk_link_window_apply_fwd: device ordinal %d out of range", dev);
-  if (cache[dev] == 0) {
-    int occ = 0;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CA_WARPS * 32, Cfg::SMEM) != cudaSuccess || occ < 1) {
-      cache[dev] = -1;
-      (void)cudaGetLastError();
-    } else {
-      cache[dev] = occ;
-    }
-  }
-  LK_REQUIRE(cache[dev] > 0, "lk_link_window_apply_fwd: cannot configure the chunk kernel (shared memory %d bytes)", Cfg::SMEM);
-  // all warps resident; every warp gets the same number of chunks (k = ceil(chunks / resident warps))
-  const int64_t nitems = (n + 31) / 32;
-  const int64_t warp_cap = (int64_t)LK_SM_COUNT * cache[dev] * CA_WARPS;
-  const int64_t k = (nitems + warp_cap - 1) / warp_cap;
-  const int64_t warps = (nitems + k - 1) / k;
-  const int grid = (int)((warps + CA_WARPS - 1) / CA_WARPS);
-  kern<<<grid, CA_WARPS * 32, Cfg::SMEM, st>>>((const float4*)d_sums, d_nbr, d_seg, d_order, d_rank, n, r3, d_fin,
-                                               (const int4*)d_coords, g, d_local, g1, b1, g2, b2, d_out,
-                                               (float4*)d_mean, d_tot);
-  LK_LAUNCHED();
-  return LK_OK;
-}
-
-extern "C" int lk_link_window_apply_supported(int c) { return c == 16 || c == 32 || c == 64 || c == 128; }
-
-extern "C" int lk_link_window_apply_fwd(const float* d_sums, const int32_t* d_nbr, const int32_t* d_seg,
-                                        const int32_t* d_order, const int32_t* d_sorted_rank,
-                                        const int32_t* d_num, int64_t capacity,
-                                        int r3, const float* d_fin, const int32_t* d_coords,
-                                        const lk_kernelgen_t* gen, int fuse_norm, const float* d_local,
-                                        const float* d_g1, const float* d_b1, const float* d_g2,
-                                        const float* d_b2, float* d_out, float* d_mean_out,
-                                        float* d_tot_out, lk_stream_t s) {
-  GenDev g;
-  int rc = check_gen(gen, &g, "lk_link_window_apply_fwd");
-  if (rc) return rc;
-  LK_REQUIRE(lk_link_window_apply_supported(g.c), "lk_link_window_apply_fwd: C must be 16, 32, 64 or 128");
-  LK_REQUIRE(capacity >= 0 && r3 > 0 && r3 <= 32, "lk_link_window_apply_fwd: bad sizes (needs r^3 <= 32)");
-  if (capacity == 0) return LK_OK;
-  LK_REQUIRE(d_sums && d_nbr && d_seg && d_order && d_sorted_rank && d_num && d_coords && d_out,
-             "lk_link_window_apply_fwd: null pointer");
-  LK_REQUIRE(g.op != LK_OP_COSX || d_fin, "lk_link_window_apply_fwd: cos_x needs the input features");
-  LK_REQUIRE(!fuse_norm || (d_local && d_g1 && d_b1 && d_g2 && d_b2),
-             "lk_link_window_apply_fwd: fused norms need local features and both LayerNorm parameters");
-  LK_REQUIRE((uintptr_t)d_sums % 16 == 0 && (uintptr_t)d_out % 16 == 0 &&
-                 (!d_mean_out || (uintptr_t)d_mean_out % 16 == 0),
-             "lk_link_window_apply_fwd: feature buffers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)s;
-  const int lpr = g.c / 8, span = 4 * lpr;
-  const int ib = (g.wrows % span == 0 && g.wrows / span == 1) ? 1 : 2;
-  static const bool by_block = [] {
-    const char* e = getenv("LINKB200_WINDOW_APPLY");     // tuning knob: "block" = one warp per block
-    return e && e[0] == 'b';
-  }();
-  if (!by_block) {
-#define CA_ARGS d_sums, d_nbr, d_seg, d_order, d_sorted_rank, capacity, r3, d_fin, d_coords, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out, d_mean_out, d_tot_out, st
-#define CA_N(LPRV, IBV, O)                                                     \
-  (fuse_norm ? launch_chunk_apply<LPRV, IBV, O, true>(CA_ARGS)                 \
-             : launch_chunk_apply<LPRV, IBV, O, false>(CA_ARGS))
-#define CA_O(LPRV, IBV)                                                        \
-  (g.op == LK_OP_COS ? CA_N(LPRV, IBV, LK_OP_COS)                              \
-                     : g.op == LK_OP_SIN ? CA_N(LPRV, IBV, LK_OP_SIN) : CA_N(LPRV, IBV, LK_OP_COSX))
-#define CA_I(LPRV) (ib == 1 ? CA_O(LPRV, 1) : CA_O(LPRV, 2))
-    switch (lpr) {
-      case 2: return CA_I(2);
-      case 4: return CA_I(4);
-      case 8: return CA_I(8);
-      default: return CA_I(16);
-    }
-#undef CA_I
-#undef CA_O
-#undef CA_N
-#undef CA_ARGS
-  }
-#define WA_ARGS d_sums, d_nbr, d_seg, d_order, d_num, capacity, r3, d_fin, d_coords, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out, d_mean_out, d_tot_out, st
-#define WA_N(LPRV, IBV, O)                                                      \
-  (fuse_norm ? launch_window_apply<LPRV, IBV, O, true>(WA_ARGS)                 \
-             : launch_window_apply<LPRV, IBV, O, false>(WA_ARGS))
-#define WA_O(LPRV, IBV)                                                         \
-  (g.op == LK_OP_COS ? WA_N(LPRV, IBV, LK_OP_COS)                               \
-                     : g.op == LK_OP_SIN ? WA_N(LPRV, IBV, LK_OP_SIN) : WA_N(LPRV, IBV, LK_OP_COSX))
-#define WA_I(LPRV) (ib == 1 ? WA_O(LPRV, 1) : WA_O(LPRV, 2))
-  switch (lpr) {
-    case 2: return WA_I(2);
-    case 4: return WA_I(4);
-    case 8: return WA_I(8);
-    default: return WA_I(16);
-  }
-#undef WA_I
-#undef WA_O
-#undef WA_N
-#undef WA_ARGS
-}
+extern "C" int lk_link_bwd_supported(int c) { return c == 16 || c == 32 || c == 64 || c == 128; }
 
 // ------------------------------------------------------------------ backward entry points
 template <int LPR, int IB, int OP>
@@ -972,7 +504,7 @@ static int launch_bwd_apply(const float* d_gsum, const float* d_mean, const int3
 static int check_bwd_gen(const lk_kernelgen_t* gen, GenDev* g, const char* who) {
   int rc = check_gen(gen, g, who);
   if (rc) return rc;
-  if (!lk_link_window_apply_supported(g->c) || g->op == LK_OP_COSX) {
+  if (!lk_link_bwd_supported(g->c) || g->op == LK_OP_COSX) {
     lk_set_error("%s: the fused backward serves C in {16, 32, 64, 128} and the ops cos / sin", who);
     return LK_EINVAL;
   }

@@ -38,8 +38,6 @@ NATIVE_EXECUTOR = os.environ.get('LINKB200_NATIVE_EXECUTOR', '1') != '0'
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 # 1: keep the whole block on the caller's stream (default 0: two-chain schedule inside the executor)
 SINGLE_STREAM = os.environ.get('LINKB200_SINGLE_STREAM', '0') == '1'
-# 1 (default): window mean + apply as one block-centric kernel; 0: the two-kernel form
-USE_WINDOW_APPLY = os.environ.get('LINKB200_WINDOW_APPLY', '1') != '0'
 # 1 (default): training runs the fused forward + hand-written backward (cos / sin, C in {16,32,64,128});
 # 0: the reference's op sequence on differentiable voxelize / devoxelize kernels
 FUSED_BACKWARD = os.environ.get('LINKB200_FUSED_BACKWARD', '1') != '0'
@@ -269,22 +267,11 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
         g1, b1, g2, b2 = (t.detach().contiguous().float() for t in norm)
     # read coords + block index (+ local, + F_in for cos_x) once, the M block-sum rows, write out
     nb = n * (16 + 4 + 4 * c * (1 + fuse + (1 if op == 'cos_x' else 0))) + m_hint * 4 * k * c
-    if USE_WINDOW_APPLY and L.lk_link_window_apply_supported(c):
-        # passes 2a + 2b as one block-centric kernel (no [M,kC] mean round trip)
-        with _capi.timed('lk_link_window_apply_fwd', nb + m_hint * (4 * nbr.shape[1] + 8)):
-            _capi.check(L.lk_link_window_apply_fwd(
-                _capi.ptr(sums), _capi.ptr(nbr), _capi.ptr(bi.seg), _capi.ptr(bi.order), _capi.ptr(bi.sorted_rank),
-                _capi.ptr(bi.num), n, nbr.shape[1], _capi.ptr(f_input), _capi.ptr(coords), C.byref(gen), fuse,
-                _capi.ptr(local) if fuse else None, _capi.ptr(g1), _capi.ptr(b1), _capi.ptr(g2), _capi.ptr(b2),
-                _capi.ptr(out), _capi.ptr(save[0]) if save else None, _capi.ptr(save[1]) if save else None, st),
-                'lk_link_window_apply_fwd')
-        return out
-    assert save is None
-    mean = torch.empty(n, k * c, dtype=torch.float32, device=dev)
+    mean = save[0] if save else torch.empty(n, k * c, dtype=torch.float32, device=dev)
     with _capi.timed('lk_link_window_mean', m_hint * (2 * 4 * k * c + 4 * nbr.shape[1] + 4)):
-        _capi.check(L.lk_link_window_mean(_capi.ptr(sums), _capi.ptr(bi.counts), _capi.ptr(nbr),
-                                          _capi.ptr(bi.num), n, nbr.shape[1], k * c,
-                                          _capi.ptr(mean), st), 'lk_link_window_mean')
+        _capi.check(L.lk_link_window_mean_tot(_capi.ptr(sums), _capi.ptr(bi.seg), _capi.ptr(nbr),
+                                              _capi.ptr(bi.num), n, nbr.shape[1], k * c, _capi.ptr(mean),
+                                              _capi.ptr(save[1]) if save else None, st), 'lk_link_window_mean_tot')
     with _capi.timed('lk_link_apply_fwd', nb):
         _capi.check(L.lk_link_apply_fwd(_capi.ptr(mean), _capi.ptr(f_input), _capi.ptr(coords),
                                         _capi.ptr(bi.idx_query), n, C.byref(gen), fuse,
@@ -490,7 +477,7 @@ class ELKBlock(nn.Module):
         F_input, local_mix = self.pre_mix(st.F), self.local_mix(st)
         c = self.inc
         if (FUSED_BACKWARD and self.baseop in ('cos', 'sin') and st._feats.dtype == torch.float32
-                and _capi.lib().lk_link_window_apply_supported(c)):
+                and _capi.lib().lk_link_bwd_supported(c)):
             # training: fused forward + hand-written backward of the linear-kernel path; pre_mix and
             # local_mix stay autograd nodes of their own (dense Linear+LayerNorm, sparse conv)
             st.F = LinkAggregateFunction.apply(
