@@ -71,6 +71,17 @@ def workload_name(args, n):
     return workload_name_for(args.workload, n)
 
 
+def config_for(workload, n, world):
+    """`config` of the JSON line -- the SAME keys and strings from both arms (--impl ours / reference):
+    it names the workload; how each arm ran it is in the arm's own keys."""
+    return {'workload': workload_name_for(workload, n),
+            'l2': 'flushed between timed iterations (256 MiB memset, outside the events)',
+            'bounds': 'device-resident loop: the scan\'s coordinate bounds (8 ints, a loader-side property) are '
+                      'pre-seeded; e2e loop: computed on the host from the pinned coordinate buffer inside '
+                      'the timed region (SparseTensor.from_host)',
+            'parallelism': f'{world} independent frame streams (no data-path collective)'}
+
+
 def workload_name_for(workload, n):
     if workload == 'block':
         return (f'ELKBlock cos:(3x7)^3 C={C_BLOCK} groups={GROUPS} fwd, synthetic '
@@ -163,15 +174,18 @@ def main_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # every step = the whole scan (0.7 s of CPU work at 120k voxels on 16 cores), so K steps + W warm-up
+    # steps as asked stay within minutes for the driver's K, W; the encoder workload (minutes per scan
+    # on the CPU) is sampled at 30k voxels
     n_sample = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     v, dt, n, cores = run_cpu(args, n_sample, steps, warmup)
     sample = f'{steps} steps after {warmup} warm-up of the same workload at N={n} voxels'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args, n)},
+        'config': config_for(args.workload, n, args.gpus),
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
@@ -208,8 +222,9 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     def step(i, coords, feats):
         return step_st(i, SparseTensor(feats, coords, 1))
 
-    def step_st(i, st):
-        _index.set_coord_bounds(st.kmaps, bounds[i][0], bounds[i][1])
+    def step_st(i, st, seed_bounds=True):
+        if seed_bounds:
+            _index.set_coord_bounds(st.kmaps, bounds[i][0], bounds[i][1])
         with torch.no_grad():
             if workload == 'block':
                 return model(st, S_BLK, R_BLK).F
@@ -290,8 +305,8 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         e0.record()
         # public API: SparseTensor.from_host uploads the coordinates on the current stream and the
         # features on a copy stream; the block's index build overlaps the feature upload
-        st = SparseTensor.from_host(feats_host[i], coords_host[i], 1, device=dev)
-        out = step_st(i, st)
+        st = SparseTensor.from_host(feats_host[i], coords_host[i], 1, device=dev)   # seeds the bounds itself
+        out = step_st(i, st, seed_bounds=False)
         out_host.copy_(out.sum(dim=0), non_blocking=True)
         e1.record()
         if k >= w_e2e:
@@ -307,13 +322,13 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         from link_b200.tensor import UploadRing
         ring = UploadRing(max(n_vox), feats_host[0].shape[1], device=dev, depth=2)
         for k in range(w_e2e):
-            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1)).sum(dim=0), non_blocking=True)
+            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1), seed_bounds=False).sum(dim=0), non_blocking=True)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_h = time.perf_counter()
         for k in range(steps):
-            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1)).sum(dim=0), non_blocking=True)
+            out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1), seed_bounds=False).sum(dim=0), non_blocking=True)
         host_ms = (time.perf_counter() - t_h) * 1e3 / steps
         e1.record()
         barrier()
@@ -492,9 +507,7 @@ def main_ours(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
         'warmup': m['warmup'], 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name_for(args.workload, m['n0']),
-                   'l2': 'flushed between timed iterations (256 MiB memset, outside the events)',
-                   'parallelism': f'{world} independent frame streams (no data-path collective)'},
+        'config': config_for(args.workload, m['n0'], world),
         'clocks': m['clocks'],
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'],
                 'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps},

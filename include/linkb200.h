@@ -423,6 +423,21 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);
+/* The same product on tcgen05 (kind::tf32, 3xTF32; C_in, C_out in {32, 64, 128}, K <= 32) --
+ * replaces the per-offset gather + torch::mm(in^T, grad_out) of convolution_backward_cuda
+ * (torchsparse/backend/convolution/convolution_cuda.cu:217-278).  Two calls:
+ *   lk_conv_wgrad_prepass   once per relation (kernel map direction): d_masks [ceil(n/64)] = offsets
+ *                           with at least one pair per 64-row tile; with a tile order d_perm [n]
+ *                           (lk_conv_plan) also d_nbrp [K, n] = d_nbr[:, d_perm] (both NULL otherwise);
+ *   lk_conv_wgrad_tc        d_gw [K, c_in, c_out] (zeroed by the call) from d_in rows gathered through
+ *                           d_nbrp (= d_nbr when there is no order) and d_gout rows d_perm[pos];
+ *                           slots_per_cta <= 512 / c_out accumulator slots per CTA (0 = as many as fit). */
+int lk_conv_wgrad_tc_supported(int c_in, int c_out);
+int lk_conv_wgrad_prepass(const int32_t* d_nbr, const int32_t* d_perm, int64_t n, int k,
+                          int32_t* d_nbrp, uint32_t* d_masks, lk_stream_t s);
+int lk_conv_wgrad_tc(const float* d_in, const float* d_gout, const int32_t* d_nbrp,
+                     const int32_t* d_perm, const uint32_t* d_masks, int64_t n, int k, int c_in,
+                     int c_out, float* d_gw, int slots_per_cta, lk_stream_t s);
 /* ------------------------------------------------------------------------------------
  * Rotated bird's-eye-view IoU of 3D boxes (x, y, z, dx, dy, dz, heading): d_out [n, m] =
  * IoU(d_a[i], d_b[j]).  Replaces iou3d_nms_cuda.boxes_iou_bev_gpu / the IoU inside nms_gpu

@@ -114,6 +114,9 @@ PROTOTYPES = {
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
+    'lk_conv_wgrad_tc_supported': (i32, [i32, i32]),
+    'lk_conv_wgrad_prepass': (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    'lk_conv_wgrad_tc': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32, vp]),
     'lk_boxes_iou_bev': (i32, [vp, i64, vp, i64, vp, vp]),
     'lk_boxes_iou_bev_hostcheck': (i32, [vp, i64, vp, i64, vp]),
 }

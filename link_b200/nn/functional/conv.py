@@ -39,6 +39,7 @@ class KernelMap:
         self._ref = None
         self.offsets = None      # int32 [K,3] offsets the map was built with (classes of the plan)
         self._plan = None        # (perm [n_out], tile_mask [tiles]) or False
+        self._wgrad = {}         # direction -> (nbrp, perm, masks) of the tensor-core weight gradient
 
     @property
     def inv(self) -> torch.Tensor:
@@ -77,6 +78,25 @@ class KernelMap:
                                                _capi.ptr(ws), ws_bytes, _capi.stream()), 'lk_conv_plan')
                 self._plan = (perm, tmask)
         return self._plan or None
+
+    def wgrad_relation(self, transposed: bool):
+        """Relation of the weight-gradient contraction as the tensor-core kernel walks it
+        (lk_conv_wgrad_prepass, once per map and direction, shared by every conv on the map):
+        rows = forward OUTPUT rows (grad rows), in the order of the forward tile plan when there is
+        one.  Returns (nbrp [K, n], perm [n] or None, masks [ceil(n/64)])."""
+        hit = self._wgrad.get(transposed)
+        if hit is None:
+            rel = self.inv if transposed else self.nbr
+            k, n = rel.shape
+            plan = None if transposed else self.plan()
+            perm = plan[0] if plan is not None else None
+            masks = torch.empty((n + 63) // 64, dtype=torch.int32, device=rel.device)
+            nbrp = torch.empty_like(rel) if perm is not None else None
+            _capi.check(_capi.lib().lk_conv_wgrad_prepass(_capi.ptr(rel), _capi.ptr(perm), n, k, _capi.ptr(nbrp),
+                                                          _capi.ptr(masks), _capi.stream()),
+                        'lk_conv_wgrad_prepass')
+            hit = self._wgrad[transposed] = (nbrp if nbrp is not None else rel, perm, masks)
+        return hit
 
     def _reference_layout(self):
         if self._ref is None:
@@ -150,6 +170,9 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_pl
 USE_TENSOR_CORES = os.environ.get('LINKB200_TENSOR_CORES', '1') != '0'
 # tile-skipping plan (lk_conv_plan) for the tensor-core conv; '0' runs every (offset, tile) step
 USE_PLAN = os.environ.get('LINKB200_CONV_PLAN', '1') != '0'
+# weight gradient on tcgen05 (lk_conv_wgrad_tc); '0' keeps the FFMA kernel (lk_conv_bwd_weight)
+USE_TC_WGRAD = os.environ.get('LINKB200_TC_WGRAD', '1') != '0'
+WGRAD_SLOTS = int(os.environ.get('LINKB200_WGRAD_SLOTS', '0'))
 _tc_supported = {}
 
 
@@ -306,9 +329,18 @@ class ConvolutionFunction(Function):
             grad_feats = _conv_fwd(g, None, to_in, n_in_rows, weight_t=weight).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
-            _capi.check(_capi.lib().lk_conv_bwd_weight(
-                _capi.ptr(feats), _capi.ptr(g), _capi.ptr(to_out), g.shape[0], k, c_in, c_out,
-                _capi.ptr(grad_weight), _capi.stream()), 'lk_conv_bwd_weight')
+            L = _capi.lib()
+            if USE_TENSOR_CORES and USE_TC_WGRAD and k <= 32 and L.lk_conv_wgrad_tc_supported(c_in, c_out) \
+                    and g.shape[0] * k < 2 ** 31:
+                nbrp, perm, masks = kmap.wgrad_relation(transposed)
+                _capi.check(L.lk_conv_wgrad_tc(
+                    _capi.ptr(feats), _capi.ptr(g), _capi.ptr(nbrp), _capi.ptr(perm), _capi.ptr(masks),
+                    g.shape[0], k, c_in, c_out, _capi.ptr(grad_weight), WGRAD_SLOTS, _capi.stream()),
+                    'lk_conv_wgrad_tc')
+            else:
+                _capi.check(L.lk_conv_bwd_weight(
+                    _capi.ptr(feats), _capi.ptr(g), _capi.ptr(to_out), g.shape[0], k, c_in, c_out,
+                    _capi.ptr(grad_weight), _capi.stream()), 'lk_conv_bwd_weight')
         return grad_feats, grad_weight, None, None
 
 

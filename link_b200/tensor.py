@@ -24,6 +24,15 @@ def _copy_stream(device):
     return st
 
 
+def _seed_bounds_from_host(st, coords_host: torch.Tensor) -> None:
+    """Coordinate bounds of an uploaded scan, computed on the HOST copy while the upload is in flight
+    (one pass over [N,4] int32), so the index build never reads them back from the device."""
+    if coords_host.device.type == 'cpu' and coords_host.dim() == 2 and coords_host.shape[0] > 0:
+        from link_b200.nn.functional import _index
+        lo, hi = torch.aminmax(coords_host, dim=0)
+        _index.set_coord_bounds(st.kmaps, lo.tolist(), hi.tolist())
+
+
 class SparseTensor:
 
     def __init__(self, feats: torch.Tensor, coords: torch.Tensor,
@@ -77,6 +86,7 @@ class SparseTensor:
             ev.record(copy_stream)
         st = cls(f_dev, c_dev, stride)
         st._feats_ready = ev
+        _seed_bounds_from_host(st, coords)
         return st
 
     @property
@@ -202,4 +212,5 @@ class UploadRing:
         self._count += 1
         st = SparseTensor(f_dev, c_dev, stride)
         st._feats_ready = ev
+        _seed_bounds_from_host(st, coords)
         return st

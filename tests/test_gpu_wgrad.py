@@ -1,0 +1,103 @@
+"""GPU tests of the tensor-core weight gradient (lk_conv_wgrad_prepass + lk_conv_wgrad_tc) against a
+float64 contraction of the same kernel map, and through ConvolutionFunction.backward."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'gpu-marked tests need a CUDA device'
+    from link_b200 import _capi
+    _capi.lib()
+    return torch.device('cuda:0')
+
+
+def _kmap(dev, n, ksize, stride, cin):
+    from link_b200 import SparseTensor
+    from link_b200.nn.functional.conv import build_kernel_map
+    from link_b200.utils.synthetic import kitti_like_voxels, random_voxels
+    if n >= 9_000:
+        c3, _ = kitti_like_voxels(n, seed=3)
+        coords = np.concatenate([c3, np.zeros((len(c3), 1), np.int32)], 1).astype(np.int32)
+    else:
+        coords = random_voxels(n, 24, seed=n)
+    st = SparseTensor(torch.zeros(len(coords), cin, device=dev), torch.from_numpy(coords).to(dev), 1)
+    return build_kernel_map(st, (ksize,) * 3, (stride,) * 3, (1, 1, 1), want_plan=True)
+
+
+def _want(x, g, rel):
+    """float64: gw[k] = sum_{o: rel[k,o] >= 0} x[rel[k,o]]^T g[o]"""
+    K = rel.shape[0]
+    xn, gn = x.double().cpu().numpy(), g.double().cpu().numpy()
+    out = np.zeros((K, xn.shape[1], gn.shape[1]))
+    for k in range(K):
+        hit = rel[k] >= 0
+        out[k] = xn[rel[k][hit]].T @ gn[hit]
+    return out
+
+
+@pytest.mark.parametrize('n,cin,cout,ksize,stride', [(20_000, 64, 64, 3, 1), (3_000, 32, 64, 3, 1),
+                                                     (130, 64, 32, 3, 1), (9_000, 32, 32, 2, 2),
+                                                     (1, 64, 64, 3, 1), (9_000, 128, 128, 3, 1),
+                                                     (2_000, 64, 128, 3, 1), (2_500, 128, 32, 2, 2),
+                                                     (700, 128, 64, 3, 1), (300, 32, 128, 3, 1),
+                                                     (40_000, 32, 32, 3, 1)])
+@pytest.mark.parametrize('transposed', [False, True])
+def test_wgrad_tc_vs_float64(dev, n, cin, cout, ksize, stride, transposed):
+    """Both directions of the relation (forward map with the plan order; inverted map without), all
+    nine channel combinations, maps with 8 and 27 offsets, a single row, tiles past the end."""
+    from link_b200 import _capi
+    km = _kmap(dev, n, ksize, stride, cin)
+    rel = (km.inv if transposed else km.nbr)
+    K, rows = rel.shape
+    n_src = km.n_out if transposed else km.n_in
+    gen = torch.Generator().manual_seed(n + cin)
+    x = torch.randn(n_src, cin, generator=gen).to(dev)
+    g = torch.randn(rows, cout, generator=gen).to(dev)
+    nbrp, perm, masks = km.wgrad_relation(transposed)
+    assert (perm is not None) == (not transposed)
+    # the pre-pass: masks and the permuted relation
+    rel_h = rel.cpu().numpy()
+    perm_h = perm.cpu().numpy() if perm is not None else np.arange(rows)
+    relp = rel_h[:, perm_h]
+    assert np.array_equal(nbrp.cpu().numpy(), relp)
+    pad = (-rows) % 64
+    hit = np.concatenate([relp >= 0, np.zeros((K, pad), bool)], 1).reshape(K, -1, 64).any(2)
+    want_masks = (hit * (1 << np.arange(K, dtype=np.int64))[:, None]).sum(0)
+    assert np.array_equal(masks.cpu().numpy().view(np.uint32).astype(np.int64), want_masks)
+    want = _want(x, g, rel_h)
+    scale = max(1.0, float(np.abs(want).max()))
+    for slots in (0, 1, 2):
+        gw = torch.full((K, cin, cout), float('nan'), device=dev)
+        _capi.check(_capi.lib().lk_conv_wgrad_tc(_capi.ptr(x), _capi.ptr(g), _capi.ptr(nbrp), _capi.ptr(perm),
+                                                 _capi.ptr(masks), rows, K, cin, cout, _capi.ptr(gw), slots,
+                                                 _capi.stream()), 'lk_conv_wgrad_tc')
+        err = float(np.abs(gw.cpu().numpy() - want).max()) / scale
+        assert err < 2e-5, (slots, err)          # 3xTF32: ~1e-6 relative to the largest entry
+
+
+def test_wgrad_tc_through_autograd_matches_ffma(dev, monkeypatch):
+    """ConvolutionFunction.backward: the tensor-core weight gradient equals the FFMA kernel's."""
+    import link_b200.nn.functional as F
+    import link_b200.nn.functional.conv as conv_mod
+    from link_b200 import SparseTensor
+    from link_b200.utils.synthetic import random_voxels
+    coords = torch.from_numpy(random_voxels(6_000, 32, seed=9)).to(dev)
+    gen = torch.Generator().manual_seed(3)
+    f = torch.randn(len(coords), 32, generator=gen).to(dev)
+    ws = [(torch.randn(27, 32, 64, generator=gen) * 0.1).to(dev), (torch.randn(8, 64, 128, generator=gen) * 0.1).to(dev),
+          (torch.randn(8, 128, 32, generator=gen) * 0.1).to(dev)]
+    grads = {}
+    for flag in (True, False):
+        monkeypatch.setattr(conv_mod, 'USE_TC_WGRAD', flag)
+        x = SparseTensor(f.clone().requires_grad_(True), coords, 1)
+        x.cmaps[x.stride] = x.coords
+        w = [t.clone().requires_grad_(True) for t in ws]
+        y = F.conv3d(F.conv3d(F.conv3d(x, w[0], 3), w[1], 2, stride=2), w[2], 2, stride=2, transposed=True)
+        y.F.square().sum().backward()
+        grads[flag] = [t.grad.clone() for t in w]
+    for a, b in zip(grads[True], grads[False]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * float(b.abs().max()))
