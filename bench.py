@@ -38,7 +38,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='block', choices=['block', 'encoder'])
+    ap.add_argument('--workload', default='block', choices=['block', 'encoder', 'train_encoder'])
+    ap.add_argument('--no-train', action='store_true', help='skip the extra DDP training measurement')
     ap.add_argument('--voxels', type=int, default=120_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-encoder', action='store_true', help='skip the extra encoder measurement')
@@ -347,6 +348,108 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
             'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
 
 
+def run_train(args, steps, warmup, dev, rank, world, local):
+    """BASELINE config 3: one DDP training step of ELKEncoder (cr = 1.0, cos (3x7)^3) per rank on its own
+    batch of 2 synthetic SemanticKITTI-shaped scans capped at 80 000 voxels each (reference:
+    segmentation/train.py:82-100 -- DistributedSampler + DistributedDataParallel(find_unused_parameters=
+    True); configs/semantic_kitti/default.yaml: batch_size 2, num_points 80000, SGD momentum 0.9 nesterov,
+    weight decay 1e-4; lr 0.024 here -- the reference's 0.24 comes with a warm-up schedule).  Frames never cross ranks; the ONLY collective is DDP's gradient
+    all-reduce over NCCL (5.8 M parameters = 23 MB fp32).  Timed region per step, end to end: H2D of
+    the batch (coords, feats, labels) from pinned memory -> forward -> cross-entropy -> backward (+
+    all-reduce) -> SGD step -> D2H of the loss.  The same steps under `no_sync()` give the step
+    without the all-reduce; the difference is the exposed communication time."""
+    import contextlib
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from link_b200 import SparseTensor, _capi
+    from link_b200.linkencoder import ELKEncoder
+    from link_b200.sharding import frame_seed
+
+    per_scan = min(args.voxels, 80_000)
+    batches = []
+    for b in range(2):                                        # two alternating batches per rank
+        cs, fs = [], []
+        for j in range(2):
+            c, f = make_scan(per_scan, seed=frame_seed(rank, 10 + 2 * b + j))
+            c = c.copy()
+            c[:, 3] = j
+            cs.append(c)
+            fs.append(f)
+        c, f = np.concatenate(cs), np.concatenate(fs)
+        y = np.random.default_rng(frame_seed(rank, b)).integers(0, 19, size=len(c))
+        batches.append((torch.from_numpy(c).pin_memory(), torch.from_numpy(f).pin_memory(),
+                        torch.from_numpy(y).pin_memory()))
+    torch.manual_seed(0)                                      # identical initial weights on every rank
+    net = ELKEncoder(num_classes=19, cr=1.0, baseop=BASEOP, r=R_BLK, s=S_BLK, groups=GROUPS).to(dev).train()
+    model = net
+    if world > 1:
+        model = DDP(net, device_ids=[local], find_unused_parameters=True)
+    opt = torch.optim.SGD(model.parameters(), lr=0.024, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(i, sync=True):
+        c_h, f_h, y_h = batches[i % 2]
+        st = SparseTensor.from_host(f_h, c_h, 1, device=dev)
+        y = y_h.to(dev, non_blocking=True)
+        ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
+        with ctx:
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(model(st), y, ignore_index=0)
+            loss.backward()
+        opt.step()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(device_ids=[local])                   # NCCL barrier: communicator exists from here on
+        torch.cuda.synchronize()
+
+    def timed_loop(sync):
+        for k in range(warmup):
+            step(k, sync)
+        barrier()
+        launches0 = _capi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(steps):
+            step(k, sync)
+        e1.record()
+        host_ms = (time.perf_counter() - t0) * 1e3 / steps
+        barrier()
+        return e0.elapsed_time(e1), host_ms, _capi.launch_count() - launches0
+
+    ms, host_ms, launches = timed_loop(True)
+    ms_nosync = timed_loop(False)[0] if world > 1 else ms
+    loss_val = float(loss_host.item())
+    vox = float(sum(len(batches[k % 2][0]) for k in range(steps)))
+    h2d = sum(t.numel() * t.element_size() for t in batches[0])
+    nparam = sum(p.numel() for p in net.parameters())
+    return {'ms': ms, 'ms_nosync': ms_nosync, 'voxels': vox, 'steps': steps, 'warmup': warmup, 'h2d': h2d, 'd2h': 4,
+            'launches': int(launches), 'host_ms': host_ms, 'loss': loss_val, 'nparam': nparam,
+            'n_batch': len(batches[0][0])}
+
+
+def train_line(tr, world, dev):
+    """Whole-job numbers of the training workload (max time over ranks, summed voxels)."""
+    from link_b200.sharding import reduce_throughput
+    ms, vox = reduce_throughput(tr['ms'], tr['voxels'], None)
+    ms_ns, _ = reduce_throughput(tr['ms_nosync'], tr['voxels'], None)
+    steps = tr['steps']
+    return {'workload': (f"ELKEncoder cos:(3x7)^3 cr=1.0 DDP training step (fwd + cross-entropy + bwd + gradient "
+                         f"all-reduce + SGD), 2 synthetic scans per rank, {tr['n_batch']} voxels per batch, fp32"),
+            'value': vox / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps, 'warmup': tr['warmup'],
+            'scaling': 'weak', 'collective': f'NCCL all-reduce of {tr["nparam"] * 4 / 1e6:.1f} MB fp32 gradients '
+                                             f'per step (torch DDP, {world} ranks)' if world > 1 else 'none (1 rank)',
+            'ms_per_step_no_allreduce': ms_ns / steps,
+            'allreduce_exposed_ms_per_step': max(0.0, (ms - ms_ns) / steps),
+            'timed_region': 'H2D of the batch from pinned memory, forward, loss, backward, all-reduce, SGD step, '
+                            'D2H of the loss; CUDA events around the K steps, max over ranks',
+            'h2d_bytes_per_step': tr['h2d'], 'd2h_bytes_per_step': tr['d2h'], 'gpu_launches': tr['launches'],
+            'host_enqueue_ms_per_step': tr['host_ms'], 'loss': tr['loss']}
+
+
 def reference_gpu_leg(dev, coords, feats, blk, flush, steps=5, warmup=2):
     try:
         from oracle import ref_gpu
@@ -454,6 +557,25 @@ def main_ours(args):
         dist.init_process_group('cpu:gloo,cuda:nccl')
     _capi.lib()
 
+    if world > 1:
+        print(f'[bench rank {rank}] torch.distributed: cuda backend nccl (NCCL {".".join(map(str, torch.cuda.nccl.version()))}), '
+              f'cpu backend gloo, world_size {world}', file=sys.stderr, flush=True)
+    if args.workload == 'train_encoder':
+        tr = run_train(args, args.steps, args.warmup, dev, rank, world, local)
+        tl = train_line(tr, world, dev)
+        if rank == 0:
+            line = {'metric': 'ELKEncoder training voxels/sec (DDP)', 'value': tl['value'], 'unit': UNIT, 'n_gpus': world,
+                    'steps': tl['steps'], 'warmup': tl['warmup'], 'ms_per_step': tl['ms_per_step'],
+                    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                    'data': 'synthetic', 'config': {'workload': tl['workload']},
+                    'e2e': {'value': tl['value'], 'unit': UNIT, 'h2d_bytes_per_step': tl['h2d_bytes_per_step'],
+                            'd2h_bytes_per_step': tl['d2h_bytes_per_step'],
+                            'note': 'the timed region of this workload IS end to end (host batch in, loss out)'},
+                    'gpu_launches': tl['gpu_launches'], 'train': tl}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     m = run_workload(args, args.workload, args.steps, args.warmup, dev, rank, world, local, rank == 0)
     dev_ms, e2e_ms, vox_total = summarize(m, world, dev)
     extra = None
@@ -467,6 +589,17 @@ def main_ours(args):
                  'e2e': {'value': ev / (ee * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': me['h2d'],
                          'd2h_bytes_per_step': me['d2h']},
                  'gpu_launches': me['launches'], 'host_enqueue_ms_per_step': me['host_enqueue_ms']}
+    train = None
+    if args.workload == 'block' and not args.no_train:
+        # BASELINE config 3 (DDP training step; the one place of the path with a collective), as
+        # additional evidence next to the headline metric
+        try:
+            train = train_line(run_train(args, max(3, args.steps // 2), min(3, args.warmup), dev, rank, world, local),
+                               world, dev)
+        except Exception as e:   # noqa: BLE001 -- an extra leg must never take the bench line down
+            if world > 1:
+                raise            # ... but a rank that leaves a collective would hang the others: fail loudly
+            train = {'unavailable': repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -519,6 +652,8 @@ def main_ours(args):
     }
     if extra is not None:
         line['encoder'] = extra
+    if train is not None:
+        line['train_encoder'] = train
     if m.get('ref_gpu'):
         line['reference_gpu'] = m['ref_gpu']
     if world == 1 and not args.no_cpu_baseline:

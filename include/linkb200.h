@@ -349,8 +349,11 @@ typedef struct {
   const float* d_shift;     /* [c_out] or NULL */
   const float* d_residual;  /* [n_out, c_out] or NULL */
   int32_t relu;
-  int32_t reserved;
+  int32_t precision;        /* tensor-core kernels only: LK_PREC_FP32 (0, default) = 3xTF32, fp32-level accuracy;
+                               LK_PREC_TF32 (1) = single-pass TF32 (operands truncated to tf32, ~1e-3 relative) */
 } lk_conv_epilogue_t;
+#define LK_PREC_FP32 0
+#define LK_PREC_TF32 1
 int lk_conv_fwd_ex(const float* d_in, const float* d_w, const int32_t* d_nbr, int64_t n_out, int k,
                    int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out, lk_stream_t s);
 int lk_conv_tc_fwd_ex(const float* d_in, const float* d_wimg, const int32_t* d_nbr, int64_t n_out,
@@ -420,6 +423,9 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
                        const float* coors_range, int max_points, int max_voxels, float* d_voxels,
                        int32_t* d_coors, int32_t* d_num_points, int32_t* d_voxel_num, void* d_ws,
                        int64_t ws_bytes, lk_stream_t s);
+/* HOST helper (no device work): column-wise min / max of a host int32 [n,4] coordinate array -> lo4, hi4
+ * (the bounds that size the packed sort keys; SparseTensor.from_host calls it while the upload is in flight). */
+int lk_host_coord_bounds(const int32_t* h_coords, int64_t n, int32_t* lo4, int32_t* hi4);
 /* grad_w[k] = sum_o in[nbr[k,o]]^T @ grad_out[o]; d_gw [K,c_in,c_out] zeroed by this call. */
 int lk_conv_bwd_weight(const float* d_in, const float* d_gout, const int32_t* d_nbr,
                        int64_t n_out, int k, int c_in, int c_out, float* d_gw, lk_stream_t s);

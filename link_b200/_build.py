@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, 'liblinkb200.so')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-Xptxas', '-O3']
+         '-Xcompiler', '-fPIC,-msse4.1', '-Xptxas', '-O3']
 
 
 def sources():

@@ -33,7 +33,7 @@ class KernelGen(C.Structure):
 
 class ConvEpilogue(C.Structure):
     _fields_ = [('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('d_residual', C.c_void_p),
-                ('relu', C.c_int32), ('reserved', C.c_int32)]
+                ('relu', C.c_int32), ('precision', C.c_int32)]
 
 
 class ElkBlockArgs(C.Structure):
@@ -114,6 +114,7 @@ PROTOTYPES = {
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
+    'lk_host_coord_bounds': (i32, [vp, i64, vp, vp]),
     'lk_conv_wgrad_tc_supported': (i32, [i32, i32]),
     'lk_conv_wgrad_prepass': (i32, [vp, vp, i64, i32, vp, vp, vp]),
     'lk_conv_wgrad_tc': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32, vp]),

@@ -68,7 +68,10 @@ struct ConvTcCfg {
 };
 
 
-template <int CIN, int COUT, int NST>
+// PREC = 0: 3xTF32 (fp32-level accuracy, three MMAs per k-slice on tf32 hi / lo planes);
+// PREC = 1: single-pass TF32 (the tensor core truncates the fp32 operands to tf32: ~1e-3 relative,
+//           what frameworks call "allow_tf32"): no split, one TMEM store, one MMA per k-slice.
+template <int CIN, int COUT, int NST, int PREC>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wimg /*[K] packed B-operand images*/,
     const int* __restrict__ nbr /*[K][n_out]*/,
@@ -219,9 +222,13 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           for (int ks = 0; ks < CE / 8; ++ks) {
             // B descriptor start address is in 16-byte units: K-block ks/4, 32-byte slice ks%4
             const uint64_t bo = (uint64_t)(((ks >> 2) * Cfg::B_BLK + (ks & 3) * 32) >> 4);
-            tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
-            tc::mma_tf32_ts(d, a_hi + 8 * ks, db_lo + bo, idesc, 1);
-            tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
+            if (PREC == 0) {
+              tc::mma_tf32_ts(d, a_lo + 8 * ks, db_hi + bo, idesc, acc);
+              tc::mma_tf32_ts(d, a_hi + 8 * ks, db_lo + bo, idesc, 1);
+              tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, 1);
+            } else {
+              tc::mma_tf32_ts(d, a_hi + 8 * ks, db_hi + bo, idesc, acc);
+            }
             acc = 1;
           }
 #endif
@@ -278,10 +285,10 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 #ifndef CT_DEBUG_NO_ST
         if (CPT == 16) {
           tc::tmem_st16(a_hi, hi);
-          tc::tmem_st16(a_hi + 64, lo);
+          if (PREC == 0) tc::tmem_st16(a_hi + 64, lo);
         } else {
           tc::tmem_st8(a_hi, hi);
-          tc::tmem_st8(a_hi + 64, lo);
+          if (PREC == 0) tc::tmem_st8(a_hi + 64, lo);
         }
         tc::tmem_st_wait();
 #endif
@@ -369,8 +376,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
             const float4 v4 = *(const float4*)(slot + read_off[i]);
-            float4 h4, l4;
-            tc::split_tf32(v4, h4, l4);
+            float4 h4 = v4, l4 = v4;
+            if (PREC == 0) tc::split_tf32(v4, h4, l4);
             hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
             lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
           }
@@ -394,8 +401,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           float hi[16], lo[16];
 #pragma unroll
           for (int i = 0; i < CPT / 4; ++i) {
-            float4 h4, l4;
-            tc::split_tf32(cur[i], h4, l4);
+            float4 h4 = cur[i], l4 = cur[i];
+            if (PREC == 0) tc::split_tf32(cur[i], h4, l4);
             hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
             lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
           }
@@ -469,21 +476,21 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int CIN, int COUT, int NST>
+template <int CIN, int COUT, int NST, int PREC>
 static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
   using Cfg = ConvTcCfg<CIN, COUT, NST>;
   static bool attr_set = false;
   if (!attr_set) {
-    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)Cfg::SMEM));
     attr_set = true;
   }
   int64_t tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   int grid = (int)(tiles < LK_SM_COUNT ? tiles : LK_SM_COUNT);   // persistent: one CTA per SM
-  conv_tc_kernel<CIN, COUT, NST><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
-                                                                      n_out, k, ep, out);
+  conv_tc_kernel<CIN, COUT, NST, PREC><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
+                                                                            n_out, k, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -506,10 +513,12 @@ static int launch_conv_tc(const float* in, const float* wimg, const int* nbr, co
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
 #ifdef CT_WITH_3_STAGES
   if (conv_tc_stages() == 3)
-    return launch_conv_tc_n<CIN, COUT, 3>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+    return launch_conv_tc_n<CIN, COUT, 3, 0>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
 #endif
   (void)conv_tc_stages;
-  return launch_conv_tc_n<CIN, COUT, 2>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+  if (ep.precision == LK_PREC_TF32)
+    return launch_conv_tc_n<CIN, COUT, 2, 1>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+  return launch_conv_tc_n<CIN, COUT, 2, 0>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
 }
 
 extern "C" int lk_conv_tc_supported(int c_in, int c_out) {

@@ -8,6 +8,9 @@
 //                   unpack, count left on the device
 //                   (reference: F.spdownsample, nn/functional/downsample.py:11-51)
 #include "common.cuh"
+#if defined(__SSE4_1__)
+#include <smmintrin.h>
+#endif
 
 static inline int64_t ix_al(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
@@ -75,5 +78,45 @@ extern "C" int lk_downsample(const int32_t* d_coords, int64_t n, const lk_keyspe
   LK_TRY(lk_sort_unique(keys, n, key_bits, uniq, nullptr, nullptr, nullptr, nullptr, d_num, sws,
                         lk_sort_unique_ws_bytes(n), s));
   LK_TRY(lk_unpack_keys(uniq, d_num, n, spec, d_out_coords, s));
+  return LK_OK;
+}
+
+/* Host helper: per-column minimum and maximum of a HOST int32 [n, 4] coordinate array (the bounds
+ * that size the packed sort keys), one pass, while the scan's upload is in flight. */
+extern "C" int lk_host_coord_bounds(const int32_t* h_coords, int64_t n, int32_t* lo4, int32_t* hi4) {
+  LK_REQUIRE(n >= 0 && lo4 && hi4 && (n == 0 || h_coords), "lk_host_coord_bounds: null pointer");
+  int32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  if (n > 0) {
+    for (int a = 0; a < 4; ++a) lo[a] = hi[a] = h_coords[a];
+    int64_t i = 1;
+#if defined(__SSE4_1__)
+    // one 128-bit min / max per row, four independent accumulator pairs (the loop is bound by the
+    // 1-cycle latency of pminsd / pmaxsd otherwise)
+    __m128i l0 = _mm_loadu_si128((const __m128i*)h_coords), l1 = l0, l2 = l0, l3 = l0;
+    __m128i h0 = l0, h1 = l0, h2 = l0, h3 = l0;
+    for (; i + 4 <= n; i += 4) {
+      const __m128i r0 = _mm_loadu_si128((const __m128i*)(h_coords + 4 * i));
+      const __m128i r1 = _mm_loadu_si128((const __m128i*)(h_coords + 4 * i + 4));
+      const __m128i r2 = _mm_loadu_si128((const __m128i*)(h_coords + 4 * i + 8));
+      const __m128i r3 = _mm_loadu_si128((const __m128i*)(h_coords + 4 * i + 12));
+      l0 = _mm_min_epi32(l0, r0); h0 = _mm_max_epi32(h0, r0);
+      l1 = _mm_min_epi32(l1, r1); h1 = _mm_max_epi32(h1, r1);
+      l2 = _mm_min_epi32(l2, r2); h2 = _mm_max_epi32(h2, r2);
+      l3 = _mm_min_epi32(l3, r3); h3 = _mm_max_epi32(h3, r3);
+    }
+    l0 = _mm_min_epi32(_mm_min_epi32(l0, l1), _mm_min_epi32(l2, l3));
+    h0 = _mm_max_epi32(_mm_max_epi32(h0, h1), _mm_max_epi32(h2, h3));
+    _mm_storeu_si128((__m128i*)lo, l0);
+    _mm_storeu_si128((__m128i*)hi, h0);
+#endif
+    for (; i < n; ++i) {
+      const int32_t* r = h_coords + 4 * i;
+      for (int a = 0; a < 4; ++a) {
+        lo[a] = r[a] < lo[a] ? r[a] : lo[a];
+        hi[a] = r[a] > hi[a] ? r[a] : hi[a];
+      }
+    }
+  }
+  for (int a = 0; a < 4; ++a) { lo4[a] = lo[a]; hi4[a] = hi[a]; }
   return LK_OK;
 }

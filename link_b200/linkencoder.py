@@ -255,8 +255,27 @@ class ELKEncoder(_ELKBackbone):
         x0, x1, x2, x3, x4 = self.forward_levels(x)
         if not torch.is_grad_enabled() and x0.F.dtype == torch.float32 and x0.F.is_cuda:
             return self._classify_pushdown([x4, x3, x2, x1, x0])
-        ys = [upsample_voxel(lv, x0).F for lv in (x4, x3, x2, x1)]
-        return self._classify(torch.cat(ys + [x0.F], dim=1))
+        return self._classify_levels([x4, x3, x2, x1, x0])
+
+    def _classify_levels(self, levels) -> torch.Tensor:
+        """Differentiable head (training).  Same push-down as the inference head: group l of the
+        grouped 1x1 conv (linkencoder.py:323-327, 376-379) is applied at level l's own size as a plain
+        fp32 matmul and the 24-channel result is gathered to the N0 voxels (`index_select`, whose
+        backward is an `index_add`), instead of gathering five 64-channel tensors, concatenating them
+        to [N0, 320] and running the grouped conv there -- as an einsum that was a strided batched
+        SIMT GEMM of 3.7 ms per backward product on 160k voxels."""
+        c0, c2 = self.classifier[0], self.classifier[2]
+        g = c0.groups
+        w0 = c0.weight.view(g, c0.out_channels // g, -1)                 # [5, 24, C]
+        x0 = levels[-1]
+        hs = []
+        for i, lv in enumerate(levels):
+            z = torch.mm(lv.F, w0[i].t())
+            if lv is not x0:
+                z = z.index_select(0, upsample_index(lv, x0))
+            hs.append(z)
+        h = torch.relu(torch.cat(hs, dim=1) + c0.bias)
+        return torch.addmm(c2.bias, h, c2.weight.view(c2.out_channels, -1).t())
 
     def _classify_pushdown(self, levels) -> torch.Tensor:
         """Inference head.  The reference upsamples every level to N0 rows x 64 channels,

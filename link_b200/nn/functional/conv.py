@@ -330,13 +330,21 @@ class ConvolutionFunction(Function):
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             L = _capi.lib()
-            if USE_TENSOR_CORES and USE_TC_WGRAD and k <= 32 and L.lk_conv_wgrad_tc_supported(c_in, c_out) \
-                    and g.shape[0] * k < 2 ** 31:
+            ci, co = _pad_to_tc(c_in), _pad_to_tc(c_out)
+            if USE_TENSOR_CORES and USE_TC_WGRAD and k <= 32 and ci and co and g.shape[0] * k < 2 ** 31:
+                # channel counts other than 32 / 64 / 128 (the 5- and 16-channel layers of the detection
+                # backbone) are zero-padded like in the forward: the FFMA kernel is ~4x slower there too
                 nbrp, perm, masks = kmap.wgrad_relation(transposed)
+                f_p = feats if ci == c_in else torch.nn.functional.pad(feats, (0, ci - c_in))
+                g_p = g if co == c_out else torch.nn.functional.pad(g, (0, co - c_out))
+                gw_p = grad_weight if (ci == c_in and co == c_out) else torch.empty(k, ci, co, dtype=torch.float32,
+                                                                                    device=g.device)
                 _capi.check(L.lk_conv_wgrad_tc(
-                    _capi.ptr(feats), _capi.ptr(g), _capi.ptr(nbrp), _capi.ptr(perm), _capi.ptr(masks),
-                    g.shape[0], k, c_in, c_out, _capi.ptr(grad_weight), WGRAD_SLOTS, _capi.stream()),
+                    _capi.ptr(f_p), _capi.ptr(g_p), _capi.ptr(nbrp), _capi.ptr(perm), _capi.ptr(masks),
+                    g.shape[0], k, ci, co, _capi.ptr(gw_p), WGRAD_SLOTS, _capi.stream()),
                     'lk_conv_wgrad_tc')
+                if gw_p is not grad_weight:
+                    grad_weight = gw_p[:, :c_in, :c_out].contiguous()
             else:
                 _capi.check(L.lk_conv_bwd_weight(
                     _capi.ptr(feats), _capi.ptr(g), _capi.ptr(to_out), g.shape[0], k, c_in, c_out,

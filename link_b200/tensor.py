@@ -27,10 +27,15 @@ def _copy_stream(device):
 def _seed_bounds_from_host(st, coords_host: torch.Tensor) -> None:
     """Coordinate bounds of an uploaded scan, computed on the HOST copy while the upload is in flight
     (one pass over [N,4] int32), so the index build never reads them back from the device."""
-    if coords_host.device.type == 'cpu' and coords_host.dim() == 2 and coords_host.shape[0] > 0:
+    if (coords_host.device.type == 'cpu' and coords_host.dim() == 2 and coords_host.shape[0] > 0
+            and coords_host.shape[1] == 4 and coords_host.dtype == torch.int32 and coords_host.is_contiguous()):
+        import ctypes as C
+        from link_b200 import _capi
         from link_b200.nn.functional import _index
-        lo, hi = torch.aminmax(coords_host, dim=0)
-        _index.set_coord_bounds(st.kmaps, lo.tolist(), hi.tolist())
+        lo, hi = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        _capi.check(_capi.lib().lk_host_coord_bounds(coords_host.data_ptr(), coords_host.shape[0], lo, hi),
+                    'lk_host_coord_bounds')                 # ~0.1 ms for 120k voxels; ctypes drops the GIL
+        _index.set_coord_bounds(st.kmaps, list(lo), list(hi))
 
 
 class SparseTensor:

@@ -121,3 +121,16 @@ def test_compat_shim_lets_reference_style_imports_resolve():
     assert spnn.Conv3d is not None and hasattr(F, 'sphashquery') and hasattr(F, 'spdevoxelize')
     assert torchsparse.__version__
     compat.uninstall()
+
+
+@pytest.mark.parametrize('n', [0, 1, 3, 4, 5, 1001])
+def test_host_coord_bounds(n):
+    """lk_host_coord_bounds (host code, no device): column-wise min / max, vector body + scalar tail."""
+    from link_b200 import _capi
+    c = torch.randint(-1000, 1000, (n, 4), dtype=torch.int32)
+    lo, hi = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 4)()
+    _capi.check(_capi.lib().lk_host_coord_bounds(c.data_ptr() if n else None, n, lo, hi), 'bounds')
+    if n:
+        assert list(lo) == c.min(0).values.tolist() and list(hi) == c.max(0).values.tolist()
+    else:
+        assert list(lo) == [0] * 4 and list(hi) == [0] * 4

@@ -47,7 +47,8 @@ def test_window_mean_saves_populations(dev):
     tot = torch.zeros(n, device=dev)
     got = elk.link_aggregate(f, st.C, bi, r, 'cos', w, save=(mean, tot))
     want = elk.link_aggregate(f, st.C, bi, r, 'cos', w)
-    assert torch.equal(got, want)
+    # two runs of the pre-aggregation join per-run partial sums with float atomics in a different order
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
     nbr = bi.neighbors(r)[:m].long()
     cnt = bi.counts[:m]
     want_tot = torch.where(nbr >= 0, cnt[nbr.clamp(min=0)], 0).sum(1)
