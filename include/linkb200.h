@@ -285,7 +285,7 @@ typedef struct {
   const float* d_g1; const float* d_b1;   /* norm        weight / bias */
   const float* d_g2; const float* d_b2;   /* norm_local  weight / bias */
   int32_t use_tensor_cores;
-  int32_t reserved;
+  int32_t conv_precision;        /* LK_PREC_FP32 (0, default) / LK_PREC_TF32 for the local_mix conv */
   void* d_ws; int64_t ws_bytes;
   int32_t single_stream;         /* 0 (default): the sort / pre-aggregation chain runs on a library-owned
                                     side stream next to the kernel-map / conv chain (fork/join by

@@ -46,7 +46,7 @@ class ElkBlockArgs(C.Structure):
                 ('keyspec', KeySpec), ('key_bits', C.c_int32), ('r3', C.c_int32),
                 ('d_block_offsets', C.c_void_p), ('gen', KernelGen),
                 ('d_g1', C.c_void_p), ('d_b1', C.c_void_p), ('d_g2', C.c_void_p), ('d_b2', C.c_void_p),
-                ('use_tensor_cores', C.c_int32), ('reserved', C.c_int32),
+                ('use_tensor_cores', C.c_int32), ('conv_precision', C.c_int32),
                 ('d_ws', C.c_void_p), ('ws_bytes', C.c_int64), ('single_stream', C.c_int32),
                 ('reserved1', C.c_int32), ('feats_ready', C.c_void_p)]
 

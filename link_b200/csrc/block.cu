@@ -157,11 +157,12 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
                         ws + w.plan_ws, lk_conv_plan_ws_bytes(n), s));
   if (a->feats_ready && bs) LK_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)a->feats_ready, 0));
   if (tc_conv) {
+    lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, a->conv_precision};
     if (planned)
       LK_TRY(lk_conv_tc_fwd_plan(a->d_feats, a->d_conv_wt, kmap, a->d_plan_perm, a->d_plan_mask, n,
-                                 a->kvol, c, c, nullptr, local, s));
+                                 a->kvol, c, c, &ep, local, s));
     else
-      LK_TRY(lk_conv_tc_fwd(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, nullptr, local, s));
+      LK_TRY(lk_conv_tc_fwd_ex(a->d_feats, a->d_conv_wt, kmap, n, a->kvol, c, c, &ep, local, s));
   } else {
     LK_REQUIRE(a->d_conv_w, "lk_elk_block_fwd: FFMA conv needs the untransposed weights");
     LK_TRY(lk_conv_fwd(a->d_feats, a->d_conv_w, kmap, n, a->kvol, c, c, nullptr, local, s));

@@ -22,6 +22,7 @@ from link_b200 import _capi
 import link_b200.nn as spnn
 import link_b200.nn.functional as F
 from link_b200.nn.functional import _index
+from link_b200.nn.functional import conv as _conv_mod
 from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import PointTensor, SparseTensor
 
@@ -406,6 +407,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     a.d_g2, a.d_b2 = (_capi.ptr(norm_local.weight.detach()),
                       _capi.ptr(norm_local.bias.detach()))
     a.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
+    a.conv_precision = _conv_mod.precision_code()
     ws_bytes = L.lk_elk_block_ws_bytes(n, c, a.gen.op, r3, a.kvol, a.build_kmap)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes

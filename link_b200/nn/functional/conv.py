@@ -19,7 +19,7 @@ from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import SparseTensor
 from link_b200.utils import make_ntuple
 
-__all__ = ['conv3d', 'conv_bn_act', 'fusable', 'KernelMap', 'build_kernel_map']
+__all__ = ['conv3d', 'conv_bn_act', 'fusable', 'KernelMap', 'build_kernel_map', 'set_precision']
 
 
 class KernelMap:
@@ -173,6 +173,24 @@ USE_PLAN = os.environ.get('LINKB200_CONV_PLAN', '1') != '0'
 # weight gradient on tcgen05 (lk_conv_wgrad_tc); '0' keeps the FFMA kernel (lk_conv_bwd_weight)
 USE_TC_WGRAD = os.environ.get('LINKB200_TC_WGRAD', '1') != '0'
 WGRAD_SLOTS = int(os.environ.get('LINKB200_WGRAD_SLOTS', '0'))
+# Arithmetic of the tensor-core convs: 'fp32' (default) = 3xTF32, fp32-level accuracy (the parity
+# configuration); 'tf32' = single-pass TF32 -- operands truncated to tf32 by the tensor core, ~1e-3
+# relative error per product, fp32 accumulation: the reduced-precision mode for training / throughput
+# (the reference runs its conv in fp16 under autocast, nn/functional/conv.py:19).
+PRECISION = os.environ.get('LINKB200_CONV_PRECISION', 'fp32')
+
+
+def set_precision(p: str) -> None:
+    global PRECISION
+    if p not in ('fp32', 'tf32'):
+        raise ValueError("precision must be 'fp32' or 'tf32'")
+    PRECISION = p
+
+
+def precision_code() -> int:
+    return 1 if PRECISION == 'tf32' else 0
+
+
 _tc_supported = {}
 
 
@@ -265,6 +283,7 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
         ep.d_residual = _capi.ptr(residual) if fuse_tail else None
         ep.relu = 1 if (relu and (fuse_tail or residual is None)) else 0
+        ep.precision = precision_code()
         out = torch.empty(n_out, co, dtype=torch.float32, device=feats.device)
         plan = kmap.plan() if kmap is not None else None      # only for the forward map (kmap.nbr)
         with _capi.timed('lk_conv_fwd', nb):

@@ -73,20 +73,29 @@ class SparseTensor:
 
     @classmethod
     def from_host(cls, feats: torch.Tensor, coords: torch.Tensor,
-                  stride: Union[int, Tuple[int, ...]] = 1, device=None) -> 'SparseTensor':
+                  stride: Union[int, Tuple[int, ...]] = 1, device=None, dtype=None) -> 'SparseTensor':
         """Upload a scan from (pinned) host memory.  The coordinates go first on the current stream;
         the features -- 16x more bytes at C = 64 -- follow on a dedicated copy stream, so the index
         build of the first layer (hash grid, kernel map, conv plan, block sort: ~45 % of a LinK
         block) runs while they are still crossing PCIe.  Consumers join the upload through
-        `feats` / `take_feats_event`."""
+        `feats` / `take_feats_event`.
+
+        The step is PCIe-bound end to end, so the features may cross the wire narrower than they are
+        computed in: host features in bf16 / fp16 are uploaded as they are (half the bytes) and widened
+        to `dtype` (default: kept) on the device, on the copy stream, before the upload event."""
         device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
         main = torch.cuda.current_stream(device)
         c_dev = coords.to(device, non_blocking=True)
-        f_dev = torch.empty(feats.shape, dtype=feats.dtype, device=device)
+        f_wire = torch.empty(feats.shape, dtype=feats.dtype, device=device)
+        widen = dtype is not None and dtype != feats.dtype
+        f_dev = torch.empty(feats.shape, dtype=dtype, device=device) if widen else f_wire
         copy_stream = _copy_stream(device)
-        copy_stream.wait_stream(main)      # f_dev may recycle memory still in use by queued kernels
+        copy_stream.wait_stream(main)      # the buffers may recycle memory still in use by queued kernels
         with torch.cuda.stream(copy_stream):
-            f_dev.copy_(feats, non_blocking=True)
+            f_wire.copy_(feats, non_blocking=True)
+            if widen:
+                f_dev.copy_(f_wire)
+                f_wire.record_stream(copy_stream)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         st = cls(f_dev, c_dev, stride)

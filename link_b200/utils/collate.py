@@ -1,6 +1,11 @@
-"""Batch collation with the reference's layout (torchsparse/utils/collate.py:11-66):
-the batch index is appended as the 4th coordinate column."""
-from typing import Any, List
+"""Batch collation for data loaders.
+
+Contract = the reference's `sparse_collate` / `sparse_collate_fn` (torchsparse/utils/collate.py:11-66):
+a list of per-frame SparseTensors with [N_i, 3] coordinates becomes ONE SparseTensor whose 4th
+coordinate column is the frame index (the column the hash / kernel-map / block kernels treat as the
+batch), and a list of sample dicts is merged key by key (nested dicts recursively, arrays and tensors
+stacked, SparseTensors collated, everything else kept as a list)."""
+from typing import Any, Dict, List
 
 import numpy as np
 import torch
@@ -10,38 +15,51 @@ from link_b200.tensor import SparseTensor
 __all__ = ['sparse_collate', 'sparse_collate_fn']
 
 
+def _as_tensor(x) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x)).clone()
+    if not isinstance(x, torch.Tensor):
+        raise AssertionError(type(x))
+    return x
+
+
 def sparse_collate(inputs: List[SparseTensor]) -> SparseTensor:
-    coords, feats = [], []
     stride = inputs[0].stride
-    for k, x in enumerate(inputs):
-        if isinstance(x.coords, np.ndarray):
-            x.coords = torch.tensor(x.coords)
-        if isinstance(x.feats, np.ndarray):
-            x.feats = torch.tensor(x.feats)
-        assert isinstance(x.coords, torch.Tensor), type(x.coords)
-        assert isinstance(x.feats, torch.Tensor), type(x.feats)
-        assert x.stride == stride, (x.stride, stride)
-        batch = torch.full((x.coords.shape[0], 1), k, device=x.coords.device, dtype=torch.int)
-        coords.append(torch.cat((x.coords, batch), dim=1))
-        feats.append(x.feats)
-    return SparseTensor(coords=torch.cat(coords, dim=0), feats=torch.cat(feats, dim=0),
-                        stride=stride)
+    sizes = []
+    for x in inputs:
+        if x.stride != stride:
+            raise AssertionError((x.stride, stride))
+        x.coords, x.feats = _as_tensor(x.coords), _as_tensor(x.feats)   # the reference converts in place too
+        sizes.append(x.coords.shape[0])
+    total, dev = sum(sizes), inputs[0].coords.device
+    # one [total, 4] buffer: xyz blocks copied in, the frame index written as a run per frame
+    coords = torch.empty(total, 4, dtype=inputs[0].coords.dtype, device=dev)
+    row = 0
+    for frame, (x, n) in enumerate(zip(inputs, sizes)):
+        coords[row:row + n, :3] = x.coords[:, :3]
+        coords[row:row + n, 3] = frame
+        row += n
+    feats = torch.cat([x.feats for x in inputs], dim=0)
+    return SparseTensor(coords=coords, feats=feats, stride=stride)
+
+
+def _merge(values: List[Any]) -> Any:
+    head = values[0]
+    if isinstance(head, dict):
+        return sparse_collate_fn(values)
+    if isinstance(head, np.ndarray):
+        return torch.stack([torch.from_numpy(np.ascontiguousarray(v)).clone() for v in values], dim=0)
+    if isinstance(head, torch.Tensor):
+        return torch.stack(values, dim=0)
+    if isinstance(head, SparseTensor):
+        return sparse_collate(values)
+    return values
 
 
 def sparse_collate_fn(inputs: List[Any]) -> Any:
-    if not isinstance(inputs[0], dict):
+    if not inputs or not isinstance(inputs[0], dict):
         return inputs
-    output = {}
-    for name in inputs[0].keys():
-        first = inputs[0][name]
-        if isinstance(first, dict):
-            output[name] = sparse_collate_fn([inp[name] for inp in inputs])
-        elif isinstance(first, np.ndarray):
-            output[name] = torch.stack([torch.tensor(inp[name]) for inp in inputs], dim=0)
-        elif isinstance(first, torch.Tensor):
-            output[name] = torch.stack([inp[name] for inp in inputs], dim=0)
-        elif isinstance(first, SparseTensor):
-            output[name] = sparse_collate([inp[name] for inp in inputs])
-        else:
-            output[name] = [inp[name] for inp in inputs]
-    return output
+    merged: Dict[Any, Any] = {}
+    for name in inputs[0]:
+        merged[name] = _merge([sample[name] for sample in inputs])
+    return merged

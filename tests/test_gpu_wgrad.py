@@ -101,3 +101,31 @@ def test_wgrad_tc_through_autograd_matches_ffma(dev, monkeypatch):
         grads[flag] = [t.grad.clone() for t in w]
     for a, b in zip(grads[True], grads[False]):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * float(b.abs().max()))
+
+
+def test_conv_tf32_mode_tolerance(dev):
+    """Reduced-precision mode of the tensor-core conv (set_precision('tf32'): one MMA on operands
+    truncated to tf32, fp32 accumulation).  Stated tolerance: 2e-3 of the largest output (10-bit
+    mantissas, truncation: <= 2^-10 relative per operand); the default mode stays at 1e-5."""
+    from link_b200.nn.functional import conv as conv_mod
+    km = _kmap(dev, 20_000, 3, 1, 64)
+    K, rows = km.nbr.shape
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(rows, 64, generator=gen).to(dev)
+    w = (torch.randn(K, 64, 64, generator=gen) / 16).to(dev)
+    rel = km.nbr.cpu().numpy()
+    want = np.zeros((rows, 64))
+    xn, wn = x.double().cpu().numpy(), w.double().cpu().numpy()
+    for k in range(K):
+        hit = rel[k] >= 0
+        want[hit] += xn[rel[k][hit]] @ wn[k]
+    scale = np.abs(want).max()
+    try:
+        errs = {}
+        for prec in ('fp32', 'tf32'):
+            conv_mod.set_precision(prec)
+            got = conv_mod._conv_fwd(x, w, km.nbr, rows, kmap=km).double().cpu().numpy()
+            errs[prec] = np.abs(got - want).max() / scale
+    finally:
+        conv_mod.set_precision('fp32')
+    assert errs['fp32'] < 1e-5 and 1e-5 < errs['tf32'] < 2e-3, errs
