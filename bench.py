@@ -407,8 +407,12 @@ def run_train(args, steps, warmup, dev, rank, world, local):
     net = ELKEncoder(num_classes=19, cr=1.0, baseop=BASEOP, r=R_BLK, s=S_BLK, groups=GROUPS).to(dev).train()
     model = net
     if world > 1:
-        model = DDP(net, device_ids=[local], find_unused_parameters=True)
-    opt = torch.optim.SGD(model.parameters(), lr=0.024, momentum=0.9, weight_decay=1e-4, nesterov=True)
+        if os.environ.get('LINKB200_DDP_REFERENCE_STYLE') == '1':      # the reference's own wrapping, for A/B
+            model = DDP(net, device_ids=[local], find_unused_parameters=True)
+        else:
+            from link_b200.sharding import wrap_ddp
+            model = wrap_ddp(net, local)                               # unused decoder branches ignored, no graph walk
+    opt = torch.optim.SGD([p for p in net.parameters()], lr=0.024, momentum=0.9, weight_decay=1e-4, nesterov=True)
     loss_host = torch.zeros(1).pin_memory()
 
     def step(i, sync=True):

@@ -423,6 +423,16 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
                        const float* coors_range, int max_points, int max_voxels, float* d_voxels,
                        int32_t* d_coors, int32_t* d_num_points, int32_t* d_voxel_num, void* d_ws,
                        int64_t ws_bytes, lk_stream_t s);
+/* ------------------------------------------------------------------------------------
+ * Sparse -> dense BEV scatter of the detection backbone output and its transpose (the backward).
+ * Replaces spconv's `.dense()` + permute in `ret = self.extra_conv(x).dense(); ret.view(N, C*D, H, W)`
+ * (detection/det3d/models/backbones/scn.py:612-617).  d_indices int32 [n,4] = (batch, z, y, x), rows
+ * unique; d_dense [batch, c, depth, height, width] channels-first (== [batch, c*depth, height, width]):
+ * lk_bev_scatter zero-fills it and writes every row; lk_bev_gather reads grad rows back. */
+int lk_bev_scatter(const float* d_feats, const int32_t* d_indices, int64_t n, int c, int batch,
+                   int depth, int height, int width, float* d_dense, lk_stream_t s);
+int lk_bev_gather(const float* d_dense, const int32_t* d_indices, int64_t n, int c, int batch,
+                  int depth, int height, int width, float* d_feats, lk_stream_t s);
 /* HOST helper (no device work): column-wise min / max of a host int32 [n,4] coordinate array -> lo4, hi4
  * (the bounds that size the packed sort keys; SparseTensor.from_host calls it while the upload is in flight). */
 int lk_host_coord_bounds(const int32_t* h_coords, int64_t n, int32_t* lo4, int32_t* hi4);
@@ -454,6 +464,14 @@ int lk_conv_wgrad_tc(const float* d_in, const float* d_gout, const int32_t* d_nb
  * ---------------------------------------------------------------------------------- */
 int lk_boxes_iou_bev(const float* d_a, int64_t n, const float* d_b, int64_t m, float* d_out,
                      lk_stream_t s);
+/* Greedy rotated NMS over boxes already sorted by descending score: d_keep [n] (uint8) = 1 for the
+ * boxes that survive (a box is dropped when an earlier KEPT box overlaps it with BEV IoU > thresh).
+ * Replaces nms_gpu (iou3d_nms_kernel.cu:328-414 + the host-side greedy loop of iou3d_nms.cpp): the
+ * 64 x 64 overlap bitmasks AND the greedy scan run on the device, nothing is copied to the host.
+ * d_ws: lk_nms_bev_ws_bytes(n) bytes (the bitmask matrix), 8-byte aligned. */
+int64_t lk_nms_bev_ws_bytes(int64_t n);
+int lk_nms_bev(const float* d_boxes_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
+               uint8_t* d_keep, lk_stream_t s);
 int lk_boxes_iou_bev_hostcheck(const float* a, int64_t n, const float* b, int64_t m, float* out);
 
 #ifdef __cplusplus

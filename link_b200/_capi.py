@@ -115,10 +115,14 @@ PROTOTYPES = {
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
     'lk_host_coord_bounds': (i32, [vp, i64, vp, vp]),
+    'lk_bev_scatter': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]),
+    'lk_bev_gather': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]),
     'lk_conv_wgrad_tc_supported': (i32, [i32, i32]),
     'lk_conv_wgrad_prepass': (i32, [vp, vp, i64, i32, vp, vp, vp]),
     'lk_conv_wgrad_tc': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32, vp]),
     'lk_boxes_iou_bev': (i32, [vp, i64, vp, i64, vp, vp]),
+    'lk_nms_bev_ws_bytes': (i64, [i64]),
+    'lk_nms_bev': (i32, [vp, i64, C.c_float, vp, i64, vp, vp]),
     'lk_boxes_iou_bev_hostcheck': (i32, [vp, i64, vp, i64, vp]),
 }
 

@@ -119,6 +119,70 @@ extern "C" int lk_boxes_iou_bev(const float* d_a, int64_t n, const float* d_b, i
   return LK_OK;
 }
 
+// ---- rotated NMS: 64 x 64 overlap bitmasks + a greedy scan that stays on the device -----------------
+// (reference: nms_kernel, iou3d_nms_kernel.cu:328-414, builds the same bitmask matrix, then copies it to
+// the HOST and runs the greedy loop there, iou3d_nms.cpp nms_gpu.)  Boxes arrive sorted by descending
+// score.  mask[i][w] bit b = IoU(box i, box 64 w + b) > thresh, for 64 w + b > i.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ boxes, int n, float thresh,
+                                                      int words, unsigned long long* __restrict__ mask) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;                                   // only the upper triangle is ever read
+  __shared__ float cbox[64][7];
+  const int ncol = min(n - cb * 64, 64);
+  if ((int)threadIdx.x < ncol) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cbox[threadIdx.x][k] = __ldg(boxes + (int64_t)(cb * 64 + threadIdx.x) * 7 + k);
+  }
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= n) return;
+  float bi[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) bi[k] = __ldg(boxes + (int64_t)i * 7 + k);
+  unsigned long long bits = 0;
+  for (int j = (rb == cb) ? (int)threadIdx.x + 1 : 0; j < ncol; ++j)
+    if (lk_iou_pair(bi, cbox[j]) > thresh) bits |= 1ULL << j;
+  mask[(int64_t)i * words + cb] = bits;
+}
+
+// one warp: keep[i] = box i is not suppressed by an earlier kept box; removed bits live in shared memory
+__global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int words,
+                                                      uint8_t* __restrict__ keep) {
+  extern __shared__ unsigned long long remv[];
+  for (int w = threadIdx.x; w < words; w += 32) remv[w] = 0ULL;
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    const int wi = i >> 6;
+    const bool dead = (remv[wi] >> (i & 63)) & 1ULL;     // same word for every lane: a broadcast read
+    if (!dead) {
+      for (int w = wi + (int)threadIdx.x; w < words; w += 32) remv[w] |= __ldg(mask + (int64_t)i * words + w);
+    }
+    if (threadIdx.x == 0) keep[i] = dead ? 0 : 1;
+    __syncwarp();
+  }
+}
+
+extern "C" int64_t lk_nms_bev_ws_bytes(int64_t n) { return n * ((n + 63) / 64) * 8 + 256; }
+
+extern "C" int lk_nms_bev(const float* d_boxes_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
+                          uint8_t* d_keep, lk_stream_t s) {
+  LK_REQUIRE(n >= 0 && n <= 65536, "lk_nms_bev: at most 65536 boxes");
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_boxes_sorted && d_ws && d_keep && (uintptr_t)d_ws % 8 == 0, "lk_nms_bev: null or misaligned pointer");
+  const int words = (int)((n + 63) / 64);
+  if (ws_bytes < lk_nms_bev_ws_bytes(n)) {
+    lk_set_error("lk_nms_bev: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)lk_nms_bev_ws_bytes(n));
+    return LK_ENOSPC;
+  }
+  cudaStream_t st = (cudaStream_t)s;
+  dim3 grid((unsigned)words, (unsigned)words);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(d_boxes_sorted, (int)n, thresh, words, (unsigned long long*)d_ws);
+  LK_LAUNCHED();
+  nms_scan_kernel<<<1, 32, (size_t)words * 8, st>>>((const unsigned long long*)d_ws, (int)n, words, d_keep);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 extern "C" int lk_boxes_iou_bev_hostcheck(const float* a, int64_t n, const float* b, int64_t m, float* out) {
   LK_REQUIRE(n >= 0 && m >= 0 && (n == 0 || m == 0 || (a && b && out)), "lk_boxes_iou_bev_hostcheck: bad arguments");
   for (int64_t i = 0; i < n; ++i)

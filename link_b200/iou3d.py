@@ -8,8 +8,10 @@ src/iou3d_cpu.cpp:59-252), called through `rotate_nms_pcdet`
 crossings plus the corners of either box that lie inside the other (margin 1e-2), ordered by angle
 around their mean and measured with the shoelace sum.
 
-This first version is plain PyTorch (library kernels); a fused CUDA kernel for the pairwise matrix
-is the follow-up.  Parity: tests/test_iou3d_cpu.py against the reference's own compiled
+CUDA tensors take the fused kernels of csrc/iou3d.cu (lk_boxes_iou_bev: one thread per pair;
+lk_nms_bev: overlap bitmasks + an on-device greedy scan); the tensor-op formulation below serves CPU
+tensors (fixture generation and the CPU tests) and stays the readable statement of the arithmetic.
+Parity: tests/test_iou3d_cpu.py against the reference's own compiled
 `boxes_iou_bev_cpu` (oracle/_ref/iou3d_cpu_ref.so in the build container, tests/golden/iou3d.npz
 everywhere).
 """
@@ -148,7 +150,20 @@ def rotate_nms(boxes: torch.Tensor, scores: torch.Tensor, thresh: float, pre_max
     if order.numel() == 0:
         return order
     b = boxes[order].contiguous()
-    keep = nms_fixed_point(boxes_iou_bev(b, b) > thresh)
+    if b.is_cuda and b.shape[0] <= 65536:
+        # device NMS (csrc/iou3d.cu): 64 x 64 overlap bitmasks + a one-warp greedy scan, no host round trip
+        from link_b200 import _capi
+        b = b.float().contiguous()
+        n = b.shape[0]
+        L = _capi.lib()
+        ws_bytes = L.lk_nms_bev_ws_bytes(n)
+        ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=b.device)
+        keep8 = torch.empty(n, dtype=torch.uint8, device=b.device)
+        _capi.check(L.lk_nms_bev(_capi.ptr(b), n, float(thresh), _capi.ptr(ws), ws.numel() * 8, _capi.ptr(keep8),
+                                 _capi.stream()), 'lk_nms_bev')
+        keep = keep8.bool()
+    else:
+        keep = nms_fixed_point(boxes_iou_bev(b, b) > thresh)
     sel = order[keep]
     return sel[:post_max_size] if post_max_size is not None else sel
 

@@ -9,7 +9,7 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput']
+__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput', 'wrap_ddp']
 
 
 def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
@@ -34,3 +34,23 @@ def reduce_throughput(local_ms: float, local_units: float, device=None) -> Tuple
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def wrap_ddp(model: torch.nn.Module, device_index=None, unused_prefixes: Sequence[str] = ('up1', 'up2', 'up3', 'up4'),
+             **kwargs):
+    """DistributedDataParallel around a LinK model (reference: segmentation/train.py:99-100 wraps with
+    `find_unused_parameters=True` because ELKEncoder.forward never touches the decoder branches
+    up1..up4 it constructs, linkencoder.py:289-320 vs 339-381).  Here those parameters are declared
+    to DDP as ignored instead: the reducer neither waits for their gradients nor walks the autograd
+    graph after every forward to find them (host time on a host-bound step), and the gradient
+    buckets alias the .grad tensors."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    ignored = [n for n, _ in model.named_parameters() if n.split('.')[0] in unused_prefixes]
+    ignored += [n for n, _ in model.named_buffers() if n.split('.')[0] in unused_prefixes]
+    if ignored:
+        DDP._set_params_and_buffers_to_ignore_for_model(model, ignored)
+    kw = dict(find_unused_parameters=False, gradient_as_bucket_view=True)
+    kw.update(kwargs)
+    if device_index is not None:
+        kw['device_ids'] = [device_index]
+    return DDP(model, **kw)

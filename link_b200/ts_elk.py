@@ -19,6 +19,33 @@ __all__ = ['SparseConvTensor', 'spconv2ts', 'ts2spconv', 'large_to_small', 'smal
            'TSELKBlock']
 
 
+class BevScatterFunction(torch.autograd.Function):
+    """features [n, C], indices int32 [n, 4] (b, z, y, x) -> dense [B, C, D, H, W]; the backward is the
+    gather of the same positions (lk_bev_gather)."""
+
+    @staticmethod
+    def forward(ctx, feats, indices, batch, d, h, w):
+        from link_b200 import _capi
+        feats = feats.contiguous()
+        n, c = feats.shape
+        out = torch.empty(batch, c, d, h, w, dtype=torch.float32, device=feats.device)
+        _capi.check(_capi.lib().lk_bev_scatter(_capi.ptr(feats), _capi.ptr(indices), n, c, batch, d, h, w,
+                                               _capi.ptr(out), _capi.stream()), 'lk_bev_scatter')
+        ctx.save_for_backward(indices)
+        ctx.shape = (n, c, batch, d, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        from link_b200 import _capi
+        (indices,) = ctx.saved_tensors
+        n, c, batch, d, h, w = ctx.shape
+        g = torch.empty(n, c, dtype=torch.float32, device=grad.device)
+        _capi.check(_capi.lib().lk_bev_gather(_capi.ptr(grad.contiguous()), _capi.ptr(indices), n, c, batch, d, h, w,
+                                              _capi.ptr(g), _capi.stream()), 'lk_bev_gather')
+        return g, None, None, None, None, None
+
+
 class SparseConvTensor:
     """Minimal stand-in for spconv.pytorch.SparseConvTensor (scn.py:581): features [N,C],
     indices int32 [N,4] = (batch, z, y, x), spatial_shape [D,H,W], batch_size."""
@@ -42,9 +69,12 @@ class SparseConvTensor:
         return out
 
     def dense(self, channels_first: bool = True):
-        """[B, C, D, H, W] dense tensor (scn.py:614)."""
+        """[B, C, D, H, W] dense tensor (scn.py:614).  CUDA fp32 features take the fused scatter kernel
+        (lk_bev_scatter: zero fill + one pass, channels-first written directly; differentiable)."""
         d, h, w = self.spatial_shape
         c = self.features.shape[1]
+        if channels_first and self.features.is_cuda and self.features.dtype == torch.float32:
+            return BevScatterFunction.apply(self.features, self.indices.int().contiguous(), self.batch_size, d, h, w)
         out = torch.zeros(self.batch_size, d, h, w, c, dtype=self.features.dtype,
                           device=self.features.device)
         i = self.indices.long()

@@ -50,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('what', nargs='?', default='det')
     ap.add_argument('--top', type=int, default=25)
+    ap.add_argument('--cprofile', action='store_true')
     a = ap.parse_args()
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
@@ -88,6 +89,27 @@ def main():
         print(f'encoder N={coords.shape[0]}: fwd (eval, fused) {timed(fwd):.2f} ms', flush=True)
         net.train()
     print(f'fwd+bwd (train): {timed(step):.2f} ms', flush=True)
+    if a.cprofile:
+        # host side: where the python time of a training step goes (the step is host-bound)
+        import cProfile
+        import pstats
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step()
+        host_ms = (time.perf_counter() - t0) * 1e3 / 3
+        torch.cuda.synchronize()
+        print(f'host enqueue per step: {host_ms:.2f} ms', flush=True)
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats('tottime').print_stats(45)
+        pstats.Stats(pr).sort_stats('cumulative').print_stats(40)
+        return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(2):

@@ -115,3 +115,54 @@ def test_two_rank_ddp_gradients_equal_mean_over_frames():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert scale > 0 and err <= 1e-5 * max(1.0, scale)
+
+
+def _wrap_worker(rank, world, port, out):
+    """wrap_ddp: a model with a never-used branch named like the encoder's decoder (`up1`) trains under
+    DDP WITHOUT find_unused_parameters -- the branch is declared ignored -- and the used parameters'
+    gradients are the mean over the ranks."""
+    from link_b200.sharding import wrap_ddp
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = torch.nn.Linear(4, 8)
+            self.head = torch.nn.Linear(8, 3)
+            self.up1 = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8))   # built, never used
+
+        def forward(self, x):
+            return self.head(torch.relu(self.stem(x)))
+
+    net = Net()
+    ddp = wrap_ddp(net)
+    xs = [torch.randn(5, 4, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+    for _ in range(2):                                      # two steps: a reducer waiting for `up1` would raise on the 2nd
+        net.zero_grad(set_to_none=True)
+        ddp(xs[rank]).square().mean().backward()
+    got = torch.cat([p.grad.flatten() for n, p in net.named_parameters() if not n.startswith('up1')])
+    assert all(p.grad is None for n, p in net.named_parameters() if n.startswith('up1'))
+    ref = Net()
+    ref.load_state_dict(net.state_dict())
+    (sum(ref(x).square().mean() for x in xs) / world).backward()
+    want = torch.cat([p.grad.flatten() for n, p in ref.named_parameters() if not n.startswith('up1')])
+    if rank == 0:
+        out.put(float((got - want).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_wrap_ddp_ignores_unused_decoder_branches():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wrap_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err <= 1e-6
