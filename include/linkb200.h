@@ -423,6 +423,14 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
                        const float* coors_range, int max_points, int max_voxels, float* d_voxels,
                        int32_t* d_coors, int32_t* d_num_points, int32_t* d_voxel_num, void* d_ws,
                        int64_t ws_bytes, lk_stream_t s);
+/* Reference-layout kernel map -> the output-stationary map of the conv kernels: d_nbmaps int32 [P, 2]
+ * (input row, output row) ordered by offset, h_nbsizes int32 [K] ON THE HOST -- exactly the
+ * (neighbor_map, neighbor_offset) arguments of convolution_{forward,backward}_cuda
+ * (torchsparse/backend/pybind_cuda.cpp:20-21, convolution_cuda.cu:53-57).  d_nbr [K, n_rows] = partner
+ * row of the pair whose column row_col is the row, or -1; identity_mid = 1: the centre offset maps
+ * every row to itself (the reference's precompute_mid shortcut, convolution_cuda.cu:74-88). */
+int lk_kmap_from_pairs(const int32_t* d_nbmaps, const int32_t* h_nbsizes, int k, int64_t n_rows,
+                       int row_col, int identity_mid, int32_t* d_nbr, lk_stream_t s);
 /* ------------------------------------------------------------------------------------
  * Sparse -> dense BEV scatter of the detection backbone output and its transpose (the backward).
  * Replaces spconv's `.dense()` + permute in `ret = self.extra_conv(x).dense(); ret.view(N, C*D, H, W)`

@@ -8,6 +8,7 @@ import sys
 _MAP = {
     'torchsparse': 'link_b200',
     'torchsparse.tensor': 'link_b200.tensor',
+    'torchsparse.backend': 'link_b200.backend',
     'torchsparse.operators': 'link_b200.operators',
     'torchsparse.nn': 'link_b200.nn',
     'torchsparse.nn.functional': 'link_b200.nn.functional',

@@ -120,3 +120,58 @@ extern "C" int lk_host_coord_bounds(const int32_t* h_coords, int64_t n, int32_t*
   for (int a = 0; a < 4; ++a) { lo4[a] = lo[a]; hi4[a] = hi[a]; }
   return LK_OK;
 }
+
+/* Reference-layout kernel map -> the output-stationary map the conv kernels consume.
+ * The reference keeps a kernel map as a pair list (nn/functional/conv.py:114-121): neighbor_map [P, 2]
+ * = (input row, output row) ordered by offset, neighbor_offset [K] = pairs per offset (on the HOST,
+ * convolution_cuda.cu:53-57).  d_nbr [K, n_rows] gets, for every offset k and row r, the partner row of
+ * the pair whose column `row_col` equals r, or -1.  row_col = 1: rows are output rows (forward,
+ * weight gradient); row_col = 0: rows are input rows (transposed conv, input gradient).
+ * identity_mid = 1 reproduces the reference's shortcut for the centre offset of an odd kernel with
+ * n_in == n_out (convolution_cuda.cu:74-88: W[mid] is applied to every row, its pairs are not read). */
+struct PairPrefix { int32_t start[129]; };
+
+__global__ void __launch_bounds__(256) kmap_from_pairs_kernel(const int32_t* __restrict__ pairs, PairPrefix pre, int k,
+                                                              int64_t n_rows, int row_col, int mid,
+                                                              int32_t* __restrict__ nbr) {
+  const int64_t total = pre.start[k];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = k;                          // offset of pair p: last start <= p
+    while (hi - lo > 1) {
+      const int m = (lo + hi) >> 1;
+      if (pre.start[m] <= p) lo = m; else hi = m;
+    }
+    if (lo == mid) continue;
+    const int32_t row = __ldg(pairs + 2 * p + row_col), other = __ldg(pairs + 2 * p + (1 - row_col));
+    if (row >= 0 && row < n_rows) nbr[(int64_t)lo * n_rows + row] = other;
+  }
+  if (mid >= 0)
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+      nbr[(int64_t)mid * n_rows + r] = (int32_t)r;
+}
+
+extern "C" int lk_kmap_from_pairs(const int32_t* d_nbmaps, const int32_t* h_nbsizes, int k, int64_t n_rows,
+                                  int row_col, int identity_mid, int32_t* d_nbr, lk_stream_t s) {
+  LK_REQUIRE(k > 0 && k <= 128 && n_rows >= 0 && (row_col == 0 || row_col == 1) && h_nbsizes,
+             "lk_kmap_from_pairs: bad arguments (1 <= K <= 128)");
+  if (n_rows == 0) return LK_OK;
+  LK_REQUIRE(d_nbr, "lk_kmap_from_pairs: null output");
+  PairPrefix pre;
+  int64_t total = 0;
+  for (int i = 0; i < k; ++i) {
+    LK_REQUIRE(h_nbsizes[i] >= 0, "lk_kmap_from_pairs: negative pair count");
+    pre.start[i] = (int32_t)total;
+    total += h_nbsizes[i];
+  }
+  LK_REQUIRE(total < (1LL << 31), "lk_kmap_from_pairs: more than 2^31 pairs");
+  pre.start[k] = (int32_t)total;
+  LK_REQUIRE(total == 0 || d_nbmaps, "lk_kmap_from_pairs: null pair list");
+  cudaStream_t st = (cudaStream_t)s;
+  LK_CUDA(cudaMemsetAsync(d_nbr, 0xFF, (size_t)k * n_rows * sizeof(int32_t), st));
+  lk_count_launch();
+  const int mid = identity_mid ? k / 2 : -1;
+  const int64_t work = total > n_rows ? total : n_rows;
+  kmap_from_pairs_kernel<<<lk_grid(work, 256, 8), 256, 0, st>>>(d_nbmaps, pre, k, n_rows, row_col, mid, d_nbr);
+  LK_LAUNCHED();
+  return LK_OK;
+}
