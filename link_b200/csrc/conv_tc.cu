@@ -71,7 +71,17 @@ struct ConvTcCfg {
 // PREC = 0: 3xTF32 (fp32-level accuracy, three MMAs per k-slice on tf32 hi / lo planes);
 // PREC = 1: single-pass TF32 (the tensor core truncates the fp32 operands to tf32: ~1e-3 relative,
 //           what frameworks call "allow_tf32"): no split, one TMEM store, one MMA per k-slice.
-template <int CIN, int COUT, int NST, int PREC>
+// WS = true (the configurations with a shared-memory gather ring): the 16 producer warps are
+// SPECIALISED instead of marching through every step in lock step -- warps 8..15 only gather
+// (cp.async rows of step j+1, j+2 into the ring, completion reported through
+// cp.async.mbarrier.arrive on a per-slot mbarrier), warps 0..7 only convert (ring slot -> tf32 hi / lo
+// -> tcgen05.st), each side running ahead as far as the ring / the TMEM stages allow.  In the
+// lock-step form every step paid  wait_group + a 512-thread bar.sync + LDGSTS issue + LDS + split +
+// STTM  back to back on all warps, so the LSU, the shared-memory port and the TMEM store path were
+// used one after the other (issue slots 26 % busy, no pipe above 35 %); here they overlap.
+#define CT_CONV_WARPS 8
+#define CT_GATHER_THREADS 256
+template <int CIN, int COUT, int NST, int PREC, bool WS>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wimg /*[K] packed B-operand images*/,
     const int* __restrict__ nbr /*[K][n_out]*/,
@@ -89,6 +99,9 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   __shared__ uint64_t empty_bar[NST]; // A stage consumed  (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
   __shared__ uint64_t wfull_bar[Cfg::NWB];  // W[k] image landed (bulk copy, complete_tx)
+  __shared__ uint64_t round_bar;            // every MMA of the round has completed (tcgen05.commit after the last step)
+  __shared__ uint64_t slot_full[4];         // WS: ring slot filled   (cp.async.mbarrier.arrive of the gather threads)
+  __shared__ uint64_t slot_empty[4];        // WS: ring slot consumed (one arrival per convert warp)
   __shared__ uint16_t steps_s[64 * MAXT];   // active (virtual offset, tile slot) steps: kv << 4 | t
   __shared__ uint8_t klist_s[64];           // distinct virtual offsets of the round, ascending
   __shared__ int orow_s[MAXT][CT_ROWS];     // output row of every tile-slot row (-1 past the end)
@@ -105,8 +118,14 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   if (tid == 0) {
 #pragma unroll
     for (int b = 0; b < NST; ++b) {
-      tc::mbar_init(&full_bar[b], CT_THREADS / 32);
+      tc::mbar_init(&full_bar[b], (WS && Cfg::GST > 0) ? CT_CONV_WARPS : CT_THREADS / 32);
       tc::mbar_init(&empty_bar[b], 1);
+    }
+    tc::mbar_init(&round_bar, 1);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      tc::mbar_init(&slot_full[b], CT_GATHER_THREADS);
+      tc::mbar_init(&slot_empty[b], CT_CONV_WARPS);
     }
 #pragma unroll
     for (int b = 0; b < Cfg::NWB; ++b) tc::mbar_init(&wfull_bar[b], 1);
@@ -237,6 +256,14 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         __syncwarp();
         touched |= 1u << t;
       }
+      // end of the round: one more commit, on a barrier of its own, that every producer warp waits for
+      // before the epilogue.  (Waiting for the last commit of each A stage by parity is only safe for a
+      // thread that has followed that barrier phase by phase; the gather warps have not.)
+      if (tc::elect_one()) {
+        if (nsteps > 0) tc::mma_commit(&round_bar);
+        else tc::mbar_arrive(&round_bar);
+      }
+      __syncwarp();
     } else {
       // ================= producer warps (gather + tf32 split + tcgen05.st), later the epilogue ====
       // TMEM access rule: warp w touches lanes [32 (w%4), +32).  Thread (q = w%4, lane) owns tile row
@@ -296,7 +323,118 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
       };
-      if constexpr (Cfg::GST > 0) {
+      if constexpr (WS && Cfg::GST > 0) {
+        constexpr int GST = Cfg::GST;
+        constexpr int CH_ROW = CE / 4;                  // 16-byte chunks per row
+        if (warp >= CT_CONV_WARPS) {
+          // ================= gather warps: rows of step j -> ring slot (jbase + j) % GST =================
+          const int gt = tid - CT_CONV_WARPS * 32;
+          constexpr int RPP = CT_GATHER_THREADS / CH_ROW;   // rows per pass (16 lanes fetch one 256-byte row)
+          constexpr int NP = CT_ROWS / RPP;                 // passes per step
+          const uint32_t g_base = tc::smem_u32(b_base + Cfg::NWB * Cfg::B_STAGE);
+          const int f_chunk = gt % CH_ROW, f_row0 = gt / CH_ROW;
+          uint32_t fetch_off[NP];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            const int fr = f_row0 + i * RPP;
+            fetch_off[i] = (uint32_t)(fr * (CE * 4) + ((f_chunk ^ (fr & (CH_ROW - 1))) << 4));
+          }
+          auto load_idx = [&](int jj, int* src) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) src[i] = -1;
+            if (jj < nsteps) {
+              const int kv2 = steps_s[jj] >> 4, t2 = steps_s[jj] & 15;
+#pragma unroll
+              for (int i = 0; i < NP; ++i) {
+                const int o = orow_s[t2][f_row0 + i * RPP];
+                const int sr = o >= 0 ? __ldg(nbr + (uint32_t)((kv2 / KH) * n32 + o)) : -1;
+                src[i] = (KH > 1 && sr >= 0) ? (sr | ((kv2 % KH) << 30)) : sr;
+              }
+            }
+          };
+          auto gstep = [&](int j, int* src) {
+            const int jg = jbase + j;
+            const int slot = jg % GST, use = jg / GST;
+            if (use >= 1) tc::mbar_wait(&slot_empty[slot], (uint32_t)(use - 1) & 1u);
+            const uint32_t dst = g_base + (uint32_t)slot * Cfg::G_STAGE;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              const int sv = src[i];
+              const int half = (KH > 1 && sv >= 0) ? (sv >> 30) : 0;
+              const int row = sv >= 0 ? (KH > 1 ? (sv & 0x3FFFFFFF) : sv) : 0;
+              const float* rp = in + (int64_t)row * CIN + half * CE + 4 * f_chunk;
+              const int nbytes = sv >= 0 ? 16 : 0;      // 0: zero-fill (missing neighbour)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                           ::"r"(dst + fetch_off[i]), "l"(rp), "r"(nbytes) : "memory");
+            }
+            // this thread's arrival on the slot's mbarrier fires when its copies above have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];"
+                         ::"r"(tc::smem_u32(&slot_full[slot])) : "memory");
+            load_idx(j + 2, src);                        // indices two steps ahead of their use
+          };
+          int idx_a[NP], idx_b[NP];
+          load_idx(0, idx_a);
+          load_idx(1, idx_b);
+          for (int j = 0; j < nsteps; j += 2) {
+            gstep(j, idx_a);
+            if (j + 1 < nsteps) gstep(j + 1, idx_b);
+          }
+        } else {
+          // ================= convert warps: ring slot -> tf32 hi / lo -> TMEM A stage =================
+          const int cq = warp & 3, ccs = warp >> 2;       // TMEM lane quarter, channel half
+          const int crow = cq * 32 + lane;
+          constexpr int CPC = CE / 2;                     // channels per convert thread (32 or 16)
+          constexpr int NCC = CPC / 4;                    // 16-byte chunks per thread and step
+          const int ccol0 = ccs * CPC;
+          const uint32_t clane = (uint32_t)(cq * 32) << 16;
+          uint32_t read_off[NCC];
+#pragma unroll
+          for (int i = 0; i < NCC; ++i)
+            read_off[i] = (uint32_t)(crow * (CE * 4) + (((ccs * NCC + i) ^ (crow & (CH_ROW - 1))) << 4));
+          int k_prev = -1, wc = wcount;
+          for (int j = 0; j < nsteps; ++j) {
+            const int jg = jbase + j;
+            const int slot = jg % GST, stage = jg % NST;
+            const int k = steps_s[j] >> 4;
+            tc::mbar_wait(&slot_full[slot], (uint32_t)(jg / GST) & 1u);
+            const uint8_t* sp = b_base + Cfg::NWB * Cfg::B_STAGE + (uint32_t)slot * Cfg::G_STAGE;
+            const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + clane + (uint32_t)ccol0;
+            bool waited = false;
+#pragma unroll
+            for (int h = 0; h < NCC / 4; ++h) {           // 16 channels at a time
+              float hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 v4 = *(const float4*)(sp + read_off[4 * h + i]);
+                float4 h4 = v4, l4 = v4;
+                if (PREC == 0) tc::split_tf32(v4, h4, l4);
+                hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+                lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+              }
+              if (h == NCC / 4 - 1) {                     // every value of the slot is in registers
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&slot_empty[slot]);
+              }
+              if (!waited) {
+                waited = true;
+                if (jg >= NST) tc::mbar_wait(&empty_bar[stage], (uint32_t)((jg / NST) - 1) & 1u);
+                tc::fence_after_sync();
+                if (k != k_prev) {                        // an offset begins: prefetch the W image after next
+                  k_prev = k;
+                  if (tid == 0) issue_w(wc - wcount + Cfg::NWB - NST);
+                  ++wc;
+                }
+              }
+              tc::tmem_st16(a_hi + 16 * h, hi);
+              if (PREC == 0) tc::tmem_st16(a_hi + 64 + 16 * h, lo);
+            }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+          }
+        }
+      } else if constexpr (Cfg::GST > 0) {
         // ---- shared-memory gather ring with COALESCED row fetches.  Measured: when
         // every thread fetches its own row quarter, a warp-level 16-byte load touches 32 different
         // rows = 32 L1TEX tag cycles, 2 048 cycles per step and SM -- the kernel was bound by that,
@@ -415,13 +553,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           if (j + 1 < nsteps) produce(j + 1, vb, idx_b);
         }
       }
-      // ---- drain: the last commit on each stage ----
-      const int gtot = jbase + nsteps;
-#pragma unroll
-      for (int b = 0; b < NST; ++b) {
-        const int cb = gtot > b ? (gtot - b + NST - 1) / NST : 0;   // commits seen by stage b so far
-        if (cb) tc::mbar_wait(&empty_bar[b], (uint32_t)(cb - 1) & 1u);
-      }
+      // ---- drain: every MMA of the round has completed ----
+      tc::mbar_wait(&round_bar, (uint32_t)round & 1u);
       tc::fence_after_sync();
       // ---- epilogue: thread = output row (TMEM lane quarter q), 16 columns per warp ----
       constexpr int NSLICE = COUT / 16;
@@ -476,21 +609,21 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int CIN, int COUT, int NST, int PREC>
+template <int CIN, int COUT, int NST, int PREC, bool WS>
 static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
   using Cfg = ConvTcCfg<CIN, COUT, NST>;
   static bool attr_set = false;
   if (!attr_set) {
-    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST, PREC, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)Cfg::SMEM));
     attr_set = true;
   }
   int64_t tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   int grid = (int)(tiles < LK_SM_COUNT ? tiles : LK_SM_COUNT);   // persistent: one CTA per SM
-  conv_tc_kernel<CIN, COUT, NST, PREC><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
-                                                                            n_out, k, ep, out);
+  conv_tc_kernel<CIN, COUT, NST, PREC, WS><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
+                                                                                n_out, k, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -511,14 +644,23 @@ template <int CIN, int COUT>
 static int launch_conv_tc(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
-#ifdef CT_WITH_3_STAGES
-  if (conv_tc_stages() == 3)
-    return launch_conv_tc_n<CIN, COUT, 3, 0>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
-#endif
   (void)conv_tc_stages;
+  // warp-specialised producers wherever the configuration has a shared-memory gather ring
+  // (LINKB200_CONV_LOCKSTEP=1 selects the lock-step producers for A/B measurements)
+  static int lockstep = -1;
+  if (lockstep < 0) {
+    const char* e = getenv("LINKB200_CONV_LOCKSTEP");
+    lockstep = (e && e[0] == '1') ? 1 : 0;
+  }
+  constexpr bool has_ring = ConvTcCfg<CIN, COUT, 2>::GST > 0;
+  if (has_ring && !lockstep) {
+    if (ep.precision == LK_PREC_TF32)
+      return launch_conv_tc_n<CIN, COUT, 2, 1, true>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+    return launch_conv_tc_n<CIN, COUT, 2, 0, true>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+  }
   if (ep.precision == LK_PREC_TF32)
-    return launch_conv_tc_n<CIN, COUT, 2, 1>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
-  return launch_conv_tc_n<CIN, COUT, 2, 0>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+    return launch_conv_tc_n<CIN, COUT, 2, 1, false>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
+  return launch_conv_tc_n<CIN, COUT, 2, 0, false>(in, wimg, nbr, perm, tile_mask, n_out, k, ep, out, st);
 }
 
 extern "C" int lk_conv_tc_supported(int c_in, int c_out) {

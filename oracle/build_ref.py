@@ -180,3 +180,33 @@ def load_iou3d():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's PYTHON layer, staged for the GPU box (where /root/reference does not exist): the
+# torchsparse package WITHOUT its backend/ sources, and the two model files of the hot path.  They
+# go under baseline/_ref/ (git-ignored like the reference install of the base contract, shipped by
+# gpurun), untouched.  tests/test_gpu_reference_python_on_shim.py runs them on top of
+# link_b200.backend: the reference's own nn/functional glue and its own ELKBlock / ELKEncoder, our kernels.
+PY_STAGE = os.path.join(os.path.dirname(HERE), 'baseline', '_ref', 'py')
+_SEG = '/root/reference/segmentation'
+
+
+def stage_python(force: bool = False) -> str:
+    import shutil
+    if not os.path.isdir(_SEG):
+        return PY_STAGE if os.path.isdir(os.path.join(PY_STAGE, 'torchsparse')) else ''
+    if os.path.isdir(os.path.join(PY_STAGE, 'torchsparse')) and not force:
+        return PY_STAGE
+    shutil.rmtree(PY_STAGE, ignore_errors=True)
+    os.makedirs(PY_STAGE)
+    shutil.copytree(os.path.join(_SEG, 'torchsparse-u', 'torchsparse'), os.path.join(PY_STAGE, 'torchsparse'),
+                    ignore=shutil.ignore_patterns('backend', '__pycache__', '*.so'))
+    dst = os.path.join(PY_STAGE, 'core', 'models', 'semantic_kitti')
+    os.makedirs(dst)
+    for pkg in ('core', os.path.join('core', 'models'), os.path.join('core', 'models', 'semantic_kitti')):
+        open(os.path.join(PY_STAGE, pkg, '__init__.py'), 'w').close()       # empty packages: only two modules are used
+    shutil.copy(os.path.join(_SEG, 'core', 'models', 'utils.py'), os.path.join(PY_STAGE, 'core', 'models', 'utils.py'))
+    shutil.copy(os.path.join(_SEG, 'core', 'models', 'semantic_kitti', 'linkencoder.py'),
+                os.path.join(dst, 'linkencoder.py'))
+    return PY_STAGE
