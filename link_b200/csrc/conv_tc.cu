@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const int* __restrict__ nbr /*[K][n_out]*/,
     const int* __restrict__ perm /*[n_out] plan position -> output row, or NULL = identity*/,
     const unsigned* __restrict__ tile_mask /*[tiles] offsets present in each tile, or NULL = all*/,
-    int64_t n_out, int K, lk_conv_epilogue_t ep, float* __restrict__ out) {
+    int64_t n_out, int K, int tgroup /*adjacent tiles per slot group: 1, 2 or 4*/, int snake, lk_conv_epilogue_t ep,
+    float* __restrict__ out) {
   using Cfg = ConvTcCfg<CIN, COUT, NST>;
   constexpr int CPT = Cfg::CPT;                 // 16 (CIN = 64) or 8 (CIN = 32)
   constexpr int MAXT = Cfg::MAX_TILES;
@@ -145,13 +146,26 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   int jbase = 0;      // steps issued in earlier rounds: A-stage index and mbarrier phase continue
   int wcount = 0;     // offsets (W[k] images) consumed so far: weight ring index / phase continue
   for (int round = 0;; ++round) {
-    const int64_t first_tile = (int64_t)blockIdx.x + (int64_t)round * MAXT * gridDim.x;
-    if (first_tile >= total_tiles) break;
-    int ntiles = (int)((total_tiles - first_tile + gridDim.x - 1) / gridDim.x);
-    if (ntiles > MAXT) ntiles = MAXT;
+    // tile of slot t: groups of `tgroup` ADJACENT tiles, the groups interleaved over the CTAs.  Adjacent
+    // tiles of the plan order share their offset class, so a round needs fewer distinct W[k] images
+    // (each is a 32 KB bulk copy per CTA and round: at tgroup = 1 the weight traffic, 256 MB per conv at
+    // N = 119k, equals the gather traffic), while interleaving the groups still spreads the heavy
+    // classes at the end of the plan order over all CTAs.
+    const int64_t round0 = (int64_t)round * MAXT * gridDim.x;
+    // Stripes of gridDim.x groups alternate direction (CTA b takes group b of even stripes, group
+    // grid-1-b of odd ones): the plan order is roughly ascending in cost, so a fixed direction hands the
+    // high CTAs the heavier end of EVERY stripe.
+    auto tile_of = [&](int t) -> int64_t {
+      const int stripe = round * (MAXT / tgroup) + t / tgroup;
+      const int bb = (snake && (stripe & 1)) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      const int64_t tile = round0 + ((int64_t)(t / tgroup) * gridDim.x + bb) * tgroup + (t % tgroup);
+      return tile < total_tiles ? tile : -1;
+    };
+    if (round0 >= total_tiles) break;
+    const int ntiles = MAXT;                                              // slots; invalid ones have no mask and no rows
     // ---- active step list of the round, k-major (W[k] is staged once per offset and round) ----
     if (tid < MAXT)
-      tmask_s[tid] = tid < ntiles ? (tile_mask ? tile_mask[first_tile + (int64_t)tid * gridDim.x] & kmask : kmask) : 0u;
+      tmask_s[tid] = tile_of(tid) >= 0 ? (tile_mask ? tile_mask[tile_of(tid)] & kmask : kmask) : 0u;
     __syncthreads();
     if (tid < CT_THREADS) {
       const int kk = tid / MAXT, tt = tid % MAXT;            // kk = virtual offset (k, h) = k KH + h
@@ -178,8 +192,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     for (int i = tid; i < MAXT * CT_ROWS; i += CT_THREADS + 32) {
       const int t = i / CT_ROWS, r = i % CT_ROWS;
       int o = -1;
-      if (t < ntiles) {
-        const int64_t pos = (first_tile + (int64_t)t * gridDim.x) * CT_ROWS + r;
+      if (tile_of(t) >= 0) {
+        const int64_t pos = tile_of(t) * CT_ROWS + r;
         if (pos < n_out) o = perm ? __ldg(perm + pos) : (int)pos;
       }
       orow_s[t][r] = o;
@@ -201,10 +215,11 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         uint64_t* bar = &wfull_bar[wg % Cfg::NWB];
         const uint32_t dst = tc::smem_u32(b_base + (wg % Cfg::NWB) * Cfg::B_STAGE);
         const float* src = wimg + (int64_t)klist_s[local_idx] * (Cfg::B_STAGE / 4);
+        constexpr uint32_t W_BYTES = PREC == 0 ? Cfg::B_STAGE : Cfg::B_PLANE;   // single-pass TF32 reads the hi plane only
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                     ::"r"(tc::smem_u32(bar)), "r"(Cfg::B_STAGE) : "memory");
+                     ::"r"(tc::smem_u32(bar)), "r"(W_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst), "l"(src), "r"(Cfg::B_STAGE), "r"(tc::smem_u32(bar)) : "memory");
+                     ::"r"(dst), "l"(src), "r"(W_BYTES), "r"(tc::smem_u32(bar)) : "memory");
       }
     };
     if (tid == 0) {
@@ -622,8 +637,24 @@ static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, 
   }
   int64_t tiles = (n_out + CT_ROWS - 1) / CT_ROWS;
   int grid = (int)(tiles < LK_SM_COUNT ? tiles : LK_SM_COUNT);   // persistent: one CTA per SM
+  // adjacent-tile groups only pay with a plan order (classes are contiguous there) and when every CTA
+  // still gets a full group; LINKB200_CONV_TGROUP overrides (A/B measurements)
+  static int tg_env = -1;
+  if (tg_env < 0) {
+    const char* e = getenv("LINKB200_CONV_TGROUP");
+    tg_env = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
+  }
+  int tgroup = 1;                                      // measured: 2 / 4 adjacent tiles per group are 23 % / 70 % slower
+  if (tg_env) tgroup = tg_env;                         // (the CTAs that draw the heavy classes finish last)
+  while (tgroup > 1 && (Cfg::MAX_TILES % tgroup)) tgroup >>= 1;
+  static int snake = -1;
+  if (snake < 0) {
+    const char* e = getenv("LINKB200_CONV_SNAKE");
+    snake = (e && e[0] == '1') ? 1 : 0;        // measured slower (77 vs 69 us): the plain interleave already pairs the light end of
+                                                  // every stripe with the extra heavy tile of the last, partial stripe
+  }
   conv_tc_kernel<CIN, COUT, NST, PREC, WS><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
-                                                                                n_out, k, ep, out);
+                                                                                n_out, k, tgroup, snake, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }
