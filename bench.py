@@ -294,6 +294,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     roof = None
     if workload == 'block':
         roof = preagg_roofline(dev, coords_dev[0], bounds[0], model)
+        roof['path'] = path_roofline(dev, coords_dev[0], bounds[0], model)
     # ---- end-to-end loop: pinned host buffers -> H2D -> step -> D2H of a per-channel checksum --
     h2d = d2h = 0
     e2e_evs = []
@@ -505,6 +506,21 @@ def reference_gpu_leg(dev, coords, feats, blk, flush, steps=5, warmup=2):
         return {'unavailable': repr(e)[:200]}
 
 
+def reference_model_leg(what, voxels, steps=5, warmup=2):
+    """The unmodified reference (its python package + model class on its own CUDA backend) on the same
+    synthetic scan, in its own process (oracle/ref_model_gpu.py)."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'ref_model_gpu.py'), '--what', what, '--voxels',
+                            str(voxels), '--steps', str(steps), '--warmup', str(warmup)], capture_output=True, text=True,
+                           timeout=300)
+        lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
+        if p.returncode != 0 or not lines:
+            return {'unavailable': (p.stderr or 'no output')[-300:]}
+        return json.loads(lines[-1])
+    except Exception as e:   # noqa: BLE001 -- a baseline leg must never take the bench line down
+        return {'unavailable': repr(e)[:200]}
+
+
 def preagg_roofline(dev, coords, bounds, blk, nbuf=6, reps=4):
     import ctypes as C
     from link_b200 import SparseTensor, _capi
@@ -558,6 +574,64 @@ def preagg_roofline(dev, coords, bounds, blk, nbuf=6, reps=4):
     return {'avg_us': us, 'python_launch_avg_us': us_py, 'how': how, 'bytes': float(nbytes),
             'launches': nbuf * reps, 'm': m,
             'inputs': f'{nbuf} rotating [N,{C_BLOCK}] fp32 feature buffers ({nbuf * n * C_BLOCK * 4 / 1e6:.0f} MB > L2)'}
+
+
+def path_roofline(dev, coords, bounds, blk, nbuf=6, rounds=24):
+    """The whole pre-aggregation PATH of SURVEY 8d -- everything between F_input and the pre-LayerNorm
+    [N, C] output: zeroing of the block sums, segmented pre-aggregation (kernel generator + block sums),
+    window mean over the r^3 neighbour blocks, per-voxel combine -- as ONE CUDA graph of `rounds` rounds
+    over `nbuf` rotating input / output buffer sets (> L2), replayed; CUDA events around the replay.
+    Algorithmic bytes: N (2*4C + 2*16 + 2*4) + M (2 (4kC + 4))."""
+    import ctypes as C
+    from link_b200 import SparseTensor, _capi
+    from link_b200.elk import block_index, _kernel_gen
+    from link_b200.nn.functional import _index
+    n = coords.shape[0]
+    c, k = C_BLOCK, 2
+    st = SparseTensor(torch.zeros(n, 1, device=dev), coords, 1)
+    _index.set_coord_bounds(st.kmaps, bounds[0], bounds[1])
+    bi = block_index(st, S_BLK)
+    m = bi.m
+    nbr = bi.neighbors(R_BLK)
+    w = blk.pos_weight[0].weight.detach().contiguous().float()
+    gen = _kernel_gen(BASEOP, c, w, None, 1.0)
+    fin = [torch.randn(n, c, device=dev) for _ in range(nbuf)]
+    out = [torch.empty(n, c, device=dev) for _ in range(nbuf)]
+    sums = torch.zeros(n, k * c, device=dev)
+    mean = torch.zeros(n, k * c, device=dev)
+    L, P = _capi.lib(), _capi.ptr
+
+    def one_round(i, s):
+        _capi.check(L.lk_zero_rows(P(sums), P(bi.num), n, k * c, s), 'zero')
+        _capi.check(L.lk_link_preagg_seg_fwd(P(fin[i % nbuf]), P(coords), P(bi.order), P(bi.sorted_rank), n,
+                                             C.byref(gen), P(sums), s), 'preagg')
+        _capi.check(L.lk_link_window_mean_seg(P(sums), P(bi.seg), P(nbr), P(bi.num), n, nbr.shape[1], k * c,
+                                              P(mean), s), 'wmean')
+        _capi.check(L.lk_link_apply_fwd(P(mean), P(fin[i % nbuf]), P(coords), P(bi.idx_query), n, C.byref(gen), 0,
+                                        None, None, None, None, None, P(out[i % nbuf]), s), 'apply')
+    try:
+        for i in range(2):
+            one_round(i, _capi.stream())
+        torch.cuda.synchronize()
+        gr, cap = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.graph(gr, stream=cap):
+            cs = _capi.stream()
+            for i in range(rounds):
+                one_round(i, cs)
+        gr.replay()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, 1e3 * e0.elapsed_time(e1) / rounds)
+    except Exception as e:   # noqa: BLE001
+        return {'unavailable': repr(e)[:200]}
+    nbytes = n * (2 * 4 * c + 2 * 16 + 2 * 4) + m * (2 * (4 * k * c + 4))
+    return {'avg_us': best, 'bytes': float(nbytes), 'm': m, 'launches_per_round': 4, 'rounds': rounds}
 
 
 def summarize(m, world, dev):
@@ -664,6 +738,16 @@ def main_ours(args):
                         'same launches issued one by one from python (host-paced: ~10 us per ctypes call); '
                         'in_step_avg_us = the same kernel inside the step (events around the single '
                         'python-level call, includes launch latency)'}
+    roof_path = None
+    if m.get('roof') and m['roof'].get('path') and 'avg_us' in m['roof']['path']:
+        rp = m['roof']['path']
+        gbs = rp['bytes'] / (rp['avg_us'] * 1e-6) / 1e9
+        roof_path = {'kernels': ['lk_zero_rows', 'link_preagg_ring_kernel', 'link_window_mean_kernel', 'link_apply_kernel (plain)'],
+                     'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                     'algorithmic_bytes_per_round': rp['bytes'], 'avg_us': rp['avg_us'],
+                     'note': 'SURVEY 8d pre-aggregation PATH (F_input -> pre-LayerNorm output): 4 launches per round, '
+                             f"{rp['rounds']} rounds over rotating buffers (> L2) in one CUDA graph, replayed; bytes = "
+                             'N (2*4C + 2*16 + 2*4) + M (2 (4kC + 4))'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
         'warmup': m['warmup'], 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
@@ -677,9 +761,14 @@ def main_ours(args):
         'e2e_ring': m.get('e2e_ring'),
         'e2e_bf16_wire': m.get('e2e_bf16'),
         'roofline': roof,
+        'roofline_path': roof_path,
         'kernels': kern,
     }
     if extra is not None:
+        if world == 1 and not args.no_cpu_baseline:
+            extra['reference_gpu'] = reference_model_leg('encoder', args.voxels)
+            if extra['reference_gpu'].get('ms_per_step'):
+                extra['vs_reference_gpu'] = extra['reference_gpu']['ms_per_step'] / extra['ms_per_step']
         line['encoder'] = extra
     if train is not None:
         line['train_encoder'] = train

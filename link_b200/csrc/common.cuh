@@ -83,3 +83,52 @@ __device__ __forceinline__ void lk_red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A chain of short dependent kernels pays launch latency + CTA scheduling + prologue at every
+// boundary (~2-4 us each on B200; the LinK block has ~10 boundaries on its critical chain).  Kernels
+// launched through lk_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: the grid may
+// be scheduled while its predecessor in the stream is still running, and every thread executes
+// lk_pdl_enter() -- griddepcontrol.wait: block until the predecessor grid has completed and its writes
+// are visible -- before it touches global memory, then griddepcontrol.launch_dependents, which lets the
+// NEXT kernel of the stream be scheduled early in turn.  Because every such kernel waits before it
+// does anything else, completion stays transitive along the chain (kernel C may rely on the output of
+// A through B).  Without the attribute (LINKB200_PDL=0, or an event / memset in between) both
+// instructions are no-ops and the launch is an ordinary one.
+__device__ __forceinline__ void lk_pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool lk_pdl_enabled();
+bool lk_pdl_enabled_link();   // the four kernels of the pre-aggregation path (link.cu): measured SLOWER with PDL
+                              // (graph replay of the path 27.3 -> 29.5 us: the early-resident CTAs of the next
+                              // kernel take shared memory and issue slots from the tail of a bandwidth-bound
+                              // one), so they keep ordinary launches unless LINKB200_PDL_LINK=1
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lk_launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args... args);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lk_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, Args... args) {
+  return lk_launch_pdl_if(lk_pdl_enabled(), kernel, grid, block, smem, st, args...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lk_launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define LK_PDL_LAUNCH(kernel, grid, block, smem, st, ...) \
+  LK_CUDA(lk_launch_pdl(kernel, dim3((unsigned)(grid)), dim3((unsigned)(block)), (size_t)(smem), st, __VA_ARGS__))
+#define LK_PDL_LAUNCH_LINK(kernel, grid, block, smem, st, ...)                                          \
+  LK_CUDA(lk_launch_pdl_if(lk_pdl_enabled_link(), kernel, dim3((unsigned)(grid)), dim3((unsigned)(block)), \
+                           (size_t)(smem), st, __VA_ARGS__))

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) plan_class_kernel(const int* __restrict__
                                                          unsigned char* __restrict__ cls,
                                                          unsigned* __restrict__ hist,
                                                          unsigned* __restrict__ tile_mask, int tiles) {
+  lk_pdl_enter();
   __shared__ unsigned h[256];
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tiles;
        t += (int64_t)gridDim.x * blockDim.x)
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) plan_scatter_kernel(const unsigned char* 
                                                            const unsigned* __restrict__ rowmask,
                                                            int* __restrict__ perm,
                                                            unsigned* __restrict__ tile_mask) {
+  lk_pdl_enter();
   __shared__ unsigned base[256];
   __shared__ unsigned wsum[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -141,9 +143,9 @@ extern "C" int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const in
   LK_CUDA(cudaMemsetAsync(hist, 0, 2 * cp_al(256 * 4), st));
   lk_count_launch();
   const int grid = lk_grid(n_out, 256, 4);
-  plan_class_kernel<<<grid, 256, 0, st>>>(d_nbr, n_out, k, d_offsets, rowmask, cls, hist, d_tile_mask, tiles);
+  LK_PDL_LAUNCH(plan_class_kernel, grid, 256, 0, st, d_nbr, n_out, k, d_offsets, rowmask, cls, hist, d_tile_mask, tiles);
   LK_LAUNCHED();
-  plan_scatter_kernel<<<grid, 256, 0, st>>>(cls, n_out, hist, cursor, rowmask, d_perm, d_tile_mask);
+  LK_PDL_LAUNCH(plan_scatter_kernel, grid, 256, 0, st, cls, n_out, hist, cursor, rowmask, d_perm, d_tile_mask);
   LK_LAUNCHED();
   return LK_OK;
 }

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  lk_pdl_enter();      // nothing above reads global memory: TMEM allocation and barrier set-up overlap the predecessor
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_a0 = tmem_base + Cfg::ACC_COLS;        // A stage s at + s * 128 columns
 
@@ -653,8 +654,8 @@ static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, 
     snake = (e && e[0] == '1') ? 1 : 0;        // measured slower (77 vs 69 us): the plain interleave already pairs the light end of
                                                   // every stripe with the extra heavy tile of the last, partial stripe
   }
-  conv_tc_kernel<CIN, COUT, NST, PREC, WS><<<grid, CT_THREADS + 32, Cfg::SMEM, st>>>(in, wimg, nbr, perm, tile_mask,
-                                                                                n_out, k, tgroup, snake, ep, out);
+  LK_PDL_LAUNCH((conv_tc_kernel<CIN, COUT, NST, PREC, WS>), grid, CT_THREADS + 32, Cfg::SMEM, st, in, wimg, nbr, perm,
+                tile_mask, n_out, k, tgroup, snake, ep, out);
   LK_LAUNCHED();
   return LK_OK;
 }

@@ -19,6 +19,7 @@ template <int C>
 __global__ void __launch_bounds__(DT_THREADS) linear_ln_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int64_t n, float* __restrict__ out) {
+  lk_pdl_enter();
   constexpr int KB = C / 32;                         // 128-byte K-blocks per row
   constexpr uint32_t A_BLK = DT_ROWS * 128;          // bytes of one [128 x 32] K-block
   constexpr uint32_t B_BLK = C * 128;                // bytes of one [C x 32] K-block
@@ -171,7 +172,7 @@ static int launch_tc(const float* x, const float* w, const float* g, const float
   int64_t tiles = (n + DT_ROWS - 1) / DT_ROWS;
   int ctas_per_sm = (smem <= 100 * 1024) ? 2 : 1;
   int grid = (int)(tiles < (int64_t)LK_SM_COUNT * ctas_per_sm ? tiles : (int64_t)LK_SM_COUNT * ctas_per_sm);
-  linear_ln_tc_kernel<C><<<grid, DT_THREADS, smem, st>>>(x, w, g, b, eps, n, out);
+  LK_PDL_LAUNCH(linear_ln_tc_kernel<C>, grid, DT_THREADS, smem, st, x, w, g, b, eps, n, out);
   LK_LAUNCHED();
   return LK_OK;
 }

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) table_query_kernel(const int64_t* __restr
 // same table, keys hashed on the fly from the coordinates (saves the hash array round trip and a launch)
 __global__ void __launch_bounds__(256) table_insert_coords_kernel(const int4* __restrict__ coords,
                                                                   int64_t n, Slot* table, uint64_t mask) {
+  lk_pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int4 c = coords[i];
@@ -130,9 +131,8 @@ extern "C" int lk_table_build_coords(const int32_t* d_coords, int64_t n, void* d
   lk_count_launch();
   if (n == 0) return LK_OK;
   LK_REQUIRE(d_coords, "lk_table_build_coords: null coords");
-  table_insert_coords_kernel<<<lk_grid(n, 256, 8), 256, 0, (cudaStream_t)s>>>((const int4*)d_coords, n,
-                                                                             (Slot*)d_table,
-                                                                             (uint64_t)capacity - 1);
+  LK_PDL_LAUNCH(table_insert_coords_kernel, lk_grid(n, 256, 8), 256, 0, (cudaStream_t)s, (const int4*)d_coords, n,
+                (Slot*)d_table, (uint64_t)capacity - 1);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256) kmap_query_subm_kernel(const int4* __rest
                                                               int64_t n, const int* __restrict__ offsets,
                                                               int K, const Slot* __restrict__ table,
                                                               uint64_t mask, unsigned* nbr) {
+  lk_pdl_enter();
   const int half = K / 2;
   int64_t total = n * (half + 1);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
@@ -238,9 +239,9 @@ extern "C" int lk_kmap_query_subm(const int32_t* d_coords, int64_t n, const int3
   cudaStream_t st = (cudaStream_t)s;
   LK_CUDA(cudaMemsetAsync(d_nbr, 0xFF, (size_t)k * n * sizeof(int), st));
   lk_count_launch();
-  kmap_query_subm_kernel<<<lk_grid(n * (k / 2 + 1), 256, 8), 256, 0, st>>>(
-      (const int4*)d_coords, n, d_offsets, k, (const Slot*)d_table, (uint64_t)capacity - 1,
-      (unsigned*)d_nbr);
+  LK_PDL_LAUNCH(kmap_query_subm_kernel, lk_grid(n * (k / 2 + 1), 256, 8), 256, 0, st,
+                (const int4*)d_coords, n, d_offsets, k, (const Slot*)d_table, (uint64_t)capacity - 1,
+                (unsigned*)d_nbr);
   LK_LAUNCHED();
   return LK_OK;
 }

@@ -330,6 +330,7 @@ template <int LPR, int IB, int OP>
 __global__ void __launch_bounds__(PR_WARPS * 32, PR_MINB) link_preagg_ring_kernel(
     const float* __restrict__ fin, const int4* __restrict__ coords, const int* __restrict__ order,
     const int* __restrict__ rank, int64_t n, int q, GenDev g, float* sums) {
+  lk_pdl_enter();
   using Cfg = RingCfg<LPR>;
   constexpr int VPL = 2;
   constexpr int G = Cfg::G, RC = Cfg::RC, CR = Cfg::CR, ROW_BYTES = Cfg::ROW_BYTES, SLOT = Cfg::SLOT;
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, PR_MINB) link_preagg_ring_kerne
 __global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p,
                                                         const int* __restrict__ d_num,
                                                         int64_t capacity, int row_vec) {
+  lk_pdl_enter();
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
   int64_t total = m * row_vec;
@@ -484,8 +486,8 @@ extern "C" int lk_zero_rows(float* d_buf, const int32_t* d_num, int64_t capacity
   LK_REQUIRE(capacity >= 0 && row_floats > 0 && row_floats % 4 == 0, "lk_zero_rows: bad sizes");
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_buf && d_num && (uintptr_t)d_buf % 16 == 0, "lk_zero_rows: bad pointer");
-  zero_rows_kernel<<<lk_grid(capacity * (row_floats / 4), 256, 8), 256, 0, (cudaStream_t)s>>>(
-      (float4*)d_buf, d_num, capacity, row_floats / 4);
+  LK_PDL_LAUNCH_LINK(zero_rows_kernel, lk_grid(capacity * (row_floats / 4), 256, 8), 256, 0, (cudaStream_t)s,
+                (float4*)d_buf, d_num, capacity, row_floats / 4);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
                                                                int64_t capacity, int R, int kc,
                                                                float* __restrict__ mean,
                                                                float* __restrict__ tot_out) {
+  lk_pdl_enter();
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
   const int lane = threadIdx.x & 31;
@@ -571,6 +574,7 @@ __global__ void __launch_bounds__(128, VPL >= 4 ? AP_MINB : 5) link_apply_kernel
     const int* __restrict__ blk, int64_t n, GenDev g, const float* __restrict__ local,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
     const float* __restrict__ b2, float* __restrict__ out) {
+  lk_pdl_enter();
   constexpr int G = 32 / LPR;
   constexpr int K = (OP == LK_OP_COSX) ? 3 : 2;
   constexpr bool COSX = (OP == LK_OP_COSX);
@@ -709,7 +713,7 @@ static int launch_ring(const float* d_fin, const int32_t* d_coords, const int32_
   if (q_env > 0 && q_env >= q) q = q_env;
   const int64_t groups = (n + q - 1) / q;
   const int grid = (int)((groups + (int64_t)Cfg::G * PR_WARPS - 1) / ((int64_t)Cfg::G * PR_WARPS));
-  kern<<<grid, PR_WARPS * 32, Cfg::SMEM, st>>>(d_fin, (const int4*)d_coords, d_order, d_rank, n, (int)q, g, d_sums);
+  LK_PDL_LAUNCH_LINK(kern, grid, PR_WARPS * 32, Cfg::SMEM, st, d_fin, (const int4*)d_coords, d_order, d_rank, n, (int)q, g, d_sums);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -838,8 +842,8 @@ extern "C" int lk_link_window_mean(const float* d_sums, const int32_t* d_counts,
              "lk_link_window_mean: bad sizes (needs r^3 <= 32)");
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_sums && d_counts && d_nbr && d_num && d_mean, "lk_link_window_mean: null pointer");
-  link_window_mean_kernel<false><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean, nullptr);
+  LK_PDL_LAUNCH_LINK(link_window_mean_kernel<false>, lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s,
+                d_sums, d_counts, d_nbr, d_num, capacity, r3, kc, d_mean, (float*)nullptr);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -851,8 +855,8 @@ extern "C" int lk_link_window_mean_tot(const float* d_sums, const int32_t* d_seg
              "lk_link_window_mean_seg: bad sizes (needs r^3 <= 32)");
   if (capacity == 0) return LK_OK;
   LK_REQUIRE(d_sums && d_seg && d_nbr && d_num && d_mean, "lk_link_window_mean_seg: null pointer");
-  link_window_mean_kernel<true><<<lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean, d_tot);
+  LK_PDL_LAUNCH_LINK(link_window_mean_kernel<true>, lk_grid(capacity * 32, 256, 8), 256, 0, (cudaStream_t)s,
+                d_sums, d_seg, d_nbr, d_num, capacity, r3, kc, d_mean, d_tot);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -888,8 +892,8 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
     const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
     const int grid = lk_grid(steps * 32, 128, AP_MINB);
 #define LAUNCH_A4_ON(LPRV, IBV, O, NRM)                                                        \
-  link_apply_kernel<LPRV, 4, IBV, O, NRM><<<grid, 128, 0, st>>>(                               \
-      d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
+  LK_PDL_LAUNCH_LINK((link_apply_kernel<LPRV, 4, IBV, O, NRM>), grid, 128, 0, st,                      \
+                d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
 #define LAUNCH_A4_O(LPRV, IBV, O)                           \
   do {                                                      \
     if (fuse_norm) LAUNCH_A4_ON(LPRV, IBV, O, true);        \
@@ -925,8 +929,8 @@ extern "C" int lk_link_apply_fwd(const float* d_mean, const float* d_fin, const 
   const int64_t steps = (n + rows_per_step - 1) / rows_per_step;
   const int grid = lk_grid(steps * 32, 128, 5);
 #define LAUNCH_APPLY_ON(LPRV, O, NRM)                                                          \
-  link_apply_kernel<LPRV, 1, 1, O, NRM><<<grid, 128, 0, st>>>(                                 \
-      d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
+  LK_PDL_LAUNCH_LINK((link_apply_kernel<LPRV, 1, 1, O, NRM>), grid, 128, 0, st,                        \
+                d_mean, d_fin, (const int4*)d_coords, d_blk, n, g, d_local, d_g1, d_b1, d_g2, d_b2, d_out)
 #define LAUNCH_APPLY_O(LPRV, O)                         \
   do {                                                  \
     if (fuse_norm) LAUNCH_APPLY_ON(LPRV, O, true);      \

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Error string, version and launch counter of liblinkb200.
 #include <stdarg.h>
 #include <atomic>
@@ -18,3 +19,19 @@ void lk_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed)
 extern "C" const char* lk_last_error(void) { return g_err; }
 extern "C" int lk_version(void) { return 100; }
 extern "C" int64_t lk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// programmatic dependent launch on/off (LINKB200_PDL=0 restores ordinary launches; common.cuh)
+bool lk_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LINKB200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+bool lk_pdl_enabled_link() {
+  static const bool on = [] {
+    const char* e = getenv("LINKB200_PDL_LINK");
+    return lk_pdl_enabled() && e && e[0] == '1';
+  }();
+  return on;
+}

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) block_neighbors_kernel(
     const unsigned long long* __restrict__ uniq, const int* __restrict__ d_num, int64_t capacity,
     KeySpecDev sp, const int* __restrict__ offsets, int R, int* __restrict__ nbr,
     float4* __restrict__ zero_buf, int zero_row_vec) {
+  lk_pdl_enter();
   int64_t m = *d_num;
   if (m > capacity) m = capacity;
   int64_t total = m * R;
@@ -179,9 +180,9 @@ extern "C" int lk_block_neighbors_zero(const uint64_t* d_unique, const int32_t* 
   LK_REQUIRE(d_unique && d_num && d_offsets && d_nbr && r3 > 0 && d_zero && row_floats > 0 &&
                  row_floats % 4 == 0 && (uintptr_t)d_zero % 16 == 0,
              "lk_block_neighbors_zero: bad arguments");
-  block_neighbors_kernel<<<lk_grid(capacity * r3, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      (const unsigned long long*)d_unique, d_num, capacity, sp, d_offsets, r3, d_nbr, (float4*)d_zero,
-      row_floats / 4);
+  LK_PDL_LAUNCH(block_neighbors_kernel, lk_grid(capacity * r3, 256, 8), 256, 0, (cudaStream_t)s,
+                (const unsigned long long*)d_unique, d_num, capacity, sp, d_offsets, r3, d_nbr, (float4*)d_zero,
+                row_floats / 4);
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
 // blocked arrangement: thread t owns items [t*8, t*8+8) of its tile
 __global__ void __launch_bounds__(RS_THREADS) uniq_count_kernel(
     const unsigned long long* __restrict__ keys, int64_t n, unsigned* __restrict__ tile_heads) {
+  lk_pdl_enter();
   __shared__ unsigned wsum[RS_WARPS];
   int64_t i0 = (int64_t)blockIdx.x * RS_TILE + (int64_t)threadIdx.x * RS_ITEMS;
   unsigned c = 0;
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_tm_kernel(
 __global__ void __launch_bounds__(RS_THREADS) radix_pack_hist_tm_kernel(
     const int4* __restrict__ coords, int64_t n, KeySpecDev sp, unsigned long long* __restrict__ keys,
     unsigned* __restrict__ hist) {
+  lk_pdl_enter();
   __shared__ unsigned h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_fused_kernel(
     unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out, int64_t n,
     int shift, const unsigned* __restrict__ hist /*[T][256]*/, unsigned* hist_next /*or NULL*/,
     int T) {
+  lk_pdl_enter();
   __shared__ unsigned cnt[RS_WARPS][257];
   __shared__ unsigned wsum[RS_WARPS];
   int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -549,6 +553,7 @@ __global__ void __launch_bounds__(RS_THREADS) uniq_write_fused_kernel(
     const unsigned* __restrict__ tile_heads, int T, unsigned long long* __restrict__ uniq,
     int* __restrict__ inverse, int* __restrict__ order, int* __restrict__ seg, int* __restrict__ d_num,
     int* __restrict__ rank_sorted) {
+  lk_pdl_enter();
   __shared__ unsigned wsum[RS_WARPS];
   __shared__ unsigned red[2][RS_WARPS];
   __shared__ unsigned tile_base_s;
@@ -707,14 +712,14 @@ static int sort_unique_impl(const uint64_t* d_keys, const int32_t* d_coords, con
       lk_count_launch();
     }
     if (d_coords)
-      radix_pack_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>((const int4*)d_coords, n, spd, kb, hist);
+      LK_PDL_LAUNCH(radix_pack_hist_tm_kernel, T, RS_THREADS, 0, st, (const int4*)d_coords, n, spd, kb, hist);
     else
       radix_hist_tm_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, 0, hist);
     LK_LAUNCHED();
     for (int pss = 0; pss < passes; ++pss) {
-      radix_scatter_fused_kernel<<<T, RS_THREADS, 0, st>>>(
-          kin, vin, kout, vout, n, 8 * pss, hist + pss * hsz,
-          pss + 1 < passes ? hist + (pss + 1) * hsz : nullptr, T);
+      LK_PDL_LAUNCH(radix_scatter_fused_kernel, T, RS_THREADS, 0, st,
+                    kin, vin, kout, vout, n, 8 * pss, hist + pss * hsz,
+                    pss + 1 < passes ? hist + (pss + 1) * hsz : nullptr, T);
       LK_LAUNCHED();
       kin = kout; vin = vout;
       kout = (kout == ka) ? kb : ka;
@@ -735,12 +740,11 @@ static int sort_unique_impl(const uint64_t* d_keys, const int32_t* d_coords, con
   }
   int* seg = d_seg ? d_seg : seg_tmp;
   int* num = d_num ? d_num : num_tmp;
-  uniq_count_kernel<<<T, RS_THREADS, 0, st>>>(kin, n, tile_heads);
+  LK_PDL_LAUNCH(uniq_count_kernel, T, RS_THREADS, 0, st, kin, n, tile_heads);
   LK_LAUNCHED();
   if (fused) {
-    uniq_write_fused_kernel<<<T, RS_THREADS, 0, st>>>(kin, vin, n, tile_heads, T,
-                                                      (unsigned long long*)d_unique, d_inverse,
-                                                      d_order, seg, num, d_sorted_rank);
+    LK_PDL_LAUNCH(uniq_write_fused_kernel, T, RS_THREADS, 0, st, kin, vin, n, tile_heads, T,
+                  (unsigned long long*)d_unique, d_inverse, d_order, seg, num, d_sorted_rank);
     LK_LAUNCHED();
   } else {
     scan_single_cta_kernel<<<1, 1024, 0, st>>>(tile_heads, T, num, seg, (int)n);
