@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='block', choices=['block', 'encoder', 'train_encoder'])
     ap.add_argument('--no-train', action='store_true', help='skip the extra DDP training measurement')
+    ap.add_argument('--amp', default='none', choices=['none', 'bf16'], help='train_encoder: torch.autocast(bfloat16) + single-pass TF32 sparse convs')
     ap.add_argument('--voxels', type=int, default=120_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-encoder', action='store_true', help='skip the extra encoder measurement')
@@ -391,6 +392,10 @@ def run_train(args, steps, warmup, dev, rank, world, local):
     from link_b200.sharding import frame_seed
 
     per_scan = min(args.voxels, 80_000)
+    amp = getattr(args, 'amp', 'none') == 'bf16'
+    if amp:
+        from link_b200.nn.functional import conv as conv_mod
+        conv_mod.set_precision('tf32')
     batches = []
     for b in range(2):                                        # two alternating batches per rank
         cs, fs = [], []
@@ -423,7 +428,9 @@ def run_train(args, steps, warmup, dev, rank, world, local):
         ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
         with ctx:
             opt.zero_grad(set_to_none=True)
-            loss = torch.nn.functional.cross_entropy(model(st), y, ignore_index=0)
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+                logits = model(st)
+            loss = torch.nn.functional.cross_entropy(logits.float(), y, ignore_index=0)
             loss.backward()
         opt.step()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -457,7 +464,7 @@ def run_train(args, steps, warmup, dev, rank, world, local):
     nparam = sum(p.numel() for p in net.parameters())
     return {'ms': ms, 'ms_nosync': ms_nosync, 'voxels': vox, 'steps': steps, 'warmup': warmup, 'h2d': h2d, 'd2h': 4,
             'launches': int(launches), 'host_ms': host_ms, 'loss': loss_val, 'nparam': nparam,
-            'n_batch': len(batches[0][0])}
+            'n_batch': len(batches[0][0]), 'amp': amp}
 
 
 def train_line(tr, world, dev):
@@ -467,7 +474,9 @@ def train_line(tr, world, dev):
     ms_ns, _ = reduce_throughput(tr['ms_nosync'], tr['voxels'], None)
     steps = tr['steps']
     return {'workload': (f"ELKEncoder cos:(3x7)^3 cr=1.0 DDP training step (fwd + cross-entropy + bwd + gradient "
-                         f"all-reduce + SGD), 2 synthetic scans per rank, {tr['n_batch']} voxels per batch, fp32"),
+                         f"all-reduce + SGD), 2 synthetic scans per rank, {tr['n_batch']} voxels per batch, "
+                         + ('bf16 autocast (dense layers bf16, sparse convs single-pass TF32, fp32 accumulation and master weights)'
+                            if tr.get('amp') else 'fp32')),
             'value': vox / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps, 'warmup': tr['warmup'],
             'scaling': 'weak', 'collective': f'NCCL all-reduce of {tr["nparam"] * 4 / 1e6:.1f} MB fp32 gradients '
                                              f'per step (torch DDP, {world} ranks)' if world > 1 else 'none (1 rank)',
@@ -668,7 +677,8 @@ def main_ours(args):
         if rank == 0:
             line = {'metric': 'ELKEncoder training voxels/sec (DDP)', 'value': tl['value'], 'unit': UNIT, 'n_gpus': world,
                     'steps': tl['steps'], 'warmup': tl['warmup'], 'ms_per_step': tl['ms_per_step'],
-                    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                    'dtype': 'bf16' if args.amp == 'bf16' else 'f32',
                     'data': 'synthetic', 'config': {'workload': tl['workload']},
                     'e2e': {'value': tl['value'], 'unit': UNIT, 'h2d_bytes_per_step': tl['h2d_bytes_per_step'],
                             'd2h_bytes_per_step': tl['d2h_bytes_per_step'],

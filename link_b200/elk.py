@@ -366,6 +366,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     build = kmap is None
     if build:
         kmap = KernelMap(torch.empty(conv.kernel_volume, n, dtype=torch.int32, device=dev), n, n, coords)
+        kmap.subm = conv.kernel_volume % 2 == 1 and all(s == 1 for s in conv.stride)
         st.kmaps[key] = kmap
     conv_off = get_kernel_offsets(conv.kernel_size, stride=st.stride, device=dev)
     blk_off = get_kernel_offsets(r, 1, 1, device=dev)

@@ -40,6 +40,7 @@ class KernelMap:
         self.offsets = None      # int32 [K,3] offsets the map was built with (classes of the plan)
         self._plan = None        # (perm [n_out], tile_mask [tiles]) or False
         self._wgrad = {}         # direction -> (nbrp, perm, masks) of the tensor-core weight gradient
+        self.subm = False        # submanifold map (stride 1, odd kernel): inv[k] == nbr[K - 1 - k]
 
     @property
     def inv(self) -> torch.Tensor:
@@ -163,6 +164,7 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_pl
                                     _capi.stream()), 'lk_kmap_build')
     if plan:
         kmap._plan = plan
+    kmap.subm = bool(subm)
     return kmap
 
 
@@ -340,12 +342,20 @@ class ConvolutionFunction(Function):
         k, c_in, c_out = weight.shape
         grad_feats = grad_weight = None
         # the relation seen from the forward INPUT rows / from the forward OUTPUT rows
-        to_in = kmap.inv if not transposed else kmap.nbr
         to_out = kmap.nbr if not transposed else kmap.inv
         n_in_rows = feats.shape[0]
         if ctx.needs_input_grad[0]:
             # dX = sum_k dY[to_in[k]] @ W[k]^T: the forward weight IS the transposed operand
-            grad_feats = _conv_fwd(g, None, to_in, n_in_rows, weight_t=weight).to(ctx.in_dtype)
+            if kmap.subm and not transposed:
+                # submanifold map: input i reaches output o through offset k exactly when o reaches i
+                # through -offset[k] = offset[K-1-k], so inv[k] == nbr[K-1-k]: the gradient runs on the
+                # FORWARD map with the offsets of W reversed -- no inverted map is built, and the forward
+                # tile-skipping plan applies (the unplanned dgrad ran all 27 x tiles steps: 173 vs 73 us
+                # at N = 119k, C = 64)
+                grad_feats = _conv_fwd(g, None, kmap.nbr, n_in_rows, weight_t=weight.flip(0), kmap=kmap).to(ctx.in_dtype)
+            else:
+                to_in = kmap.inv if not transposed else kmap.nbr
+                grad_feats = _conv_fwd(g, None, to_in, n_in_rows, weight_t=weight).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             L = _capi.lib()

@@ -135,6 +135,7 @@ class SubMConv3d(_SparseConvBase):
                            table.capacity, _capi.ptr(nbr), _capi.stream()), 'lk_kmap_query')
             kmap = KernelMap(nbr, n, n, coords)
             kmap.offsets = taps                      # classes of the tile-skipping plan
+            kmap.subm = all(k % 2 == 1 for k in self.kernel_size)   # symmetric taps: taps[K-1-k] == -taps[k]
             x.indice_dict[key] = kmap
         return kmap
 

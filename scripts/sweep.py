@@ -1,6 +1,9 @@
 """BASELINE config 5 (active-voxel sweep) and config 4 (detection backbone) on one GPU.
 
-    python scripts/sweep.py [--out gpurun_out/sweep.json] [--quick]
+    python scripts/sweep.py [--out gpurun_out/sweep.json] [--quick] [--skip-det]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/sweep.py ...
+        N replicas (one process per GPU, frames are independent: no data-path collective): every row then carries
+        n_gpus = N, ms = max over the ranks, voxels_per_s = N * n / that time
 
 ELKBlock forward (cos, groups=2), N in {10k..500k} x C in {16,64,128} x (r,s) in {(2,3),(3,5),(3,7)},
 synthetic SemanticKITTI-shaped scans, index + kernel maps rebuilt every iteration, L2 flushed
@@ -40,8 +43,30 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default='gpurun_out/sweep.json')
     ap.add_argument('--quick', action='store_true')
+    ap.add_argument('--skip-det', action='store_true')
     a = ap.parse_args()
-    dev = torch.device('cuda:0')
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', '1'), ('RANK', '0'), ('LOCAL_RANK', '0')))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')
+
+    def over_ranks(ms):
+        """max over the ranks of a per-rank time (gloo, CPU tensor); identity for one process"""
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def emit(row):
+        row['ms'] = over_ranks(row['ms'])
+        row['n_gpus'] = world
+        row['voxels_per_s'] = world * row['n'] / (row['ms'] * 1e-3)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+        rows.append(row)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     ns = [10_000, 50_000, 120_000] if a.quick else [10_000, 20_000, 50_000, 120_000, 250_000, 500_000]
@@ -73,12 +98,11 @@ def main():
                     with torch.no_grad():
                         return blk(st, s, r).F
                 ms = timed(step, flush)
-                row = {'workload': 'ELKBlock fwd', 'n': n, 'c': c, 'r': r, 's': s, 'ms': ms,
-                       'voxels_per_s': n / (ms * 1e-3)}
-                print(json.dumps(row), flush=True)
-                rows.append(row)
+                emit({'workload': 'ELKBlock fwd', 'n': n, 'c': c, 'r': r, 's': s, 'ms': ms})
     # ---- detection backbone (config 4): nuScenes-shaped grid
     try:
+        if a.skip_det:
+            raise KeyboardInterrupt
         from link_b200.scn import SpMiddleResNetFHDELKv3
         pts = np.concatenate([lidar_scan(seed=10 + k, beams=32, azimuths=1100) for k in range(10)], 0)
         rng = [-54, -54, -5, 54, 54, 3]
@@ -97,10 +121,7 @@ def main():
             with torch.no_grad():
                 return net(featsd, idx_d, 1, [1440, 1440, 40])[0]
         ms = timed(det_fwd, flush, warm=2, reps=5)
-        row = {'workload': 'SpMiddleResNetFHDELKv3 fwd (eval, fused)', 'n': len(idx), 'ms': ms,
-               'voxels_per_s': len(idx) / (ms * 1e-3)}
-        print(json.dumps(row), flush=True)
-        rows.append(row)
+        emit({'workload': 'SpMiddleResNetFHDELKv3 fwd (eval, fused)', 'n': len(idx), 'ms': ms})
         net.train()
 
         def det_fwd_bwd():
@@ -109,10 +130,7 @@ def main():
             out.square().mean().backward()
             net.zero_grad(set_to_none=True)
         ms = timed(det_fwd_bwd, flush, warm=2, reps=5)
-        row = {'workload': 'SpMiddleResNetFHDELKv3 fwd+bwd (train)', 'n': len(idx), 'ms': ms,
-               'voxels_per_s': len(idx) / (ms * 1e-3)}
-        print(json.dumps(row), flush=True)
-        rows.append(row)
+        emit({'workload': 'SpMiddleResNetFHDELKv3 fwd+bwd (train)', 'n': len(idx), 'ms': ms})
         # ---- full detector of config 4: reader -> backbone -> RPN -> CenterHead + losses, fwd+bwd
         from link_b200.centerpoint import NUSC_TASKS, build_nusc_centerpoint
         torch.manual_seed(0)
@@ -134,14 +152,30 @@ def main():
             sum(det(example, return_loss=True)['loss']).backward()
             det.zero_grad(set_to_none=True)
         ms = timed(detector_fwd_bwd, flush, warm=2, reps=5)
-        row = {'workload': 'CenterPoint detector (VFE + SpMiddleResNetFHDELKv3 + RPN + CenterHead + losses) fwd+bwd',
-               'n': len(idx), 'ms': ms, 'voxels_per_s': len(idx) / (ms * 1e-3)}
-        print(json.dumps(row), flush=True)
-        rows.append(row)
+        emit({'workload': 'CenterPoint detector (VFE + SpMiddleResNetFHDELKv3 + RPN + CenterHead + losses) fwd+bwd',
+              'n': len(idx), 'ms': ms})
+        # ---- inference: detector forward + CenterHead.predict (decode, filters, NMS on the device)
+        det.eval()
+        from link_b200.centerpoint import NUSC_TEST_CFG
+        for name, circ in (('circle NMS', True), ('rotated NMS (lk_nms_bev)', False)):
+            tcfg = dict(NUSC_TEST_CFG, circular_nms=circ)
+
+            def det_predict():
+                det.test_cfg = tcfg
+                with torch.no_grad():
+                    return det(example, return_loss=False)
+            ms = timed(det_predict, flush, warm=2, reps=5)
+            emit({'workload': f'CenterPoint detector inference fwd + predict, {name}', 'n': len(idx), 'ms': ms})
+    except KeyboardInterrupt:
+        pass
     except Exception as e:   # the sweep above is the point; report rather than hide a failure here
-        print(json.dumps({'workload': 'detection backbone / detector', 'error': repr(e)[:300]}), flush=True)
-    os.makedirs(os.path.dirname(a.out) or '.', exist_ok=True)
-    json.dump(rows, open(a.out, 'w'), indent=0)
+        if rank == 0:
+            print(json.dumps({'workload': 'detection backbone / detector', 'error': repr(e)[:300]}), flush=True)
+    if rank == 0:
+        os.makedirs(os.path.dirname(a.out) or '.', exist_ok=True)
+        json.dump(rows, open(a.out, 'w'), indent=0)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -129,3 +129,31 @@ def test_conv_tf32_mode_tolerance(dev):
     finally:
         conv_mod.set_precision('fp32')
     assert errs['fp32'] < 1e-5 and 1e-5 < errs['tf32'] < 2e-3, errs
+
+
+def test_encoder_under_bf16_autocast(dev):
+    """BASELINE config 3 names bf16: ELKEncoder trains under torch.autocast(bfloat16) the way the reference
+    trains under fp16 autocast (its three custom Functions cast at their boundary, nn/functional/conv.py:19,
+    voxelize.py:13, devoxelize.py:54): dense layers run in bf16, the sparse convs / the LinK aggregation take
+    bf16 activations, accumulate in fp32 on their own kernels and hand bf16 back.  Stated tolerance of the
+    logits against the fp32 run: 5e-2 of their range (8-bit mantissas through ~40 layers); gradients finite."""
+    from link_b200 import SparseTensor
+    from link_b200.linkencoder import ELKEncoder
+    from link_b200.utils.synthetic import random_voxels
+    coords = torch.from_numpy(random_voxels(4000, 40, seed=6, batch=2)).to(dev)
+    torch.manual_seed(6)
+    feats = torch.randn(coords.shape[0], 4, device=dev)
+    target = torch.randint(0, 19, (coords.shape[0],), device=dev)
+    net = ELKEncoder(num_classes=19, cr=0.5, baseop='cos', r=3, s=7, groups=2).to(dev).train()
+    ref = net(SparseTensor(feats.clone(), coords, 1)).detach()
+    net.zero_grad(set_to_none=True)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        logits = net(SparseTensor(feats.clone(), coords, 1))
+        loss = torch.nn.functional.cross_entropy(logits.float(), target)
+    loss.backward()
+    assert torch.isfinite(loss)
+    for n, p in net.named_parameters():
+        if not n.startswith('up'):
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    err = float((logits.float() - ref).abs().max())
+    assert err <= 5e-2 * float(ref.abs().max() - ref.min()) + 5e-2, err
