@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--voxels', type=int, default=120_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-encoder', action='store_true', help='skip the extra encoder measurement')
-    ap.add_argument('--e2e-ring', action='store_true', help='e2e loop through tensor.UploadRing (staging ring), one event pair around the loop')
+    ap.add_argument('--e2e-ring', action='store_true', help='(kept for compatibility: the pipelined e2e loop always runs)')
     return ap.parse_args()
 
 
@@ -77,7 +77,8 @@ def config_for(workload, n, world):
     """`config` of the JSON line -- the SAME keys and strings from both arms (--impl ours / reference):
     it names the workload; how each arm ran it is in the arm's own keys."""
     return {'workload': workload_name_for(workload, n),
-            'l2': 'flushed between timed iterations (256 MiB memset, outside the events)',
+            'l2': 'flushed between timed iterations (256 MiB memsets, outside the events), repeated until they '
+                  'outlast the host enqueue of one step so that the timed region is device time, not launch waiting',
             'bounds': 'device-resident loop: the scan\'s coordinate bounds (8 ints, a loader-side property) are '
                       'pre-seeded; e2e loop: computed on the host from the pinned coordinate buffer inside '
                       'the timed region (SparseTensor.from_host)',
@@ -239,9 +240,33 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         torch.cuda.synchronize()
 
     # ---- device-resident loop (value) ------------------------------------------------------
+    # The step is enqueued from python (one FFI call per block, ~185 calls per encoder) and the host needs
+    # longer per step than the device: if the first event is recorded while the stream is empty, the
+    # event window contains the device WAITING for launches (measured: 0.25 ms per block step against
+    # 0.197 ms when the launches are already queued, and 0.199 ms for a CUDA-graph replay of the same
+    # step; scripts/step_graph_probe.py).  So the L2 flush in front of every timed step is repeated
+    # until it outlasts the host's enqueue time of one step (measured during warm-up): the device
+    # reaches the first event with the whole step queued behind it and `value` is device time.  The host
+    # side is reported separately (`host_enqueue_ms_per_step`) and is inside `e2e`.
+    host_us = []
     for w in range(warmup):
-        step(w % 2, coords_dev[w % 2], feats_dev[w % 2].clone())
+        f = feats_dev[w % 2].clone()
+        t_h = time.perf_counter()
+        step(w % 2, coords_dev[w % 2], f)
+        host_us.append((time.perf_counter() - t_h) * 1e6)
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        flush.zero_()
+    e1.record()
+    torch.cuda.synchronize()
+    flush_us = 1e3 * e0.elapsed_time(e1) / 4
+    n_flush = int(min(48, max(2, np.ceil(3.0 * float(np.median(host_us[-3:])) / flush_us) + 2)))
+
+    def flush_l2():
+        for _ in range(n_flush):
+            flush.zero_()
     sampler = ClockSampler(local)
     if with_clocks:
         sampler.start()
@@ -258,7 +283,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     for k in range(steps):
         i = k % 2
         f = feats_dev[i].clone()          # the block overwrites st.F; clone outside the timed region
-        flush.zero_()                     # L2 flush between timed iterations (outside the events)
+        flush_l2()                        # L2 flush between timed iterations (outside the events)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step(i, coords_dev[i], f)
@@ -279,7 +304,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     for k in range(steps):
         i = k % 2
         f = feats_dev[i].clone()
-        flush.zero_()
+        flush_l2()
         step(i, coords_dev[i], f)
     barrier()
     timers, _capi.TIMERS = _capi.TIMERS, None
@@ -343,7 +368,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
                     'note': 'host features stored as bf16 (inputs rounded to bf16), widened to fp32 on the device; '
                             'arithmetic unchanged (fp32); this rank only'}
     e2e_ring = None
-    if getattr(args, 'e2e_ring', False):
+    if workload in ('block', 'encoder'):
         # same calls through a caller-owned staging ring, issued back to back, ONE event pair around
         # the loop: the upload of scan i+1 overlaps the processing of scan i
         from link_b200.tensor import UploadRing
@@ -359,7 +384,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         host_ms = (time.perf_counter() - t_h) * 1e3 / steps
         e1.record()
         barrier()
-        e2e_ring = {'ms_per_step': e0.elapsed_time(e1) / steps, 'host_enqueue_ms_per_step': host_ms}
+        e2e_ring = {'ms': e0.elapsed_time(e1), 'ms_per_step': e0.elapsed_time(e1) / steps, 'host_enqueue_ms_per_step': host_ms}
     # clocks / throttle reasons sampled under load over all timed loops of this workload (device-resident,
     # instrumented, roofline and end-to-end passes): the device-resident loop alone lasts a few ms
     clocks = sampler.finish(t_wall0, time.time()) if with_clocks else None
@@ -371,7 +396,8 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
     return {'dev_ms': dev_ms, 'e2e_ms': e2e_ms, 'voxels': float(sum(n_vox[k % 2] for k in range(steps))),
             'launches': int(launches), 'kernels': kern, 'clocks': clocks, 'h2d': h2d, 'd2h': d2h,
             'roof': roof, 'ref_gpu': ref_gpu, 'e2e_ring': e2e_ring, 'e2e_bf16': e2e_bf16,
-            'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup}
+            'host_enqueue_ms': host_enqueue_ms, 'n0': n_vox[0], 'steps': steps, 'warmup': warmup,
+            'n_flush': n_flush, 'flush_us': flush_us}
 
 
 def run_train(args, steps, warmup, dev, rank, world, local):
@@ -644,10 +670,13 @@ def path_roofline(dev, coords, bounds, blk, nbuf=6, rounds=24):
 
 
 def summarize(m, world, dev):
-    """Local measurements -> whole-job numbers (max time over ranks, summed voxels)."""
+    """Local measurements -> whole-job numbers (max time over ranks, summed voxels).  e2e = the pipelined
+    loop (UploadRing); the single-step latency loop is kept in m['e2e_latency_ms']."""
     from link_b200.sharding import reduce_throughput
     dev_ms, vox = reduce_throughput(m['dev_ms'], m['voxels'], None)     # CPU tensors -> gloo
-    e2e_ms, _ = reduce_throughput(m['e2e_ms'], m['voxels'], None)
+    lat_ms, _ = reduce_throughput(m['e2e_ms'], m['voxels'], None)
+    m['e2e_latency_ms'] = lat_ms
+    e2e_ms, _ = reduce_throughput(m['e2e_ring']['ms'] if m.get('e2e_ring') else m['e2e_ms'], m['voxels'], None)
     return dev_ms, e2e_ms, vox
 
 
@@ -765,10 +794,16 @@ def main_ours(args):
         'config': config_for(args.workload, m['n0'], world),
         'clocks': m['clocks'],
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'],
-                'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps},
+                'd2h_bytes_per_step': m['d2h'], 'ms_per_step': e2e_ms / steps,
+                'how': 'K steps back to back through the public API: UploadRing.upload (pinned host coords + features '
+                       '-> device, bounds computed on the host copy) -> ELKBlock -> per-channel checksum -> D2H; the '
+                       'upload of scan i+1 overlaps the processing of scan i; ONE CUDA-event pair around the K steps, '
+                       'max over ranks',
+                'single_step_latency_ms': m['e2e_latency_ms'] / steps},
         'gpu_launches': m['launches'],
         'host_enqueue_ms_per_step': m['host_enqueue_ms'],
-        'e2e_ring': m.get('e2e_ring'),
+        'l2_flush_memsets_per_step': m.get('n_flush'),
+        'e2e_host_enqueue_ms_per_step': (m.get('e2e_ring') or {}).get('host_enqueue_ms_per_step'),
         'e2e_bf16_wire': m.get('e2e_bf16'),
         'roofline': roof,
         'roofline_path': roof_path,

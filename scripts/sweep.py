@@ -158,7 +158,7 @@ def main():
         det.eval()
         from link_b200.centerpoint import NUSC_TEST_CFG
         for name, circ in (('circle NMS', True), ('rotated NMS (lk_nms_bev)', False)):
-            tcfg = dict(NUSC_TEST_CFG, circular_nms=circ)
+            tcfg = dict(NUSC_TEST_CFG, circular_nms=circ, min_radius=[4, 12, 10, 1, 0.85, 0.175])
 
             def det_predict():
                 det.test_cfg = tcfg
