@@ -331,6 +331,11 @@ int lk_kmap_query(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_o
  * and nbr[K-1-k, j] = i; the centre offset is the identity.  Same result as lk_kmap_query. */
 int lk_kmap_query_subm(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
                        const void* d_table, int64_t capacity, int32_t* d_nbr, lk_stream_t s);
+/* Same, with the hash table built on another stream: the query waits for `table_ready` (a cudaEvent_t
+ * recorded after lk_table_build* there, or NULL) after it has cleared the map on `s`. */
+int lk_kmap_query_subm_ev(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
+                          const void* d_table, int64_t capacity, int32_t* d_nbr, void* table_ready,
+                          lk_stream_t s);
 /* Transposed relation: d_inv [K, n_in] (prefilled with -1 by this call):
  * d_inv[k, i] = o  whenever d_nbr[k, o] = i. */
 int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_t n_in, int32_t* d_inv,
@@ -480,6 +485,12 @@ int lk_boxes_iou_bev(const float* d_a, int64_t n, const float* d_b, int64_t m, f
 int64_t lk_nms_bev_ws_bytes(int64_t n);
 int lk_nms_bev(const float* d_boxes_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
                uint8_t* d_keep, lk_stream_t s);
+/* Centre-distance NMS of CenterPoint (det3d/core/utils/circle_nms_jit.py:4-28, a numba loop on the host
+ * in the reference): d_centers_sorted float32 [n, 2] = (x, y) of the boxes sorted by descending score;
+ * box j is dropped when an earlier KEPT box lies within `thresh` in SQUARED distance.  Same workspace
+ * and d_keep convention as lk_nms_bev. */
+int lk_nms_circle(const float* d_centers_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
+                  uint8_t* d_keep, lk_stream_t s);
 int lk_boxes_iou_bev_hostcheck(const float* a, int64_t n, const float* b, int64_t m, float* out);
 
 #ifdef __cplusplus

@@ -97,6 +97,7 @@ PROTOTYPES = {
     'lk_linear_ln_tc_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
     'lk_kmap_query_subm': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
+    'lk_kmap_query_subm_ev': (i32, [vp, i64, vp, i32, vp, i64, vp, vp, vp]),
     'lk_kmap_invert': (i32, [vp, i64, i32, i64, vp, vp]),
     'lk_conv_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_fwd_ex': (i32, [vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
@@ -124,6 +125,7 @@ PROTOTYPES = {
     'lk_boxes_iou_bev': (i32, [vp, i64, vp, i64, vp, vp]),
     'lk_nms_bev_ws_bytes': (i64, [i64]),
     'lk_nms_bev': (i32, [vp, i64, C.c_float, vp, i64, vp, vp]),
+    'lk_nms_circle': (i32, [vp, i64, C.c_float, vp, i64, vp, vp]),
     'lk_boxes_iou_bev_hostcheck': (i32, [vp, i64, vp, i64, vp]),
 }
 

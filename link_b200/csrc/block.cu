@@ -65,7 +65,7 @@ extern "C" int64_t lk_elk_block_ws_bytes(int64_t n, int c, int op, int r3, int k
 // (the only CUDA objects the library owns; no memory is allocated, nothing is synchronised)
 struct BlockSide {
   cudaStream_t stream;
-  cudaEvent_t fork, join;
+  cudaEvent_t fork, join, table;
 };
 static BlockSide* block_side() {
   static BlockSide sides[64];
@@ -83,6 +83,7 @@ static BlockSide* block_side() {
     if (cudaStreamCreateWithPriority(&sides[dev].stream, cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&sides[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&sides[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&sides[dev].table, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     made[dev] = true;
   }
   return &sides[dev];
@@ -135,6 +136,20 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
     LK_CUDA(cudaStreamWaitEvent(bs->stream, bs->fork, 0));
   }
   // ---- side chain ----
+  // LINKB200_TABLE_SIDE=1 builds the hash table of the kernel map HERE, ahead of the sort, and lets the main
+  // stream pick it up through an event (the main chain, table -> map -> plan -> conv, is the longer one).
+  // Measured SLOWER on the same box (0.213 vs 0.197 ms per step, twice each, scripts/ab_table_side.sh): the
+  // insert kernel's atomics then compete with the radix sort for the same L2 slices, and the sort gates
+  // the pre-aggregation chain.  Off by default; kept as a knob.
+  static const bool table_side_env = [] {
+    const char* e = getenv("LINKB200_TABLE_SIDE");
+    return e && e[0] == '1';
+  }();
+  const bool table_on_side = bs && need_kmap && table_side_env;
+  if (table_on_side) {
+    LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, side));
+    LK_CUDA(cudaEventRecord(bs->table, bs->stream));
+  }
   LK_TRY(lk_sort_unique_coords(a->d_coords, &a->keyspec, n, a->key_bits, uniq, inverse, order, seg,
                                nullptr, num, srank, ws + w.sort_ws, lk_sort_unique_ws_bytes(n), side));
   LK_TRY(lk_block_neighbors_zero(uniq, num, n, &a->keyspec, a->d_block_offsets, a->r3, nbr, sums, kc, side));
@@ -148,9 +163,9 @@ extern "C" int lk_elk_block_fwd(const lk_elk_block_args_t* a, lk_stream_t s) {
   if (bs) LK_CUDA(cudaEventRecord(bs->join, bs->stream));
   // ---- main chain ----
   if (need_kmap) {
-    LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, s));
-    LK_TRY(lk_kmap_query_subm(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
-                              a->d_kmap, s));
+    if (!table_on_side) LK_TRY(lk_table_build_coords(a->d_coords, n, ws + w.table, w.table_cap, s));
+    LK_TRY(lk_kmap_query_subm_ev(a->d_coords, n, a->d_conv_offsets, a->kvol, ws + w.table, w.table_cap,
+                                 a->d_kmap, table_on_side ? (void*)bs->table : nullptr, s));
   }
   if (planned && a->build_plan)
     LK_TRY(lk_conv_plan(kmap, n, a->kvol, a->d_conv_offsets, a->d_plan_perm, a->d_plan_mask,

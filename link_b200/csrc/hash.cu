@@ -254,12 +254,21 @@ __global__ void __launch_bounds__(256) kmap_query_subm_kernel(const int4* __rest
 extern "C" int lk_kmap_query_subm(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
                                   const void* d_table, int64_t capacity, int32_t* d_nbr,
                                   lk_stream_t s) {
+  return lk_kmap_query_subm_ev(d_coords, n, d_offsets, k, d_table, capacity, d_nbr, nullptr, s);
+}
+
+// table_ready: cudaEvent_t recorded after the table build on ANOTHER stream, or NULL (table built on s).
+// The map is cleared first, so that part overlaps a table that is still being built.
+extern "C" int lk_kmap_query_subm_ev(const int32_t* d_coords, int64_t n, const int32_t* d_offsets, int k,
+                                     const void* d_table, int64_t capacity, int32_t* d_nbr,
+                                     void* table_ready, lk_stream_t s) {
   if (n == 0 || k == 0) return LK_OK;
   LK_REQUIRE(d_coords && d_offsets && d_table && d_nbr && k > 0 && (k & 1) == 1,
              "lk_kmap_query_subm: needs an odd kernel volume");
   cudaStream_t st = (cudaStream_t)s;
   LK_CUDA(cudaMemsetAsync(d_nbr, 0xFF, (size_t)k * n * sizeof(int), st));
   lk_count_launch();
+  if (table_ready) LK_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)table_ready, 0));
   LK_PDL_LAUNCH(kmap_query_subm_kernel, lk_grid(n * (k / 2 + 1), 256, 8), 256, 0, st,
                 (const int4*)d_coords, n, d_offsets, k, (const Slot*)d_table, (uint64_t)capacity - 1,
                 (unsigned*)d_nbr);

@@ -162,7 +162,48 @@ __global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* 
   }
 }
 
+// centre-distance ("circle") NMS of CenterPoint (det3d/core/utils/circle_nms_jit.py:4-28): the same greedy
+// rule with  suppress(i, j) = |c_i - c_j|^2 <= thresh  on the (x, y) centres; same bitmask + scan kernels
+__global__ void __launch_bounds__(64) circle_mask_kernel(const float2* __restrict__ centers, int n, float thresh,
+                                                         int words, unsigned long long* __restrict__ mask) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ float2 cc[64];
+  const int ncol = min(n - cb * 64, 64);
+  if ((int)threadIdx.x < ncol) cc[threadIdx.x] = __ldg(centers + cb * 64 + threadIdx.x);
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= n) return;
+  const float2 ci = __ldg(centers + i);
+  unsigned long long bits = 0;
+  for (int j = (rb == cb) ? (int)threadIdx.x + 1 : 0; j < ncol; ++j) {
+    const float dx = ci.x - cc[j].x, dy = ci.y - cc[j].y;
+    if (dx * dx + dy * dy <= thresh) bits |= 1ULL << j;
+  }
+  mask[(int64_t)i * words + cb] = bits;
+}
+
 extern "C" int64_t lk_nms_bev_ws_bytes(int64_t n) { return n * ((n + 63) / 64) * 8 + 256; }
+
+extern "C" int lk_nms_circle(const float* d_centers_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
+                             uint8_t* d_keep, lk_stream_t s) {
+  LK_REQUIRE(n >= 0 && n <= 65536, "lk_nms_circle: at most 65536 boxes");
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_centers_sorted && d_ws && d_keep && (uintptr_t)d_ws % 8 == 0 && (uintptr_t)d_centers_sorted % 8 == 0,
+             "lk_nms_circle: null or misaligned pointer");
+  const int words = (int)((n + 63) / 64);
+  if (ws_bytes < lk_nms_bev_ws_bytes(n)) {
+    lk_set_error("lk_nms_circle: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)lk_nms_bev_ws_bytes(n));
+    return LK_ENOSPC;
+  }
+  cudaStream_t st = (cudaStream_t)s;
+  dim3 grid((unsigned)words, (unsigned)words);
+  circle_mask_kernel<<<grid, 64, 0, st>>>((const float2*)d_centers_sorted, (int)n, thresh, words, (unsigned long long*)d_ws);
+  LK_LAUNCHED();
+  nms_scan_kernel<<<1, 32, (size_t)words * 8, st>>>((const unsigned long long*)d_ws, (int)n, words, d_keep);
+  LK_LAUNCHED();
+  return LK_OK;
+}
 
 extern "C" int lk_nms_bev(const float* d_boxes_sorted, int64_t n, float thresh, void* d_ws, int64_t ws_bytes,
                           uint8_t* d_keep, lk_stream_t s) {

@@ -103,3 +103,24 @@ def test_device_nms_vs_reference_fixture_misses_are_threshold_noise(dev):
         return order.cpu().numpy()[keep][:83]
     lo, hi = greedy(iou > 0.2 + 1e-4), greedy(iou > 0.2 - 1e-4)
     assert np.array_equal(want, lo) or np.array_equal(want, hi) or np.array_equal(want, greedy(np.where(band, ~(iou > 0.2), iou > 0.2)))
+
+
+@pytest.mark.parametrize('n,thresh', [(3000, 4.0), (64, 0.5), (129, 100.0), (1, 1.0)])
+def test_device_circle_nms_equals_sequential_rule(dev, n, thresh):
+    """lk_nms_circle == the reference's sequential loop (circle_nms_jit.py:4-28) == the masked-reduction form."""
+    from link_b200.centerpoint import circle_nms
+    g = torch.Generator().manual_seed(n)
+    centers = (torch.rand(n, 2, generator=g) * 60 - 30)
+    scores = torch.rand(n, generator=g)
+    sel = circle_nms(centers.to(dev), scores.to(dev), thresh, post_max_size=10 ** 6)
+    order = torch.argsort(scores, descending=True).numpy()
+    c = centers.numpy()[order]
+    keep, dead = [], np.zeros(n, bool)
+    for i in range(n):
+        if dead[i]:
+            continue
+        keep.append(i)
+        d = ((c[i] - c) ** 2).sum(1)
+        dead |= (d <= thresh) & (np.arange(n) > i)
+    assert sel.cpu().numpy().tolist() == order[keep].tolist()
+    assert circle_nms(centers, scores, thresh, post_max_size=10 ** 6).tolist() == order[keep].tolist()   # CPU tensor path
