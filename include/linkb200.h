@@ -397,6 +397,15 @@ int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wimg, const int32_t* d
                         const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
                         int c_in, int c_out, const lk_conv_epilogue_t* ep, float* d_out,
                         lk_stream_t s);
+/* The same kernel on bf16 feature rows: d_in [n_in, c_in], ep->d_residual [n_out, c_out] and d_out
+ * [n_out, c_out] are bf16 (scale / shift stay fp32); accumulation in fp32, weights rounded to tf32 (one
+ * MMA per k-slice: a bf16 value is exact in tf32).  c_in in {32, 64, 128}, c_out in {32, 64}.  The reduced-
+ * precision path of BASELINE config 3 (the reference runs this conv in fp16 under autocast,
+ * torchsparse/nn/functional/conv.py:19). */
+int lk_conv_tc_bf16_supported(int c_in, int c_out);
+int lk_conv_tc_fwd_bf16(const void* d_in, const float* d_wimg, const int32_t* d_nbr,
+                        const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
+                        int c_in, int c_out, const lk_conv_epilogue_t* ep, void* d_out, lk_stream_t s);
 /* Composite index builds (one call = the launches of several entry points above; they exist to
  * keep the host side off the critical path of the encoder forward).
  * lk_kmap_build: [hash(d_in_coords) -> table build ->] kernel-map query [-> lk_conv_plan]

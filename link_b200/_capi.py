@@ -113,6 +113,8 @@ PROTOTYPES = {
     'lk_conv_tc_pack_weights': (i32, [vp, i32, i32, i32, vp, vp]),
     'lk_conv_tc_fwd_plan': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_supported': (i32, [i32, i32]),
+    'lk_conv_tc_bf16_supported': (i32, [i32, i32]),
+    'lk_conv_tc_fwd_bf16': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
     'lk_host_coord_bounds': (i32, [vp, i64, vp, vp]),

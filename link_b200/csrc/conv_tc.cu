@@ -30,6 +30,8 @@
 // No atomics, no temporaries, deterministic, output written exactly once.
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -81,7 +83,11 @@ struct ConvTcCfg {
 // used one after the other (issue slots 26 % busy, no pipe above 35 %); here they overlap.
 #define CT_CONV_WARPS 8
 #define CT_GATHER_THREADS 256
-template <int CIN, int COUT, int NST, int PREC, bool WS>
+// IO16 = true (warp-specialised configurations only, PREC = 1): the feature rows, the residual and the
+// output are bf16.  A bf16 value is exact in tf32, so the A operand needs no lo plane and one MMA per
+// k-slice remains (weights rounded to tf32); a gathered row is half the bytes -- half the LDGSTS per
+// step and a ring twice as deep in the same shared memory -- and the accumulation stays fp32 in TMEM.
+template <int CIN, int COUT, int NST, int PREC, bool WS, bool IO16>
 __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     const float* __restrict__ in, const float* __restrict__ wimg /*[K] packed B-operand images*/,
     const int* __restrict__ nbr /*[K][n_out]*/,
@@ -101,8 +107,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   __shared__ uint32_t tmem_base_s;
   __shared__ uint64_t wfull_bar[Cfg::NWB];  // W[k] image landed (bulk copy, complete_tx)
   __shared__ uint64_t round_bar;            // every MMA of the round has completed (tcgen05.commit after the last step)
-  __shared__ uint64_t slot_full[4];         // WS: ring slot filled   (cp.async.mbarrier.arrive of the gather threads)
-  __shared__ uint64_t slot_empty[4];        // WS: ring slot consumed (one arrival per convert warp)
+  __shared__ uint64_t slot_full[8];         // WS: ring slot filled   (cp.async.mbarrier.arrive of the gather threads)
+  __shared__ uint64_t slot_empty[8];        // WS: ring slot consumed (one arrival per convert warp)
   __shared__ uint16_t steps_s[64 * MAXT];   // active (virtual offset, tile slot) steps: kv << 4 | t
   __shared__ uint8_t klist_s[64];           // distinct virtual offsets of the round, ascending
   __shared__ int orow_s[MAXT][CT_ROWS];     // output row of every tile-slot row (-1 past the end)
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
     }
     tc::mbar_init(&round_bar, 1);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       tc::mbar_init(&slot_full[b], CT_GATHER_THREADS);
       tc::mbar_init(&slot_empty[b], CT_CONV_WARPS);
     }
@@ -340,8 +346,12 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
         if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
       };
       if constexpr (WS && Cfg::GST > 0) {
-        constexpr int GST = Cfg::GST;
-        constexpr int CH_ROW = CE / 4;                  // 16-byte chunks per row
+        constexpr int EB = IO16 ? 2 : 4;                // bytes per feature element
+        constexpr int GST = IO16 ? 2 * Cfg::GST : Cfg::GST;   // same shared memory, rows half the size
+        constexpr int CH_ROW = CE * EB / 16;            // 16-byte chunks per row
+        constexpr uint32_t ROW_B = CE * EB;             // row pitch in a ring slot
+        constexpr uint32_t SLOT_B = CT_ROWS * ROW_B;
+        static_assert(!IO16 || PREC == 1, "bf16 rows run as single-pass TF32");
         if (warp >= CT_CONV_WARPS) {
           // ================= gather warps: rows of step j -> ring slot (jbase + j) % GST =================
           const int gt = tid - CT_CONV_WARPS * 32;
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
             const int fr = f_row0 + i * RPP;
-            fetch_off[i] = (uint32_t)(fr * (CE * 4) + ((f_chunk ^ (fr & (CH_ROW - 1))) << 4));
+            fetch_off[i] = (uint32_t)(fr * ROW_B + ((f_chunk ^ (fr & (CH_ROW - 1))) << 4));
           }
           auto load_idx = [&](int jj, int* src) {
 #pragma unroll
@@ -372,13 +382,13 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
             const int jg = jbase + j;
             const int slot = jg % GST, use = jg / GST;
             if (use >= 1) tc::mbar_wait(&slot_empty[slot], (uint32_t)(use - 1) & 1u);
-            const uint32_t dst = g_base + (uint32_t)slot * Cfg::G_STAGE;
+            const uint32_t dst = g_base + (uint32_t)slot * SLOT_B;
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
               const int sv = src[i];
               const int half = (KH > 1 && sv >= 0) ? (sv >> 30) : 0;
               const int row = sv >= 0 ? (KH > 1 ? (sv & 0x3FFFFFFF) : sv) : 0;
-              const float* rp = in + (int64_t)row * CIN + half * CE + 4 * f_chunk;
+              const uint8_t* rp = (const uint8_t*)in + ((int64_t)row * CIN + half * CE) * EB + 16 * f_chunk;
               const int nbytes = sv >= 0 ? 16 : 0;      // 0: zero-fill (missing neighbour)
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                            ::"r"(dst + fetch_off[i]), "l"(rp), "r"(nbytes) : "memory");
@@ -400,34 +410,47 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
           const int cq = warp & 3, ccs = warp >> 2;       // TMEM lane quarter, channel half
           const int crow = cq * 32 + lane;
           constexpr int CPC = CE / 2;                     // channels per convert thread (32 or 16)
-          constexpr int NCC = CPC / 4;                    // 16-byte chunks per thread and step
+          constexpr int NCC = CPC * EB / 16;              // 16-byte chunks per thread and step
           const int ccol0 = ccs * CPC;
           const uint32_t clane = (uint32_t)(cq * 32) << 16;
           uint32_t read_off[NCC];
 #pragma unroll
           for (int i = 0; i < NCC; ++i)
-            read_off[i] = (uint32_t)(crow * (CE * 4) + (((ccs * NCC + i) ^ (crow & (CH_ROW - 1))) << 4));
+            read_off[i] = (uint32_t)(crow * ROW_B + (((ccs * NCC + i) ^ (crow & (CH_ROW - 1))) << 4));
           int k_prev = -1, wc = wcount;
           for (int j = 0; j < nsteps; ++j) {
             const int jg = jbase + j;
             const int slot = jg % GST, stage = jg % NST;
             const int k = steps_s[j] >> 4;
             tc::mbar_wait(&slot_full[slot], (uint32_t)(jg / GST) & 1u);
-            const uint8_t* sp = b_base + Cfg::NWB * Cfg::B_STAGE + (uint32_t)slot * Cfg::G_STAGE;
+            const uint8_t* sp = b_base + Cfg::NWB * Cfg::B_STAGE + (uint32_t)slot * SLOT_B;
             const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * Cfg::A_STAGE_COLS) + clane + (uint32_t)ccol0;
             bool waited = false;
 #pragma unroll
-            for (int h = 0; h < NCC / 4; ++h) {           // 16 channels at a time
+            for (int h = 0; h < CPC / 16; ++h) {          // 16 channels at a time
               float hi[16], lo[16];
+              if constexpr (IO16) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 v4 = *(const float4*)(sp + read_off[4 * h + i]);
-                float4 h4 = v4, l4 = v4;
-                if (PREC == 0) tc::split_tf32(v4, h4, l4);
-                hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
-                lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+                for (int i = 0; i < 2; ++i) {             // 8 bf16 per chunk: fp32 = bits << 16 (exact, and exact in tf32)
+                  const uint4 v = *(const uint4*)(sp + read_off[2 * h + i]);
+                  const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    hi[8 * i + 2 * e] = __uint_as_float(w4[e] << 16);
+                    hi[8 * i + 2 * e + 1] = __uint_as_float(w4[e] & 0xFFFF0000u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 v4 = *(const float4*)(sp + read_off[4 * h + i]);
+                  float4 h4 = v4, l4 = v4;
+                  if (PREC == 0) tc::split_tf32(v4, h4, l4);
+                  hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+                  lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+                }
               }
-              if (h == NCC / 4 - 1) {                     // every value of the slot is in registers
+              if (h == CPC / 16 - 1) {                    // every value of the slot is in registers
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&slot_empty[slot]);
               }
@@ -585,7 +608,43 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = 0.f;
           }
-          if (orow >= 0) {
+          if (orow >= 0 && IO16) {
+            // bf16 rows: 16 channels = 32 bytes = two 128-bit stores; residual rows are bf16 as well
+            const int64_t o = orow;
+            float y[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              y[e] = acc[e];
+              if (ep.d_scale) y[e] *= __ldg(ep.d_scale + c_base + e);
+              if (ep.d_shift) y[e] += __ldg(ep.d_shift + c_base + e);
+            }
+            if (ep.d_residual) {
+              const uint4* rp = (const uint4*)((const __nv_bfloat16*)ep.d_residual + o * COUT + c_base);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint4 v = __ldg(rp + i);
+                const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  y[8 * i + 2 * e] += __uint_as_float(w4[e] << 16);
+                  y[8 * i + 2 * e + 1] += __uint_as_float(w4[e] & 0xFFFF0000u);
+                }
+              }
+            }
+            uint4* dst16 = (uint4*)((__nv_bfloat16*)out + o * COUT + c_base);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              unsigned w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = y[8 * i + 2 * e], a1 = y[8 * i + 2 * e + 1];
+                if (ep.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);      // .x = low half = the even channel
+                w4[e] = *(const unsigned*)&pk;
+              }
+              dst16[i] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else if (orow >= 0) {
             const int64_t o = orow;
             float* dst = out + o * COUT + c_base;
 #pragma unroll
@@ -625,14 +684,14 @@ __global__ void __launch_bounds__(CT_THREADS + 32, 1) conv_tc_kernel(
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int CIN, int COUT, int NST, int PREC, bool WS>
+template <int CIN, int COUT, int NST, int PREC, bool WS, bool IO16 = false>
 static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, const int* perm,
                           const unsigned* tile_mask, int64_t n_out, int k,
                           const lk_conv_epilogue_t& ep, float* out, cudaStream_t st) {
   using Cfg = ConvTcCfg<CIN, COUT, NST>;
   static bool attr_set = false;
   if (!attr_set) {
-    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST, PREC, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, NST, PREC, WS, IO16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)Cfg::SMEM));
     attr_set = true;
   }
@@ -654,7 +713,7 @@ static int launch_conv_tc_n(const float* in, const float* wimg, const int* nbr, 
     snake = (e && e[0] == '1') ? 1 : 0;        // measured slower (77 vs 69 us): the plain interleave already pairs the light end of
                                                   // every stripe with the extra heavy tile of the last, partial stripe
   }
-  LK_PDL_LAUNCH((conv_tc_kernel<CIN, COUT, NST, PREC, WS>), grid, CT_THREADS + 32, Cfg::SMEM, st, in, wimg, nbr, perm,
+  LK_PDL_LAUNCH((conv_tc_kernel<CIN, COUT, NST, PREC, WS, IO16>), grid, CT_THREADS + 32, Cfg::SMEM, st, in, wimg, nbr, perm,
                 tile_mask, n_out, k, tgroup, snake, ep, out);
   LK_LAUNCHED();
   return LK_OK;
@@ -778,3 +837,40 @@ extern "C" int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wt, const i
   lk_set_error("lk_conv_tc_fwd: unsupported channel combination");
   return LK_EINVAL;
 }
+
+// bf16 feature rows in, bf16 rows out (fp32 accumulation in TMEM, weights rounded to tf32, the epilogue's
+// residual rows bf16 as well): the configurations with a shared-memory gather ring.
+extern "C" int lk_conv_tc_bf16_supported(int c_in, int c_out) {
+  return (c_in == 32 || c_in == 64 || c_in == 128) && (c_out == 32 || c_out == 64);
+}
+
+extern "C" int lk_conv_tc_fwd_bf16(const void* d_in, const float* d_wimg, const int32_t* d_nbr,
+                                   const int32_t* d_perm, const uint32_t* d_tile_mask, int64_t n_out, int k,
+                                   int c_in, int c_out, const lk_conv_epilogue_t* epp, void* d_out,
+                                   lk_stream_t s) {
+  lk_conv_epilogue_t ep = {nullptr, nullptr, nullptr, 0, 0};
+  if (epp) ep = *epp;
+  ep.precision = LK_PREC_TF32;
+  LK_REQUIRE(n_out >= 0 && k > 0 && k <= 32 && n_out * k < (1LL << 31), "lk_conv_tc_fwd_bf16: bad sizes (1 <= K <= 32, K n_out < 2^31)");
+  LK_REQUIRE(lk_conv_tc_bf16_supported(c_in, c_out), "lk_conv_tc_fwd_bf16: c_in in {32,64,128}, c_out in {32,64}");
+  LK_REQUIRE((d_perm == nullptr) == (d_tile_mask == nullptr), "lk_conv_tc_fwd_bf16: perm and tile_mask come together");
+  if (n_out == 0) return LK_OK;
+  LK_REQUIRE(d_in && d_wimg && d_nbr && d_out, "lk_conv_tc_fwd_bf16: null pointer");
+  LK_REQUIRE((uintptr_t)d_in % 16 == 0 && (uintptr_t)d_wimg % 16 == 0 && (uintptr_t)d_out % 16 == 0 &&
+                 (uintptr_t)ep.d_residual % 16 == 0, "lk_conv_tc_fwd_bf16: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)s;
+#define LK_CONV_BF16_CASE(CI, CO)                                                                          \
+  if (c_in == CI && c_out == CO)                                                                           \
+    return launch_conv_tc_n<CI, CO, 2, 1, true, true>((const float*)d_in, d_wimg, d_nbr, d_perm, d_tile_mask, n_out, k, \
+                                                      ep, (float*)d_out, st)
+  LK_CONV_BF16_CASE(32, 32);
+  LK_CONV_BF16_CASE(32, 64);
+  LK_CONV_BF16_CASE(64, 32);
+  LK_CONV_BF16_CASE(64, 64);
+  LK_CONV_BF16_CASE(128, 32);
+  LK_CONV_BF16_CASE(128, 64);
+#undef LK_CONV_BF16_CASE
+  lk_set_error("lk_conv_tc_fwd_bf16: unsupported channel combination");
+  return LK_EINVAL;
+}
+

@@ -474,7 +474,14 @@ class ELKBlock(nn.Module):
                                             any(p.requires_grad for p in self.parameters()))
 
     def forward(self, st: SparseTensor, s, r):
-        composed = self._needs_grad(st) or st._feats.dtype != torch.float32   # (no upload join here)
+        needs_grad = self._needs_grad(st)
+        if not needs_grad and st._feats.dtype in (torch.bfloat16, torch.float16):
+            # reduced-precision activations at inference: the fused block computes in fp32 (its kernels read
+            # fp32 rows) and hands the activation dtype back -- two casts instead of the composed op sequence
+            dt = st._feats.dtype
+            st.F = st.F.float()
+            return self._cast_back(self.forward(st, s, r), dt)
+        composed = needs_grad or st._feats.dtype != torch.float32   # (no upload join here)
         if not composed:
             if self.baseop == 'cos_x' and self.groups != 1:
                 raise RuntimeError("baseop='cos_x' needs groups == 1 (the reference's phase tensor "
@@ -497,6 +504,11 @@ class ELKBlock(nn.Module):
                 self.baseop)
             return st
         return self._forward_composed(st, F_input, local_mix, s, r)
+
+    @staticmethod
+    def _cast_back(st, dtype):
+        st.F = st.F.to(dtype)
+        return st
 
     def _forward_composed(self, st, F_input, local_mix, s, r):
         """The reference's op sequence (linkencoder.py:135-183) on differentiable kernels."""

@@ -245,12 +245,61 @@ def _pad_to_tc(c: int) -> int:
     return 0
 
 
+# bf16 feature rows on the tensor-core conv itself (lk_conv_tc_fwd_bf16); '0': convert at the op boundary
+BF16_NATIVE = os.environ.get('LINKB200_BF16_NATIVE', '1') != '0'
+
+
+def _conv_fwd_bf16(feats, weight, nbr, n_out, weight_t, scale, shift, residual, relu, kmap, cache_on, k, c_in, c_out):
+    """bf16 rows in / bf16 rows out on the tensor-core kernel (fp32 accumulation, tf32 weights)."""
+    L = _capi.lib()
+    ci, co = _pad_to_tc(c_in), _pad_to_tc(c_out)
+    if ci != c_in:
+        feats = torch.nn.functional.pad(feats, (0, ci - c_in))
+    if weight_t is not None:
+        wt = weight_t.float()
+        if ci != c_in or co != c_out:
+            wt = torch.nn.functional.pad(wt, (0, ci - c_in, 0, co - c_out))
+        img = _pack(wt)
+    else:
+        img = _tc_image(weight, ci if ci != c_in else 0, co if co != c_out else 0, cache_on=cache_on)
+    fuse_tail = co == c_out
+    ep = _capi.ConvEpilogue()
+    if co != c_out:
+        scale = torch.nn.functional.pad(scale, (0, co - c_out), value=1.0) if scale is not None else None
+        shift = torch.nn.functional.pad(shift, (0, co - c_out)) if shift is not None else None
+    if residual is not None and fuse_tail:
+        residual = residual.to(torch.bfloat16).contiguous()
+    ep.d_scale, ep.d_shift = _capi.ptr(scale), _capi.ptr(shift)
+    ep.d_residual = _capi.ptr(residual) if (fuse_tail and residual is not None) else None
+    ep.relu = 1 if (relu and (fuse_tail or residual is None)) else 0
+    out = torch.empty(n_out, co, dtype=torch.bfloat16, device=feats.device)
+    plan = kmap.plan() if kmap is not None else None
+    nb = n_out * (4 * k + 2 * c_out) + feats.shape[0] * 2 * c_in + 4 * k * c_in * c_out
+    with _capi.timed('lk_conv_fwd', nb):
+        _capi.check(L.lk_conv_tc_fwd_bf16(_capi.ptr(feats, torch.bfloat16), _capi.ptr(img, torch.float32),
+                                          _capi.ptr(nbr, torch.int32),
+                                          _capi.ptr(plan[0]) if plan is not None else None,
+                                          _capi.ptr(plan[1]) if plan is not None else None,
+                                          n_out, k, ci, co, C.byref(ep), _capi.ptr(out), _capi.stream()),
+                    'lk_conv_tc_fwd_bf16')
+    if not fuse_tail:
+        out = out[:, :c_out]
+        if residual is not None:
+            out = out + residual.to(out.dtype)
+            if relu:
+                out = torch.relu_(out)
+        out = out.contiguous()
+    return out
+
+
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
               relu=False, kmap=None, cache_on=None):
     """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
     None when its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies).
     epilogue: y = relu?(acc * scale + shift + residual), each part optional.  `cache_on`: the
-    nn.Parameter that `weight` is a view of (its packed image is cached there)."""
+    nn.Parameter that `weight` is a view of (its packed image is cached there).  The result has the
+    dtype of `feats`: fp32 rows run in fp32 (3xTF32 / TF32), bf16 rows on the bf16 kernel where it
+    covers the shape (c_out <= 64 after padding), else through fp32 at this boundary."""
     if weight is not None:
         k, c_in, c_out = weight.shape
     else:
@@ -258,6 +307,16 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
     if feats.shape[1] != c_in:
         raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
     L = _capi.lib()
+    in_dtype = feats.dtype
+    if in_dtype != torch.float32:
+        if (in_dtype == torch.bfloat16 and BF16_NATIVE and USE_TENSOR_CORES and k <= 32 and _pad_to_tc(c_in)
+                and _pad_to_tc(c_out) in (32, 64)):
+            return _conv_fwd_bf16(feats.contiguous(), weight, nbr, n_out, weight_t, scale, shift, residual, relu, kmap,
+                                  cache_on, k, c_in, c_out)
+        out = _conv_fwd(feats.float(), weight.float() if weight is not None else None, nbr, n_out,
+                        weight_t.float() if weight_t is not None else None, scale, shift,
+                        residual.float() if residual is not None else None, relu, kmap, cache_on)
+        return out.to(in_dtype)
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
     if residual is not None:
@@ -324,7 +383,9 @@ class ConvolutionFunction(Function):
     @staticmethod
     def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool = False):
         in_dtype = feats.dtype
-        feats = feats.contiguous().float()
+        feats = feats.contiguous()
+        if in_dtype != torch.bfloat16:          # bf16 rows stay bf16 (native kernel or boundary conversion in _conv_fwd)
+            feats = feats.float()
         weight = weight.contiguous().float()
         if not transposed:
             out = _conv_fwd(feats, weight, kmap.nbr, kmap.n_out, kmap=kmap)
@@ -338,7 +399,9 @@ class ConvolutionFunction(Function):
     def backward(ctx, grad_output):
         feats, weight = ctx.saved_tensors
         kmap, transposed = ctx.kmap, ctx.transposed
-        g = grad_output.contiguous().float()
+        g = grad_output.contiguous()
+        if not (g.dtype == torch.bfloat16 and feats.dtype == torch.bfloat16):
+            g, feats = g.float(), feats.float()
         k, c_in, c_out = weight.shape
         grad_feats = grad_weight = None
         # the relation seen from the forward INPUT rows / from the forward OUTPUT rows
@@ -359,6 +422,7 @@ class ConvolutionFunction(Function):
         if ctx.needs_input_grad[1]:
             grad_weight = torch.empty_like(weight)
             L = _capi.lib()
+            feats, g = feats.float(), g.float()          # the weight gradient contracts fp32 rows (3xTF32)
             ci, co = _pad_to_tc(c_in), _pad_to_tc(c_out)
             if USE_TENSOR_CORES and USE_TC_WGRAD and k <= 32 and ci and co and g.shape[0] * k < 2 ** 31:
                 # channel counts other than 32 / 64 / 128 (the 5- and 16-channel layers of the detection
@@ -400,7 +464,7 @@ def fusable(conv, bn, x: SparseTensor) -> bool:
     """True when conv (+ eval-mode BatchNorm) can run as ONE kernel with a fused epilogue:
     inference only (no autograd, BN in eval mode), fp32, a real sparse kernel (volume > 1)."""
     return (not torch.is_grad_enabled() and conv.kernel_volume > 1 and conv.bias is None
-            and x.feats.dtype == torch.float32 and x.feats.is_cuda
+            and x.feats.dtype in (torch.float32, torch.bfloat16) and x.feats.is_cuda
             and (bn is None or (not bn.training and bn.track_running_stats and bn.affine)))
 
 

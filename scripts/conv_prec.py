@@ -50,4 +50,16 @@ for n, c in [(120_000, 64), (160_000, 64), (120_000, 32), (40_000, 128), (15_000
             us = graph_us(lambda i: conv_mod._conv_fwd(xs[i % 4], w, km.nbr, rows, kmap=km))
         err = np.abs(got - want).max() / np.abs(want).max()
         line += f'  {prec}: {us:7.1f} us  err/max {err:.2e}'
+    conv_mod.set_precision('fp32')
+    xb = [t.to(torch.bfloat16) for t in xs]
+    if c <= 64:
+        with torch.no_grad():
+            got = conv_mod._conv_fwd(xb[0], w, km.nbr, rows, kmap=km).double().cpu().numpy()
+            us = graph_us(lambda i: conv_mod._conv_fwd(xb[i % 4], w, km.nbr, rows, kmap=km))
+        xq = xb[0].double().cpu().numpy()
+        wantq = np.zeros((rows, c))
+        for k in range(K):
+            hit = rel[k] >= 0
+            wantq[hit] += xq[rel[k][hit]] @ wn[k]
+        line += f'  bf16 rows: {us:7.1f} us  err/max {np.abs(got - wantq).max() / np.abs(wantq).max():.2e}'
     print(line, flush=True)

@@ -81,12 +81,17 @@ def main():
             with torch.no_grad():
                 return net(SparseTensor(feats, coords, 1))
 
+        def fwd16():
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                return net(SparseTensor(feats.to(torch.bfloat16), coords, 1))
+
         def step():
             loss = torch.nn.functional.cross_entropy(net(SparseTensor(feats, coords, 1)), target)
             loss.backward()
             net.zero_grad(set_to_none=True)
         net.eval()
         print(f'encoder N={coords.shape[0]}: fwd (eval, fused) {timed(fwd):.2f} ms', flush=True)
+        print(f'encoder N={coords.shape[0]}: fwd (eval, fused, bf16 activations) {timed(fwd16):.2f} ms', flush=True)
         net.train()
     print(f'fwd+bwd (train): {timed(step):.2f} ms', flush=True)
     if a.cprofile:

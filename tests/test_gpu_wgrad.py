@@ -157,3 +157,51 @@ def test_encoder_under_bf16_autocast(dev):
             assert p.grad is not None and torch.isfinite(p.grad).all(), n
     err = float((logits.float() - ref).abs().max())
     assert err <= 5e-2 * float(ref.abs().max() - ref.min()) + 5e-2, err
+
+
+@pytest.mark.parametrize('n,cin,cout,ksize,stride', [(20_000, 64, 64, 3, 1), (3_000, 32, 64, 3, 1), (130, 64, 32, 3, 1),
+                                                     (9_000, 32, 32, 2, 2), (2_500, 128, 32, 2, 2), (700, 128, 64, 3, 1),
+                                                     (4_000, 16, 16, 3, 1), (1, 64, 64, 3, 1)])
+def test_conv_bf16_rows_vs_float64(dev, n, cin, cout, ksize, stride):
+    """lk_conv_tc_fwd_bf16: bf16 rows in / bf16 rows out, fp32 accumulation, tf32 weights, fused epilogue
+    with a bf16 residual.  Against a float64 contraction of the SAME bf16-rounded inputs; stated
+    tolerance: 1.5 * 2^-8 of the output range (the bf16 rounding of the result dominates) -- and the
+    planned launch equals the unplanned one bit for bit."""
+    from link_b200.nn.functional import conv as conv_mod
+    km = _kmap(dev, n, ksize, stride, cin)
+    K, rows = km.nbr.shape
+    gen = torch.Generator().manual_seed(n + cout)
+    x = torch.randn(km.n_in, cin, generator=gen).to(dev).to(torch.bfloat16)
+    w = (torch.randn(K, cin, cout, generator=gen) / np.sqrt(cin * 4)).to(dev)
+    res = torch.randn(rows, cout, generator=gen).to(dev).to(torch.bfloat16)
+    scale, shift = (torch.rand(cout, generator=gen) + 0.5).to(dev), torch.randn(cout, generator=gen).to(dev)
+    got = conv_mod._conv_fwd(x, w, km.nbr, rows, None, scale, shift, res, True, kmap=km)
+    plain = conv_mod._conv_fwd(x, w, km.nbr, rows, None, scale, shift, res, True)
+    assert got.dtype == torch.bfloat16 and torch.equal(got, plain)
+    rel = km.nbr.cpu().numpy()
+    acc = np.zeros((rows, cout))
+    xn, wn = x.double().cpu().numpy(), w.double().cpu().numpy()
+    for k in range(K):
+        hit = rel[k] >= 0
+        acc[hit] += xn[rel[k][hit]] @ wn[k]
+    want = np.maximum(acc * scale.double().cpu().numpy() + shift.double().cpu().numpy() + res.double().cpu().numpy(), 0)
+    err = np.abs(got.double().cpu().numpy() - want).max()
+    assert err <= 1.5 * 2.0 ** -8 * max(1.0, np.abs(want).max()), err
+
+
+def test_encoder_inference_bf16_activations(dev):
+    """ELKEncoder forward on bf16 activations (bf16 conv kernel, LinK blocks through fp32 at their boundary):
+    logits within 5e-2 of the fp32 run's range."""
+    from link_b200 import SparseTensor
+    from link_b200.linkencoder import ELKEncoder
+    from link_b200.utils.synthetic import random_voxels
+    coords = torch.from_numpy(random_voxels(6000, 48, seed=8, batch=2)).to(dev)
+    torch.manual_seed(8)
+    feats = torch.randn(coords.shape[0], 4, device=dev)
+    net = ELKEncoder(num_classes=19, cr=1.0, baseop='cos', r=3, s=7, groups=2).to(dev).eval()
+    with torch.no_grad():
+        ref = net(SparseTensor(feats.clone(), coords, 1))
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            got = net(SparseTensor(feats.clone().to(torch.bfloat16), coords, 1))
+    err = float((got.float() - ref).abs().max())
+    assert torch.isfinite(got).all() and err <= 5e-2 * float(ref.max() - ref.min()) + 5e-2, err
