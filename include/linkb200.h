@@ -391,6 +391,11 @@ int lk_conv_plan(const int32_t* d_nbr, int64_t n_out, int k, const int32_t* d_of
  * d_img: K * 8 * c_in * c_out bytes.  Packed once per weight update (cached by the caller). */
 int lk_conv_tc_pack_weights(const float* d_wt, int k, int c_in, int c_out, float* d_img,
                             lk_stream_t s);
+/* General form: d_w is [K, src_c_in, src_c_out] (layout 1: the module parameter, transposed on the fly) or
+ * [K, src_c_out, src_c_in] (layout 0), zero padded to the image's c_in x c_out, offsets reversed when
+ * flip_k (the input gradient of a submanifold conv): no transposed / padded / flipped copy is made. */
+int lk_conv_tc_pack_weights_ex(const float* d_w, int k, int c_in, int c_out, int src_c_in, int src_c_out,
+                               int layout, int flip_k, float* d_img, lk_stream_t s);
 /* The tensor-core conv on packed weights, optionally with a plan: d_perm and d_tile_mask as
  * produced by lk_conv_plan (both NULL = identity order, no skipping). */
 int lk_conv_tc_fwd_plan(const float* d_in, const float* d_wimg, const int32_t* d_nbr,

@@ -111,6 +111,7 @@ PROTOTYPES = {
     'lk_conv_plan_ws_bytes': (i64, [i64]),
     'lk_conv_plan': (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp]),
     'lk_conv_tc_pack_weights': (i32, [vp, i32, i32, i32, vp, vp]),
+    'lk_conv_tc_pack_weights_ex': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     'lk_conv_tc_fwd_plan': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, C.POINTER(ConvEpilogue), vp, vp]),
     'lk_conv_tc_supported': (i32, [i32, i32]),
     'lk_conv_tc_bf16_supported': (i32, [i32, i32]),

@@ -783,6 +783,57 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
+// General form: the source may be the module parameter itself ([K][src_cin][src_cout], transposed on the
+// fly: layout 1) or its per-offset transpose ([K][src_cout][src_cin]: layout 0), narrower than the image
+// (zero padded to cin x cout) and read with the offsets reversed (flip_k: the input gradient of a
+// submanifold conv) -- no transposed / padded / flipped copy is made on the way.
+__global__ void __launch_bounds__(256) pack_weights_ex_kernel(const float* __restrict__ w, int K, int cin, int cout,
+                                                              int src_cin, int src_cout, int layout, int flip_k,
+                                                              float* __restrict__ img) {
+  const int kh = cin > 64 ? 2 : 1, ce = cin / kh;
+  const int kb_n = ce / 32;
+  const int64_t per_v = (int64_t)cout * kb_n * 8;
+  const int64_t total = (int64_t)K * kh * per_v;
+  const int64_t stage_floats = (int64_t)2 * ce * cout;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int kv = (int)(t / per_v);
+    const int r = (int)(t - (int64_t)kv * per_v);
+    const int k = kv / kh, h = kv % kh;
+    const int chunk = r & 7, kb = (r >> 3) % kb_n, row = r / (8 * kb_n);       // row = output channel
+    const int ks = flip_k ? K - 1 - k : k;
+    const int ci0 = h * ce + kb * 32 + chunk * 4;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ci = ci0 + e;
+      float x = 0.f;
+      if (row < src_cout && ci < src_cin)
+        x = layout ? __ldg(w + ((int64_t)ks * src_cin + ci) * src_cout + row)
+                   : __ldg(w + ((int64_t)ks * src_cout + row) * src_cin + ci);
+      v[e] = x;
+    }
+    float4 w4 = make_float4(v[0], v[1], v[2], v[3]), hi, lo;
+    tc::split_tf32(w4, hi, lo);
+    const uint32_t off = (uint32_t)kb * (uint32_t)(cout * 128) + tc::sw128_offset(row, chunk);
+    float* base = img + (int64_t)kv * stage_floats;
+    *(float4*)((uint8_t*)base + off) = hi;
+    *(float4*)((uint8_t*)base + (size_t)ce * cout * 4 + off) = lo;
+  }
+}
+
+extern "C" int lk_conv_tc_pack_weights_ex(const float* d_w, int k, int c_in, int c_out, int src_c_in, int src_c_out,
+                                          int layout, int flip_k, float* d_img, lk_stream_t s) {
+  LK_REQUIRE(k > 0 && lk_conv_tc_supported(c_in, c_out) && src_c_in > 0 && src_c_in <= c_in && src_c_out > 0 &&
+                 src_c_out <= c_out && (layout == 0 || layout == 1),
+             "lk_conv_tc_pack_weights_ex: image channels must be 32, 64 or 128 and cover the source");
+  LK_REQUIRE(d_w && d_img && (uintptr_t)d_img % 128 == 0, "lk_conv_tc_pack_weights_ex: null or misaligned pointer");
+  pack_weights_ex_kernel<<<lk_grid((int64_t)k * c_out * (c_in / 32) * 8, 256, 4), 256, 0, (cudaStream_t)s>>>(
+      d_w, k, c_in, c_out, src_c_in, src_c_out, layout, flip_k, d_img);
+  LK_LAUNCHED();
+  return LK_OK;
+}
+
 extern "C" int lk_conv_tc_pack_weights(const float* d_wt, int k, int c_in, int c_out, float* d_img,
                                        lk_stream_t s) {
   LK_REQUIRE(k > 0 && lk_conv_tc_supported(c_in, c_out), "lk_conv_tc_pack_weights: channels must be 32, 64 or 128");

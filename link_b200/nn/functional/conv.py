@@ -196,14 +196,17 @@ def precision_code() -> int:
 _tc_supported = {}
 
 
-def _pack(wt: torch.Tensor) -> torch.Tensor:
-    """[K, Cout, Cin] (per-offset transposed weights) -> packed tensor-core image
-    (lk_conv_tc_pack_weights: tf32 hi/lo planes in the SWIZZLE_128B shared-memory layout)."""
-    k, c_out, c_in = wt.shape
-    wt = wt.contiguous().float()
-    img = torch.empty(k * 2 * c_in * c_out, dtype=torch.float32, device=wt.device)
-    _capi.check(_capi.lib().lk_conv_tc_pack_weights(_capi.ptr(wt), k, c_in, c_out, _capi.ptr(img),
-                                                    _capi.stream()), 'lk_conv_tc_pack_weights')
+def _pack_ex(w: torch.Tensor, layout: int, ci: int, co: int, flip_k: bool = False) -> torch.Tensor:
+    """Packed tensor-core image (ci x co channels, zero padded) straight from `w`: [K, Cin, Cout] (layout 1,
+    the module parameter) or [K, Cout, Cin] (layout 0), optionally with the offsets reversed -- the
+    transposition, the padding and the flip happen inside lk_conv_tc_pack_weights_ex, not as torch copies."""
+    w = w.detach().contiguous().float()
+    k = w.shape[0]
+    src_ci, src_co = (w.shape[1], w.shape[2]) if layout else (w.shape[2], w.shape[1])
+    img = torch.empty(k * 2 * ci * co, dtype=torch.float32, device=w.device)
+    _capi.check(_capi.lib().lk_conv_tc_pack_weights_ex(_capi.ptr(w), k, ci, co, src_ci, src_co, layout,
+                                                       1 if flip_k else 0, _capi.ptr(img), _capi.stream()),
+                'lk_conv_tc_pack_weights_ex')
     return img
 
 
@@ -219,12 +222,7 @@ def _tc_image(weight: torch.Tensor, c_pad: int = 0, c_pad_out: int = 0, cache_on
         hit = holder.__dict__.get('_lk_img')
         if hit is not None and hit[0] == ver:
             return hit[1]
-    wt = weight.detach().transpose(1, 2)                      # [K, Cout, Cin]
-    pad_in = max(c_pad - weight.shape[1], 0) if c_pad else 0
-    pad_out = max(c_pad_out - weight.shape[2], 0) if c_pad_out else 0
-    if pad_in or pad_out:
-        wt = torch.nn.functional.pad(wt, (0, pad_in, 0, pad_out))
-    img = _pack(wt)
+    img = _pack_ex(weight, 1, max(c_pad, weight.shape[1]), max(c_pad_out, weight.shape[2]))
     if holder is not None:
         holder.__dict__['_lk_img'] = (ver, img)
     return img
@@ -249,17 +247,15 @@ def _pad_to_tc(c: int) -> int:
 BF16_NATIVE = os.environ.get('LINKB200_BF16_NATIVE', '1') != '0'
 
 
-def _conv_fwd_bf16(feats, weight, nbr, n_out, weight_t, scale, shift, residual, relu, kmap, cache_on, k, c_in, c_out):
+def _conv_fwd_bf16(feats, weight, nbr, n_out, weight_t, scale, shift, residual, relu, kmap, cache_on, k, c_in, c_out,
+                   flip_k=False):
     """bf16 rows in / bf16 rows out on the tensor-core kernel (fp32 accumulation, tf32 weights)."""
     L = _capi.lib()
     ci, co = _pad_to_tc(c_in), _pad_to_tc(c_out)
     if ci != c_in:
         feats = torch.nn.functional.pad(feats, (0, ci - c_in))
     if weight_t is not None:
-        wt = weight_t.float()
-        if ci != c_in or co != c_out:
-            wt = torch.nn.functional.pad(wt, (0, ci - c_in, 0, co - c_out))
-        img = _pack(wt)
+        img = _pack_ex(weight_t, 0, ci, co, flip_k)
     else:
         img = _tc_image(weight, ci if ci != c_in else 0, co if co != c_out else 0, cache_on=cache_on)
     fuse_tail = co == c_out
@@ -293,7 +289,7 @@ def _conv_fwd_bf16(feats, weight, nbr, n_out, weight_t, scale, shift, residual, 
 
 
 def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, residual=None,
-              relu=False, kmap=None, cache_on=None):
+              relu=False, kmap=None, cache_on=None, flip_k=False):
     """out[o] = epilogue(sum_k feats[nbr[k, o]] @ weight[k]).  `weight` is [K, Cin, Cout] (may be
     None when its transpose `weight_t` [K, Cout, Cin] is given and the tensor-core kernel applies).
     epilogue: y = relu?(acc * scale + shift + residual), each part optional.  `cache_on`: the
@@ -312,10 +308,10 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         if (in_dtype == torch.bfloat16 and BF16_NATIVE and USE_TENSOR_CORES and k <= 32 and _pad_to_tc(c_in)
                 and _pad_to_tc(c_out) in (32, 64)):
             return _conv_fwd_bf16(feats.contiguous(), weight, nbr, n_out, weight_t, scale, shift, residual, relu, kmap,
-                                  cache_on, k, c_in, c_out)
+                                  cache_on, k, c_in, c_out, flip_k)
         out = _conv_fwd(feats.float(), weight.float() if weight is not None else None, nbr, n_out,
                         weight_t.float() if weight_t is not None else None, scale, shift,
-                        residual.float() if residual is not None else None, relu, kmap, cache_on)
+                        residual.float() if residual is not None else None, relu, kmap, cache_on, flip_k)
         return out.to(in_dtype)
     # algorithmic bytes: kernel map + each input row once + output once + the weights
     nb = n_out * (4 * k + 4 * c_out) + feats.shape[0] * 4 * c_in + 4 * k * c_in * c_out
@@ -330,10 +326,7 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         if ci != c_in:
             feats = torch.nn.functional.pad(feats, (0, ci - c_in))
         if weight_t is not None:
-            wt = weight_t
-            if ci != c_in or co != c_out:
-                wt = torch.nn.functional.pad(wt, (0, ci - c_in, 0, co - c_out))
-            img = _pack(wt)
+            img = _pack_ex(weight_t, 0, ci, co, flip_k)
         else:
             img = _tc_image(weight, ci if ci != c_in else 0, co if co != c_out else 0, cache_on=cache_on)
         fuse_tail = co == c_out               # residual / ReLU stay in the epilogue unless C_out is padded
@@ -368,7 +361,7 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
     ep.d_residual = _capi.ptr(residual)
     ep.relu = 1 if relu else 0
     if weight is None:
-        weight = weight_t.transpose(1, 2).contiguous()
+        weight = (weight_t.flip(0) if flip_k else weight_t).transpose(1, 2).contiguous()
     with _capi.timed('lk_conv_fwd', nb):
         _capi.check(L.lk_conv_fwd_ex(_capi.ptr(feats, torch.float32), _capi.ptr(weight, torch.float32),
                                      _capi.ptr(nbr, torch.int32), n_out, k, c_in, c_out, C.byref(ep),
@@ -415,7 +408,7 @@ class ConvolutionFunction(Function):
                 # FORWARD map with the offsets of W reversed -- no inverted map is built, and the forward
                 # tile-skipping plan applies (the unplanned dgrad ran all 27 x tiles steps: 173 vs 73 us
                 # at N = 119k, C = 64)
-                grad_feats = _conv_fwd(g, None, kmap.nbr, n_in_rows, weight_t=weight.flip(0), kmap=kmap).to(ctx.in_dtype)
+                grad_feats = _conv_fwd(g, None, kmap.nbr, n_in_rows, weight_t=weight, kmap=kmap, flip_k=True).to(ctx.in_dtype)
             else:
                 to_in = kmap.inv if not transposed else kmap.nbr
                 grad_feats = _conv_fwd(g, None, to_in, n_in_rows, weight_t=weight).to(ctx.in_dtype)
