@@ -182,6 +182,14 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
+def check_device(t) -> None:
+    """liblinkb200 launches on the CURRENT device's current stream: a tensor that lives on another GPU
+    would be read through a foreign stream (or fault).  Called once per high-level op."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f'tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: '
+                           'wrap the call in `with torch.cuda.device(tensor.device):`')
+
+
 def launch_count() -> int:
     return int(lib().lk_launch_count())
 

@@ -518,45 +518,34 @@ __global__ void __launch_bounds__(256) link_window_mean_kernel(const float* __re
       if (src >= 0) cnt = SEG ? __ldg(counts + src + 1) - __ldg(counts + src) : __ldg(counts + src);
     }
     const unsigned present = __ballot_sync(0xffffffffu, src >= 0);
-    // The population loads (cnt) are NOT consumed before the row loads are in flight: the kernel is a
-    // chain of dependent L2 round trips (block count -> neighbour table -> {populations, rows} -> store),
-    // and reducing `cnt` first put one more round trip in front of the rows.  Rows are fetched eight at
-    // a time (a LiDAR block has ~9-12 present neighbours: two batches instead of three).
-    float tot = 0.f;
+    int tot_i = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
+    const float tot = (float)tot_i;
+    if (tot_out && lane == 0) tot_out[b] = tot;
     for (int v0 = 0; v0 < vpr; v0 += 32) {
       const int v = v0 + lane;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       unsigned rest = present;
       while (rest) {                             // warp-uniform loop over the present neighbours
-        int s8[8];
-        bool on[8];
+        int s4[4];
+        bool on[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+        for (int t = 0; t < 4; ++t) {
           on[t] = rest != 0;
           const int l = on[t] ? __ffs(rest) - 1 : 0;
           rest &= rest - 1;
-          s8[t] = __shfl_sync(0xffffffffu, src, l);
+          s4[t] = __shfl_sync(0xffffffffu, src, l);
         }
-        // unconditional loads (absent slots re-read this block's own row and are masked in the add): with
-        // predicated loads the compiler recycled three registers and serialised the batch
-        const int vv = v < vpr ? v : 0;
-        float4 r8[8];
+        float4 r4[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          r8[t] = lk_ldg_stream((const float4*)(sums + (int64_t)(on[t] ? s8[t] : (int)b) * kc) + vv);   // asm volatile: issue order kept
+        for (int t = 0; t < 4; ++t)
+          r4[t] = (v < vpr && on[t]) ? __ldg((const float4*)(sums + (int64_t)s4[t] * kc) + v)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float m = on[t] ? 1.f : 0.f;
-          acc.x = fmaf(m, r8[t].x, acc.x); acc.y = fmaf(m, r8[t].y, acc.y);
-          acc.z = fmaf(m, r8[t].z, acc.z); acc.w = fmaf(m, r8[t].w, acc.w);
+        for (int t = 0; t < 4; ++t) {
+          acc.x += r4[t].x; acc.y += r4[t].y; acc.z += r4[t].z; acc.w += r4[t].w;
         }
-      }
-      if (v0 == 0) {
-        int tot_i = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
-        tot = (float)tot_i;
-        if (tot_out && lane == 0) tot_out[b] = tot;
       }
       if (v < vpr) {
         acc.x /= tot; acc.y /= tot; acc.z /= tot; acc.w /= tot;

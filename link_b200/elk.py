@@ -241,6 +241,7 @@ def link_aggregate(f_input: torch.Tensor, coords: torch.Tensor, bi: BlockIndex, 
     form is `LinkAggregateFunction`); `save` = (mean [n,kC], tot [n]) buffers that receive the window
     means / populations the backward pass needs."""
     n, c = f_input.shape
+    _capi.check_device(f_input)
     f_input = f_input.contiguous()
     coords = coords.contiguous()
     pos_weight = pos_weight.detach().contiguous().float()
@@ -356,6 +357,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
     from link_b200.nn.functional.conv import KernelMap, _tc_image
     L = _capi.lib()
+    _capi.check_device(st._feats)
     x, ready = st.take_feats_event()          # a pending async upload is joined ON THE DEVICE, after
     x = x.contiguous()                         # the index-only kernels (SparseTensor.from_host)
     coords = st.C.contiguous()

@@ -19,7 +19,7 @@ from link_b200.nn.utils import get_kernel_offsets
 from link_b200.tensor import SparseTensor
 from link_b200.utils import make_ntuple
 
-__all__ = ['conv3d', 'conv_bn_act', 'fusable', 'KernelMap', 'build_kernel_map', 'set_precision']
+__all__ = ['conv3d', 'conv_bn_act', 'fusable', 'KernelMap', 'build_kernel_map', 'set_precision', 'invalidate_caches']
 
 
 class KernelMap:
@@ -228,6 +228,20 @@ def _tc_image(weight: torch.Tensor, c_pad: int = 0, c_pad_out: int = 0, cache_on
     return img
 
 
+def invalidate_caches(module: torch.nn.Module) -> None:
+    """Drop every derived copy cached on a model's modules / parameters (packed weight images, folded
+    BatchNorm affines, the block executor's argument templates).  The caches are keyed by the
+    parameters' `_version` and storage address, so optimizer steps, `load_state_dict` and `copy_` refresh
+    them by themselves; writes through `.data` (EMA `p.data.mul_()`, clamping) do NOT bump the version --
+    call this after such an update."""
+    for m in module.modules():
+        for key in ('_lk_fold', '_lk_native_args', '_lk_kio', '_lk_refs', '_lk_dil'):
+            m.__dict__.pop(key, None)
+    for p in module.parameters():
+        p.__dict__.pop('_lk_img', None)
+        p.__dict__.pop('_lk_kio', None)
+
+
 def _tc_ok(L, c_in, c_out) -> bool:
     ok = _tc_supported.get((c_in, c_out))
     if ok is None:
@@ -302,6 +316,7 @@ def _conv_fwd(feats, weight, nbr, n_out, weight_t=None, scale=None, shift=None, 
         k, c_out, c_in = weight_t.shape
     if feats.shape[1] != c_in:
         raise ValueError('Input feature size and kernel size mismatch')   # convolution_cuda.cu:57
+    _capi.check_device(feats)
     L = _capi.lib()
     in_dtype = feats.dtype
     if in_dtype != torch.float32:

@@ -96,6 +96,9 @@ class SparseTensor:
             if widen:
                 f_dev.copy_(f_wire)
                 f_wire.record_stream(copy_stream)
+            # the buffers were allocated on the main stream but are written here: if the tensor is dropped
+            # before a consumer joins the upload, the allocator must not hand the block out while the copy runs
+            f_dev.record_stream(copy_stream)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         st = cls(f_dev, c_dev, stride)
