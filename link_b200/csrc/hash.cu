@@ -230,23 +230,56 @@ __global__ void __launch_bounds__(256) kmap_query_subm_kernel(const int4* __rest
                                                               int K, const Slot* __restrict__ table,
                                                               uint64_t mask, unsigned* nbr) {
   lk_pdl_enter();
+  // blockIdx.y = offset k <= K/2, blockIdx.x strides over the voxels: no (voxel, offset) index to take
+  // apart -- the 64-bit division of the flat form was half of this kernel's ~220 instructions per probe
+  // (issue 56 % busy in the ncu capture of the flat kernel).
   const int half = K / 2;
-  int64_t total = n * (half + 1);
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int k = (int)(t / n);
-    int64_t i = t - (int64_t)k * n;
-    if (k == half) {                                  // centre offset: identity
+  const int k = blockIdx.y;
+  if (k == half) {                                    // centre offset: identity
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       nbr[(int64_t)half * n + i] = (unsigned)i;
-      continue;
+    return;
+  }
+  const int ox = __ldg(offsets + 3 * k), oy = __ldg(offsets + 3 * k + 1), oz = __ldg(offsets + 3 * k + 2);
+  unsigned* const fwd = nbr + (int64_t)k * n;
+  unsigned* const bwd = nbr + (int64_t)(K - 1 - k) * n;
+  // Four voxels per thread and iteration, their coordinate loads and then their first probes in flight
+  // together: the kernel is a chain of two dependent L2 round trips per probe (57 % long-scoreboard
+  // stalls on the key compare), so the way to go faster is more loads in flight per thread.
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    int4 c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      c[u] = coords[i < n ? i : i0];
     }
-    int4 c = coords[i];
-    int64_t h = lk_fnv4(c.x + __ldg(offsets + 3 * k), c.y + __ldg(offsets + 3 * k + 1),
-                        c.z + __ldg(offsets + 3 * k + 2), c.w);
-    int j = table_find(table, mask, (unsigned long long)h);
-    if (j >= 0) {
-      nbr[(int64_t)k * n + i] = (unsigned)j;
-      atomicMin(&nbr[(int64_t)(K - 1 - k) * n + j], (unsigned)i);   // 0xFFFFFFFF == -1 prefill
+    unsigned long long key[U];
+    uint64_t slot[U];
+    int4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      key[u] = (unsigned long long)lk_fnv4(c[u].x + ox, c[u].y + oy, c[u].z + oz, c[u].w);
+      slot[u] = slot_of(key[u], mask);
+      raw[u] = __ldg((const int4*)&table[slot[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) continue;
+      int j = -1;
+      while (true) {                                   // linear probing; the first probe is already here
+        const unsigned long long k2 = ((unsigned long long)(unsigned)raw[u].y << 32) | (unsigned)raw[u].x;
+        if (k2 == key[u]) { j = raw[u].z; break; }
+        if (k2 == LK_EMPTY) break;
+        slot[u] = (slot[u] + 1) & mask;
+        raw[u] = __ldg((const int4*)&table[slot[u]]);
+      }
+      if (j >= 0) {
+        fwd[i] = (unsigned)j;
+        atomicMin(&bwd[j], (unsigned)i);              // 0xFFFFFFFF == -1 prefill
+      }
     }
   }
 }
@@ -269,9 +302,17 @@ extern "C" int lk_kmap_query_subm_ev(const int32_t* d_coords, int64_t n, const i
   LK_CUDA(cudaMemsetAsync(d_nbr, 0xFF, (size_t)k * n * sizeof(int), st));
   lk_count_launch();
   if (table_ready) LK_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)table_ready, 0));
-  LK_PDL_LAUNCH(kmap_query_subm_kernel, lk_grid(n * (k / 2 + 1), 256, 8), 256, 0, st,
-                (const int4*)d_coords, n, d_offsets, k, (const Slot*)d_table, (uint64_t)capacity - 1,
-                (unsigned*)d_nbr);
+  {
+    // (k/2 + 1) offset rows x enough CTAs per row to fill the machine once (8 resident CTAs per SM)
+    const int rows = k / 2 + 1;
+    int per_row = (LK_SM_COUNT * 8 + rows - 1) / rows;
+    const int64_t need = (n + 255) / 256;
+    if (per_row > need) per_row = (int)need;
+    if (per_row < 1) per_row = 1;
+    const dim3 grid((unsigned)per_row, (unsigned)rows);
+    LK_CUDA(lk_launch_pdl(kmap_query_subm_kernel, grid, dim3(256), 0, st, (const int4*)d_coords, n, d_offsets, k,
+                          (const Slot*)d_table, (uint64_t)capacity - 1, (unsigned*)d_nbr));
+  }
   LK_LAUNCHED();
   return LK_OK;
 }
@@ -279,13 +320,12 @@ extern "C" int lk_kmap_query_subm_ev(const int32_t* d_coords, int64_t n, const i
 __global__ void __launch_bounds__(256) kmap_invert_kernel(const int* __restrict__ nbr,
                                                           int64_t n_out, int K, int64_t n_in,
                                                           int* __restrict__ inv) {
-  int64_t total = (int64_t)K * n_out;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int i = nbr[t];
-    if (i >= 0) {
-      int64_t k = t / n_out;
-      inv[k * n_in + i] = (int)(t - k * n_out);
+  for (int k = blockIdx.y; k < K; k += gridDim.y) {           // offset rows on grid.y: no 64-bit division per entry
+    const int* row = nbr + (int64_t)k * n_out;
+    int* dst = inv + (int64_t)k * n_in;
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_out; o += (int64_t)gridDim.x * blockDim.x) {
+      const int i = row[o];
+      if (i >= 0) dst[i] = (int)o;
     }
   }
 }
@@ -298,8 +338,14 @@ extern "C" int lk_kmap_invert(const int32_t* d_nbr, int64_t n_out, int k, int64_
     lk_count_launch();
   }
   if (n_out == 0 || n_in == 0) return LK_OK;
-  kmap_invert_kernel<<<lk_grid((int64_t)k * n_out, 256, 8), 256, 0, (cudaStream_t)s>>>(
-      d_nbr, n_out, k, n_in, d_inv);
+  {
+    int per_row = (LK_SM_COUNT * 8 + k - 1) / k;
+    const int64_t need = (n_out + 255) / 256;
+    if (per_row > need) per_row = (int)need;
+    if (per_row < 1) per_row = 1;
+    kmap_invert_kernel<<<dim3((unsigned)per_row, (unsigned)(k < 65535 ? k : 65535)), 256, 0, (cudaStream_t)s>>>(
+        d_nbr, n_out, k, n_in, d_inv);
+  }
   LK_LAUNCHED();
   return LK_OK;
 }

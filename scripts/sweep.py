@@ -26,14 +26,26 @@ from link_b200.utils.synthetic import kitti_like_voxels, lidar_scan
 
 
 def timed(fn, flush, warm=3, reps=10):
-    ts = []
+    """Median device time of fn(): the L2 flush in front of every timed call is repeated until it outlasts
+    the host's enqueue time of one call, so the event window holds device work, not launch waiting
+    (see bench.py / scripts/step_graph_probe.py)."""
+    import time
+    ts, host = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); flush.zero_(); flush.zero_(); e1.record(); torch.cuda.synchronize()
+    flush_ms = e0.elapsed_time(e1) / 2
+    n_flush = 1
     for k in range(warm + reps):
-        flush.zero_()
+        for _ in range(n_flush):
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         fn()
+        host.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         torch.cuda.synchronize()
+        n_flush = int(min(64, max(2, np.ceil(2.0 * np.median(host[-3:]) / flush_ms) + 1)))
         if k >= warm:
             ts.append(e0.elapsed_time(e1))
     return float(np.median(ts))
