@@ -63,10 +63,11 @@ def block_params(seed=0):
     return blk
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# captures (profiles/), keyed by kernel; None = not captured for this build.
-NCU_TRAFFIC = {'link_preagg_smem_kernel': 40.68e6,   # profiles/r01_ncu_full_v3.md (two launches: 41.64 / 39.72 MB read, <1 KB written)
-               'link_preagg_ring_kernel': 41.62e6}   # profiles/r01_ncu_full_v8.md (41.62 MB read, 3.6 KB written)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+# `ncu --set full` capture of THIS round (profiles/r02_ncu_full.md: 39.7 MB read, < 0.1 MB written, two
+# launches); ncu cannot run inside the bench, so the line names its source next to the number.
+NCU_TRAFFIC = {'link_preagg_ring_kernel': 39.7e6}
+NCU_TRAFFIC_SOURCE = 'profiles/r02_ncu_full.md (ncu --set full --clock-control none, scripts/profile_step.py, same scan and kernel)'
 
 
 def workload_name(args, n):
@@ -768,7 +769,7 @@ def main_ours(args):
         instep = kern.get('lk_link_preagg_fwd', {})
         roof = {'kernel': 'link_preagg_ring_kernel', 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
-                'traffic': NCU_TRAFFIC.get('link_preagg_ring_kernel'),
+                'traffic': NCU_TRAFFIC.get('link_preagg_ring_kernel'), 'traffic_source': NCU_TRAFFIC_SOURCE,
                 'algorithmic_bytes_per_launch': r['bytes'], 'avg_us': r['avg_us'],
                 'python_launch_avg_us': r['python_launch_avg_us'],
                 'in_step_avg_us': instep.get('avg_us'),
