@@ -450,6 +450,15 @@ int lk_points_to_voxel(const float* d_points, int64_t n, int ndim, const float* 
  * every row to itself (the reference's precompute_mid shortcut, convolution_cuda.cu:74-88). */
 int lk_kmap_from_pairs(const int32_t* d_nbmaps, const int32_t* h_nbsizes, int k, int64_t n_rows,
                        int row_col, int identity_mid, int32_t* d_nbr, lk_stream_t s);
+/* Candidate output sites of a strided / padded sparse conv that creates new active sites (spconv
+ * SparseConv3d as used by detection/det3d/models/backbones/scn.py:494-566; spconv itself is not in the
+ * reference tree): d_indices int32 [n,4] = (batch, z, y, x); kernel / stride / padding /
+ * out_shape are HOST int32[3] in (z, y, x) order; d_cand int32 [n * cap, 4] = (x, y, z, batch) with
+ * cap = prod ceil(k_a / s_a); invalid slots are (0, 0, 0, batch_size) and set *d_any_invalid (device int).
+ * Sort-unique d_cand by (batch, z, y, x) and drop the trailing sentinel to get the output sites. */
+int lk_strided_candidates(const int32_t* d_indices, int64_t n, const int32_t* kernel3, const int32_t* stride3,
+                          const int32_t* padding3, const int32_t* out_shape3, int batch_size,
+                          int32_t* d_cand, int32_t* d_any_invalid, lk_stream_t s);
 /* ------------------------------------------------------------------------------------
  * Sparse -> dense BEV scatter of the detection backbone output and its transpose (the backward).
  * Replaces spconv's `.dense()` + permute in `ret = self.extra_conv(x).dense(); ret.view(N, C*D, H, W)`

@@ -119,6 +119,7 @@ PROTOTYPES = {
     'lk_conv_tc_fwd': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'lk_conv_bwd_weight': (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp]),
     'lk_host_coord_bounds': (i32, [vp, i64, vp, vp]),
+    'lk_strided_candidates': (i32, [vp, i64, vp, vp, vp, vp, i32, vp, vp, vp]),
     'lk_kmap_from_pairs': (i32, [vp, vp, i32, i64, i32, i32, vp, vp]),
     'lk_bev_scatter': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]),
     'lk_bev_gather': (i32, [vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]),

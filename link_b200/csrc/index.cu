@@ -175,3 +175,66 @@ extern "C" int lk_kmap_from_pairs(const int32_t* d_nbmaps, const int32_t* h_nbsi
   LK_LAUNCHED();
   return LK_OK;
 }
+
+/* Output sites of a strided / padded sparse conv that creates new active sites (spconv SparseConv3d,
+ * detection/det3d/models/backbones/scn.py:494-566): input site i reaches output o through tap kappa when
+ * i + p - kappa = s * o with 0 <= o < out_shape.  Per axis only the taps kappa = (i + p) mod s + s * t
+ * (t < ceil(k / s)) can divide, so a voxel has at most cap = prod ceil(k_a / s_a) candidates (8 for
+ * k = 3, s = 2) instead of the K = 27 the tensor-op formulation expands, filters and compacts with a
+ * host round trip.  d_indices [n,4] = (batch, z, y, x); d_cand [n * cap, 4] = (x, y, z, batch) of every
+ * candidate, invalid slots = (0, 0, 0, batch_size) -- one past the last batch, so that after a sort by
+ * (batch, z, y, x) they collapse into ONE trailing key -- and *d_any_invalid is set if there is one. */
+struct StridedSpec { int k[3], s[3], p[3], out[3], cap[3]; };
+
+__global__ void __launch_bounds__(256) strided_candidates_kernel(const int4* __restrict__ indices, int64_t n,
+                                                                 StridedSpec sp, int batch_size,
+                                                                 int4* __restrict__ cand, int* __restrict__ any_invalid) {
+  const int cap = sp.cap[0] * sp.cap[1] * sp.cap[2];
+  const int64_t total = n * cap;
+  bool bad = false;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / cap;
+    int slot = (int)(t - i * cap);
+    const int4 v = __ldg(indices + i);                 // (b, z, y, x)
+    const int pos[3] = {v.y, v.z, v.w};
+    int o[3];
+    bool ok = true;
+#pragma unroll
+    for (int a = 2; a >= 0; --a) {
+      const int ta = slot % sp.cap[a];
+      slot /= sp.cap[a];
+      const int num = pos[a] + sp.p[a];
+      const int kappa = (num % sp.s[a]) + sp.s[a] * ta;           // num >= 0
+      o[a] = (num - kappa) / sp.s[a];
+      ok = ok && kappa < sp.k[a] && num >= kappa && o[a] < sp.out[a];
+    }
+    cand[t] = ok ? make_int4(o[2], o[1], o[0], v.x) : make_int4(0, 0, 0, batch_size);
+    bad = bad || !ok;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *any_invalid = 1;
+}
+
+extern "C" int lk_strided_candidates(const int32_t* d_indices, int64_t n, const int32_t* kernel3,
+                                     const int32_t* stride3, const int32_t* padding3, const int32_t* out_shape3,
+                                     int batch_size, int32_t* d_cand, int32_t* d_any_invalid, lk_stream_t s) {
+  LK_REQUIRE(n >= 0 && kernel3 && stride3 && padding3 && out_shape3 && batch_size > 0,
+             "lk_strided_candidates: bad arguments");
+  StridedSpec sp;
+  for (int a = 0; a < 3; ++a) {
+    LK_REQUIRE(kernel3[a] > 0 && stride3[a] > 0 && padding3[a] >= 0 && out_shape3[a] > 0,
+               "lk_strided_candidates: kernel / stride / shape must be positive");
+    sp.k[a] = kernel3[a]; sp.s[a] = stride3[a]; sp.p[a] = padding3[a]; sp.out[a] = out_shape3[a];
+    sp.cap[a] = (kernel3[a] + stride3[a] - 1) / stride3[a];
+  }
+  if (n == 0) return LK_OK;
+  LK_REQUIRE(d_indices && d_cand && d_any_invalid && (uintptr_t)d_indices % 16 == 0 && (uintptr_t)d_cand % 16 == 0,
+             "lk_strided_candidates: null or misaligned pointer");
+  cudaStream_t st = (cudaStream_t)s;
+  LK_CUDA(cudaMemsetAsync(d_any_invalid, 0, sizeof(int32_t), st));
+  lk_count_launch();
+  const int cap = sp.cap[0] * sp.cap[1] * sp.cap[2];
+  strided_candidates_kernel<<<lk_grid(n * cap, 256, 8), 256, 0, st>>>((const int4*)d_indices, n, sp, batch_size,
+                                                                     (int4*)d_cand, d_any_invalid);
+  LK_LAUNCHED();
+  return LK_OK;
+}

@@ -151,21 +151,27 @@ class SparseConv3d(_SparseConvBase):
         ks, st, pd = self.kernel_size, self.stride, self.padding
         in_shape = list(x.spatial_shape)
         out_shape = [(in_shape[a] + 2 * pd[a] - ks[a]) // st[a] + 1 for a in range(3)]
-        idx = x.indices.int()
-        # candidate outputs: o = (i + p - kappa) / s where divisible and in range   (axes z,y,x)
-        kz, ky, kx = ks
-        kap = torch.tensor([[z, y, x_] for z in range(kz) for y in range(ky) for x_ in range(kx)],
-                           dtype=torch.int32, device=dev)                       # [K,3] (z,y,x)
-        s_t = torch.tensor(st, dtype=torch.int32, device=dev)
-        p_t = torch.tensor(pd, dtype=torch.int32, device=dev)
-        hi_t = torch.tensor(out_shape, dtype=torch.int32, device=dev)
-        num = idx[:, None, 1:] + p_t - kap[None]                                 # [N,K,3]
-        o = torch.div(num, s_t, rounding_mode='floor')
-        ok = ((num - o * s_t) == 0) & (o >= 0) & (o < hi_t)
-        ok = ok.all(dim=2)
-        cand = torch.cat([idx[:, None, :1].expand(-1, kap.shape[0], -1), o], dim=2)[ok]  # (b,z,y,x)
-        cand_xyzb = cand[:, [3, 2, 1, 0]].contiguous()
-        uniq, _, _ = _index.unique_coords(cand_xyzb, (1, 1, 1), (3, 2, 1, 0))    # sorted (b,z,y,x)
+        idx = x.indices.int().contiguous()
+        # candidate outputs o = (i + p - kappa) / s where divisible and in range: at most prod ceil(k/s)
+        # per input site, written by one kernel (lk_strided_candidates), sorted + uniqued on the device;
+        # the only host read-back is the (count, sentinel flag) pair that sizes the output
+        import ctypes as C
+        n = idx.shape[0]
+        bs = int(x.batch_size)
+        cap = 1
+        for a in range(3):
+            cap *= (ks[a] + st[a] - 1) // st[a]
+        cand = torch.empty(n * cap, 4, dtype=torch.int32, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        i3 = C.c_int32 * 3
+        _capi.check(_capi.lib().lk_strided_candidates(_capi.ptr(idx), n, i3(*ks), i3(*st), i3(*pd), i3(*out_shape), bs,
+                                                      _capi.ptr(cand), _capi.ptr(flag), _capi.stream()),
+                    'lk_strided_candidates')
+        spec, bits = _index.make_keyspec(((0, 0, 0, 0), (out_shape[2] - 1, out_shape[1] - 1, out_shape[0] - 1, bs)),
+                                         (1, 1, 1), (3, 2, 1, 0))
+        su = _index.sort_unique(_index.pack_keys(cand, spec), bits)
+        m, any_invalid = torch.cat([su.num, flag]).tolist()
+        uniq = _index.unpack_keys(su.unique, m - (1 if any_invalid else 0), spec)         # (x,y,z,b), sorted (b,z,y,x)
         out_indices = uniq[:, [3, 2, 1, 0]].contiguous()
         # kernel map: input site feeding output o through tap kappa is  o*s - p + kappa
         q = uniq.clone()

@@ -89,6 +89,12 @@ def spconv2ts(sct):
     save = {k: getattr(sct, k, None) for k in ('batch_size', 'benchmark', 'benchmark_record', 'grid',
                                                'indice_dict', 'spatial_shape', 'voxel_num')}
     save['cls'] = type(sct)
+    shape, bs = getattr(sct, 'spatial_shape', None), getattr(sct, 'batch_size', None)
+    if shape is not None and bs and coords.is_cuda:
+        # indices lie inside the declared grid: bounds from the shape, no min / max read-back per block
+        from link_b200.nn.functional import _index
+        _index.set_coord_bounds(st.kmaps, (0, 0, 0, 0),
+                                (int(shape[2]) - 1, int(shape[1]) - 1, int(shape[0]) - 1, int(bs) - 1))
     return st, save
 
 
