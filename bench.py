@@ -697,6 +697,11 @@ def main_ours(args):
         # bookkeeping below, done on CPU tensors over gloo, so no NCCL communicator is ever created
         dist.init_process_group('cpu:gloo,cuda:nccl')
     _capi.lib()
+    # pinned staging buffers on the GPU's own NUMA node: bind before anything is pinned (sharding.py)
+    from link_b200.sharding import bind_host_to_gpu
+    aff0 = os.sched_getaffinity(0)
+    affinity = bind_host_to_gpu(local)
+    print(f'[bench rank {rank}] host affinity: {affinity}', file=sys.stderr, flush=True)
 
     if world > 1:
         print(f'[bench rank {rank}] torch.distributed: cuda backend nccl (NCCL {".".join(map(str, torch.cuda.nccl.version()))}), '
@@ -802,6 +807,7 @@ def main_ours(args):
                        'max over ranks',
                 'single_step_latency_ms': m['e2e_latency_ms'] / steps},
         'gpu_launches': m['launches'],
+        'host_affinity': affinity,
         'host_enqueue_ms_per_step': m['host_enqueue_ms'],
         'l2_flush_memsets_per_step': m.get('n_flush'),
         'e2e_host_enqueue_ms_per_step': (m.get('e2e_ring') or {}).get('host_enqueue_ms_per_step'),
@@ -821,6 +827,7 @@ def main_ours(args):
     if m.get('ref_gpu'):
         line['reference_gpu'] = m['ref_gpu']
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, aff0)        # the CPU leg gets every core the process started with
         n_s = args.voxels if args.workload == 'block' else min(args.voxels, 30_000)
         v, dt, n, cores = run_cpu(args, n_s, 2, 1)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -40,6 +40,10 @@ const char* lk_last_error(void);
 int lk_version(void);
 /* Number of kernel launches (and memsets) issued through this library by this process. */
 int64_t lk_launch_count(void);
+/* PCI address "dddd:bb:dd.f" of CUDA device `device` (cudaDeviceGetPCIBusId) -- the name of its sysfs
+ * node; the host side pins its staging buffers on that device's NUMA node (link_b200/sharding.py:
+ * bind_host_to_gpu).  No counterpart in the reference (its loaders leave placement to the OS). */
+int lk_device_pci_bus_id(int device, char* buf, int len);
 
 /* ------------------------------------------------------------------------------------
  * Hashing -- replaces hash_cuda / kernel_hash_cuda (backend/hash/hash_cuda.cu:10-84).

@@ -56,6 +56,7 @@ PROTOTYPES = {
     'lk_last_error': (C.c_char_p, []),
     'lk_version': (i32, []),
     'lk_launch_count': (i64, []),
+    'lk_device_pci_bus_id': (i32, [i32, C.c_char_p, i32]),
     'lk_hash': (i32, [vp, i64, vp, vp]),
     'lk_kernel_hash': (i32, [vp, i64, vp, i32, vp, vp]),
     'lk_table_capacity': (i64, [i64]),

@@ -19,6 +19,17 @@ void lk_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed)
 extern "C" const char* lk_last_error(void) { return g_err; }
 extern "C" int lk_version(void) { return 100; }
 extern "C" int64_t lk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+// "domain:bus:device.function" of a CUDA device (the sysfs name under /sys/bus/pci/devices): the host
+// side uses it to place pinned staging buffers on the NUMA node the GPU hangs off (sharding.py).
+extern "C" int lk_device_pci_bus_id(int device, char* buf, int len) {
+  if (!buf || len < 16) return LK_EINVAL;
+  cudaError_t e = cudaDeviceGetPCIBusId(buf, len, device);
+  if (e != cudaSuccess) {
+    lk_set_error("cudaDeviceGetPCIBusId(%d): %s", device, cudaGetErrorString(e));
+    return LK_ECUDA;
+  }
+  return LK_OK;
+}
 
 // programmatic dependent launch on/off (LINKB200_PDL=0 restores ordinary launches; common.cuh)
 bool lk_pdl_enabled() {

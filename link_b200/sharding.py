@@ -9,7 +9,7 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput', 'wrap_ddp']
+__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput', 'wrap_ddp', 'bind_host_to_gpu', 'parse_cpulist']
 
 
 def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
@@ -34,6 +34,52 @@ def reduce_throughput(local_ms: float, local_units: float, device=None) -> Tuple
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (the sysfs cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus: List[int] = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int, sysfs: str = '/sys') -> dict:
+    """One process per GPU: pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE
+    the pinned staging buffers are allocated -- `cudaHostAlloc` places pages by the calling thread's
+    policy (local node), so the per-step host->device copy (32 MB per scan, the e2e bound) then
+    leaves memory that is one PCIe root away instead of crossing the socket interconnect, and eight
+    ranks no longer draw from one node's memory controllers.  The device's sysfs node
+    (`/sys/bus/pci/devices/<id>/local_cpulist`) names the CPUs; they are intersected with the
+    affinity the process already has (container cpusets).  Returns what was done; never raises for a
+    missing sysfs entry (single-node hosts report numa_node = -1: nothing to do)."""
+    import os
+    info = {'device': device_index, 'bound': False}
+    try:
+        import ctypes as C
+        from link_b200 import _capi
+        buf = C.create_string_buffer(32)
+        _capi.check(_capi.lib().lk_device_pci_bus_id(device_index, buf, 32), 'lk_device_pci_bus_id')
+        bus = buf.value.decode().lower()
+        info['pci'] = bus
+        base = os.path.join(sysfs, 'bus', 'pci', 'devices', bus)
+        with open(os.path.join(base, 'numa_node')) as f:
+            info['numa_node'] = int(f.read().strip())
+        with open(os.path.join(base, 'local_cpulist')) as f:
+            local = set(parse_cpulist(f.read()))
+        have = os.sched_getaffinity(0)
+        want = sorted(local & have)
+        info['local_cpus'], info['allowed_cpus'] = len(local), len(have)
+        if info['numa_node'] >= 0 and want and len(want) < len(have):
+            os.sched_setaffinity(0, want)
+            info['bound'] = True
+            info['cpus'] = len(want)
+    except (OSError, ValueError, RuntimeError) as e:
+        info['skipped'] = f'{type(e).__name__}: {e}'
+    return info
 
 
 def wrap_ddp(model: torch.nn.Module, device_index=None, unused_prefixes: Sequence[str] = ('up1', 'up2', 'up3', 'up4'),

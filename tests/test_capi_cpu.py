@@ -134,3 +134,16 @@ def test_host_coord_bounds(n):
         assert list(lo) == c.min(0).values.tolist() and list(hi) == c.max(0).values.tolist()
     else:
         assert list(lo) == [0] * 4 and list(hi) == [0] * 4
+
+
+def test_bind_host_to_gpu_is_safe_without_a_device():
+    """sharding.bind_host_to_gpu: cpulist parsing, and no exception / no affinity change when the
+    device (or its sysfs node) is not there."""
+    import os
+    from link_b200.sharding import bind_host_to_gpu, parse_cpulist
+    assert parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist('5') == [5] and parse_cpulist('') == []
+    before = os.sched_getaffinity(0)
+    info = bind_host_to_gpu(0, sysfs='/nonexistent')
+    assert info['bound'] is False
+    assert os.sched_getaffinity(0) == before
