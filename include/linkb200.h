@@ -301,10 +301,66 @@ typedef struct {
                                     host or device synchronisation) before the first feature kernel */
 } lk_elk_block_args_t;
 /* sizeof of the structs above as compiled (0: lk_keyspec_t, 1: lk_kernelgen_t,
- * 2: lk_elk_block_args_t): lets an FFI binding verify its struct layouts at load time. */
+ * 2: lk_elk_block_args_t, 3: lk_conv_layer_t, 4: lk_enc_level_t, 5: lk_elk_encoder_args_t): lets an FFI
+ * binding verify its struct layouts at load time. */
 int lk_abi_sizeof(int which);
 int64_t lk_elk_block_ws_bytes(int64_t n, int c, int op, int r3, int kvol, int need_kmap);
 int lk_elk_block_fwd(const lk_elk_block_args_t* args, lk_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Native executor for the inference forward of the encoder backbone (ELKEncoder.forward without the
+ * classifier head, linkencoder.py:339-375): stem, four strided levels of  down conv -> (conv stage ||
+ * LinK block) -> merge, every Conv3d + eval-mode BatchNorm [+ shortcut] [+ ReLU] group as one tensor-core
+ * conv launch with a fused epilogue, all kernel maps / hash tables / tile plans built on a library-
+ * owned index stream ahead of the feature kernels, the LinK block of a level on a third stream next
+ * to the level's conv stage.  One call per scan; the only synchronisations are the four 4-byte
+ * read-backs of the strided levels' sizes.  Level outputs (d_out0, level[l].d_out / d_coords) and the
+ * workspace are caller-owned and sized for n0 rows (a strided level never outgrows its input).
+ * ---------------------------------------------------------------------------------- */
+#define LK_ENC_MAX_LEVELS 4
+typedef struct {
+  const float* d_wimg;     /* packed tensor-core image of the kernel (lk_conv_tc_pack_weights[_ex]) */
+  const float* d_scale;    /* folded eval-mode BatchNorm, [c_out] each, or NULL */
+  const float* d_shift;
+  int32_t c_in, c_out;     /* as packed: 32 / 64 / 128 (narrower layers zero padded by the caller) */
+  int32_t relu;
+  int32_t reserved;
+} lk_conv_layer_t;
+typedef struct {
+  lk_conv_layer_t down;        /* BasicConvolutionBlock(ks = 2, stride = 2)            linkencoder.py:228 */
+  lk_conv_layer_t stage[4];    /* two ResidualBlocks: conv a, conv b (+ identity shortcut) each  :231 */
+  lk_conv_layer_t tail;        /* stageN_tail: Conv3d + BatchNorm                                :216 */
+  lk_conv_layer_t elk_tail;    /* elkN_tail, merged with the conv branch: relu(x_conv + .)       :350 */
+  lk_elk_block_args_t elk;     /* the level's LinK block: parameter fields, keyspec, key_bits, r3, gen,
+                                  d_block_offsets filled by the caller; n / buffers / map by the executor */
+  lk_keyspec_t down_spec;      /* key layout of the level's output sites: floor(c / 2^l) 2^l, order (b,x,y,z) */
+  int32_t down_bits;
+  int32_t reserved;
+  const int32_t* d_off2;       /* [8,3]  offsets of the 2^3 strided conv at the INPUT level's stride */
+  const int32_t* d_off3;       /* [27,3] offsets of the 3^3 convs at THIS level's stride */
+  float* d_out;                /* [n0, c] level output x_l (first n_out[l] rows valid) */
+  int32_t* d_coords;           /* [n0, 4] level coordinates (first n_out[l] rows valid) */
+} lk_enc_level_t;
+typedef struct {
+  int64_t n0;
+  const int32_t* d_coords0;    /* [n0,4] */
+  const float* d_feats0;       /* [n0, stem[0].c_in] input features, channel-padded by the caller */
+  void* feats_ready;           /* cudaEvent_t or NULL (see lk_elk_block_args_t) */
+  int32_t levels;              /* strided levels, <= LK_ENC_MAX_LEVELS */
+  int32_t c_max;               /* widest feature row of any layer */
+  int32_t conv_precision;      /* LK_PREC_FP32 / LK_PREC_TF32 */
+  int32_t single_stream;       /* 1: everything on the caller's stream */
+  int32_t overlap_branches;    /* 1: LinK block of a level on its own stream next to the conv stage */
+  int32_t reserved;
+  lk_conv_layer_t stem[2];
+  const int32_t* d_off3_0;     /* [27,3] offsets at stride 1 */
+  float* d_out0;               /* [n0, stem[1].c_out] */
+  lk_enc_level_t level[LK_ENC_MAX_LEVELS];
+  void* d_ws; int64_t ws_bytes;
+  int64_t n_out[LK_ENC_MAX_LEVELS + 1];   /* written (host): active voxels per level */
+} lk_elk_encoder_args_t;
+int64_t lk_elk_encoder_ws_bytes(int64_t n0, int levels, int c_max, int elk_op, int r3);
+int lk_elk_encoder_fwd(lk_elk_encoder_args_t* args, lk_stream_t s);
 
 /* Fused bias-free Linear + LayerNorm: out = LN(x @ W^T; gamma, beta, eps); x, out [n, c],
  * W [c, c] (nn.Linear layout).  ELKBlock.pre_mix (linkencoder.py:112-115).  c in {16,32,64,128}. */

@@ -51,6 +51,32 @@ class ElkBlockArgs(C.Structure):
                 ('reserved1', C.c_int32), ('feats_ready', C.c_void_p)]
 
 
+ENC_MAX_LEVELS = 4
+
+
+class ConvLayer(C.Structure):
+    """lk_conv_layer_t"""
+    _fields_ = [('d_wimg', C.c_void_p), ('d_scale', C.c_void_p), ('d_shift', C.c_void_p),
+                ('c_in', C.c_int32), ('c_out', C.c_int32), ('relu', C.c_int32), ('reserved', C.c_int32)]
+
+
+class EncLevel(C.Structure):
+    """lk_enc_level_t"""
+    _fields_ = [('down', ConvLayer), ('stage', ConvLayer * 4), ('tail', ConvLayer), ('elk_tail', ConvLayer),
+                ('elk', ElkBlockArgs), ('down_spec', KeySpec), ('down_bits', C.c_int32), ('reserved', C.c_int32),
+                ('d_off2', C.c_void_p), ('d_off3', C.c_void_p), ('d_out', C.c_void_p), ('d_coords', C.c_void_p)]
+
+
+class ElkEncoderArgs(C.Structure):
+    """lk_elk_encoder_args_t"""
+    _fields_ = [('n0', C.c_int64), ('d_coords0', C.c_void_p), ('d_feats0', C.c_void_p), ('feats_ready', C.c_void_p),
+                ('levels', C.c_int32), ('c_max', C.c_int32), ('conv_precision', C.c_int32),
+                ('single_stream', C.c_int32), ('overlap_branches', C.c_int32), ('reserved', C.c_int32),
+                ('stem', ConvLayer * 2), ('d_off3_0', C.c_void_p), ('d_out0', C.c_void_p),
+                ('level', EncLevel * ENC_MAX_LEVELS), ('d_ws', C.c_void_p), ('ws_bytes', C.c_int64),
+                ('n_out', C.c_int64 * (ENC_MAX_LEVELS + 1))]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/linkb200.h
 PROTOTYPES = {
     'lk_last_error': (C.c_char_p, []),
@@ -94,6 +120,8 @@ PROTOTYPES = {
     'lk_abi_sizeof': (i32, [i32]),
     'lk_elk_block_ws_bytes': (i64, [i64, i32, i32, i32, i32, i32]),
     'lk_elk_block_fwd': (i32, [C.POINTER(ElkBlockArgs), vp]),
+    'lk_elk_encoder_ws_bytes': (i64, [i64, i32, i32, i32, i32]),
+    'lk_elk_encoder_fwd': (i32, [C.POINTER(ElkEncoderArgs), vp]),
     'lk_linear_ln_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_linear_ln_tc_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),
@@ -147,7 +175,7 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        for which, struct in enumerate((KeySpec, KernelGen, ElkBlockArgs)):
+        for which, struct in enumerate((KeySpec, KernelGen, ElkBlockArgs, ConvLayer, EncLevel, ElkEncoderArgs)):
             if _lib.lk_abi_sizeof(which) != C.sizeof(struct):
                 raise RuntimeError(f'ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, '
                                    f'{_lib.lk_abi_sizeof(which)} in liblinkb200.so -- rebuild the library')

@@ -195,6 +195,9 @@ extern "C" int lk_abi_sizeof(int which) {
     case 0: return (int)sizeof(lk_keyspec_t);
     case 1: return (int)sizeof(lk_kernelgen_t);
     case 2: return (int)sizeof(lk_elk_block_args_t);
+    case 3: return (int)sizeof(lk_conv_layer_t);
+    case 4: return (int)sizeof(lk_enc_level_t);
+    case 5: return (int)sizeof(lk_elk_encoder_args_t);
     default: return -1;
   }
 }

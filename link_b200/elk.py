@@ -352,6 +352,39 @@ def _pre_mix_fused(pre_mix, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _native_template(op, c, pre_mix, conv, pos_weight, alpha, coord_scale, norm, norm_local, dev):
+    """(version, ElkBlockArgs with every parameter-only field filled, tensors kept alive): the 12
+    parameter pointers, the kernel-generator struct and the packed conv image are filled once per
+    parameter version (cached on the conv module) and copied per call."""
+    params = (pre_mix[0].weight, pre_mix[1].weight, pre_mix[1].bias, conv.kernel, pos_weight, alpha,
+              norm.weight, norm.bias, norm_local.weight, norm_local.bias)
+    ver = tuple((p._version, p.data_ptr()) if p is not None else None for p in params) + (
+        op, c, float(coord_scale), USE_TENSOR_CORES, ACCURATE_TRIG, _conv_mod.precision_code(), SINGLE_STREAM, str(dev))
+    hit = conv.__dict__.get('_lk_native_args')
+    if hit is None or hit[0] != ver:
+        from link_b200.nn.functional.conv import _tc_image
+        t = _capi.ElkBlockArgs()
+        lin, ln = pre_mix[0], pre_mix[1]
+        keep = [lin.weight.detach().contiguous(), ln.weight.detach(), ln.bias.detach(), conv.kernel.detach().contiguous(),
+                pos_weight.detach().contiguous().float(),
+                alpha.detach().reshape(-1).contiguous().float() if alpha is not None else None,
+                norm.weight.detach(), norm.bias.detach(), norm_local.weight.detach(), norm_local.bias.detach()]
+        t.d_premix_w, t.d_premix_g, t.d_premix_b = _capi.ptr(keep[0]), _capi.ptr(keep[1]), _capi.ptr(keep[2])
+        t.premix_eps = float(ln.eps)
+        t.kvol = conv.kernel_volume
+        t.d_conv_w = _capi.ptr(keep[3])
+        wt = _tc_image(conv.kernel) if (USE_TENSOR_CORES and c in (32, 64, 128)) else None   # cached on the Parameter
+        keep.append(wt)
+        t.d_conv_wt = _capi.ptr(wt)
+        t.gen = _kernel_gen(op, c, keep[4], keep[5], coord_scale)
+        t.d_g1, t.d_b1, t.d_g2, t.d_b2 = (_capi.ptr(x) for x in keep[6:10])
+        t.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
+        t.conv_precision = _conv_mod.precision_code()
+        t.single_stream = 1 if SINGLE_STREAM else 0
+        hit = conv.__dict__['_lk_native_args'] = (ver, t, keep)
+    return hit
+
+
 def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, alpha, coord_scale, norm,
                     norm_local) -> torch.Tensor:
     """Whole block through lk_elk_block_fwd: one FFI call, one workspace allocation."""
@@ -373,33 +406,7 @@ def _forward_native(st: SparseTensor, s, r, *, op, pre_mix, conv, pos_weight, al
     conv_off = get_kernel_offsets(conv.kernel_size, stride=st.stride, device=dev)
     blk_off = get_kernel_offsets(r, 1, 1, device=dev)
     r3 = blk_off.shape[0]
-    # everything that depends only on the module's parameters (12 pointers, the kernel-generator struct,
-    # the packed conv image) is filled once per parameter version and copied per call
-    params = (lin_w := pre_mix[0].weight, pre_mix[1].weight, pre_mix[1].bias, conv.kernel, pos_weight, alpha,
-              norm.weight, norm.bias, norm_local.weight, norm_local.bias)
-    ver = tuple((p._version, p.data_ptr()) if p is not None else None for p in params) + (
-        op, c, float(coord_scale), USE_TENSOR_CORES, ACCURATE_TRIG, _conv_mod.precision_code(), SINGLE_STREAM, str(dev))
-    hit = conv.__dict__.get('_lk_native_args')
-    if hit is None or hit[0] != ver:
-        t = _capi.ElkBlockArgs()
-        lin, ln = pre_mix[0], pre_mix[1]
-        keep = [lin.weight.detach().contiguous(), ln.weight.detach(), ln.bias.detach(), conv.kernel.detach().contiguous(),
-                pos_weight.detach().contiguous().float(),
-                alpha.detach().reshape(-1).contiguous().float() if alpha is not None else None,
-                norm.weight.detach(), norm.bias.detach(), norm_local.weight.detach(), norm_local.bias.detach()]
-        t.d_premix_w, t.d_premix_g, t.d_premix_b = _capi.ptr(keep[0]), _capi.ptr(keep[1]), _capi.ptr(keep[2])
-        t.premix_eps = float(ln.eps)
-        t.kvol = conv.kernel_volume
-        t.d_conv_w = _capi.ptr(keep[3])
-        wt = _tc_image(conv.kernel) if (USE_TENSOR_CORES and c in (32, 64, 128)) else None   # cached on the Parameter
-        keep.append(wt)
-        t.d_conv_wt = _capi.ptr(wt)
-        t.gen = _kernel_gen(op, c, keep[4], keep[5], coord_scale)
-        t.d_g1, t.d_b1, t.d_g2, t.d_b2 = (_capi.ptr(x) for x in keep[6:10])
-        t.use_tensor_cores = 1 if USE_TENSOR_CORES else 0
-        t.conv_precision = _conv_mod.precision_code()
-        t.single_stream = 1 if SINGLE_STREAM else 0
-        hit = conv.__dict__['_lk_native_args'] = (ver, t, keep)
+    hit = _native_template(op, c, pre_mix, conv, pos_weight, alpha, coord_scale, norm, norm_local, dev)
     a = _capi.ElkBlockArgs.from_buffer_copy(hit[1])
     a.n = n
     a.d_coords, a.d_feats = _capi.ptr(coords, torch.int32), _capi.ptr(x, torch.float32)

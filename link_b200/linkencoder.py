@@ -4,6 +4,8 @@ Same constructor kwargs (`num_classes, cr, baseop, r, s, groups, run_up`), sub-m
 parameter shapes as the reference (segmentation/core/models/semantic_kitti/linkencoder.py:188-381)
 so that `seg/core/builder.make_model` can instantiate it and published state dicts load; every
 sparse op underneath runs on liblinkb200."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -15,6 +17,25 @@ from link_b200 import _capi
 from link_b200.elk import ELKBlock, upsample_index, upsample_voxel
 from link_b200.tensor import SparseTensor
 from link_b200.utils import make_ntuple
+
+# inference: run the LinK block of a level on a side stream next to the level's conv stage
+# (LINKB200_BRANCH_OVERLAP=0: one stream, the reference's order).  Inside the native executor the fork /
+# join are two event calls from C; the same schedule driven from python (LINKB200_PY_BRANCH_OVERLAP=1,
+# per-layer path) measured SLOWER (2.8 vs 2.5 ms per scan): the coarse levels are paced by the
+# interpreter, and the stream switches add host time exactly there.
+BRANCH_OVERLAP = os.environ.get('LINKB200_BRANCH_OVERLAP', '1') != '0'
+PY_BRANCH_OVERLAP = os.environ.get('LINKB200_PY_BRANCH_OVERLAP', '0') == '1'
+_BRANCH_STREAMS = {}
+# inference: the whole backbone behind one library call (lk_elk_encoder_fwd); '0': one call per layer
+NATIVE_ENCODER = os.environ.get('LINKB200_NATIVE_ENCODER', '1') != '0'
+
+
+def _branch_stream(device) -> 'torch.cuda.Stream':
+    st = _BRANCH_STREAMS.get(device)
+    if st is None:
+        st = _BRANCH_STREAMS[device] = torch.cuda.Stream(device)
+    return st
+
 
 __all__ = ['ELKEncoder', 'LinKEncoder', 'BasicConvolutionBlock', 'BasicDeconvolutionBlock',
            'ResidualBlock']
@@ -192,20 +213,50 @@ class _ELKBackbone(nn.Module):
 
     def _forward_levels_fused(self, x: SparseTensor):
         """forward_levels for inference: every Conv3d -> BatchNorm(eval) [-> + shortcut] [-> ReLU]
-        group is one fused sparse-conv launch, every LinK block one native-executor call."""
+        group is one fused sparse-conv launch, every LinK block one native-executor call.
+
+        The two branches of a level -- the conv stage and the LinK block, both functions of x_in
+        (linkencoder.py:346-349) -- are enqueued on two streams: the stage's first conv builds the
+        level's 3^3 kernel map and tile plan on the main stream, then the block runs on a side stream
+        while the main stream continues with the rest of the stage; the tail conv that merges them
+        waits for the block.  On the coarse levels (<= 28k voxels) neither branch fills the 148 SMs
+        (a sparse conv there is one 128-row tile per CTA on 29-84 CTAs, ~26 us of latency), so the
+        branches overlap instead of queueing.  Off by default on this per-layer path (see
+        PY_BRANCH_OVERLAP); the native executor does it from C."""
         s, r = self.kwargs.get('s'), self.kwargs.get('r')
         cba = F.conv_bn_act
         (c0, b0, c1, b1), lv_refs = self._fused_refs()
         x0 = cba(cba(x, c0, b0, True), c1, b1, True)
         feats = [x0]
         cur = x0
+        overlap = PY_BRANCH_OVERLAP
+        if overlap:
+            main = torch.cuda.current_stream()
+            side = _branch_stream(x0.feats.device)
         for (dc, db), stage, (tc_, tb), elk_mod, (ec, eb) in lv_refs:
             x_in = cba(cur, dc, db, True)
             y = x_in
-            for ca, ba, cb, bb in stage:
-                y = cba(cba(y, ca, ba, True), cb, bb, True, y.feats)
+            join = None
+            for i, (ca, ba, cb, bb) in enumerate(stage):
+                y1 = cba(y, ca, ba, True)
+                if i == 0 and overlap:
+                    # the level's kernel map + plan are now enqueued (main); the block reads them and x_in
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    x_br = SparseTensor(x_in.feats, x_in.coords, x_in.stride)
+                    x_br.cmaps, x_br.kmaps = x_in.cmaps, x_in.kmaps
+                    with torch.cuda.stream(side):
+                        side.wait_event(fork)
+                        x_lk = elk_mod.forward(x_br, x_in.stride[0] * s, r)
+                        join = torch.cuda.Event()
+                        join.record(side)
+                    x_lk.feats.record_stream(main)      # allocated on the side stream, consumed on main
+                y = cba(y1, cb, bb, True, y.feats)
             x_conv = cba(y, tc_, tb, False)
-            x_lk = elk_mod.forward(x_in, x_in.stride[0] * s, r)
+            if join is not None:
+                main.wait_event(join)
+            else:
+                x_lk = elk_mod.forward(x_in, x_in.stride[0] * s, r)
             cur = cba(x_lk, ec, eb, True, x_conv.feats)
             feats.append(cur)
         return feats
@@ -252,10 +303,150 @@ class ELKEncoder(_ELKBackbone):
         self.weight_initialization()
 
     def forward(self, x: SparseTensor) -> torch.Tensor:
+        if self._native_ok(x):
+            x0, x1, x2, x3, x4 = self._forward_levels_native(x)
+            return self._classify_pushdown([x4, x3, x2, x1, x0])
         x0, x1, x2, x3, x4 = self.forward_levels(x)
         if not torch.is_grad_enabled() and x0.F.dtype == torch.float32 and x0.F.is_cuda:
             return self._classify_pushdown([x4, x3, x2, x1, x0])
         return self._classify_levels([x4, x3, x2, x1, x0])
+
+    # ---- native executor (lk_elk_encoder_fwd): the whole backbone behind one library call ----
+
+    def _native_ok(self, x: SparseTensor) -> bool:
+        """Inference on fp32 CUDA rows, BatchNorm in eval mode, every layer at a tensor-core width
+        (32 / 64 / 128 channels; the stem's input is zero padded), identity shortcuts, a LinK block the
+        block executor serves, no per-kernel timers."""
+        import link_b200.elk as elk_mod
+        from link_b200.nn.functional import conv as cv
+        f = x._feats                      # (not x.feats: that would join a pending upload here)
+        if not (NATIVE_ENCODER and not torch.is_grad_enabled() and not self.training and f.is_cuda
+                and f.dtype == torch.float32 and _capi.TIMERS is None and elk_mod.NATIVE_EXECUTOR
+                and cv.USE_TENSOR_CORES and cv.USE_PLAN and f.shape[0] > 0
+                and tuple(x.stride) == (1, 1, 1) and f.shape[1] == self.stem[0].in_channels):
+            return False
+        ok = self.__dict__.get('_lk_native_static')
+        if ok is None:
+            widths = set(self.cs[:5])
+            elks = [getattr(self, f'elk{lv}') for lv in (1, 2, 3, 4)]
+            ok = (all(w in (32, 64, 128) for w in widths) and self.stem[0].in_channels <= 32
+                  and all(len(rb.downsample) == 0 for lv in (1, 2, 3, 4) for rb in getattr(self, f'stage{lv}'))
+                  and all(e.baseop in ('cos', 'sin') or e.groups == 1 for e in elks)
+                  and all(m.bias is None for m in self.modules() if isinstance(m, spnn.Conv3d))
+                  and self.kwargs.get('r') in (2, 3))
+            self.__dict__['_lk_native_static'] = ok
+        return ok and all(not m.training and m.track_running_stats and m.affine
+                          for m in self.modules() if isinstance(m, nn.BatchNorm1d))
+
+    def _native_template(self, dev):
+        """lk_elk_encoder_args_t with every parameter-only field filled (packed weight images, folded
+        BatchNorm affines, the four block templates), cached until a parameter changes."""
+        import link_b200.elk as elk_mod
+        from link_b200.nn.functional import conv as cv
+        (c0, b0, c1, b1), lv_refs = self._fused_refs()
+        convs = [(c0, b0), (c1, b1)]
+        for (dc, db), stage, (tc_, tb), elk, (ec, eb) in lv_refs:
+            convs += [(dc, db)] + [p for ca, ba, cb, bb in stage for p in ((ca, ba), (cb, bb))] + [(tc_, tb), (ec, eb)]
+        ver = tuple((c.kernel._version, c.kernel.data_ptr(), b.weight._version, b.bias._version,
+                     b.running_mean._version, b.running_var._version, b.running_mean.data_ptr()) for c, b in convs)
+        ver += tuple(p._version for _, _, _, elk, _ in lv_refs for p in elk.parameters())
+        ver += (cv.precision_code(), elk_mod.SINGLE_STREAM, elk_mod.ACCURATE_TRIG, str(dev))
+        hit = self.__dict__.get('_lk_enc_native')
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        keep = []
+
+        def layer(dst, conv, bn, relu, pad_in=0):
+            img = cv._tc_image(conv.kernel, pad_in, 0)
+            scale, shift = cv._folded_bn(bn)
+            keep.extend((img, scale, shift))
+            dst.d_wimg, dst.d_scale, dst.d_shift = _capi.ptr(img), _capi.ptr(scale), _capi.ptr(shift)
+            dst.c_in, dst.c_out, dst.relu = max(pad_in, conv.kernel.shape[1]), conv.kernel.shape[2], 1 if relu else 0
+
+        a = _capi.ElkEncoderArgs()
+        a.levels = 4
+        a.c_max = max(self.cs[:5] + [32])
+        a.conv_precision = cv.precision_code()
+        a.single_stream = 1 if elk_mod.SINGLE_STREAM else 0
+        a.overlap_branches = 1 if BRANCH_OVERLAP else 0
+        layer(a.stem[0], c0, b0, True, pad_in=cv._pad_to_tc(c0.kernel.shape[1]))
+        layer(a.stem[1], c1, b1, True)
+        r = self.kwargs.get('r')
+        for i, ((dc, db), stage, (tc_, tb), elk, (ec, eb)) in enumerate(lv_refs):
+            L = a.level[i]
+            layer(L.down, dc, db, True)
+            for j, (ca, ba, cb, bb) in enumerate(stage):
+                layer(L.stage[2 * j], ca, ba, True)
+                layer(L.stage[2 * j + 1], cb, bb, True)
+            layer(L.tail, tc_, tb, False)
+            layer(L.elk_tail, ec, eb, True)
+            scale = float(2 ** (i + 1)) if (elk.baseop == 'cos_x' and elk.variant == 'encoder') else 1.0
+            t = elk_mod._native_template(elk.baseop, elk.inc, elk.pre_mix, elk.local_mix[0], elk.pos_weight[0].weight,
+                                         getattr(elk, 'alpha', None), scale, elk.norm, elk.norm_local, dev)
+            keep.append(t)
+            C.memmove(C.byref(L.elk), C.byref(t[1]), C.sizeof(_capi.ElkBlockArgs))
+            L.elk.r3 = r ** 3
+        self.__dict__['_lk_enc_native'] = (ver, a, keep)
+        return a, keep
+
+    def _forward_levels_native(self, x: SparseTensor):
+        """[x0 .. x4] through lk_elk_encoder_fwd: the level outputs and coordinates are caller-owned
+        buffers of n0 rows (a strided level never outgrows its input), sliced to the sizes the
+        executor reports."""
+        from link_b200.nn.functional import _index
+        from link_b200.nn.utils import get_kernel_offsets
+        L = _capi.lib()
+        feats, ready = x.take_feats_event()
+        _capi.check_device(feats)
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+        dev = feats.device
+        tmpl, keep = self._native_template(dev)
+        a = _capi.ElkEncoderArgs.from_buffer_copy(tmpl)
+        coords = x.coords.contiguous()
+        n0 = coords.shape[0]
+        ci = a.stem[0].c_in
+        feats = feats.contiguous()
+        if feats.shape[1] != ci:
+            feats = torch.nn.functional.pad(feats, (0, ci - feats.shape[1]))
+        x.cmaps.setdefault(x.stride, x.coords)
+        bounds = _index.coord_bounds(coords, x.kmaps)
+        s, r = self.kwargs.get('s'), self.kwargs.get('r')
+        blk_off = get_kernel_offsets(r, 1, 1, device=dev)
+        off3 = [get_kernel_offsets(3, stride=(2 ** l,) * 3, device=dev) for l in range(5)]
+        a.n0, a.d_coords0, a.d_feats0 = n0, _capi.ptr(coords, torch.int32), _capi.ptr(feats, torch.float32)
+        a.d_off3_0 = _capi.ptr(off3[0])
+        outs = [torch.empty(n0, self.cs[l], dtype=torch.float32, device=dev) for l in range(5)]
+        lv_coords = [coords] + [torch.empty(n0, 4, dtype=torch.int32, device=dev) for _ in range(4)]
+        a.d_out0 = _capi.ptr(outs[0])
+        keep_off = [blk_off, off3]
+        b = bounds
+        for l in range(1, 5):
+            Lv = a.level[l - 1]
+            ss = (2 ** l,) * 3
+            # sites of level l straight from the input coordinates: floor(c0 / 2^l) 2^l, order (b, x, y, z)
+            Lv.down_spec, Lv.down_bits = _index.make_keyspec(bounds, ss, (3, 0, 1, 2), ss)
+            off2 = get_kernel_offsets(2, stride=(2 ** (l - 1),) * 3, device=dev)
+            keep_off.append(off2)
+            Lv.d_off2, Lv.d_off3 = _capi.ptr(off2), _capi.ptr(off3[l])
+            Lv.d_out, Lv.d_coords = _capi.ptr(outs[l]), _capi.ptr(lv_coords[l])
+            st4 = ss + (1,)
+            b = (tuple((b[0][k] // st4[k]) * st4[k] for k in range(4)), tuple((b[1][k] // st4[k]) * st4[k] for k in range(4)))
+            se = 2 ** l * s
+            Lv.elk.keyspec, Lv.elk.key_bits = _index.make_keyspec(b, (se, se, se), (0, 1, 2, 3))
+            Lv.elk.d_block_offsets = _capi.ptr(blk_off)
+        ws_bytes = L.lk_elk_encoder_ws_bytes(n0, 4, a.c_max, a.level[0].elk.gen.op, r ** 3)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.d_ws, a.ws_bytes = _capi.ptr(ws), ws_bytes
+        _capi.check(L.lk_elk_encoder_fwd(C.byref(a), _capi.stream()), 'lk_elk_encoder_fwd')
+        levels = []
+        for l in range(5):
+            n_l = int(a.n_out[l])
+            t = SparseTensor(outs[l][:n_l], lv_coords[l] if l == 0 else lv_coords[l][:n_l], (2 ** l,) * 3)
+            t.cmaps, t.kmaps = x.cmaps, x.kmaps
+            t.cmaps.setdefault(t.stride, t.coords)
+            levels.append(t)
+        return levels
 
     def _classify_levels(self, levels) -> torch.Tensor:
         """Differentiable head (training).  Same push-down as the inference head: group l of the

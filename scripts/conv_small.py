@@ -1,4 +1,6 @@
-"""Tensor-core vs FFMA sparse conv at small sizes (encoder levels 2-4), C = 64, K = 27, map prebuilt."""
+"""Tensor-core vs FFMA sparse conv at small sizes (encoder levels 2-4), C = 64, K = 27, map prebuilt.
+`tc` / `ffma`: 20 python launches back to back (host-paced at the small sizes); `tc graph`: the same
+launch replayed from a CUDA graph (device time)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -27,4 +29,13 @@ for stride in (1, 2, 4, 8, 16):
             cv._conv_fwd(st.F, w, km.nbr, n, kmap=km if tc else None)
         e1.record(); torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / 20 * 1e3
-    print(f'N={n:7d}  tc {res["tc"]:7.1f} us   ffma {res["ffma"]:7.1f} us', flush=True)
+    cv.USE_TENSOR_CORES = True
+    gr, cap = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.graph(gr, stream=cap):
+        for _ in range(8):
+            cv._conv_fwd(st.F, w, km.nbr, n, kmap=km)
+    gr.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+    res['graph'] = e0.elapsed_time(e1) / 8 * 1e3
+    print(f'N={n:7d}  tc {res["tc"]:7.1f} us   tc graph {res["graph"]:7.1f} us   ffma {res["ffma"]:7.1f} us', flush=True)
