@@ -325,8 +325,8 @@ class ELKEncoder(_ELKBackbone):
                 and cv.USE_TENSOR_CORES and cv.USE_PLAN and f.shape[0] > 0
                 and tuple(x.stride) == (1, 1, 1) and f.shape[1] == self.stem[0].in_channels):
             return False
-        ok = self.__dict__.get('_lk_native_static')
-        if ok is None:
+        hit = self.__dict__.get('_lk_native_static')
+        if hit is None:
             widths = set(self.cs[:5])
             elks = [getattr(self, f'elk{lv}') for lv in (1, 2, 3, 4)]
             ok = (all(w in (32, 64, 128) for w in widths) and self.stem[0].in_channels <= 32
@@ -334,9 +334,13 @@ class ELKEncoder(_ELKBackbone):
                   and all(e.baseop in ('cos', 'sin') or e.groups == 1 for e in elks)
                   and all(m.bias is None for m in self.modules() if isinstance(m, spnn.Conv3d))
                   and self.kwargs.get('r') in (2, 3))
-            self.__dict__['_lk_native_static'] = ok
-        return ok and all(not m.training and m.track_running_stats and m.affine
-                          for m in self.modules() if isinstance(m, nn.BatchNorm1d))
+            # the BatchNorms on the executor's path (the decoder branches up1..up4 are never run)
+            (c0, b0, c1, b1), lv_refs = self._fused_refs()
+            bns = [b0, b1]
+            for (dc, db), stage, (tc_, tb), elk, (ec, eb) in lv_refs:
+                bns += [db, tb, eb] + [b for ca, ba, cb, bb in stage for b in (ba, bb)]
+            hit = self.__dict__['_lk_native_static'] = (ok, bns)
+        return hit[0] and all(not m.training and m.track_running_stats and m.affine for m in hit[1])
 
     def _native_template(self, dev):
         """lk_elk_encoder_args_t with every parameter-only field filled (packed weight images, folded
@@ -349,7 +353,10 @@ class ELKEncoder(_ELKBackbone):
             convs += [(dc, db)] + [p for ca, ba, cb, bb in stage for p in ((ca, ba), (cb, bb))] + [(tc_, tb), (ec, eb)]
         ver = tuple((c.kernel._version, c.kernel.data_ptr(), b.weight._version, b.bias._version,
                      b.running_mean._version, b.running_var._version, b.running_mean.data_ptr()) for c, b in convs)
-        ver += tuple(p._version for _, _, _, elk, _ in lv_refs for p in elk.parameters())
+        elk_params = self.__dict__.get('_lk_elk_params')
+        if elk_params is None:
+            elk_params = self.__dict__['_lk_elk_params'] = [p for _, _, _, elk, _ in lv_refs for p in elk.parameters()]
+        ver += tuple(p._version for p in elk_params)
         ver += (cv.precision_code(), elk_mod.SINGLE_STREAM, elk_mod.ACCURATE_TRIG, str(dev))
         hit = self.__dict__.get('_lk_enc_native')
         if hit is not None and hit[0] == ver:

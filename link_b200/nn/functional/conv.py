@@ -235,7 +235,8 @@ def invalidate_caches(module: torch.nn.Module) -> None:
     them by themselves; writes through `.data` (EMA `p.data.mul_()`, clamping) do NOT bump the version --
     call this after such an update."""
     for m in module.modules():
-        for key in ('_lk_fold', '_lk_native_args', '_lk_kio', '_lk_refs', '_lk_dil'):
+        for key in ('_lk_fold', '_lk_native_args', '_lk_kio', '_lk_refs', '_lk_dil', '_lk_enc_native', '_lk_native_static',
+                    '_lk_elk_params'):
             m.__dict__.pop(key, None)
     for p in module.parameters():
         p.__dict__.pop('_lk_img', None)

@@ -1,7 +1,8 @@
 """Small instances of every pipeline with hand-rolled synchronisation, for compute-sanitizer
 (scripts/sanitize.sh): the tcgen05 conv (mbarrier ring + TMEM A stages + bulk-copied weights), the
 tcgen05 weight gradient (MN-major staging, two barrier families), the tcgen05 Linear+LayerNorm,
-the ring pre-aggregation kernel and the two-stream native block executor, forward and backward."""
+the ring pre-aggregation kernel, the two-stream native block executor (forward and backward) and the
+native encoder executor."""
 import os
 import sys
 
@@ -38,4 +39,14 @@ for c, groups, s, r in [(64, 2, 7, 3), (32, 1, 3, 2)]:
     blk.train()(SparseTensor(fr, coords, 1), s, r).F.sum().backward()     # fused backward kernels
     torch.cuda.synchronize()
     print(f'block C={c} ({r}x{s})^3: ok', float(out.abs().sum()), float(fr.grad.abs().sum()), flush=True)
+# the native encoder executor: five streams, four sort chains, one workspace arena carved for n0 rows per level
+from link_b200.linkencoder import ELKEncoder
+enc = ELKEncoder(num_classes=19, cr=0.5, baseop='cos', r=3, s=7, groups=2).to(dev).eval()
+xs = torch.randn(len(coords), 4, device=dev)
+with torch.no_grad():
+    for _ in range(2):
+        logits = enc(SparseTensor(xs, coords, 1))
+torch.cuda.synchronize()
+assert '_lk_enc_native' in enc.__dict__
+print('native encoder: ok', float(logits.abs().sum()), flush=True)
 print('sanitize cases done')
