@@ -362,6 +362,31 @@ typedef struct {
 int64_t lk_elk_encoder_ws_bytes(int64_t n0, int levels, int c_max, int elk_op, int r3);
 int lk_elk_encoder_fwd(lk_elk_encoder_args_t* args, lk_stream_t s);
 
+/* ------------------------------------------------------------------------------------
+ * Training-mode BatchNorm over sparse feature rows, fused with the shortcut add and the ReLU that follow it:
+ *     y = relu?( (x - mean) invstd gamma + beta [+ residual] ),   x, y, residual [n, c] fp32, c % 4 == 0.
+ * Replaces spnn.BatchNorm (= nn.BatchNorm1d over .feats, torchsparse/nn/modules/norm.py:10-13) + spnn.ReLU /
+ * the ResidualBlock add (linkencoder.py:26-37, 64-91) and nn.BatchNorm1d + nn.ReLU on .features in the
+ * detection backbone (scn.py:64-107), with nn.BatchNorm1d's semantics: biased batch variance for the
+ * normalisation, running_var updated with the unbiased one, running = (1 - momentum) running + momentum
+ * batch, num_batches_tracked += 1 (pointers may be NULL: track_running_stats = False).  d_save_mean /
+ * d_save_invstd [c] are kept for the backward.  Backward: g = dy * (y > 0) when d_y (the saved OUTPUT of
+ * the forward, ReLU case) is given, else g = dy;  d_dgamma = sum g xhat, d_dbeta = sum g,
+ * d_dx = gamma invstd (g - dbeta / n - xhat dgamma / n),  d_dresidual = g (optional).
+ * d_ws: lk_bn_ws_bytes(c) bytes (per-channel double accumulators; zeroed by the call).
+ * ---------------------------------------------------------------------------------- */
+int lk_bn_supported(int c);
+int64_t lk_bn_ws_bytes(int c);
+int lk_bn_train_fwd(const float* d_x, const float* d_residual /*or NULL*/, int64_t n, int c,
+                    const float* d_gamma /*or NULL*/, const float* d_beta /*or NULL*/, float eps, float momentum,
+                    int relu, float* d_running_mean, float* d_running_var, int64_t* d_num_batches_tracked,
+                    float* d_save_mean, float* d_save_invstd, float* d_y, void* d_ws, int64_t ws_bytes,
+                    lk_stream_t s);
+int lk_bn_train_bwd(const float* d_dy, const float* d_x, const float* d_y /*or NULL*/, int64_t n, int c,
+                    const float* d_save_mean, const float* d_save_invstd, const float* d_gamma /*or NULL*/,
+                    float* d_dx, float* d_dresidual /*or NULL*/, float* d_dgamma /*or NULL*/,
+                    float* d_dbeta /*or NULL*/, void* d_ws, int64_t ws_bytes, lk_stream_t s);
+
 /* Fused bias-free Linear + LayerNorm: out = LN(x @ W^T; gamma, beta, eps); x, out [n, c],
  * W [c, c] (nn.Linear layout).  ELKBlock.pre_mix (linkencoder.py:112-115).  c in {16,32,64,128}. */
 int lk_linear_ln_fwd(const float* d_x, const float* d_w, const float* d_gamma, const float* d_beta,

@@ -122,6 +122,10 @@ PROTOTYPES = {
     'lk_elk_block_fwd': (i32, [C.POINTER(ElkBlockArgs), vp]),
     'lk_elk_encoder_ws_bytes': (i64, [i64, i32, i32, i32, i32]),
     'lk_elk_encoder_fwd': (i32, [C.POINTER(ElkEncoderArgs), vp]),
+    'lk_bn_supported': (i32, [i32]),
+    'lk_bn_ws_bytes': (i64, [i32]),
+    'lk_bn_train_fwd': (i32, [vp, vp, i64, i32, vp, vp, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    'lk_bn_train_bwd': (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     'lk_linear_ln_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_linear_ln_tc_fwd': (i32, [vp, vp, vp, vp, C.c_float, i64, i32, vp, vp]),
     'lk_kmap_query': (i32, [vp, i64, vp, i32, vp, i64, vp, vp]),

@@ -41,6 +41,14 @@ __all__ = ['ELKEncoder', 'LinKEncoder', 'BasicConvolutionBlock', 'BasicDeconvolu
            'ResidualBlock']
 
 
+def _conv_bn_act(x: SparseTensor, conv, bn, relu: bool, residual=None) -> SparseTensor:
+    """Conv3d -> BatchNorm [-> + residual] [-> ReLU] outside the inference fast path: the conv is its
+    autograd Function, BatchNorm + add + ReLU ONE fused op (training mode: csrc/bn.cu; else PyTorch's)."""
+    y = conv(x)
+    y.F = F.batch_norm_act(y.F, bn, relu, residual)
+    return y
+
+
 class BasicConvolutionBlock(nn.Module):
     """Conv3d -> BatchNorm -> ReLU (linkencoder.py:23-39)."""
 
@@ -55,7 +63,7 @@ class BasicConvolutionBlock(nn.Module):
     def forward(self, x):
         if F.fusable(self.net[0], self.net[1], x):
             return F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
-        return self.net(x)
+        return _conv_bn_act(x, self.net[0], self.net[1], True)
 
 
 class BasicDeconvolutionBlock(nn.Module):
@@ -72,7 +80,7 @@ class BasicDeconvolutionBlock(nn.Module):
     def forward(self, x):
         if F.fusable(self.net[0], self.net[1], x):
             return F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
-        return self.net(x)
+        return _conv_bn_act(x, self.net[0], self.net[1], True)
 
 
 class ResidualBlock(nn.Module):
@@ -102,7 +110,9 @@ class ResidualBlock(nn.Module):
             shortcut = self.downsample(x).F if len(self.downsample) else x.F
             y = F.conv_bn_act(x, self.net[0], self.net[1], relu=True)
             return F.conv_bn_act(y, self.net[3], self.net[4], relu=True, residual=shortcut.contiguous())
-        return self.relu(self.net(x) + self.downsample(x))
+        shortcut = self.downsample(x).F if len(self.downsample) else x.F
+        y = _conv_bn_act(x, self.net[0], self.net[1], True)
+        return _conv_bn_act(y, self.net[3], self.net[4], True, shortcut)
 
 
 class ConvBN(nn.Sequential):
@@ -113,12 +123,7 @@ class ConvBN(nn.Sequential):
     def forward(self, x, residual=None, relu=False):
         if F.fusable(self[0], self[1], x):
             return F.conv_bn_act(x, self[0], self[1], relu=relu, residual=residual)
-        y = self[1](self[0](x))
-        if residual is not None:
-            y.F = y.F + residual
-        if relu:
-            y.F = torch.relu(y.F)
-        return y
+        return _conv_bn_act(x, self[0], self[1], relu, residual)
 
 
 def _tail(inc, outc):
@@ -275,7 +280,7 @@ class _ELKBackbone(nn.Module):
             x0 = F.conv_bn_act(F.conv_bn_act(x, self.stem[0], self.stem[1], relu=True),
                                self.stem[3], self.stem[4], relu=True)
         else:
-            x0 = self.stem(x)
+            x0 = _conv_bn_act(_conv_bn_act(x, self.stem[0], self.stem[1], True), self.stem[3], self.stem[4], True)
         feats = [x0]
         cur = x0
         for lv in (1, 2, 3, 4):

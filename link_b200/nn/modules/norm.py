@@ -8,10 +8,13 @@ __all__ = ['BatchNorm', 'GroupNorm']
 
 
 class BatchNorm(nn.BatchNorm1d):
-    """BatchNorm1d over the feature rows (reference: torchsparse/nn/modules/norm.py:10-13)."""
+    """BatchNorm1d over the feature rows (reference: torchsparse/nn/modules/norm.py:10-13).  In
+    training mode on fp32 CUDA rows the statistics / normalisation / backward run on the fused
+    kernels of csrc/bn.cu (nn.functional.batch_norm_act); same values and running statistics."""
 
     def forward(self, input: SparseTensor) -> SparseTensor:
-        return fapply(input, super().forward)
+        from link_b200.nn.functional.norm import batch_norm_act
+        return fapply(input, batch_norm_act, self)
 
 
 class GroupNorm(nn.GroupNorm):

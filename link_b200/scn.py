@@ -25,6 +25,7 @@ from link_b200 import _capi
 from link_b200.nn.functional import _index
 from link_b200.nn.functional.conv import KernelMap, ConvolutionFunction, _conv_fwd, _folded_bn
 from link_b200.nn.functional.hash import sphash
+from link_b200.nn.functional.norm import batch_norm_act
 from link_b200.nn.functional.query import HashTable
 from link_b200.ts_elk import SparseConvTensor, TSELKBlock
 
@@ -212,6 +213,11 @@ class SparseSequential(nn.Sequential):
                 continue
             if isinstance(m, (_SparseConvBase, SparseSequential, SparseBasicBlock)):
                 x = m(x)
+            elif isinstance(m, nn.BatchNorm1d) and m.training:
+                # BatchNorm1d(train) [-> ReLU] as one fused op (csrc/bn.cu)
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                x = x.replace_feature(batch_norm_act(x.features, m, relu))
+                i += 1 if relu else 0
             else:
                 x = x.replace_feature(m(x.features))
             i += 1
@@ -249,10 +255,9 @@ class SparseBasicBlock(nn.Module):
             return self.conv2(out, scale=s2, shift=h2, relu=True,
                               residual=identity.features.contiguous().float())
         out = self.conv1(x)
-        out = out.replace_feature(self.relu(self.bn1(out.features)))
+        out = out.replace_feature(batch_norm_act(out.features, self.bn1, True))
         out = self.conv2(out)
-        out = out.replace_feature(self.bn2(out.features))
-        return out.replace_feature(self.relu(out.features + identity.features))
+        return out.replace_feature(batch_norm_act(out.features, self.bn2, True, identity.features))
 
 
 class SpMiddleResNetFHDELKv3(nn.Module):
