@@ -450,7 +450,7 @@ def run_train(args, steps, warmup, dev, rank, world, local):
 
     def step(i, sync=True):
         c_h, f_h, y_h = batches[i % 2]
-        st = SparseTensor.from_host(f_h, c_h, 1, device=dev)
+        st = SparseTensor.from_host(f_h, c_h, 1, device=dev, ahead=True)   # uploads + coordinate pyramid overlap the previous step's tail
         y = y_h.to(dev, non_blocking=True)
         ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
         with ctx:

@@ -44,6 +44,11 @@ int64_t lk_launch_count(void);
  * node; the host side pins its staging buffers on that device's NUMA node (link_b200/sharding.py:
  * bind_host_to_gpu).  No counterpart in the reference (its loaders leave placement to the OS). */
 int lk_device_pci_bus_id(int device, char* buf, int len);
+/* Pinned host memory for the upload path (cudaHostAlloc); write_combined = 1 for staging buffers the host
+ * only writes (cudaHostAllocWriteCombined: uncached on the CPU side, DMA reads not snooped).  The reference
+ * leaves pinning to torch's DataLoader (pin_memory=True, segmentation/train.py). */
+int lk_host_alloc(int64_t bytes, int write_combined, void** out);
+int lk_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------
  * Hashing -- replaces hash_cuda / kernel_hash_cuda (backend/hash/hash_cuda.cu:10-84).

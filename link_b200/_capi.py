@@ -83,6 +83,8 @@ PROTOTYPES = {
     'lk_version': (i32, []),
     'lk_launch_count': (i64, []),
     'lk_device_pci_bus_id': (i32, [i32, C.c_char_p, i32]),
+    'lk_host_alloc': (i32, [i64, i32, C.POINTER(C.c_void_p)]),
+    'lk_host_free': (i32, [vp]),
     'lk_hash': (i32, [vp, i64, vp, vp]),
     'lk_kernel_hash': (i32, [vp, i64, vp, i32, vp, vp]),
     'lk_table_capacity': (i64, [i64]),

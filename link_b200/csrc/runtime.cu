@@ -31,6 +31,28 @@ extern "C" int lk_device_pci_bus_id(int device, char* buf, int len) {
   return LK_OK;
 }
 
+// Pinned host staging memory for the upload path.  write_combined = 1: cudaHostAllocWriteCombined -- the CPU
+// writes it through write-combining buffers and never caches it, so the DMA engine's reads are not snooped
+// through the CPU caches; meant for buffers the host only WRITES (features on their way to the device).
+extern "C" int lk_host_alloc(int64_t bytes, int write_combined, void** out) {
+  if (!out || bytes <= 0) return LK_EINVAL;
+  cudaError_t e = cudaHostAlloc(out, (size_t)bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    lk_set_error("cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    return LK_ECUDA;
+  }
+  return LK_OK;
+}
+extern "C" int lk_host_free(void* p) {
+  if (!p) return LK_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) {
+    lk_set_error("cudaFreeHost: %s", cudaGetErrorString(e));
+    return LK_ECUDA;
+  }
+  return LK_OK;
+}
+
 // programmatic dependent launch on/off (LINKB200_PDL=0 restores ordinary launches; common.cuh)
 bool lk_pdl_enabled() {
   static const bool on = [] {

@@ -26,6 +26,17 @@ from link_b200.utils import make_ntuple
 BRANCH_OVERLAP = os.environ.get('LINKB200_BRANCH_OVERLAP', '1') != '0'
 PY_BRANCH_OVERLAP = os.environ.get('LINKB200_PY_BRANCH_OVERLAP', '0') == '1'
 _BRANCH_STREAMS = {}
+# coordinate pyramid of plan_levels as four parallel chains on side streams (0: level by level on the current stream)
+PARALLEL_PYRAMID = os.environ.get('LINKB200_PARALLEL_PYRAMID', '1') != '0'
+_PYRAMID_STREAMS = {}
+
+
+def _pyramid_streams(device):
+    st = _PYRAMID_STREAMS.get(device)
+    if st is None:
+        st = _PYRAMID_STREAMS[device] = [torch.cuda.Stream(device) for _ in range(4)]
+    return st
+
 # inference: the whole backbone behind one library call (lk_elk_encoder_fwd); '0': one call per layer
 NATIVE_ENCODER = os.environ.get('LINKB200_NATIVE_ENCODER', '1') != '0'
 
@@ -178,12 +189,67 @@ class _ELKBackbone(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    def _pyramid_parallel(self, x: SparseTensor):
+        """Output sites of the four strided levels, or None when the fast path does not apply.  The sites
+        of level l are the distinct values of floor(c0 / 2^l) 2^l, so every level derives from the INPUT
+        coordinates: four independent pack -> sort -> unique -> unpack chains (lk_downsample) on four side
+        streams that wait only for the coordinates, and the four size read-backs synchronise those side
+        streams only.  In a training loop the current stream still holds the previous step's backward when
+        the next forward starts; read-backs on it (the level-by-level order) drain the device at every
+        step, these do not (SparseTensor.from_host(ahead=True) uploads the coordinates off-stream too)."""
+        from link_b200.nn.functional import _index
+        coords = x.coords
+        if not (PARALLEL_PYRAMID and coords.is_cuda and coords.shape[0] > 0 and tuple(x.stride) == (1, 1, 1)):
+            return None
+        convs = [getattr(self, f'down{lv}')[0].net[0] for lv in (1, 2, 3, 4)]
+        if not all(tuple(c.kernel_size) == (2, 2, 2) and tuple(c.stride) == (2, 2, 2) for c in convs):
+            return None
+        if ((1, 1, 1), (2, 2, 2), (2, 2, 2), make_ntuple(convs[0].dilation, ndim=3)) in x.kmaps:
+            return None                                   # maps already built for this scan
+        L = _capi.lib()
+        coords = coords.contiguous()
+        n0, dev = coords.shape[0], coords.device
+        bounds = _index.coord_bounds(coords, x.kmaps)
+        main = torch.cuda.current_stream(dev)
+        ev0 = getattr(x, '_coords_ready', None)
+        if ev0 is None:
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+        side = _pyramid_streams(dev)
+        ws_bytes = L.lk_downsample_ws_bytes(n0)
+        outs, nums = [], []
+        for l in (1, 2, 3, 4):
+            ss = (2 ** l,) * 3
+            spec, bits = _index.make_keyspec(bounds, ss, (3, 0, 1, 2), ss)
+            with torch.cuda.stream(side[l - 1]):
+                side[l - 1].wait_event(ev0)
+                out = torch.empty(n0, 4, dtype=torch.int32, device=dev)
+                num = torch.empty(1, dtype=torch.int32, device=dev)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _capi.check(L.lk_downsample(_capi.ptr(coords, torch.int32), n0, C.byref(spec), bits, out.data_ptr(),
+                                            num.data_ptr(), ws.data_ptr(), ws_bytes, _capi.stream()), 'lk_downsample')
+            outs.append(out)
+            nums.append(num)
+        sizes = []
+        for l in (1, 2, 3, 4):
+            with torch.cuda.stream(side[l - 1]):
+                sizes.append(int(nums[l - 1].item()))     # synchronises this side stream only
+        levels = []
+        for l in (1, 2, 3, 4):
+            main.wait_stream(side[l - 1])
+            outs[l - 1].record_stream(main)
+            c_l = outs[l - 1][:sizes[l - 1]]
+            _index.register_floored_bounds(x.kmaps, c_l, bounds, (2 ** l,) * 3)
+            levels.append(c_l)
+        return levels
+
     def plan_levels(self, x: SparseTensor) -> None:
         """Index-only prologue: builds the coordinate pyramid (the four stride-2 kernel maps and
         their output coordinates) before any feature kernel is enqueued.  The output size of each
         strided conv is data dependent (one 4-byte read-back per level); doing those read-backs
         here, while only tiny index kernels are in flight, lets the whole feature pipeline that
-        follows be enqueued without a single host<->device synchronisation."""
+        follows be enqueued without a single host<->device synchronisation on the current stream."""
+        pyramid = self._pyramid_parallel(x)
         t = x
         for lv in (1, 2, 3, 4):
             conv = getattr(self, f'down{lv}')[0].net[0]
@@ -191,7 +257,8 @@ class _ELKBackbone(nn.Module):
             key = (t.stride, conv.kernel_size, conv.stride, dil)
             kmap = t.kmaps.get(key)
             if kmap is None:
-                kmap = F.build_kernel_map(t, conv.kernel_size, conv.stride, dil)
+                kmap = F.build_kernel_map(t, conv.kernel_size, conv.stride, dil,
+                                          out_coords=pyramid[lv - 1] if pyramid is not None else None)
                 t.kmaps[key] = kmap
             nxt = SparseTensor(t.feats, kmap.out_coords,
                                tuple(t.stride[k] * conv.stride[k] for k in range(3)))

@@ -127,7 +127,8 @@ def _table_for(input: SparseTensor) -> HashTable:
     return tab
 
 
-def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_plan: bool = False) -> KernelMap:
+def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_plan: bool = False,
+                     out_coords: Optional[torch.Tensor] = None) -> KernelMap:
     """Kernel map of a conv over `input` (the kmap branch of the reference's F.conv3d,
     conv.py:103-121) through ONE library call (lk_kmap_build: hash -> table -> query [-> plan]);
     the hash table of the input level is kept in `kmaps` and reused by later maps of that level."""
@@ -135,9 +136,10 @@ def build_kernel_map(input: SparseTensor, kernel_size, stride, dilation, want_pl
     dev = coords.device
     # NB: like the reference (conv.py:105-107) the offsets ignore `dilation`.
     offsets = get_kernel_offsets(kernel_size, stride=input.stride, device=dev)
-    out_coords = coords
-    if any(s > 1 for s in stride):
-        out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
+    if out_coords is None:          # (a caller that derived the output sites already passes them in)
+        out_coords = coords
+        if any(s > 1 for s in stride):
+            out_coords = spdownsample(coords, stride, kernel_size, input.stride, cache=input.kmaps)
     k, n_in, n_out = offsets.shape[0], coords.shape[0], out_coords.shape[0]
     L = _capi.lib()
     tkey = ('lk', 'table', input.stride)
@@ -454,6 +456,27 @@ class ConvolutionFunction(Function):
         return grad_feats, grad_weight, None, None
 
 
+def _conv_autograd(feats: torch.Tensor, weight: torch.Tensor, kmap: KernelMap) -> torch.Tensor:
+    """Non-transposed conv with autograd.  Training on fp32 rows at a tensor-core width takes the C++
+    autograd node (link_b200/_ext.py: same kernels, the glue and the backward node outside the
+    interpreter); everything else the python ConvolutionFunction."""
+    from link_b200 import _ext
+    k, c_in, c_out = weight.shape
+    if (torch.is_grad_enabled() and (feats.requires_grad or weight.requires_grad) and feats.is_cuda
+            and feats.dtype == torch.float32 and weight.dtype == torch.float32 and USE_TENSOR_CORES and USE_TC_WGRAD
+            and USE_PLAN and k <= 32 and c_in in (32, 64, 128) and c_out in (32, 64, 128) and kmap.n_out > 0
+            and kmap.n_out * k < 2 ** 31 and feats.shape[1] == c_in):
+        ext = _ext.module()
+        plan = kmap.plan() if ext is not None else None
+        if plan is not None:
+            _capi.check_device(feats)
+            wg = kmap.wgrad_relation(False) if weight.requires_grad else (None, None, None)
+            inv = kmap.inv if (feats.requires_grad and not kmap.subm) else None
+            return ext.conv(feats, weight, kmap.nbr, plan[0], plan[1], inv, wg[0], wg[1], wg[2], kmap.subm,
+                            precision_code(), WGRAD_SLOTS)
+    return ConvolutionFunction.apply(feats, weight, kmap, False)
+
+
 def _folded_bn(bn):
     """Eval-mode BatchNorm as a per-channel affine (scale, shift), cached until a parameter or
     running statistic of the module changes."""
@@ -535,7 +558,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
         if kmap is None:
             kmap = build_kernel_map(input, kernel_size, stride, dilation)
             input.kmaps[key] = kmap
-        feats = ConvolutionFunction.apply(feats, weight, kmap, False)
+        feats = _conv_autograd(feats, weight, kmap)
         if bias is not None:
             feats += bias
         output = SparseTensor(coords=kmap.out_coords, feats=feats,

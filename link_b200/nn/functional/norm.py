@@ -70,6 +70,12 @@ def batch_norm_act(x: torch.Tensor, bn, relu: bool = False, residual: Optional[t
     """relu?(bn(x) [+ residual]) for a BatchNorm module `bn`: the fused kernels in training mode on
     fp32 CUDA rows (see bn_act_supported), PyTorch's ops otherwise (eval mode, other dtypes, CPU)."""
     if bn_act_supported(bn, x) and (residual is None or (residual.dtype == torch.float32 and residual.shape == x.shape)):
+        from link_b200 import _ext
+        ext = _ext.module()
+        if ext is not None:      # the same two kernels behind a C++ autograd node (no python in the backward)
+            _capi.check_device(x)
+            return ext.batch_norm_act(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var,
+                                      bn.num_batches_tracked, float(bn.eps), float(bn.momentum), bool(relu))
         return BatchNormActFunction.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var,
                                           bn.num_batches_tracked, float(bn.eps), float(bn.momentum), bool(relu))
     y = torch.nn.modules.batchnorm._BatchNorm.forward(bn, x)       # (not bn(x): spnn.BatchNorm takes SparseTensors)

@@ -44,6 +44,7 @@ class SparseTensor:
                  stride: Union[int, Tuple[int, ...]] = 1) -> None:
         self._feats = feats
         self._feats_ready = None       # CUDA event of a pending async upload (from_host), or None
+        self._coords_ready = None      # CUDA event of the coordinate upload when it ran on the copy stream (ahead=True)
         self.coords = coords
         self.stride = make_ntuple(stride, ndim=3)
         self.cmaps: Dict[Tuple[int, ...], torch.Tensor] = {}
@@ -73,7 +74,7 @@ class SparseTensor:
 
     @classmethod
     def from_host(cls, feats: torch.Tensor, coords: torch.Tensor,
-                  stride: Union[int, Tuple[int, ...]] = 1, device=None, dtype=None) -> 'SparseTensor':
+                  stride: Union[int, Tuple[int, ...]] = 1, device=None, dtype=None, ahead: bool = False) -> 'SparseTensor':
         """Upload a scan from (pinned) host memory.  The coordinates go first on the current stream;
         the features -- 16x more bytes at C = 64 -- follow on a dedicated copy stream, so the index
         build of the first layer (hash grid, kernel map, conv plan, block sort: ~45 % of a LinK
@@ -82,14 +83,40 @@ class SparseTensor:
 
         The step is PCIe-bound end to end, so the features may cross the wire narrower than they are
         computed in: host features in bf16 / fp16 are uploaded as they are (half the bytes) and widened
-        to `dtype` (default: kept) on the device, on the copy stream, before the upload event."""
+        to `dtype` (default: kept) on the device, on the copy stream, before the upload event.
+
+        `ahead=True` (training loops, where the current stream still holds the previous step's backward):
+        coordinates AND features are uploaded on the copy stream into buffers allocated there, without
+        waiting for the current stream, so the upload -- and the index work that depends only on the
+        coordinates (ELKEncoder.plan_levels builds the coordinate pyramid on side streams) -- overlaps
+        the tail of the previous step.  The current stream waits for the coordinates by an event; the
+        buffers are handed to it with `record_stream`."""
         device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
         main = torch.cuda.current_stream(device)
+        copy_stream = _copy_stream(device)
+        widen = dtype is not None and dtype != feats.dtype
+        if ahead:
+            with torch.cuda.stream(copy_stream):
+                c_dev = torch.empty(coords.shape, dtype=coords.dtype, device=device)
+                c_dev.copy_(coords, non_blocking=True)
+                ev_c = torch.cuda.Event()
+                ev_c.record(copy_stream)
+                f_wire = torch.empty(feats.shape, dtype=feats.dtype, device=device)
+                f_wire.copy_(feats, non_blocking=True)
+                f_dev = f_wire.to(dtype) if widen else f_wire
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            c_dev.record_stream(main)
+            f_dev.record_stream(main)
+            main.wait_event(ev_c)          # every later consumer of the coordinates on this stream is ordered
+            st = cls(f_dev, c_dev, stride)
+            st._feats_ready = ev
+            st._coords_ready = ev_c
+            _seed_bounds_from_host(st, coords)
+            return st
         c_dev = coords.to(device, non_blocking=True)
         f_wire = torch.empty(feats.shape, dtype=feats.dtype, device=device)
-        widen = dtype is not None and dtype != feats.dtype
         f_dev = torch.empty(feats.shape, dtype=dtype, device=device) if widen else f_wire
-        copy_stream = _copy_stream(device)
         copy_stream.wait_stream(main)      # the buffers may recycle memory still in use by queued kernels
         with torch.cuda.stream(copy_stream):
             f_wire.copy_(feats, non_blocking=True)
@@ -231,3 +258,40 @@ class UploadRing:
         st._feats_ready = ev
         _seed_bounds_from_host(st, coords)
         return st
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block (freed when the last tensor viewing it is gone)."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        import ctypes as C
+        from link_b200 import _capi
+        p = C.c_void_p()
+        _capi.check(_capi.lib().lk_host_alloc(nbytes, 1 if write_combined else 0, C.byref(p)), 'lk_host_alloc')
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        try:
+            from link_b200 import _capi
+            _capi.lib().lk_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=torch.float32, write_combined: bool = False) -> torch.Tensor:
+    """Uninitialised pinned host tensor (cudaHostAlloc through liblinkb200).  `write_combined=True` is for
+    staging buffers the host only WRITES before they are uploaded (features on their way to
+    `SparseTensor.from_host` / `UploadRing.upload`): the memory is uncached on the CPU side, so host READS of
+    it are very slow -- keep coordinates (the host computes their bounds) in ordinary pinned memory."""
+    import ctypes as C
+    import numpy as np
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)))
+    n = 1
+    for v in shape:
+        n *= v
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    block = _PinnedBlock(max(n * itemsize, 1), write_combined)
+    buf = (C.c_uint8 * (n * itemsize)).from_address(block.ptr)
+    buf._lk_owner = block                                  # the ctypes array keeps the allocation alive
+    t = torch.frombuffer(buf, dtype=torch.uint8).view(dtype).view(shape) if n else torch.empty(shape, dtype=dtype)
+    return t
