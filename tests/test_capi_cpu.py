@@ -147,3 +147,15 @@ def test_bind_host_to_gpu_is_safe_without_a_device():
     info = bind_host_to_gpu(0, sysfs='/nonexistent')
     assert info['bound'] is False
     assert os.sched_getaffinity(0) == before
+
+
+def test_autograd_extension_binds_the_library():
+    """link_b200/_ext.py: when the C++ autograd extension has been built (by __graft_entry__.build()), it
+    loads on a machine without a GPU and accepts the addresses of the library's entry points."""
+    from link_b200 import _ext
+    if _ext._so_path() is None:
+        pytest.skip('C++ autograd extension not built')
+    m = _ext.module()
+    assert m is not None and m.ready()
+    with pytest.raises(RuntimeError):
+        m.bind('lk_no_such_entry_point', 0)
