@@ -9,7 +9,7 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput', 'wrap_ddp', 'bind_host_to_gpu', 'parse_cpulist']
+__all__ = ['shard_frames', 'frame_seed', 'reduce_throughput', 'wrap_ddp', 'sync_buffers', 'bind_host_to_gpu', 'parse_cpulist']
 
 
 def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
@@ -95,8 +95,26 @@ def wrap_ddp(model: torch.nn.Module, device_index=None, unused_prefixes: Sequenc
     ignored += [n for n, _ in model.named_buffers() if n.split('.')[0] in unused_prefixes]
     if ignored:
         DDP._set_params_and_buffers_to_ignore_for_model(model, ignored)
-    kw = dict(find_unused_parameters=False, gradient_as_bucket_view=True)
+    # broadcast_buffers: DDP's default re-broadcasts every buffer (here: the running statistics of ~30
+    # BatchNorms) from rank 0 at the start of EVERY forward -- a coalesce / broadcast / scatter sequence on
+    # the critical path of a step whose only effect is that all ranks carry rank 0's running statistics.
+    # The same end state is reached by broadcasting them once, before evaluation or a checkpoint
+    # (`sync_buffers`), so it is off here.
+    kw = dict(find_unused_parameters=False, gradient_as_bucket_view=True, broadcast_buffers=False)
     kw.update(kwargs)
     if device_index is not None:
         kw['device_ids'] = [device_index]
     return DDP(model, **kw)
+
+
+def sync_buffers(model: torch.nn.Module, src: int = 0) -> None:
+    """Broadcast every buffer (BatchNorm running statistics, counters) from rank `src`: the state DDP's
+    default `broadcast_buffers=True` maintains at every step, established once -- call before evaluation
+    or saving a checkpoint when the model was wrapped with `wrap_ddp` (which turns the per-step broadcast
+    off).  Single process: no-op."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    m = model.module if hasattr(model, 'module') else model
+    with torch.no_grad():
+        for b in m.buffers():
+            dist.broadcast(b, src)

@@ -131,11 +131,12 @@ def _wrap_worker(rank, world, port, out):
         def __init__(self):
             super().__init__()
             self.stem = torch.nn.Linear(4, 8)
+            self.bn = torch.nn.BatchNorm1d(8)
             self.head = torch.nn.Linear(8, 3)
             self.up1 = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8))   # built, never used
 
         def forward(self, x):
-            return self.head(torch.relu(self.stem(x)))
+            return self.head(torch.relu(self.bn(self.stem(x))))
 
     net = Net()
     ddp = wrap_ddp(net)
@@ -145,6 +146,15 @@ def _wrap_worker(rank, world, port, out):
         ddp(xs[rank]).square().mean().backward()
     got = torch.cat([p.grad.flatten() for n, p in net.named_parameters() if not n.startswith('up1')])
     assert all(p.grad is None for n, p in net.named_parameters() if n.startswith('up1'))
+    # wrap_ddp does not re-broadcast the buffers at every forward: the ranks' running statistics differ
+    # until sync_buffers establishes rank 0's on every rank (what DDP's default does per step)
+    from link_b200.sharding import sync_buffers
+    mine = net.bn.running_mean.clone()
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert float((both[0] - both[1]).abs().max()) > 1e-4
+    sync_buffers(ddp)
+    assert torch.equal(net.bn.running_mean, both[0]) and int(net.bn.num_batches_tracked) == 2
     ref = Net()
     ref.load_state_dict(net.state_dict())
     (sum(ref(x).square().mean() for x in xs) / world).backward()
