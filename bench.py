@@ -373,7 +373,7 @@ def run_workload(args, workload, steps, warmup, dev, rank, world, local, with_cl
         # same calls through a caller-owned staging ring, issued back to back, ONE event pair around
         # the loop: the upload of scan i+1 overlaps the processing of scan i
         from link_b200.tensor import UploadRing
-        ring = UploadRing(max(n_vox), feats_host[0].shape[1], device=dev, depth=2)
+        ring = UploadRing(max(n_vox), feats_host[0].shape[1], device=dev, depth=int(os.environ.get('LINKB200_RING_DEPTH', '2')))
         for k in range(w_e2e):
             out_host.copy_(step_st(k % 2, ring.upload(feats_host[k % 2], coords_host[k % 2], 1), seed_bounds=False).sum(dim=0), non_blocking=True)
         barrier()
