@@ -39,6 +39,15 @@ for c, groups, s, r in [(64, 2, 7, 3), (32, 1, 3, 2)]:
     blk.train()(SparseTensor(fr, coords, 1), s, r).F.sum().backward()     # fused backward kernels
     torch.cuda.synchronize()
     print(f'block C={c} ({r}x{s})^3: ok', float(out.abs().sum()), float(fr.grad.abs().sum()), flush=True)
+# fused training-mode BatchNorm + shortcut + ReLU (double accumulators, odd channel-group counts), forward and backward
+import link_b200.nn.functional as F2
+for nn_, cc in [(4097, 20), (3000, 128), (257, 1024), (2, 4)]:
+    bn = torch.nn.BatchNorm1d(cc).to(dev).train()
+    xb = torch.randn(nn_, cc, device=dev, requires_grad=True)
+    rb = torch.randn(nn_, cc, device=dev, requires_grad=True)
+    F2.batch_norm_act(xb, bn, True, rb).square().sum().backward()
+    torch.cuda.synchronize()
+    print(f'bn n={nn_} c={cc}: ok', float(xb.grad.abs().sum()), flush=True)
 # the native encoder executor: five streams, four sort chains, one workspace arena carved for n0 rows per level
 from link_b200.linkencoder import ELKEncoder
 enc = ELKEncoder(num_classes=19, cr=0.5, baseop='cos', r=3, s=7, groups=2).to(dev).eval()
